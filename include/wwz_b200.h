@@ -1,0 +1,166 @@
+/*
+ * wwz_b200.h -- C ABI of the B200-native weighted wavelet Z-transform (Kirchner variant).
+ *
+ * This is the drop-in boundary for Pyleoclim's WWZ kernels.  The only native interface the
+ * reference has for this path is the f2py module
+ *
+ *     f2py_wwz.f2py_wwz.wwa(taus, omegas, c, Neff, ts, pd_ys, nthread, nts, nt, nf)
+ *         -> Neffs, a0, a1, a2                      pyleoclim/f2py/f2py_wwz.f90:13-21
+ *     (call site pyleoclim/utils/wavelet.py:1154, NaN sentinel handling :1156-1159,
+ *      amplitude / phase :1160-1161)
+ *
+ * and every entry point below keeps its conventions: inputs are borrowed read-only
+ * `const double*` vectors, `omegas` is the angular-frequency vector already produced by
+ * make_omega (utils/wavelet.py:1210-1234; NaN above Nyquist), `pd_ys` is the already
+ * preprocessed series (utils/wavelet.py:976), outputs are caller-allocated and laid out
+ * [nt, nf] row-major (C order, tau-major rows -- the layout of np.ndarray(shape=(nt, nf)),
+ * utils/wavelet.py:980-983).  Masked cells hold NaN (not the Fortran -99999 sentinel).
+ *
+ * No Python, NumPy or torch type appears in any signature.  All functions return 0 on success
+ * and a negative WWZB200_ERR_* code otherwise; wwzb200_last_error() returns a thread-local
+ * human-readable message for the last failure.  There is no CPU fallback: without a CUDA
+ * device every compute entry point fails with WWZB200_ERR_CUDA.
+ *
+ * Host-pointer entry points copy host<->device internally (pinned staging, one stream).
+ * The *_dev entry points take device pointers and a cudaStream_t (passed as void*); they
+ * enqueue work and return without synchronising.
+ */
+#ifndef WWZ_B200_H
+#define WWZ_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
+#define WWZB200_OK 0
+#define WWZB200_ERR_ARG (-1)   /* bad argument (the reference asserts, utils/wavelet.py:971) */
+#define WWZB200_ERR_CUDA (-2)  /* CUDA runtime / launch failure, or no device */
+#define WWZB200_ERR_NOMEM (-3) /* host or device allocation failure */
+
+/* flags */
+#define WWZB200_DENSE 1u        /* evaluate every (cell, point) pair; default skips point chunks \
+                                   whose weights are all exactly 0.0 in fp64 (bit-identical) */
+#define WWZB200_STANDARDIZE 2u  /* batched entry points: z-score every series on the device       \
+                                   (utils/tsutils.py:1134-1154, ddof=0, eps=1e-3 guard) */
+#define WWZB200_FAITHFUL 4u     /* validation mode: evaluate every cell with the reference's own    \
+                                   two-pass expressions (utils/wavelet.py:988-1032), one warp per   \
+                                   cell; ~10x slower, agrees with kirchner_numba to ~1e-12 */
+
+const char *wwzb200_last_error(void);
+int wwzb200_version(void);
+
+/* (6) device selection.  One CUDA context per process; one process per GPU under torchrun. */
+int wwzb200_device_count(int *count);
+int wwzb200_set_device(int device);
+int wwzb200_get_device(int *device);
+int wwzb200_sm_count(int *sms);
+/* Release every cached device workspace of the current device. */
+int wwzb200_release(void);
+/* Page-locked host buffers (so that the host-pointer entry points move data by DMA). */
+int wwzb200_alloc_pinned(size_t bytes, void **ptr);
+int wwzb200_free_pinned(void *ptr);
+
+/* (1) Single-series Kirchner transform.  Replaces f2py_wwz.wwa (f2py_wwz.f90:13-44) and the cell
+ * loop of kirchner_numba (utils/wavelet.py:985-1042), plus wwa/phase (:1044-1045).
+ * Any of a0, a1, a2, wwa, phase may be NULL (not returned).  Neffs is required. */
+int wwzb200_kirchner(const double *ts, const double *pd_ys, int64_t nts, const double *taus,
+                     int64_t nt, const double *omegas, int64_t nf, double c, int64_t Neff_threshold,
+                     uint32_t flags, double *Neffs, double *a0, double *a1, double *a2, double *wwa,
+                     double *phase);
+
+/* (2) Same transform with the wwa2psd tau-reduction fused behind it (utils/wavelet.py:1270-1278,
+ * reached from utils/spectral.py:889-896).  `psd_Neff_threshold` is the threshold wwa2psd uses;
+ * the transform itself uses `Neff_threshold` (the reference's wwz_psd does not forward its own
+ * threshold to wwz, utils/spectral.py:889-891).  The per-cell outputs may all be NULL. */
+int wwzb200_kirchner_psd(const double *ts, const double *pd_ys, int64_t nts, const double *taus,
+                         int64_t nt, const double *omegas, int64_t nf, double c,
+                         int64_t Neff_threshold, int64_t psd_Neff_threshold, uint32_t flags,
+                         double *psd, double *Neffs, double *a0, double *a1, double *a2, double *wwa,
+                         double *phase);
+
+/* wwa2psd alone on an existing scalogram (utils/wavelet.py:1270-1278): the reference skips the
+ * transform when a scalogram is supplied (utils/spectral.py:888). */
+int wwzb200_wwa2psd(const double *wwa, const double *Neffs, int64_t nt, int64_t nf, double tspan,
+                    int64_t nts, int64_t Neff_threshold, double *psd);
+
+/* (3) Batched transform of S series that share one time axis -- the AR(1)-surrogate significance
+ * loop (core/scalograms.py:515-517, core/psds.py:246-282: every surrogate of
+ * SurrogateSeries.from_series keeps the target's time axis, core/surrogateseries.py:170-174).
+ * Y is [S, nts] row-major.  The weights, Neffs and basis sums are evaluated once and contracted
+ * against all S series.  Outputs: Neffs[nt,nf] (shared), wwa[S,nt,nf]; optional a0/a1/a2/phase
+ * [S,nt,nf]; optional psd[S,nf] (wwa2psd per series with psd_Neff_threshold). */
+int wwzb200_kirchner_shared_axis(const double *ts, const double *Y, int64_t nts, int64_t S,
+                                 const double *taus, int64_t nt, const double *omegas, int64_t nf,
+                                 double c, int64_t Neff_threshold, int64_t psd_Neff_threshold,
+                                 uint32_t flags, double *Neffs, double *wwa, double *phase, double *a0,
+                                 double *a1, double *a2, double *psd);
+
+/* (4) Batched transform of M series with their own time axes and grids -- the age-ensemble case
+ * (core/ensembleseries.py:169-173 -> core/multipleseries.py:1520-1532).  Series m occupies
+ * ts/ys[ts_off[m] .. ts_off[m+1]), taus[tau_off[m] .. tau_off[m+1]), omegas[om_off[m] ..
+ * om_off[m+1]); its outputs occupy [out_off[m] .. out_off[m+1]) with out_off[m+1]-out_off[m] =
+ * nt_m*nf_m, each block [nt_m, nf_m] row-major.  Optional psd is packed by om_off. */
+int wwzb200_kirchner_ragged(const double *ts, const double *pd_ys, const int64_t *ts_off,
+                            const double *taus, const int64_t *tau_off, const double *omegas,
+                            const int64_t *om_off, const int64_t *out_off, int64_t M, double c,
+                            int64_t Neff_threshold, int64_t psd_Neff_threshold, uint32_t flags,
+                            double *Neffs, double *a0, double *a1, double *a2, double *wwa,
+                            double *phase, double *psd);
+
+/* (5) AR(1) surrogates on an uneven time axis: S realisations of ar1_model
+ * (utils/tsmodel.py:59-69) as driven by ar1_sim (:159-165) and SurrogateSeries.from_series
+ * (core/surrogateseries.py:137-139):  y[0]=0; rho_i=exp(-(t_i-t_{i-1})/tau_est);
+ * y_i = y_{i-1} rho_i + sigma sqrt(1-rho_i^2) z_i;  Y[s,i] = y_i + mu.
+ * z ~ N(0,1) from a counter-based Philox4x32-10 stream keyed by (seed, s, i); the reference
+ * draws from NumPy's unseeded legacy global generator (its `seed` argument is ineffective,
+ * core/surrogateseries.py:132-133), so streams are statistically, not bitwise, equivalent.
+ * Y is [S, nts] row-major. */
+int wwzb200_ar1_surrogates(const double *ts, int64_t nts, double tau_est, double sigma, double mu,
+                           int64_t S, uint64_t seed, double *Y);
+
+/* Per-cell quantiles over a batch: scipy.stats.mstats.mquantiles(alphap=betap=0.4) semantics as
+ * used by MultipleScalogram.quantiles (core/scalograms.py:635-641) and MultiplePSD.quantiles
+ * (core/psds.py:913).  X is [S, ncell] row-major, q is [nq, ncell]. */
+int wwzb200_quantiles(const double *X, int64_t S, int64_t ncell, const double *probs, int64_t nq,
+                      double *q);
+
+/* ---- device-pointer entry points (inputs/outputs resident in HBM; async on `stream`) ---- */
+int wwzb200_kirchner_dev(const double *d_ts, const double *d_pd_ys, int64_t nts, const double *d_taus,
+                         int64_t nt, const double *d_omegas, int64_t nf, double c,
+                         int64_t Neff_threshold, int64_t psd_Neff_threshold, uint32_t flags,
+                         double *d_Neffs, double *d_a0, double *d_a1, double *d_a2, double *d_wwa,
+                         double *d_phase, double *d_psd, int64_t out_row_stride, void *stream);
+
+int wwzb200_kirchner_shared_axis_dev(const double *d_ts, const double *d_Y, int64_t nts, int64_t S,
+                                     const double *d_taus, int64_t nt, const double *d_omegas,
+                                     int64_t nf, double c, int64_t Neff_threshold,
+                                     int64_t psd_Neff_threshold, uint32_t flags, double *d_Neffs,
+                                     double *d_wwa, double *d_phase, double *d_a0, double *d_a1,
+                                     double *d_a2, double *d_psd, void *stream);
+
+int wwzb200_ar1_surrogates_dev(const double *d_ts, int64_t nts, double tau_est, double sigma,
+                               double mu, int64_t S, uint64_t seed, double *d_Y, void *stream);
+
+int wwzb200_quantiles_dev(const double *d_X, int64_t S, int64_t ncell, const double *d_probs,
+                          int64_t nq, double *d_q, void *stream);
+
+/* FP64 FMA peak of the current device, measured by a register-resident DFMA-chain kernel
+ * (the roofline denominator; MEASURED_PEAKS.json has no FP64 entry).  Returns TFLOP/s. */
+int wwzb200_measure_fp64_peak(double *tflops, double *ms);
+
+/* Kernel launch counter (incremented by every kernel this library launches). */
+int64_t wwzb200_launch_count(void);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* WWZ_B200_H */

@@ -1,0 +1,145 @@
+"""ctypes binding of lib/libwwz_b200.so (the C ABI declared in include/wwz_b200.h).
+
+There is no fallback: if the shared library is missing or a call fails, an exception is raised.
+"""
+import ctypes
+import os
+import weakref
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libwwz_b200.so")
+
+DENSE = 1
+STANDARDIZE = 2
+FAITHFUL = 4
+
+_dp = ctypes.POINTER(ctypes.c_double)
+_ip = ctypes.POINTER(ctypes.c_int64)
+_i64 = ctypes.c_int64
+_u32 = ctypes.c_uint32
+_u64 = ctypes.c_uint64
+_vp = ctypes.c_void_p
+_dbl = ctypes.c_double
+
+_lib = None
+
+
+class WwzB200Error(RuntimeError):
+    pass
+
+
+_SIGS = {
+    "wwzb200_version": (ctypes.c_int, []),
+    "wwzb200_device_count": (ctypes.c_int, [ctypes.POINTER(ctypes.c_int)]),
+    "wwzb200_set_device": (ctypes.c_int, [ctypes.c_int]),
+    "wwzb200_get_device": (ctypes.c_int, [ctypes.POINTER(ctypes.c_int)]),
+    "wwzb200_sm_count": (ctypes.c_int, [ctypes.POINTER(ctypes.c_int)]),
+    "wwzb200_release": (ctypes.c_int, []),
+    "wwzb200_alloc_pinned": (ctypes.c_int, [ctypes.c_size_t, ctypes.POINTER(_vp)]),
+    "wwzb200_free_pinned": (ctypes.c_int, [_vp]),
+    "wwzb200_kirchner": (ctypes.c_int, [_dp, _dp, _i64, _dp, _i64, _dp, _i64, _dbl, _i64, _u32,
+                                        _dp, _dp, _dp, _dp, _dp, _dp]),
+    "wwzb200_kirchner_psd": (ctypes.c_int, [_dp, _dp, _i64, _dp, _i64, _dp, _i64, _dbl, _i64, _i64, _u32,
+                                            _dp, _dp, _dp, _dp, _dp, _dp, _dp]),
+    "wwzb200_wwa2psd": (ctypes.c_int, [_dp, _dp, _i64, _i64, _dbl, _i64, _i64, _dp]),
+    "wwzb200_kirchner_shared_axis": (ctypes.c_int, [_dp, _dp, _i64, _i64, _dp, _i64, _dp, _i64, _dbl, _i64, _i64,
+                                                    _u32, _dp, _dp, _dp, _dp, _dp, _dp, _dp]),
+    "wwzb200_kirchner_ragged": (ctypes.c_int, [_dp, _dp, _ip, _dp, _ip, _dp, _ip, _ip, _i64, _dbl, _i64, _i64,
+                                               _u32, _dp, _dp, _dp, _dp, _dp, _dp, _dp]),
+    "wwzb200_ar1_surrogates": (ctypes.c_int, [_dp, _i64, _dbl, _dbl, _dbl, _i64, _u64, _dp]),
+    "wwzb200_quantiles": (ctypes.c_int, [_dp, _i64, _i64, _dp, _i64, _dp]),
+    "wwzb200_kirchner_dev": (ctypes.c_int, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _dbl, _i64, _i64, _u32,
+                                            _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "wwzb200_kirchner_shared_axis_dev": (ctypes.c_int, [_vp, _vp, _i64, _i64, _vp, _i64, _vp, _i64, _dbl, _i64,
+                                                        _i64, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "wwzb200_ar1_surrogates_dev": (ctypes.c_int, [_vp, _i64, _dbl, _dbl, _dbl, _i64, _u64, _vp, _vp]),
+    "wwzb200_quantiles_dev": (ctypes.c_int, [_vp, _i64, _i64, _vp, _i64, _vp, _vp]),
+    "wwzb200_measure_fp64_peak": (ctypes.c_int, [_dp, _dp]),
+    "wwzb200_launch_count": (_i64, []),
+}
+
+
+def lib():
+    """Load the shared library (raises if it has not been built: there is no CPU path)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise WwzB200Error(
+                "%s not found; build it with `python -m pyleoclim_util_b200.build` "
+                "(pyleoclim_util_b200 has no CPU fallback)" % LIB_PATH)
+        handle = ctypes.CDLL(LIB_PATH)
+        handle.wwzb200_last_error.restype = ctypes.c_char_p
+        handle.wwzb200_last_error.argtypes = []
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(handle, name)      # AttributeError if the ABI is incomplete
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = lib().wwzb200_last_error().decode("utf-8", "replace")
+        if rc == -1:
+            raise ValueError("wwz_b200: " + msg)
+        raise WwzB200Error("wwz_b200 error %d: %s" % (rc, msg))
+
+
+def f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def ptr(a):
+    return None if a is None else a.ctypes.data_as(_dp)
+
+
+def iptr(a):
+    return None if a is None else a.ctypes.data_as(_ip)
+
+
+def device_count():
+    n = ctypes.c_int()
+    check(lib().wwzb200_device_count(ctypes.byref(n)))
+    return n.value
+
+
+def set_device(i):
+    check(lib().wwzb200_set_device(int(i)))
+
+
+def sm_count():
+    n = ctypes.c_int()
+    check(lib().wwzb200_sm_count(ctypes.byref(n)))
+    return n.value
+
+
+def launch_count():
+    return int(lib().wwzb200_launch_count())
+
+
+def measure_fp64_peak():
+    """FP64 FMA peak of the current device (TFLOP/s, kernel ms) from the DFMA-chain microbenchmark."""
+    tf, ms = ctypes.c_double(), ctypes.c_double()
+    check(lib().wwzb200_measure_fp64_peak(ctypes.byref(tf), ctypes.byref(ms)))
+    return tf.value, ms.value
+
+
+def _free_pinned(addr):
+    if _lib is not None:
+        _lib.wwzb200_free_pinned(_vp(addr))
+
+
+def pinned_empty(shape, dtype=np.float64):
+    """NumPy array backed by page-locked host memory (freed when the array is collected)."""
+    shape = tuple(int(s) for s in np.atleast_1d(shape))
+    dt = np.dtype(dtype)
+    nbytes = int(np.prod(shape, dtype=np.int64)) * dt.itemsize
+    p = _vp()
+    check(lib().wwzb200_alloc_pinned(max(nbytes, 1), ctypes.byref(p)))
+    buf = (ctypes.c_char * max(nbytes, 1)).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dt, count=int(np.prod(shape, dtype=np.int64))).reshape(shape)
+    weakref.finalize(buf, _free_pinned, p.value)
+    return arr

@@ -1,0 +1,75 @@
+"""Build libwwz_b200.so in-tree with nvcc for sm_100a.
+
+    python -m pyleoclim_util_b200.build [--force]
+
+The shared library is a plain C-ABI object (include/wwz_b200.h); nothing in it depends on
+Python or torch.  nvcc cross-compiles without a GPU, so this also runs in the CPU-only build
+container; the resulting .so travels to the GPU box with the repository snapshot.
+"""
+import glob
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIBDIR = os.path.join(HERE, "lib")
+LIB = os.path.join(LIBDIR, "libwwz_b200.so")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-std=c++17", "-lineinfo",
+    "-Xcompiler", "-fPIC,-fvisibility=hidden",
+    "--compiler-bindir", "/usr/bin/g++",
+    "-Xptxas", "-v",
+]
+
+
+def sources():
+    return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
+
+
+def _deps():
+    return sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "*.h")) + \
+        glob.glob(os.path.join(CSRC, "*.inc")) + [os.path.join(os.path.dirname(HERE), "include", "wwz_b200.h")]
+
+
+def up_to_date():
+    if not os.path.exists(LIB):
+        return False
+    t = os.path.getmtime(LIB)
+    return all(os.path.getmtime(f) <= t for f in _deps())
+
+
+def build(force=False, verbose=False):
+    """Compile every csrc/*.cu for sm_100a and link them into lib/libwwz_b200.so."""
+    if not force and up_to_date():
+        return LIB
+    os.makedirs(LIBDIR, exist_ok=True)
+    objs = []
+    log = []
+    for src in sources():
+        obj = os.path.join(LIBDIR, os.path.basename(src)[:-3] + ".o")
+        cmd = [NVCC] + NVCC_FLAGS + ["-c", src, "-o", obj]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        log.append(r.stderr)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("nvcc failed on %s" % src)
+        objs.append(obj)
+    cmd = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "--compiler-bindir", "/usr/bin/g++",
+           "-o", LIB] + objs
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("link failed")
+    with open(os.path.join(LIBDIR, "ptxas.log"), "w") as f:
+        f.write("\n".join(log))
+    if verbose:
+        print("\n".join(log))
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,82 @@
+// Internal host-side interface between the C ABI (wwz_capi.cu) and the kernel launchers
+// (wwz_kernels.cu).  Not part of the public boundary; see include/wwz_b200.h for that.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace wwz {
+
+constexpr int kConsumerWarps = 8;
+constexpr int kConsumerThreads = kConsumerWarps * 32;
+constexpr int kCellThreads = kConsumerThreads + 32;  // + one TMA producer warp
+constexpr int kStages = 3;
+constexpr int kNumSums = 7;  // W, Q, Ws, Wc, Wy, Wys, Wyc
+constexpr int kStageBudget = 32 * 1024;
+constexpr int kMaxPointsPerStage = 512;
+
+// Geometry of one launch of the cell kernel, derived on the host by plan_cells().
+struct CellPlan {
+    int cells_per_lane;   // M: tau-adjacent cells owned by one lane (1, 2 or 4)
+    int groups;           // G = ceil(nt / M) lane slots per frequency row
+    int ft_max;           // max number of frequency rows a 256-slot tile can touch
+    int points;           // P: points per smem stage
+    int64_t n_pad;        // series length rounded up to a multiple of P
+    int64_t row_stride;   // smem basis row stride in bytes ((P+1)*32)
+    int stage_bytes;      // bytes of one smem stage
+    int smem_bytes;       // dynamic smem of the kernel
+    int64_t tiles;        // grid size for nf rows
+};
+
+CellPlan plan_cells(int64_t n, int64_t nt, int64_t nf, int cells_per_lane_hint);
+
+// Per-frequency constants: kappa = omega*sqrt(c*log2 e), dcut = underflow distance (windowing).
+cudaError_t launch_freq_setup(const double *d_omega, int64_t nf, double c, double *d_kappa, double *d_dcut,
+                              cudaStream_t st);
+
+// (t, y) interleaved + per-frequency basis rows (sin, cos, y sin, y cos), zero padded to n_pad.
+cudaError_t launch_basis(const double *d_ts, const double *d_ys, int64_t n, int64_t n_pad,
+                         const double *d_omega, int64_t nf_batch, double2 *d_ty, double2 *d_basis,
+                         bool write_ty, cudaStream_t st);
+
+// The hot kernel: weighted sums for every (tau, f) cell of a frequency batch.
+// sums is [7][nt * nf_total] laid out like the outputs (cell = j*nf_total + k).
+cudaError_t launch_cells(const CellPlan &plan, const double2 *d_ty, const double2 *d_basis, const double *d_ts,
+                         int64_t n, const double *d_tau, int64_t nt, const double *d_kappa,
+                         const double *d_dcut, const int *d_unsorted, int64_t k0, int64_t nf_batch,
+                         int64_t nf_total, bool dense, double *d_sums, cudaStream_t st);
+
+// *d_flag = 1 if d_x is not ascending (the windowed path needs a sorted time axis).
+cudaError_t launch_unsorted_check(const double *d_x, int64_t n, int *d_flag, cudaStream_t st);
+
+// Per-cell epilogue: Neff, mask, a0, a1, a2, amplitude, phase from the seven sums.
+cudaError_t launch_finalize(const double *d_sums, const double *d_tau, const double *d_omega, int64_t nt,
+                            int64_t nf, double neff_thr, double *d_neffs, double *d_a0, double *d_a1,
+                            double *d_a2, double *d_wwa, double *d_phase, int64_t out_row_stride,
+                            unsigned int *d_fix_count, unsigned int *d_fix_list, unsigned int fix_cap,
+                            cudaStream_t st);
+
+// Faithful two-pass evaluation (one warp per cell) of the cells in fix_list (count read on the
+// device), or of every cell when fix_list is NULL.
+cudaError_t launch_faithful(const double *d_ts, const double *d_ys, int64_t n, const double *d_tau,
+                            const double *d_omega, int64_t nt, int64_t nf, double c, double neff_thr,
+                            const unsigned int *d_fix_count, const unsigned int *d_fix_list, unsigned int fix_cap,
+                            double *d_neffs, double *d_a0, double *d_a1, double *d_a2, double *d_wwa,
+                            double *d_phase, int64_t out_row_stride, int sms, cudaStream_t st);
+
+// wwa2psd tau-reduction (one thread per frequency column, rows added in order).
+cudaError_t launch_psd(const double *d_wwa, const double *d_neffs, int64_t nt, int64_t nf, int64_t row_stride,
+                       double tspan, int64_t n, double neff_thr, double *d_psd, cudaStream_t st);
+
+// min / max of a device vector (for tspan in the device-pointer entry points) -> d_out[0..1].
+cudaError_t launch_minmax(const double *d_x, int64_t n, double *d_out, cudaStream_t st);
+cudaError_t launch_psd_devspan(const double *d_wwa, const double *d_neffs, int64_t nt, int64_t nf,
+                               int64_t row_stride, const double *d_minmax, int64_t n, double neff_thr,
+                               double *d_psd, cudaStream_t st);
+
+// FP64 FMA peak microbenchmark.
+cudaError_t run_fp64_peak(double *tflops, double *ms);
+
+int64_t launch_counter();
+void bump_launch_counter(int64_t k = 1);
+
+}  // namespace wwz

@@ -1,0 +1,759 @@
+// Hand-written sm_100a kernels for the Kirchner weighted wavelet Z-transform.
+//
+// Reference semantics: pyleoclim/utils/wavelet.py:985-1045 (kirchner_numba), the same maths as
+// pyleoclim/f2py/f2py_wwz.f90:46-109.  For every (tau_j, omega_k) cell the reference forms
+// Gaussian-weighted sums over the irregular time axis.  In exact arithmetic its basis rotation by
+// omega*time_shift (:1012-1017) is undone by the rotation through omega*(time_shift - tau)
+// (:1018-1019, :1031-1032), because A and B (:1027-1028) are linear in the rotated basis, so
+//
+//   a0 = <y>,  a1 = 2( cos(w tau) cov(y,c) + sin(w tau) cov(y,s) ),
+//              a2 = 2( cos(w tau) cov(y,s) - sin(w tau) cov(y,c) ),   s = sin(w t), c = cos(w t)
+//
+// with <.> the weighted mean.  Seven weighted sums per cell suffice:
+//   W = sum w, Q = sum w^2, Ws = sum w s, Wc = sum w c, Wy = sum w y, Wys = sum w y s, Wyc = sum w y c.
+//
+// Kernels
+//   freq_setup_kernel   per-frequency constants
+//   basis_kernel        sincos(omega_k * t_i) once per (frequency, point) -> packed basis rows
+//   wwz_cells_kernel    the hot kernel: TMA-staged points, one lane per M tau-adjacent cells,
+//                       FP64 accumulation on the CUDA cores, no cross-lane reduction
+//   finalize_kernel     Neff, mask, a0/a1/a2, amplitude, phase; flags deep-underflow cells
+//   faithful_cells_kernel  one warp per cell, warp-shuffle reductions, the reference's own two-pass
+//                       expressions (exact subnormal handling; fix-up and validation mode)
+//   psd_kernel          wwa2psd tau-reduction (utils/wavelet.py:1270-1278)
+#include <math_constants.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+
+#include "wwz_device.cuh"
+#include "wwz_internal.h"
+
+namespace wwz {
+
+static std::atomic<int64_t> g_launches{0};
+int64_t launch_counter() { return g_launches.load(); }
+void bump_launch_counter(int64_t k) { g_launches.fetch_add(k); }
+
+// ------------------------------------------------------------------------------------------------
+// Per-frequency constants.
+//   kappa = omega * sqrt(c*log2(e))          so that  exp(-c*omega^2*d^2) = 2^(-(kappa*d)^2)
+//   dcut  = sqrt(1081)/|kappa|               |d| > dcut  =>  weight < 2^-1081, i.e. exactly 0.0
+//                                            (used only to window the point range of a tile)
+// omega = NaN (frequency above Nyquist, utils/wavelet.py:1229-1232): kappa = NaN is kept; NaN then
+// flows through every sum of the column and the epilogue yields NaN Neff / coefficients, exactly
+// what NaN arithmetic gives in the reference.  dcut = -1 marks the row as "no window constraint".
+// ------------------------------------------------------------------------------------------------
+__global__ void freq_setup_kernel(const double *__restrict__ omega, int64_t nf, double kscale,
+                                  double *__restrict__ kappa, double *__restrict__ dcut)
+{
+    int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k >= nf) return;
+    const double om = omega[k];
+    const double ka = om * kscale;
+    kappa[k] = ka;
+    dcut[k] = isnan(om) ? -1.0 : sqrt(1081.0) / fabs(ka);  // +inf for omega == 0
+}
+
+cudaError_t launch_freq_setup(const double *d_omega, int64_t nf, double c, double *d_kappa, double *d_dcut,
+                              cudaStream_t st)
+{
+    if (nf <= 0) return cudaSuccess;
+    const double kscale = std::sqrt(c * 1.4426950408889634074);  // sqrt(c*log2(e))
+    freq_setup_kernel<<<(unsigned)((nf + 127) / 128), 128, 0, st>>>(d_omega, nf, kscale, d_kappa, d_dcut);
+    bump_launch_counter();
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Basis rows.  theta = fl(omega*t) is the argument the reference passes to sin/cos
+// (utils/wavelet.py:1002-1003); the rounding residual of the product is folded back to first
+// order so that (s, c) are sin/cos of the exact product omega*t.
+// Record layout per (frequency, point): { sin, cos } { y*sin, y*cos } = 2 x double2 = 32 B.
+// ------------------------------------------------------------------------------------------------
+__global__ void basis_kernel(const double *__restrict__ ts, const double *__restrict__ ys, int64_t n,
+                             int64_t n_pad, const double *__restrict__ omega, double2 *__restrict__ ty,
+                             double2 *__restrict__ basis, int write_ty)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n_pad) return;
+    const int64_t k = blockIdx.y;
+    const double om = omega[k];
+    double t = 0.0, y = 0.0, s = 0.0, c = 0.0;
+    if (i < n) {
+        t = ts[i];
+        y = ys[i];
+        if (!isnan(om)) {
+            const double th = om * t;
+            const double eps = fma(om, t, -th);
+            double s0, c0;
+            sincos(th, &s0, &c0);
+            s = fma(eps, c0, s0);
+            c = fma(-eps, s0, c0);
+        }
+    }
+    double2 *row = basis + ((size_t)k * (size_t)n_pad + (size_t)i) * 2;
+    row[0] = make_double2(s, c);
+    row[1] = make_double2(y * s, y * c);
+    if (write_ty && k == 0) ty[i] = make_double2(t, y);
+}
+
+cudaError_t launch_basis(const double *d_ts, const double *d_ys, int64_t n, int64_t n_pad, const double *d_omega,
+                         int64_t nf_batch, double2 *d_ty, double2 *d_basis, bool write_ty, cudaStream_t st)
+{
+    if (nf_batch <= 0 || n_pad <= 0) return cudaSuccess;
+    dim3 grid((unsigned)((n_pad + 255) / 256), (unsigned)nf_batch);
+    basis_kernel<<<grid, 256, 0, st>>>(d_ts, d_ys, n, n_pad, d_omega, d_ty, d_basis, write_ty ? 1 : 0);
+    bump_launch_counter();
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// The hot kernel.
+//
+// Work decomposition.  Lane slots are numbered q = k*G + g over (frequency row k, tau group g),
+// G = ceil(nt/M); slot q owns the M tau-adjacent cells j = g*M .. g*M+M-1 of row k.  A CTA owns
+// 256 consecutive slots (8 consumer warps), which touch Ft <= ft_max consecutive frequency rows.
+// Every lane walks all points: no redundancy between lanes and no cross-lane reduction.
+//
+// Staging.  A ninth warp is the TMA producer: per chunk of P points it issues one 1-D bulk copy
+// for the (t, y) pairs and one per frequency row for the packed basis records into a 3-stage
+// shared-memory ring, completion tracked by mbarrier transaction bytes (full[]), slots recycled
+// through empty[] (one arrive per consumer warp).  Consumers read a point's (t, y) and its basis
+// record as warp-broadcast LDS.128.
+//
+// Arithmetic per (cell, point) on the FP64 pipe: DADD (t - tau), DMUL (kappa*d), 13 for the weight
+// (see gauss_weight), 7 accumulations = 22 instructions.
+//
+// Windowing (flag dense == 0).  ts is sorted, so the points whose weight is not exactly 0.0 for
+// any cell of the tile form one index range; chunks outside it are skipped.  Skipped points
+// would have contributed +0.0 to every sum, so the result is bit-identical to the dense run.
+// ------------------------------------------------------------------------------------------------
+struct CellArgs {
+    const double2 *ty;
+    const double2 *basis;
+    const double *ts;
+    const double *tau;
+    const double *kappa;
+    const double *dcut;
+    const int *unsorted;  // device flag: 1 if ts is not ascending (forces the dense path)
+    double *sums;
+    long long n, n_pad, nslots, ncell_total;
+    int nt, G, P, nchunks, k0, nf_total;
+    int row_stride2;    // basis row stride inside a stage, in double2 units
+    int stage_stride2;  // stage stride in double2 units
+    int dense;
+};
+
+template <int M>
+__global__ void __launch_bounds__(kCellThreads, 2) wwz_cells_kernel(const CellArgs a)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double2 *const stage_base = reinterpret_cast<double2 *>(smem_raw);
+    unsigned char *const tail = smem_raw + (size_t)kStages * (size_t)a.stage_stride2 * sizeof(double2);
+    uint64_t *const full = reinterpret_cast<uint64_t *>(tail);
+    uint64_t *const empty = full + kStages;
+    double *const red = reinterpret_cast<double *>(empty + kStages);  // [2][9]
+    int *const win = reinterpret_cast<int *>(red + 18);               // [2]
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const int lane = tid & 31;
+    const bool consumer = warp < kConsumerWarps;
+
+    const long long q0 = (long long)blockIdx.x * kConsumerThreads;
+    const long long qlast = min(q0 + (long long)kConsumerThreads - 1, a.nslots - 1);
+    const int k_first = (int)(q0 / a.G);
+    const int k_last = (int)(qlast / a.G);
+    const int Ft = k_last - k_first + 1;
+    const int P = a.P;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], kConsumerWarps);
+        }
+        mbar_fence_init();
+    }
+
+    // ---- lane-slot parameters
+    const long long q = q0 + tid;
+    const bool slot_ok = consumer && q < a.nslots;
+    int k_loc = 0, g = 0;
+    if (slot_ok) {
+        const int k = (int)(q / a.G);
+        k_loc = k - k_first;
+        g = (int)(q - (long long)k * a.G);
+    }
+    double kap = 0.0;
+    double tau_r[M];
+    double wlo = CUDART_INF, whi = -CUDART_INF;
+#pragma unroll
+    for (int r = 0; r < M; ++r) tau_r[r] = 0.0;
+    if (slot_ok) {
+        const int kg = a.k0 + k_first + k_loc;
+        kap = a.kappa[kg];
+        const double dc = a.dcut[kg];
+#pragma unroll
+        for (int r = 0; r < M; ++r) {
+            const int j = g * M + r;
+            const double tj = a.tau[min(j, a.nt - 1)];
+            tau_r[r] = tj;
+            if (j < a.nt && dc >= 0.0) {
+                wlo = fmin(wlo, tj - dc);
+                whi = fmax(whi, tj + dc);
+            }
+        }
+    }
+
+    // ---- point window of the tile
+    int c_lo = 0, c_hi = a.nchunks;
+    const bool dense = a.dense || (a.unsorted && *a.unsorted);
+    if (!dense) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            wlo = fmin(wlo, __shfl_xor_sync(0xffffffffu, wlo, o));
+            whi = fmax(whi, __shfl_xor_sync(0xffffffffu, whi, o));
+        }
+        if (lane == 0) {
+            red[warp] = wlo;
+            red[9 + warp] = whi;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            double lo = red[0], hi = red[9];
+            for (int w = 1; w < 9; ++w) {
+                lo = fmin(lo, red[w]);
+                hi = fmax(hi, red[9 + w]);
+            }
+            long long i0 = 0, i1 = 0;
+            if (lo <= hi) {
+                long long l = 0, r = a.n;  // first index with ts >= lo
+                while (l < r) {
+                    const long long m = (l + r) >> 1;
+                    if (a.ts[m] < lo) l = m + 1; else r = m;
+                }
+                i0 = l;
+                r = a.n;  // first index with ts > hi
+                while (l < r) {
+                    const long long m = (l + r) >> 1;
+                    if (a.ts[m] <= hi) l = m + 1; else r = m;
+                }
+                i1 = l;
+            }
+            win[0] = (int)(i0 / P);
+            win[1] = (i1 > i0) ? (int)((i1 + P - 1) / P) : (int)(i0 / P);
+        }
+    }
+    __syncthreads();
+    if (!dense) {
+        c_lo = win[0];
+        c_hi = win[1];
+    }
+
+    if (!consumer) {
+        // ===================== TMA producer warp =====================
+        const uint32_t bytes = (uint32_t)P * 16u + (uint32_t)Ft * (uint32_t)P * 32u;
+        int s = 0, use = 0;
+        for (int c = c_lo; c < c_hi; ++c) {
+            if (use > 0) mbar_wait(&empty[s], (uint32_t)(use - 1) & 1u);
+            double2 *const st = stage_base + (size_t)s * a.stage_stride2;
+            if (lane == 0) mbar_arrive_expect_tx(&full[s], bytes);
+            __syncwarp();
+            for (int r = lane; r <= Ft; r += 32) {
+                if (r == 0) {
+                    tma_load_1d(st, a.ty + (size_t)c * P, (uint32_t)P * 16u, &full[s]);
+                } else {
+                    const size_t row = (size_t)(k_first + r - 1);
+                    tma_load_1d(st + P + (size_t)(r - 1) * a.row_stride2,
+                                a.basis + (row * (size_t)a.n_pad + (size_t)c * P) * 2, (uint32_t)P * 32u,
+                                &full[s]);
+                }
+            }
+            if (++s == kStages) { s = 0; ++use; }
+        }
+        return;
+    }
+
+    // ===================== consumers =====================
+    double W[M], Q[M], Ws[M], Wc[M], Wy[M], Wys[M], Wyc[M];
+#pragma unroll
+    for (int r = 0; r < M; ++r) W[r] = Q[r] = Ws[r] = Wc[r] = Wy[r] = Wys[r] = Wyc[r] = 0.0;
+
+    const int row_off = P + k_loc * a.row_stride2;
+    {
+        int s = 0, use = 0;
+        for (int c = c_lo; c < c_hi; ++c) {
+            mbar_wait(&full[s], (uint32_t)use & 1u);
+            const double2 *const st = stage_base + (size_t)s * a.stage_stride2;
+            const double2 *const row = st + row_off;
+            const int cnt = (int)min((long long)P, a.n - (long long)c * P);
+#pragma unroll 2
+            for (int p = 0; p < cnt; ++p) {
+                const double2 t_y = st[p];
+                const double2 sc = row[2 * p];
+                const double2 ysc = row[2 * p + 1];
+#pragma unroll
+                for (int r = 0; r < M; ++r) {
+                    const double u = kap * (t_y.x - tau_r[r]);
+                    const double w = gauss_weight(u);
+                    W[r] += w;
+                    Q[r] = fma(w, w, Q[r]);
+                    Ws[r] = fma(w, sc.x, Ws[r]);
+                    Wc[r] = fma(w, sc.y, Wc[r]);
+                    Wy[r] = fma(w, t_y.y, Wy[r]);
+                    Wys[r] = fma(w, ysc.x, Wys[r]);
+                    Wyc[r] = fma(w, ysc.y, Wyc[r]);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
+            if (++s == kStages) { s = 0; ++use; }
+        }
+    }
+
+    if (slot_ok) {
+        const long long kcol = (long long)a.k0 + k_first + k_loc;
+#pragma unroll
+        for (int r = 0; r < M; ++r) {
+            const int j = g * M + r;
+            if (j < a.nt) {
+                const size_t cell = (size_t)j * (size_t)a.nf_total + (size_t)kcol;
+                const size_t nc = (size_t)a.ncell_total;
+                a.sums[0 * nc + cell] = W[r];
+                a.sums[1 * nc + cell] = Q[r];
+                a.sums[2 * nc + cell] = Ws[r];
+                a.sums[3 * nc + cell] = Wc[r];
+                a.sums[4 * nc + cell] = Wy[r];
+                a.sums[5 * nc + cell] = Wys[r];
+                a.sums[6 * nc + cell] = Wyc[r];
+            }
+        }
+    }
+}
+
+CellPlan plan_cells(int64_t n, int64_t nt, int64_t nf, int cells_per_lane_hint)
+{
+    CellPlan p{};
+    int M = cells_per_lane_hint;
+    if (M != 1 && M != 2 && M != 4) M = 2;
+    if (nt < M) M = 1;
+    p.cells_per_lane = M;
+    p.groups = (int)((nt + M - 1) / M);
+    int64_t ft = (kConsumerThreads + p.groups - 1) / p.groups + 1;
+    if (ft > nf) ft = nf;
+    if (ft < 1) ft = 1;
+    p.ft_max = (int)ft;
+    int64_t P = (kStageBudget - 32 * ft) / (16 + 32 * ft);
+    if (P > kMaxPointsPerStage) P = kMaxPointsPerStage;
+    if (P > n) P = ((n + 7) / 8) * 8;
+    if (P < 8) P = 8;
+    p.points = (int)P;
+    p.n_pad = ((n + P - 1) / P) * P;
+    if (p.n_pad < P) p.n_pad = P;
+    p.row_stride = (P + 1) * 32;
+    p.stage_bytes = (int)(P * 16 + ft * p.row_stride);
+    p.smem_bytes = kStages * p.stage_bytes + 2 * kStages * 8 + 18 * 8 + 16;
+    const int64_t nslots = nf * (int64_t)p.groups;
+    p.tiles = (nslots + kConsumerThreads - 1) / kConsumerThreads;
+    return p;
+}
+
+template <int M>
+static cudaError_t launch_cells_m(const CellPlan &plan, const CellArgs &args, int64_t tiles, cudaStream_t st)
+{
+    static int configured_smem = -1;
+    if (plan.smem_bytes > configured_smem) {
+        cudaError_t e = cudaFuncSetAttribute(wwz_cells_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             plan.smem_bytes);
+        if (e != cudaSuccess) return e;
+        configured_smem = plan.smem_bytes;
+    }
+    wwz_cells_kernel<M><<<(unsigned)tiles, kCellThreads, plan.smem_bytes, st>>>(args);
+    bump_launch_counter();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_cells(const CellPlan &plan, const double2 *d_ty, const double2 *d_basis, const double *d_ts,
+                         int64_t n, const double *d_tau, int64_t nt, const double *d_kappa,
+                         const double *d_dcut, const int *d_unsorted, int64_t k0, int64_t nf_batch,
+                         int64_t nf_total, bool dense, double *d_sums, cudaStream_t st)
+{
+    if (nf_batch <= 0 || nt <= 0) return cudaSuccess;
+    CellArgs a{};
+    a.ty = d_ty;
+    a.basis = d_basis;
+    a.ts = d_ts;
+    a.tau = d_tau;
+    a.kappa = d_kappa;
+    a.dcut = d_dcut;
+    a.unsorted = d_unsorted;
+    a.sums = d_sums;
+    a.n = n;
+    a.n_pad = plan.n_pad;
+    a.nslots = nf_batch * (int64_t)plan.groups;
+    a.ncell_total = nt * nf_total;
+    a.nt = (int)nt;
+    a.G = plan.groups;
+    a.P = plan.points;
+    a.nchunks = (int)((n + plan.points - 1) / plan.points);
+    a.k0 = (int)k0;
+    a.nf_total = (int)nf_total;
+    a.row_stride2 = (int)(plan.row_stride / 16);
+    a.stage_stride2 = plan.stage_bytes / 16;
+    a.dense = dense ? 1 : 0;
+    const int64_t tiles = (a.nslots + kConsumerThreads - 1) / kConsumerThreads;
+    switch (plan.cells_per_lane) {
+        case 1: return launch_cells_m<1>(plan, a, tiles, st);
+        case 4: return launch_cells_m<4>(plan, a, tiles, st);
+        default: return launch_cells_m<2>(plan, a, tiles, st);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Epilogue per cell (utils/wavelet.py:992-997, :1030-1032 in the reduced form above, :1044-1045).
+// Mask: kirchner_numba is compiled with fastmath, under which a NaN Neff lands on the masked side
+// (pinned by tests/golden/edge.npz); hence !(Neff > thr) rather than Neff <= thr.
+//
+// Deep-underflow cells.  The hot kernel flushes weights below 2^-1021 and accumulates w*w with an
+// FMA.  Where the sums are so small that subnormal weights or the underflow of w*w could matter
+// (W < 2^-500 or Q < 2^-1000: tau inside a long data gap at high frequency), the cell index is
+// appended to `fix_list` and the cell is recomputed by faithful_cells_kernel.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void store_cell(int64_t o, double neff, double a0, double a1, double a2,
+                                           double *__restrict__ neffs, double *__restrict__ a0o,
+                                           double *__restrict__ a1o, double *__restrict__ a2o,
+                                           double *__restrict__ wwa, double *__restrict__ phase)
+{
+    neffs[o] = neff;
+    if (a0o) a0o[o] = a0;
+    if (a1o) a1o[o] = a1;
+    if (a2o) a2o[o] = a2;
+    if (wwa) wwa[o] = sqrt(a1 * a1 + a2 * a2);   // utils/wavelet.py:1044
+    if (phase) phase[o] = atan2(a2, a1);         // utils/wavelet.py:1045
+}
+
+__global__ void finalize_kernel(const double *__restrict__ sums, const double *__restrict__ tau,
+                                const double *__restrict__ omega, int64_t nt, int64_t nf, double thr,
+                                double *__restrict__ neffs, double *__restrict__ a0o, double *__restrict__ a1o,
+                                double *__restrict__ a2o, double *__restrict__ wwa, double *__restrict__ phase,
+                                int64_t row_stride, unsigned int *__restrict__ fix_count,
+                                unsigned int *__restrict__ fix_list, unsigned int fix_cap)
+{
+    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t nc = nt * nf;
+    if (idx >= nc) return;
+    const int64_t j = idx / nf, k = idx - j * nf;
+    const double W = sums[idx], Q = sums[nc + idx];
+    if (fix_list && (W < 0x1p-500 || Q < 0x1p-1000)) {
+        const unsigned int slot = atomicAdd(fix_count, 1u);
+        if (slot < fix_cap) fix_list[slot] = (unsigned int)idx;
+    }
+    const double neff = W * W / Q;
+    double a0 = CUDART_NAN, a1 = CUDART_NAN, a2 = CUDART_NAN;
+    if (neff > thr) {
+        const double Ws = sums[2 * nc + idx], Wc = sums[3 * nc + idx], Wy = sums[4 * nc + idx];
+        const double Wys = sums[5 * nc + idx], Wyc = sums[6 * nc + idx];
+        const double Y = Wy / W, S = Ws / W, C = Wc / W, YS = Wys / W, YC = Wyc / W;
+        const double cyc = YC - Y * C;
+        const double cys = YS - Y * S;
+        const double om = omega[k], tj = tau[j];
+        const double th = om * tj;
+        const double eps = fma(om, tj, -th);
+        double s0, c0;
+        sincos(th, &s0, &c0);
+        const double st = fma(eps, c0, s0), ct = fma(-eps, s0, c0);
+        a0 = Y;
+        a1 = 2.0 * (ct * cyc + st * cys);
+        a2 = 2.0 * (ct * cys - st * cyc);
+    }
+    store_cell(j * row_stride + k, neff, a0, a1, a2, neffs, a0o, a1o, a2o, wwa, phase);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Faithful cell evaluator: one warp per cell, lanes stride over the points, warp-shuffle
+// reductions.  Same argument expressions and pass structure as the reference
+// (utils/wavelet.py:988-1032): weights from exp(-c*dz*dz) with subnormals kept, sin/cos(omega*ts),
+// time_shift, then sin/cos(omega*(ts - time_shift)).  Used (a) for the deep-underflow cells the
+// epilogue flags, (b) for every cell when the caller asks for WWZB200_FAITHFUL (validation mode).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__global__ void __launch_bounds__(128)
+    faithful_cells_kernel(const double *__restrict__ ts, const double *__restrict__ ys, int64_t n,
+                          const double *__restrict__ tau, const double *__restrict__ omega, int64_t nt, int64_t nf,
+                          double c, double thr, const unsigned int *__restrict__ fix_count,
+                          const unsigned int *__restrict__ fix_list, unsigned int fix_cap,
+                          double *__restrict__ neffs, double *__restrict__ a0o, double *__restrict__ a1o,
+                          double *__restrict__ a2o, double *__restrict__ wwa, double *__restrict__ phase,
+                          int64_t row_stride)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    int64_t total = nt * nf;
+    if (fix_list) {
+        const unsigned int cnt = *fix_count;
+        total = cnt < fix_cap ? cnt : fix_cap;
+    }
+    for (int64_t item = warp0; item < total; item += nwarps) {
+        const int64_t idx = fix_list ? (int64_t)fix_list[item] : item;
+        const int64_t j = idx / nf, k = idx - j * nf;
+        const double om = omega[k], tj = tau[j];
+        double sw = 0.0, sw2 = 0.0;
+        for (int64_t i = lane; i < n; i += 32) {
+            const double dz = om * (ts[i] - tj);
+            const double w = exp(-c * (dz * dz));
+            sw += w;
+            sw2 = __dadd_rn(sw2, __dmul_rn(w, w));
+        }
+        sw = warp_sum(sw);
+        sw2 = warp_sum(sw2);
+        const double neff = sw * sw / sw2;
+        double a0 = CUDART_NAN, a1 = CUDART_NAN, a2 = CUDART_NAN;
+        if (neff > thr) {
+            double s1 = 0, c1 = 0, sc = 0, ss = 0, cc = 0;
+            for (int64_t i = lane; i < n; i += 32) {
+                const double t = ts[i];
+                const double dz = om * (t - tj);
+                const double w = exp(-c * (dz * dz));
+                double sb, cb;
+                sincos(om * t, &sb, &cb);
+                s1 += w * sb;
+                c1 += w * cb;
+                sc += w * sb * cb;
+                ss += w * sb * sb;
+                cc += w * cb * cb;
+            }
+            const double sin_one = warp_sum(s1) / sw, cos_one = warp_sum(c1) / sw, sin_cos = warp_sum(sc) / sw;
+            const double sin_sin = warp_sum(ss) / sw, cos_cos = warp_sum(cc) / sw;
+            const double numerator = 2 * (sin_cos - sin_one * cos_one);
+            const double denominator = (cos_cos - cos_one * cos_one) - (sin_sin - sin_one * sin_one);
+            const double time_shift = atan2(numerator, denominator) / (2 * om);
+            double ycs = 0, yss = 0, y1 = 0, cs1 = 0, ss1 = 0;
+            for (int64_t i = lane; i < n; i += 32) {
+                const double t = ts[i], y = ys[i];
+                const double dz = om * (t - tj);
+                const double w = exp(-c * (dz * dz));
+                double sh, ch;
+                sincos(om * (t - time_shift), &sh, &ch);
+                ycs += w * y * ch;
+                yss += w * y * sh;
+                y1 += w * y;
+                cs1 += w * ch;
+                ss1 += w * sh;
+            }
+            const double ys_cos_shift = warp_sum(ycs) / sw, ys_sin_shift = warp_sum(yss) / sw;
+            const double ys_one = warp_sum(y1) / sw;
+            const double cos_shift_one = warp_sum(cs1) / sw, sin_shift_one = warp_sum(ss1) / sw;
+            double stc, ctc;
+            sincos(om * (time_shift - tj), &stc, &ctc);
+            const double A = 2 * (ys_cos_shift - ys_one * cos_shift_one);
+            const double B = 2 * (ys_sin_shift - ys_one * sin_shift_one);
+            a0 = ys_one;
+            a1 = ctc * A - stc * B;
+            a2 = stc * A + ctc * B;
+        }
+        if (lane == 0) store_cell(j * row_stride + k, neff, a0, a1, a2, neffs, a0o, a1o, a2o, wwa, phase);
+    }
+}
+
+cudaError_t launch_finalize(const double *d_sums, const double *d_tau, const double *d_omega, int64_t nt,
+                            int64_t nf, double neff_thr, double *d_neffs, double *d_a0, double *d_a1,
+                            double *d_a2, double *d_wwa, double *d_phase, int64_t out_row_stride,
+                            unsigned int *d_fix_count, unsigned int *d_fix_list, unsigned int fix_cap,
+                            cudaStream_t st)
+{
+    const int64_t nc = nt * nf;
+    if (nc <= 0) return cudaSuccess;
+    finalize_kernel<<<(unsigned)((nc + 255) / 256), 256, 0, st>>>(d_sums, d_tau, d_omega, nt, nf, neff_thr, d_neffs,
+                                                                  d_a0, d_a1, d_a2, d_wwa, d_phase, out_row_stride,
+                                                                  d_fix_count, d_fix_list, fix_cap);
+    bump_launch_counter();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_faithful(const double *d_ts, const double *d_ys, int64_t n, const double *d_tau,
+                            const double *d_omega, int64_t nt, int64_t nf, double c, double neff_thr,
+                            const unsigned int *d_fix_count, const unsigned int *d_fix_list, unsigned int fix_cap,
+                            double *d_neffs, double *d_a0, double *d_a1, double *d_a2, double *d_wwa,
+                            double *d_phase, int64_t out_row_stride, int sms, cudaStream_t st)
+{
+    if (nt * nf <= 0) return cudaSuccess;
+    int64_t blocks = (int64_t)sms * 8;
+    if (!d_fix_list) blocks = std::min<int64_t>(blocks * 2, (nt * nf + 3) / 4);
+    if (blocks < 1) blocks = 1;
+    faithful_cells_kernel<<<(unsigned)blocks, 128, 0, st>>>(d_ts, d_ys, n, d_tau, d_omega, nt, nf, c, neff_thr,
+                                                            d_fix_count, d_fix_list, fix_cap, d_neffs, d_a0, d_a1,
+                                                            d_a2, d_wwa, d_phase, out_row_stride);
+    bump_launch_counter();
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// wwa2psd (utils/wavelet.py:1270-1278): same operation order as the reference expression
+//   power = wwa**2 * 0.5 * (max(ts)-min(ts))/size(ts) * Neffs ;  d = max(Neffs - thr, 0)
+//   psd = nansum(power*d, axis=0) / nansum(d, axis=0), rows added in order j = 0..nt-1.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double psd_column(const double *__restrict__ wwa, const double *__restrict__ neffs,
+                                             int64_t nt, int64_t row_stride, int64_t k, double tspan,
+                                             double n_d, double thr)
+{
+    double sp = 0.0, se = 0.0;
+    for (int64_t j = 0; j < nt; ++j) {
+        const double a = wwa[j * row_stride + k];
+        const double ne = neffs[j * row_stride + k];
+        const double power = a * a * 0.5 * tspan / n_d * ne;
+        double d = ne - thr;
+        if (d < 0.0) d = 0.0;
+        const double pd = power * d;
+        if (!isnan(pd)) sp += pd;
+        if (!isnan(d)) se += d;
+    }
+    return sp / se;
+}
+
+__global__ void psd_kernel(const double *__restrict__ wwa, const double *__restrict__ neffs, int64_t nt,
+                           int64_t nf, int64_t row_stride, double tspan, const double *__restrict__ minmax,
+                           double n_d, double thr, double *__restrict__ psd)
+{
+    const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k >= nf) return;
+    if (minmax) tspan = minmax[1] - minmax[0];
+    psd[k] = psd_column(wwa, neffs, nt, row_stride, k, tspan, n_d, thr);
+}
+
+cudaError_t launch_psd(const double *d_wwa, const double *d_neffs, int64_t nt, int64_t nf, int64_t row_stride,
+                       double tspan, int64_t n, double neff_thr, double *d_psd, cudaStream_t st)
+{
+    if (nf <= 0) return cudaSuccess;
+    psd_kernel<<<(unsigned)((nf + 63) / 64), 64, 0, st>>>(d_wwa, d_neffs, nt, nf, row_stride, tspan, nullptr,
+                                                          (double)n, neff_thr, d_psd);
+    bump_launch_counter();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_psd_devspan(const double *d_wwa, const double *d_neffs, int64_t nt, int64_t nf,
+                               int64_t row_stride, const double *d_minmax, int64_t n, double neff_thr,
+                               double *d_psd, cudaStream_t st)
+{
+    if (nf <= 0) return cudaSuccess;
+    psd_kernel<<<(unsigned)((nf + 63) / 64), 64, 0, st>>>(d_wwa, d_neffs, nt, nf, row_stride, 0.0, d_minmax,
+                                                          (double)n, neff_thr, d_psd);
+    bump_launch_counter();
+    return cudaGetLastError();
+}
+
+__global__ void minmax_kernel(const double *__restrict__ x, int64_t n, double *__restrict__ out)
+{
+    __shared__ double slo[32], shi[32];
+    double lo = CUDART_INF, hi = -CUDART_INF;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const double v = x[i];
+        lo = fmin(lo, v);
+        hi = fmax(hi, v);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        slo[threadIdx.x >> 5] = lo;
+        shi[threadIdx.x >> 5] = hi;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
+            lo = fmin(lo, slo[w]);
+            hi = fmax(hi, shi[w]);
+        }
+        out[0] = lo;
+        out[1] = hi;
+    }
+}
+
+// 1 if x is not ascending (ties allowed), else 0.  *flag must be zeroed by the caller.
+__global__ void unsorted_kernel(const double *__restrict__ x, int64_t n, int *__restrict__ flag)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i + 1 < n && !(x[i] <= x[i + 1])) *flag = 1;
+}
+
+cudaError_t launch_unsorted_check(const double *d_x, int64_t n, int *d_flag, cudaStream_t st)
+{
+    cudaError_t e = cudaMemsetAsync(d_flag, 0, sizeof(int), st);
+    if (e != cudaSuccess || n < 2) return e;
+    unsorted_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_x, n, d_flag);
+    bump_launch_counter();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_minmax(const double *d_x, int64_t n, double *d_out, cudaStream_t st)
+{
+    minmax_kernel<<<1, 1024, 0, st>>>(d_x, n, d_out);
+    bump_launch_counter();
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// FP64 FMA peak: 8 independent register-resident DFMA chains per thread.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, int iters, double x0)
+{
+    double a0 = x0, a1 = x0 + 1, a2 = x0 + 2, a3 = x0 + 3, a4 = x0 + 4, a5 = x0 + 5, a6 = x0 + 6, a7 = x0 + 7;
+    const double m = 0.999999, b = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            a0 = fma(a0, m, b); a1 = fma(a1, m, b); a2 = fma(a2, m, b); a3 = fma(a3, m, b);
+            a4 = fma(a4, m, b); a5 = fma(a5, m, b); a6 = fma(a6, m, b); a7 = fma(a7, m, b);
+        }
+    }
+    const double r = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (r == 123.456) out[0] = r;  // keep the chains alive
+}
+
+cudaError_t run_fp64_peak(double *tflops, double *ms)
+{
+    int dev = 0, sms = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return e;
+    double *d_out = nullptr;
+    e = cudaMalloc(&d_out, sizeof(double));
+    if (e != cudaSuccess) return e;
+    const int blocks = sms * 8, threads = 256, iters = 1 << 14;
+    cudaEvent_t t0, t1;
+    cudaEventCreate(&t0);
+    cudaEventCreate(&t1);
+    float best = 1e30f;
+    for (int rep = 0; rep < 6; ++rep) {
+        cudaEventRecord(t0);
+        fp64_peak_kernel<<<blocks, threads>>>(d_out, iters, 1.0 + rep);
+        cudaEventRecord(t1);
+        e = cudaEventSynchronize(t1);
+        if (e != cudaSuccess) break;
+        float t = 0;
+        cudaEventElapsedTime(&t, t0, t1);
+        if (rep >= 2 && t < best) best = t;
+    }
+    bump_launch_counter(6);
+    cudaEventDestroy(t0);
+    cudaEventDestroy(t1);
+    cudaFree(d_out);
+    if (e != cudaSuccess) return e;
+    const double flops = 2.0 * 64.0 * (double)iters * (double)blocks * (double)threads;
+    *ms = best;
+    *tflops = flops / (best * 1e-3) / 1e12;
+    return cudaGetLastError();
+}
+
+}  // namespace wwz

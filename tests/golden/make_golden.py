@@ -1,0 +1,172 @@
+"""Generate the golden fixtures in tests/golden/ by running the *reference itself*.
+
+Run once in the build container (where /root/reference exists):
+
+    python tests/golden/make_golden.py
+
+It imports the reference's own modules through ref_shim.py (no reference source is
+copied), runs ``method='Kirchner_numba'`` (the parity target) and writes small ``.npz``
+files.  The fixtures travel to the GPU box; the reference tree does not.
+"""
+import json
+import os
+import sys
+import warnings
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+import ref_shim  # noqa: E402
+from pyleoclim_util_b200 import synth  # noqa: E402
+
+warnings.filterwarnings("ignore")
+mods = ref_shim.load()
+W, SP, TM = mods["wavelet"], mods["spectral"], mods["tsmodel"]
+
+
+def save(name, **arrays):
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **arrays)
+    print("wrote %-22s %8.1f KB" % (name + ".npz", os.path.getsize(path) / 1024))
+
+
+def run_wwz(ys, ts, method="Kirchner_numba", **kw):
+    r = W.wwz(ys, ts, method=method, nproc=1, **kw)
+    a0, a1, a2 = r.coeff
+    return dict(amplitude=r.amplitude, phase=r.phase, Neffs=r.Neffs, a0=a0, a1=a1, a2=a2,
+                coi=r.coi, freq=r.freq, tau=r.time)
+
+
+def benthic():
+    """The one known-answer artefact the reference ships: a serialized WWZ Scalogram."""
+    d = json.load(open(os.path.join(ref_shim.REF_ROOT, "example_data", "scal_signif_benthic.json")))
+    ts = np.array(d["timeseries"]["time"], float)
+    ys = np.array(d["timeseries"]["value"], float)
+    tau = np.array(d["wave_args"]["tau"], float)
+    freq = np.array(d["wave_args"]["freq"], float)
+    ref = run_wwz(ys, ts, tau=tau, freq=freq)
+    save("benthic", ts=ts, ys=ys, tau_in=tau, freq_in=freq,
+         file_amplitude=np.array(d["amplitude"], float), file_Neffs=np.array(d["wwz_Neffs"], float),
+         file_coi=np.array(d["coi"], float), **ref)
+
+
+def soi():
+    """Config 1: SOI, default tau / freq grid, wwz and wwz_psd."""
+    d = json.load(open(os.path.join(ref_shim.REF_ROOT, "doc_build", "soi.json")))
+    ts = np.array(d["time"], float)
+    ys = np.array(d["value"], float)
+    ref = run_wwz(ys, ts)
+    psd = SP.wwz_psd(ys, ts, nproc=1)
+    save("soi", ts=ts, ys=ys, psd=psd.psd, psd_freq=psd.freq, **ref)
+
+
+def synth_small():
+    """Small uneven AR(1) case with both decay constants, the numpy kernel beside the numba one,
+    a non-default Neff threshold and standardize on/off."""
+    t, y = synth.uneven_ar1(300, 10)
+    y = 3.0 * y + 7.0                      # non-trivial mean/scale so standardize matters
+    tau = np.linspace(t.min(), t.max(), 40)
+    freq = synth.freq_log(t, 30)
+    ref = run_wwz(y, t, tau=tau, freq=freq)
+    basic = run_wwz(y, t, tau=tau, freq=freq, method="Kirchner")
+    raw = run_wwz(y, t, tau=tau, freq=freq, standardize=False)
+    thr5 = run_wwz(y, t, tau=tau, freq=freq, Neff_threshold=5)
+    c3 = run_wwz(y, t, tau=tau, freq=freq, c=1e-3)
+    psd = SP.wwz_psd(y, t, freq=freq, tau=tau, nproc=1)
+    psd_thr = SP.wwz_psd(y, t, freq=freq, tau=tau, nproc=1, Neff_threshold=6)
+    psd_default_tau = SP.wwz_psd(y, t, freq=freq, nproc=1)
+    out = dict(ts=t, ys=y, tau_in=tau, freq_in=freq, psd=psd.psd, psd_thr6=psd_thr.psd,
+               psd_default_tau=psd_default_tau.psd)
+    for tag, r in [("", ref), ("basic_", basic), ("raw_", raw), ("thr5_", thr5), ("c1e3_", c3)]:
+        for k in ("amplitude", "phase", "Neffs", "a0", "a1", "a2"):
+            out[tag + k] = r[k]
+    out["coi"] = ref["coi"]
+    save("synth_small", **out)
+
+
+def edge():
+    """Three-state Neff mask: two clusters with a long gap, a frequency above Nyquist."""
+    t = np.concatenate([np.arange(10.0), 1000.0 + np.arange(10.0)])
+    rng = np.random.default_rng(5)
+    y = rng.standard_normal(t.size)
+    tau = np.array([0.0, 5.0, 30.0, 60.0, 200.0, 500.0, 1005.0, 1009.0])
+    freq = np.array([1e-3, 1e-2, 0.03, 0.05, 0.1, 0.2, 0.5, 0.6])
+    ref = W.kirchner_numba(y, t, freq, tau, standardize=True)
+    basic = W.kirchner_basic(y, t, freq, tau, standardize=True)
+    save("edge", ts=t, ys=y, tau_in=tau, freq_in=freq,
+         amplitude=ref[0], phase=ref[1], Neffs=ref[2], a0=ref[3][0], a1=ref[3][1], a2=ref[3][2],
+         basic_amplitude=basic[0], basic_Neffs=basic[2])
+
+
+def c2_subsample():
+    """Config 2 (n=2000, 1000 tau x 500 f): full reference run, every 16th tau row stored,
+    plus full-grid checksums and the full wwz_psd vector."""
+    t, y, tau, freq = synth.config_grid("C2")
+    ref = run_wwz(y, t, tau=tau, freq=freq)
+    psd = SP.wwz_psd(y, t, freq=freq, tau=tau, nproc=1)
+    rows = np.arange(0, tau.size, 16)
+    out = dict(rows=rows, psd=psd.psd,
+               full_nan_count=np.array([np.isnan(ref["amplitude"]).sum()]),
+               full_amp_nansum=np.array([np.nansum(ref["amplitude"])]),
+               full_neff_nansum=np.array([np.nansum(ref["Neffs"])]),
+               nan_mask_packed=np.packbits(np.isnan(ref["amplitude"])))
+    for k in ("amplitude", "phase", "Neffs", "a0", "a1", "a2"):
+        out[k] = ref[k][rows]
+    save("c2_sub", **out)
+
+
+def c5_sample():
+    """Config 5 inputs (n=100,000): a 24 tau x 40 f sample of the 4096 x 2048 grid."""
+    t, y, tau, freq = synth.config_grid("C5")
+    jt = np.unique(np.round(np.linspace(0, tau.size - 1, 24)).astype(int))
+    kf = np.unique(np.round(np.linspace(0, freq.size - 1, 40)).astype(int))
+    # prepare_wwz would re-truncate the series to the span of the sub-sampled tau; the sample
+    # keeps both grid ends so the series is unchanged.
+    ys_std = (y - y.mean()) / y.std()
+    ref = W.kirchner_numba(ys_std, t, freq[kf], tau[jt], standardize=False)
+    save("c5_sample", jt=jt, kf=kf, amplitude=ref[0], phase=ref[1], Neffs=ref[2],
+         a0=ref[3][0], a1=ref[3][1], a2=ref[3][2])
+
+
+def surrogates():
+    """ar1_model / tau_estimation / ar1_sim on an uneven axis with NumPy's legacy global RNG."""
+    t, y = synth.uneven_ar1(400, 21)
+    y = 2.5 * y + 1.0
+    tau_est = TM.tau_estimation(y, t)
+    np.random.seed(1234)
+    model = TM.ar1_model(t, 4.0, output_sigma=1.7)
+    np.random.seed(99)
+    sim = TM.ar1_sim(y, 3, t)
+    save("surrogates", ts=t, ys=y, tau_est=np.array([tau_est]), model_seed1234_tau4_sig1p7=model,
+         sim_seed99_p3=sim)
+
+
+def cleaning():
+    """prepare_wwz on NaNs, unsorted stamps, duplicates and a tau that is off the time axis."""
+    rng = np.random.default_rng(77)
+    t = np.sort(rng.uniform(0, 200, 260))
+    y = rng.standard_normal(260)
+    t[50] = t[49]                     # duplicate stamp
+    y[10] = np.nan
+    t[200] = np.nan
+    perm = rng.permutation(260)
+    t, y = t[perm], y[perm]
+    tau = np.linspace(5.3, 190.2, 17)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ys_cut, ts_cut, freq, tau_out = W.prepare_wwz(y, t, tau=tau)
+        ys_cut2, ts_cut2, freq2, tau_out2 = W.prepare_wwz(y, t)
+        ref = run_wwz(y, t, tau=tau)
+    save("cleaning", ts=t, ys=y, tau_in=tau, ys_cut=ys_cut, ts_cut=ts_cut, freq_out=freq,
+         tau_out=tau_out, ts_cut_default=ts_cut2, freq_default=freq2, tau_default=tau_out2,
+         amplitude=ref["amplitude"], Neffs=ref["Neffs"], phase=ref["phase"])
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["benthic", "soi", "synth_small", "edge", "c2_subsample", "c5_sample",
+                             "surrogates", "cleaning"]
+    for name in which:
+        globals()[name]()
