@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""bench.py -- WWZ tau x f cells/s on B200 (BASELINE.json metric), one JSON line on stdout.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (config.workload): BASELINE.json configs[1] -- synthetic unevenly sampled AR(1) series
+n=2,000 (seed 0), ntau=1,000, nfreq=500 (log grid).  One STEP = wwz (c=1/(8 pi^2), all six per-cell
+outputs) + wwz_psd (c=1e-3, transform fused with the wwa2psd tau-reduction) = 2 x 500,000 cells.
+
+N > 1 (torchrun, one rank per GPU): weak scaling by tau-block -- the grid has 1,000*N tau rows, rank r
+computes rows [1000 r, 1000 (r+1)); there is no data-path exchange inside the transform, one NCCL
+all-gather assembles the sharded outputs and wwa2psd runs on the gathered scalogram.
+
+`value`   : whole-job cells/s with inputs resident in HBM, device time (CUDA events, max over ranks).
+`e2e`     : same metric through the C-ABI host-pointer entry points (wwzb200_kirchner +
+            wwzb200_kirchner_psd) with host buffers: H2D of the inputs and D2H of every output inside
+            the timed region, every step.
+`roofline`: the dominant kernel (wwz_cells_kernel) -- algorithmic 50 flop per (cell, point)
+             / its CUDA-event time, against the FP64 FMA peak measured on this device.
+`cpu_baseline`: the oracle port (oracle/wwz_oracle.c, the reference's two-pass algorithm, OpenMP on
+            all host cores) on a bounded sample of the same workload.
+--impl reference: the CPU arm (same oracle port; the reference's own kernel is Python/numba +
+            Fortran and cannot travel to the GPU box), rank 0 only.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+C_WWZ = 1.0 / (8.0 * np.pi ** 2)
+C_PSD = 1e-3
+FLOP_PER_CELL_POINT = 50.0
+WORKLOAD = "C2: uneven AR(1) n=2000 (seed 0), ntau=1000/GPU, nfreq=500, wwz(c=1/(8pi^2)) + wwz_psd(c=1e-3)"
+
+
+def workload(n_gpus):
+    from pyleoclim_util_b200 import synth, wavelet as WV
+    n, ntau, nf, seed = synth.CONFIGS["C2"]
+    t, y = synth.uneven_ar1(n, seed)
+    tau = np.linspace(t.min(), t.max(), ntau * n_gpus)
+    freq = synth.freq_log(t, nf)
+    ys = WV.standardize(y)[0]
+    omega = WV.make_omega(t, freq)
+    return t, ys, tau, freq, omega
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([x.strip() for x in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        self.join(timeout=2)
+        sm, mx, reasons = [], 0.0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def oracle_step(t, ys, tau, omega, nthreads=0):
+    """One CPU step on the oracle port: both transforms + psd (faithful two-pass algorithm)."""
+    from oracle import wwz_oracle as O
+    Ne, a0, a1, a2 = O.kirchner_cells(t, ys, tau, omega, C_WWZ, 3, mode=0, nthreads=nthreads)
+    Ne2, b0, b1, b2 = O.kirchner_cells(t, ys, tau, omega, C_PSD, 3, mode=0, nthreads=nthreads)
+    amp = np.sqrt(b1 ** 2 + b2 ** 2)
+    psd = O.wwa2psd(amp, t, Ne2, Neff_threshold=3)
+    return Ne, psd
+
+
+def cpu_baseline(t, ys, tau, omega, target_seconds=12.0):
+    from oracle import wwz_oracle as O
+    cores = O.num_threads()
+    rows = max(8, min(tau.size, 16 * cores))
+    sub = tau[:: max(1, tau.size // rows)][:rows]
+    t0 = time.perf_counter()
+    oracle_step(t, ys, sub, omega)
+    dt = time.perf_counter() - t0
+    reps = int(max(1, min(20, target_seconds / max(dt, 1e-3) - 1)))
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        oracle_step(t, ys, sub, omega)
+    dt2 = (time.perf_counter() - t0) / reps
+    cells = 2 * sub.size * omega.size
+    return {"value": cells / dt2, "unit": "cells/s", "cores": cores, "kind": "port",
+            "sample": "%d of %d tau rows x %d freq, both transforms (wwz + wwz_psd), %d repetitions, "
+                      "oracle/wwz_oracle.c two-pass Kirchner with OpenMP" % (sub.size, tau.size, omega.size, reps)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    t, ys, tau, freq, omega = workload(1)
+    from oracle import wwz_oracle as O
+    cores = O.num_threads()
+    rows = max(8, min(tau.size, 8 * cores))
+    sub = tau[:: max(1, tau.size // rows)][:rows]
+    for _ in range(args.warmup):
+        oracle_step(t, ys, sub[:8], omega)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        oracle_step(t, ys, sub, omega)
+    dt = time.perf_counter() - t0
+    cells = 2 * sub.size * omega.size * args.steps
+    value = cells / dt
+    sample = "%d of %d tau rows x %d freq per step, both transforms" % (sub.size, tau.size, omega.size)
+    line = {"impl": "reference", "metric": "WWZ tau x f cells/s", "value": value, "unit": "cells/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "cells/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "reference arm = CPU restatement of pyleoclim kirchner_numba (utils/wavelet.py:985-1045) in C with "
+                    "OpenMP on all host cores; the reference's numba path adds a ~7-8 s JIT per call (BASELINE.md)"}
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    from pyleoclim_util_b200 import _lib, wavelet as WV
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        dist = None
+        torch.cuda.set_device(0)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    _lib.set_device(dev.index)
+    L = _lib.lib()
+
+    t, ys, tau_all, freq, omega = workload(world)
+    n, nf = t.size, freq.size
+    nt_local = tau_all.size // world
+    tau = np.ascontiguousarray(tau_all[rank * nt_local:(rank + 1) * nt_local])
+    nt_total = tau_all.size
+    cells_step_local = 2 * nt_local * nf
+
+    fp64_tf, _ = _lib.measure_fp64_peak()
+
+    # ---------------------------------------------------------------- device-resident leg
+    d_t, d_y, d_tau, d_om = (torch.from_numpy(np.ascontiguousarray(v)).to(dev) for v in (t, ys, tau, omega))
+    loc6 = torch.empty((6, nt_local, nf), dtype=torch.float64, device=dev)   # Neffs,a0,a1,a2,wwa,phase of wwz
+    loc2 = torch.empty((2, nt_local, nf), dtype=torch.float64, device=dev)   # Neffs, wwa of the psd pass
+    psd = torch.empty(nf, dtype=torch.float64, device=dev)
+    if world > 1:
+        g6 = torch.empty((world, 6, nt_local, nf), dtype=torch.float64, device=dev)
+        g2 = torch.empty((world, 2, nt_local, nf), dtype=torch.float64, device=dev)
+        full6 = torch.empty((6, nt_total, nf), dtype=torch.float64, device=dev)
+        full2 = torch.empty((2, nt_total, nf), dtype=torch.float64, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)             # > 126 MB L2
+    tspan = float(t.max() - t.min())
+
+    def step_device():
+        o = [loc6[i].data_ptr() for i in range(6)]
+        _lib.check(L.wwzb200_kirchner_dev(d_t.data_ptr(), d_y.data_ptr(), n, d_tau.data_ptr(), nt_local,
+                                          d_om.data_ptr(), nf, C_WWZ, 3, 3, 0, o[0], o[1], o[2], o[3], o[4], o[5],
+                                          None, nf, stream))
+        _lib.check(L.wwzb200_kirchner_dev(d_t.data_ptr(), d_y.data_ptr(), n, d_tau.data_ptr(), nt_local,
+                                          d_om.data_ptr(), nf, C_PSD, 3, 3, 0, loc2[0].data_ptr(), None, None, None,
+                                          loc2[1].data_ptr(), None, psd.data_ptr() if world == 1 else None, nf,
+                                          stream))
+        if world > 1:
+            # tau-row blocks are the shards: one NCCL all-gather per output family over NVLink, then the
+            # row blocks are laid side by side and wwa2psd reduces the gathered scalogram
+            dist.all_gather_into_tensor(g6.view(-1), loc6.view(-1))
+            dist.all_gather_into_tensor(g2.view(-1), loc2.view(-1))
+            full6.view(6, world, nt_local, nf).copy_(g6.permute(1, 0, 2, 3))
+            full2.view(2, world, nt_local, nf).copy_(g2.permute(1, 0, 2, 3))
+            _lib.check(L.wwzb200_wwa2psd_dev(full2[1].data_ptr(), full2[0].data_ptr(), nt_total, nf, tspan, n, 3,
+                                             psd.data_ptr(), stream))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    barrier()
+
+    sampler = ClockSampler(dev.index)
+    sampler.start()
+    time.sleep(0.15)
+    _lib.profile(True)
+    launches0 = _lib.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    wall0 = time.perf_counter()
+    for i in range(args.steps):
+        flush.zero_()                                  # L2 flush between timed iterations (outside the events)
+        ev[i][0].record()
+        step_device()
+        ev[i][1].record()
+    barrier()
+    wall = time.perf_counter() - wall0
+    launches = _lib.launch_count() - launches0
+    cell_ms, cell_launches, cell_points = _lib.profile_read()
+    _lib.profile(False)
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    if dist is not None:
+        tmax = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dev_ms = float(tmax.item())
+    value = world * cells_step_local * args.steps / (dev_ms * 1e-3)
+
+    # ---------------------------------------------------------------- end-to-end leg (host buffers, C ABI)
+    h_in = [_lib.pinned_empty(v.shape) for v in (t, ys, tau, omega)]
+    for dst, src in zip(h_in, (t, ys, tau, omega)):
+        dst[...] = src
+    h_out = [_lib.pinned_empty((nt_local, nf)) for _ in range(6)]
+    h_psd = _lib.pinned_empty((nf,))
+    h_ne2 = _lib.pinned_empty((nt_local, nf))
+
+    def step_e2e():
+        _lib.check(L.wwzb200_kirchner(_lib.ptr(h_in[0]), _lib.ptr(h_in[1]), n, _lib.ptr(h_in[2]), nt_local,
+                                      _lib.ptr(h_in[3]), nf, C_WWZ, 3, 0, *[_lib.ptr(o) for o in h_out]))
+        _lib.check(L.wwzb200_kirchner_psd(_lib.ptr(h_in[0]), _lib.ptr(h_in[1]), n, _lib.ptr(h_in[2]), nt_local,
+                                          _lib.ptr(h_in[3]), nf, C_PSD, 3, 3, 0, _lib.ptr(h_psd), _lib.ptr(h_ne2),
+                                          None, None, None, None, None))
+
+    for _ in range(3):
+        step_e2e()
+    barrier()
+    e0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    e2e_s = time.perf_counter() - e0
+    if dist is not None:
+        tmax = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        e2e_s = float(tmax.item())
+    e2e_value = world * cells_step_local * args.steps / e2e_s
+    h2d = 2 * 8 * (2 * n + nt_local + nf)
+    d2h = 8 * (6 * nt_local * nf + nt_local * nf + nf)
+
+    # the public Python API (fresh NumPy outputs, prepare_wwz + standardize on the host), for the record
+    api_s = None
+    if rank == 0:
+        for _ in range(2):
+            WV.wwz(ys, t, tau=tau, freq=freq)
+        a0 = time.perf_counter()
+        for _ in range(max(1, args.steps // 4)):
+            WV.wwz(ys, t, tau=tau, freq=freq)
+            WV.wwz_psd(ys, t, tau=tau, freq=freq)
+        api_s = (time.perf_counter() - a0) / max(1, args.steps // 4)
+
+    clocks = sampler.stop()
+
+    # ---------------------------------------------------------------- roofline + CPU baseline
+    achieved_tf = FLOP_PER_CELL_POINT * cell_points / (cell_ms * 1e-3) / 1e12 if cell_ms > 0 else None
+    roofline = {"bound": "fp64", "kernel": "wwz_cells_kernel", "achieved": achieved_tf, "peak": fp64_tf,
+                "unit": "TFLOP/s", "frac": (achieved_tf / fp64_tf) if achieved_tf else None, "traffic": None,
+                "launches": cell_launches, "avg_launch_ms": cell_ms / max(cell_launches, 1),
+                "kernel_share_of_step": cell_ms / dev_ms if dev_ms else None,
+                "algorithmic": "50 flop per (cell, point) x n=%d x %d cells per launch (SURVEY.md 8d)" % (n, nt_local * nf),
+                "peak_source": "of measured: register-resident DFMA-chain microbenchmark on this device "
+                               "(wwzb200_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 entry; nominal 37.2"}
+    if rank != 0:
+        return
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    cpu = cpu_baseline(t, ys, tau_all[:nt_local] if world > 1 else tau, omega) if world == 1 else None
+    line = {"metric": "WWZ tau x f cells/s", "value": value, "unit": "cells/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "n": n, "ntau_per_gpu": nt_local, "nfreq": nf,
+                       "cells_per_step_per_gpu": cells_step_local, "partition": "tau-block per GPU + NCCL all-gather"
+                       if world > 1 else "single GPU", "l2": "256 MiB buffer written between timed iterations",
+                       "window": "exact-zero weight chunks skipped (bit-identical to dense)"},
+            "e2e": {"value": e2e_value, "unit": "cells/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": 1e3 * e2e_s / args.steps, "path": "wwzb200_kirchner + wwzb200_kirchner_psd, pinned host buffers",
+                    "python_api_ms_per_step": None if api_s is None else 1e3 * api_s},
+            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+            "wall_ms_per_step_incl_l2_flush": 1e3 * wall / args.steps,
+            "hbm_gbs_measured": peaks.get("hbm_gbs")}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -137,6 +137,9 @@ int wwzb200_kirchner_dev(const double *d_ts, const double *d_pd_ys, int64_t nts,
                          double *d_Neffs, double *d_a0, double *d_a1, double *d_a2, double *d_wwa,
                          double *d_phase, double *d_psd, int64_t out_row_stride, void *stream);
 
+int wwzb200_wwa2psd_dev(const double *d_wwa, const double *d_Neffs, int64_t nt, int64_t nf, double tspan,
+                        int64_t nts, int64_t Neff_threshold, double *d_psd, void *stream);
+
 int wwzb200_kirchner_shared_axis_dev(const double *d_ts, const double *d_Y, int64_t nts, int64_t S,
                                      const double *d_taus, int64_t nt, const double *d_omegas,
                                      int64_t nf, double c, int64_t Neff_threshold,
@@ -156,6 +159,13 @@ int wwzb200_measure_fp64_peak(double *tflops, double *ms);
 
 /* Kernel launch counter (incremented by every kernel this library launches). */
 int64_t wwzb200_launch_count(void);
+
+/* In-library timing of the hot kernel (wwz_cells_kernel): while enabled, CUDA events are recorded
+ * on the launching stream around every launch.  wwzb200_profile(1) starts (and clears), (0) stops;
+ * wwzb200_profile_read waits for the recorded events and returns the summed kernel time, the
+ * number of launches and the (cell, point) pairs they covered. */
+int wwzb200_profile(int enable);
+int wwzb200_profile_read(double *cell_kernel_ms, int64_t *cell_kernel_launches, double *cell_points);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

@@ -16,6 +16,6 @@ library or a CUDA device is missing.
 from . import _lib  # noqa: F401
 from .wavelet import (kirchner_cuda, wwz, wwz_psd, wwa2psd, make_omega, make_coi, prepare_wwz,  # noqa: F401
                       make_freq_vector, freq_vector_log)
-from .register import register, unregister  # noqa: F401
+from .dispatch import register, unregister  # noqa: F401
 
 __version__ = "0.1.0"

@@ -52,12 +52,15 @@ _SIGS = {
     "wwzb200_quantiles": (ctypes.c_int, [_dp, _i64, _i64, _dp, _i64, _dp]),
     "wwzb200_kirchner_dev": (ctypes.c_int, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _dbl, _i64, _i64, _u32,
                                             _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "wwzb200_wwa2psd_dev": (ctypes.c_int, [_vp, _vp, _i64, _i64, _dbl, _i64, _i64, _vp, _vp]),
     "wwzb200_kirchner_shared_axis_dev": (ctypes.c_int, [_vp, _vp, _i64, _i64, _vp, _i64, _vp, _i64, _dbl, _i64,
                                                         _i64, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "wwzb200_ar1_surrogates_dev": (ctypes.c_int, [_vp, _i64, _dbl, _dbl, _dbl, _i64, _u64, _vp, _vp]),
     "wwzb200_quantiles_dev": (ctypes.c_int, [_vp, _i64, _i64, _vp, _i64, _vp, _vp]),
     "wwzb200_measure_fp64_peak": (ctypes.c_int, [_dp, _dp]),
     "wwzb200_launch_count": (_i64, []),
+    "wwzb200_profile": (ctypes.c_int, [ctypes.c_int]),
+    "wwzb200_profile_read": (ctypes.c_int, [_dp, ctypes.POINTER(_i64), _dp]),
 }
 
 
@@ -125,6 +128,17 @@ def measure_fp64_peak():
     tf, ms = ctypes.c_double(), ctypes.c_double()
     check(lib().wwzb200_measure_fp64_peak(ctypes.byref(tf), ctypes.byref(ms)))
     return tf.value, ms.value
+
+
+def profile(enable):
+    check(lib().wwzb200_profile(1 if enable else 0))
+
+
+def profile_read():
+    """(summed cell-kernel ms, launches, cell-points) recorded since profile(True)."""
+    ms, n, cp = ctypes.c_double(), _i64(), ctypes.c_double()
+    check(lib().wwzb200_profile_read(ctypes.byref(ms), ctypes.byref(n), ctypes.byref(cp)))
+    return ms.value, int(n.value), cp.value
 
 
 def _free_pinned(addr):

@@ -13,6 +13,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <vector>
 
 #include "../../include/wwz_b200.h"
 #include "wwz_internal.h"
@@ -40,6 +41,15 @@ int fail(int code, const char *fmt, ...)
             return fail(e_ == cudaErrorMemoryAllocation ? WWZB200_ERR_NOMEM : WWZB200_ERR_CUDA,       \
                         "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__);  \
     } while (0)
+
+// Optional in-library timing of the hot kernel (wwzb200_profile): CUDA events recorded on the
+// launching stream around every cell-kernel launch, read back by wwzb200_profile_read.
+bool g_profile = false;
+struct EventPair {
+    cudaEvent_t a, b;
+    double cell_points;
+};
+std::vector<EventPair> g_events;
 
 // Grow-only named device buffers, one set per device.
 struct Workspace {
@@ -164,8 +174,18 @@ int transform_device(Workspace *w, const double *d_ts, const double *d_ys, int64
         for (int64_t k0 = 0; k0 < nf; k0 += nf_batch) {
             const int64_t nb = std::min<int64_t>(nf_batch, nf - k0);
             CU(launch_basis(d_ts, d_ys, n, plan.n_pad, d_omega + k0, nb, d_ty, d_basis, k0 == 0, st));
+            EventPair ev{nullptr, nullptr, (double)n * (double)nt * (double)nb};
+            if (g_profile) {
+                CU(cudaEventCreate(&ev.a));
+                CU(cudaEventCreate(&ev.b));
+                CU(cudaEventRecord(ev.a, st));
+            }
             CU(launch_cells(plan, d_ty, d_basis, d_ts, n, d_tau, nt, d_kappa, d_dcut, d_unsorted, k0, nb, nf, dense,
                             d_sums, st));
+            if (g_profile) {
+                CU(cudaEventRecord(ev.b, st));
+                g_events.push_back(ev);
+            }
         }
         CU(launch_finalize(d_sums, d_tau, d_omega, nt, nf, (double)thr, d_neffs, d_a0, d_a1, d_a2, d_wwa, d_phase,
                            row_stride, d_fix_count, d_fix_list, (unsigned int)ncell, st));
@@ -363,6 +383,17 @@ int wwzb200_kirchner_dev(const double *d_ts, const double *d_pd_ys, int64_t nts,
                             static_cast<cudaStream_t>(stream));
 }
 
+int wwzb200_wwa2psd_dev(const double *d_wwa, const double *d_Neffs, int64_t nt, int64_t nf, double tspan,
+                        int64_t nts, int64_t Neff_threshold, double *d_psd, void *stream)
+{
+    if (nt < 0 || nf < 0 || nts < 1) return fail(WWZB200_ERR_ARG, "bad sizes");
+    if (nf == 0) return 0;
+    if (!d_wwa || !d_Neffs || !d_psd) return fail(WWZB200_ERR_ARG, "null pointer");
+    CU(wwz::launch_psd(d_wwa, d_Neffs, nt, nf, nf, tspan, nts, (double)Neff_threshold, d_psd,
+                       static_cast<cudaStream_t>(stream)));
+    return 0;
+}
+
 int wwzb200_measure_fp64_peak(double *tflops, double *ms)
 {
     if (!tflops || !ms) return fail(WWZB200_ERR_ARG, "null pointer");
@@ -372,5 +403,35 @@ int wwzb200_measure_fp64_peak(double *tflops, double *ms)
 }
 
 int64_t wwzb200_launch_count(void) { return wwz::launch_counter(); }
+
+int wwzb200_profile(int enable)
+{
+    std::lock_guard<std::mutex> lock(g_mu);
+    g_profile = enable != 0;
+    for (auto &e : g_events) {
+        cudaEventDestroy(e.a);
+        cudaEventDestroy(e.b);
+    }
+    g_events.clear();
+    return 0;
+}
+
+int wwzb200_profile_read(double *cell_kernel_ms, int64_t *cell_kernel_launches, double *cell_points)
+{
+    if (!cell_kernel_ms || !cell_kernel_launches || !cell_points) return fail(WWZB200_ERR_ARG, "null pointer");
+    std::lock_guard<std::mutex> lock(g_mu);
+    double ms = 0, cp = 0;
+    for (auto &e : g_events) {
+        CU(cudaEventSynchronize(e.b));
+        float t = 0;
+        CU(cudaEventElapsedTime(&t, e.a, e.b));
+        ms += t;
+        cp += e.cell_points;
+    }
+    *cell_kernel_ms = ms;
+    *cell_kernel_launches = (int64_t)g_events.size();
+    *cell_points = cp;
+    return 0;
+}
 
 }  // extern "C"

@@ -1,0 +1,277 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle and the reference's goldens.
+
+Bar (BASELINE.json north_star): identical Neff mask; amplitude, phase, PSD within 1e-9 of
+kirchner_numba (relative for amplitude/PSD, absolute mod 2 pi for phase)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import (golden, assert_scalogram_parity, as_dict, max_rel, assert_same_nan_mask, has_cuda,
+                      max_phase_abs)
+
+pytestmark = pytest.mark.gpu
+
+from pyleoclim_util_b200 import wavelet as WV   # noqa: E402
+from pyleoclim_util_b200 import _lib, synth     # noqa: E402
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_gpu():
+    assert has_cuda(), "these tests need a CUDA device and the built libwwz_b200.so (no CPU fallback)"
+
+
+def _res(r):
+    return as_dict(r.amplitude, r.phase, r.Neffs, r.coeff)
+
+
+def oracle():
+    from oracle import wwz_oracle as O
+    return O
+
+
+# ------------------------------------------------------------------ goldens from the reference
+def test_benthic_known_answer_file():
+    g = golden("benthic")
+    r = WV.wwz(g["ys"], g["ts"], tau=g["tau_in"], freq=g["freq_in"])
+    assert_same_nan_mask(r.amplitude, g["file_amplitude"])
+    assert max_rel(r.amplitude, g["file_amplitude"]) < 1e-9
+    assert max_rel(r.Neffs, g["file_Neffs"]) < 1e-12
+    assert np.array_equal(r.coi, g["file_coi"])
+    assert_scalogram_parity(_res(r), g, what="benthic vs numba")
+
+
+def test_soi_defaults_and_psd():
+    g = golden("soi")
+    r = WV.wwz(g["ys"], g["ts"])
+    assert np.array_equal(r.freq, g["freq"]) and np.array_equal(r.time, g["tau"])
+    assert np.array_equal(r.scale, 1 / g["freq"])
+    assert_scalogram_parity(_res(r), g, what="soi")
+    p = WV.wwz_psd(g["ys"], g["ts"])
+    assert np.array_equal(p.freq, g["psd_freq"])
+    assert max_rel(p.psd, g["psd"]) < 1e-9
+
+
+@pytest.mark.parametrize("tag,kw", [("", {}), ("c1e3_", {"c": 1e-3}), ("thr5_", {"Neff_threshold": 5}),
+                                     ("raw_", {"standardize": False})])
+def test_synth_small_variants(tag, kw):
+    g = golden("synth_small")
+    r = WV.wwz(g["ys"], g["ts"], tau=g["tau_in"], freq=g["freq_in"], **kw)
+    ref = {k: g[tag + k] for k in ("amplitude", "phase", "Neffs", "a0", "a1", "a2")}
+    assert_scalogram_parity(_res(r), ref, what="synth_small " + tag)
+
+
+def test_synth_small_psd():
+    g = golden("synth_small")
+    p = WV.wwz_psd(g["ys"], g["ts"], tau=g["tau_in"], freq=g["freq_in"])
+    assert max_rel(p.psd, g["psd"]) < 1e-9
+    p = WV.wwz_psd(g["ys"], g["ts"], tau=g["tau_in"], freq=g["freq_in"], Neff_threshold=6)
+    assert max_rel(p.psd, g["psd_thr6"]) < 1e-9
+    p = WV.wwz_psd(g["ys"], g["ts"], freq=g["freq_in"])
+    assert max_rel(p.psd, g["psd_default_tau"]) < 1e-9
+    # scalogram reuse path (utils/spectral.py:888): wwa2psd alone
+    r = WV.wwz(g["ys"], g["ts"], tau=g["tau_in"], freq=g["freq_in"], c=1e-3)
+    p2 = WV.wwz_psd(g["ys"], g["ts"], tau=g["tau_in"], freq=g["freq_in"], wwa=r.amplitude, wwz_Neffs=r.Neffs,
+                    wwz_freq=r.freq)
+    assert max_rel(p2.psd, g["psd"]) < 1e-9
+
+
+def test_edge_three_state_mask():
+    g = golden("edge")
+    out = WV.kirchner_cuda(g["ys"], g["ts"], g["freq_in"], g["tau_in"], standardize=True)
+    assert_scalogram_parity(as_dict(*out), g, what="edge")
+    assert np.isnan(out[2]).sum() == 13 and np.isnan(out[0]).sum() == 19
+
+
+def test_cleaning_inputs():
+    g = golden("cleaning")
+    r = WV.wwz(g["ys"], g["ts"], tau=g["tau_in"])
+    assert_scalogram_parity(dict(amplitude=r.amplitude, phase=r.phase, Neffs=r.Neffs), g, what="cleaning")
+
+
+def test_config2_full_grid_vs_golden_and_oracle():
+    g = golden("c2_sub")
+    t, y, tau, freq = synth.config_grid("C2")
+    r = WV.wwz(y, t, tau=tau, freq=freq)
+    rows = g["rows"]
+    got = {k: v[rows] for k, v in _res(r).items()}
+    assert_scalogram_parity(got, g, what="C2 golden rows")
+    assert np.array_equal(np.packbits(np.isnan(r.amplitude)), g["nan_mask_packed"])
+    p = WV.wwz_psd(y, t, tau=tau, freq=freq)
+    assert max_rel(p.psd, g["psd"]) < 1e-9
+    # every cell against the oracle (CPU, all host threads)
+    ro = oracle().wwz(y, t, tau=tau, freq=freq)
+    assert_scalogram_parity(_res(r), _res(ro), what="C2 full grid vs oracle")
+
+
+def test_config5_sample_vs_golden():
+    g = golden("c5_sample")
+    t, y, tau, freq = synth.config_grid("C5")
+    ys = (y - y.mean()) / y.std()
+    out = WV.kirchner_cuda(ys, t, freq[g["kf"]], tau[g["jt"]])
+    assert_scalogram_parity(as_dict(*out), g, what="C5 sample")
+
+
+# ------------------------------------------------------------------ kernel variants agree bit for bit
+def _grid_case(n=700, nt=37, nf=23, seed=4):
+    t, y = synth.uneven_ar1(n, seed)
+    y = (y - y.mean()) / y.std()
+    tau = np.linspace(t.min(), t.max(), nt)
+    freq = synth.freq_log(t, nf)
+    return t, y, tau, freq
+
+
+def _bits(out):
+    return [np.ascontiguousarray(a).view(np.uint64) for a in (out[0], out[1], out[2], *out[3])]
+
+
+def test_windowed_is_bit_identical_to_dense():
+    t, y, tau, freq = _grid_case(n=3000, nt=64, nf=48)
+    a = WV.kirchner_cuda(y, t, freq, tau)
+    b = WV.kirchner_cuda(y, t, freq, tau, flags=_lib.DENSE)
+    for x, z in zip(_bits(a), _bits(b)):
+        assert np.array_equal(x, z)
+
+
+@pytest.mark.parametrize("m", ["1", "2", "4"])
+def test_cells_per_lane_variants_bit_identical(m, monkeypatch):
+    t, y, tau, freq = _grid_case()
+    monkeypatch.setenv("WWZB200_CELLS_PER_LANE", "2")
+    a = WV.kirchner_cuda(y, t, freq, tau)
+    monkeypatch.setenv("WWZB200_CELLS_PER_LANE", m)
+    b = WV.kirchner_cuda(y, t, freq, tau)
+    for x, z in zip(_bits(a), _bits(b)):
+        assert np.array_equal(x, z)
+
+
+def test_frequency_batching_bit_identical(monkeypatch):
+    t, y, tau, freq = _grid_case(n=5000, nt=20, nf=40)
+    a = WV.kirchner_cuda(y, t, freq, tau)
+    monkeypatch.setenv("WWZB200_BASIS_BYTES", str(2 << 20))     # forces several frequency batches
+    b = WV.kirchner_cuda(y, t, freq, tau)
+    for x, z in zip(_bits(a), _bits(b)):
+        assert np.array_equal(x, z)
+
+
+def test_faithful_mode_matches_oracle_tightly():
+    t, y, tau, freq = _grid_case()
+    a = WV.kirchner_cuda(y, t, freq, tau, flags=_lib.FAITHFUL)
+    o = oracle().kirchner(y, t, freq, tau)
+    assert_scalogram_parity(as_dict(*a), as_dict(*o), amp_rtol=1e-11, phase_atol=1e-11, what="faithful")
+
+
+# ------------------------------------------------------------------ ragged shapes and edge inputs
+@pytest.mark.parametrize("n,nt,nf", [(2, 1, 1), (7, 3, 5), (33, 1, 17), (100, 51, 1), (257, 5, 300), (1000, 50, 101),
+                                      (513, 2, 2), (4097, 13, 9)])
+def test_ragged_shapes_vs_oracle(n, nt, nf):
+    t, y = synth.uneven_ar1(n, 100 + n)
+    tau = np.linspace(t.min(), t.max(), nt) if nt > 1 else np.array([t.mean()])
+    freq = synth.freq_log(t, nf) if nf > 1 else np.array([0.5 / np.ptp(t) * 4])
+    a = WV.kirchner_cuda(y, t, freq, tau, standardize=True, Neff_threshold=1)
+    o = oracle().kirchner(y, t, freq, tau, standardize=True, Neff_threshold=1)
+    assert_scalogram_parity(as_dict(*a), as_dict(*o), what="shape %s" % ((n, nt, nf),))
+
+
+def test_empty_grids():
+    t, y = synth.uneven_ar1(20, 1)
+    a = WV.kirchner_cuda(y, t, np.array([]), np.array([1.0, 2.0]))
+    assert a[0].shape == (2, 0)
+    a = WV.kirchner_cuda(y, t, np.array([0.1]), np.array([]))
+    assert a[0].shape == (0, 1)
+
+
+def test_unsorted_time_axis():
+    """The raw kernel accepts an unsorted axis: windowing falls back to dense on the device."""
+    t, y = synth.uneven_ar1(400, 9)
+    perm = np.random.default_rng(0).permutation(t.size)
+    tau = np.linspace(t.min(), t.max(), 11)
+    freq = np.array([0.01, 0.1, 0.3])
+    a = WV.kirchner_cuda(y[perm], t[perm], freq, tau)
+    o = oracle().kirchner(y[perm], t[perm], freq, tau)
+    assert_scalogram_parity(as_dict(*a), as_dict(*o), what="unsorted")
+    b = WV.kirchner_cuda(y, t, freq, tau)
+    assert max_rel(a[0], b[0]) < 1e-12
+
+
+def test_frequency_above_nyquist_gives_nan_column():
+    """utils/wavelet.py:1229-1232: f > f_Nyquist -> omega = NaN -> NaN Neff and coefficients."""
+    t, y = synth.uneven_ar1(400, 9)
+    tau = np.linspace(t.min(), t.max(), 11)
+    freq = np.array([0.01, 5.0, 0.1, 0.3, 7.0])
+    a = WV.kirchner_cuda(y, t, freq, tau)
+    o = oracle().kirchner(y, t, freq, tau)
+    for col in (1, 4):
+        assert np.isnan(a[2][:, col]).all() and np.isnan(a[0][:, col]).all() and np.isnan(a[3][0][:, col]).all()
+    assert_scalogram_parity(as_dict(*a), as_dict(*o), what="nyquist")
+
+
+def test_gap_series_flags_deep_underflow_cells():
+    """Long hiatus at high frequency: cells whose weights are all (sub)normal-tiny go through the
+    faithful fix-up kernel; all three mask states must match the oracle."""
+    rng = np.random.default_rng(8)
+    t = np.concatenate([np.sort(rng.uniform(0, 50, 120)), np.sort(rng.uniform(400, 450, 120))])
+    y = rng.standard_normal(t.size)
+    tau = np.linspace(t.min(), t.max(), 60)
+    freq = np.logspace(-2.5, 0.05, 40)
+    a = WV.kirchner_cuda(y, t, freq, tau, standardize=True)
+    o = oracle().kirchner(y, t, freq, tau, standardize=True)
+    assert np.isnan(o[2]).any() and np.isnan(o[0]).sum() > np.isnan(o[2]).sum()
+    assert_scalogram_parity(as_dict(*a), as_dict(*o), what="gap")
+
+
+# ------------------------------------------------------------------ size-independent properties
+def test_linearity_in_y_and_neff_independent_of_y_at_config2_size():
+    t, y, tau, freq = synth.config_grid("C2")
+    rng = np.random.default_rng(2)
+    y2 = rng.standard_normal(y.size)
+    a = WV.kirchner_cuda(y, t, freq, tau)
+    b = WV.kirchner_cuda(y2, t, freq, tau)
+    c = WV.kirchner_cuda(y + 2.0 * y2, t, freq, tau)
+    assert np.array_equal(a[2].view(np.uint64), b[2].view(np.uint64))      # Neffs do not depend on y
+    scale = np.nanmax(c[0])
+    for i in range(3):
+        lin = a[3][i] + 2.0 * b[3][i]
+        m = ~np.isnan(lin)
+        assert np.array_equal(np.isnan(lin), np.isnan(c[3][i]))
+        assert np.max(np.abs(lin[m] - c[3][i][m])) < 1e-11 * scale
+
+
+def test_time_origin_shift_invariance_of_amplitude():
+    t, y, tau, freq = _grid_case(n=1500, nt=40, nf=30)
+    a = WV.kirchner_cuda(y, t, freq, tau)
+    b = WV.kirchner_cuda(y, t + 1000.0, freq, tau + 1000.0)
+    assert_same_nan_mask(a[0], b[0])
+    assert max_rel(b[0], a[0]) < 1e-9
+
+
+# ------------------------------------------------------------------ device-pointer entry point
+def test_dev_entry_point_matches_host_entry_point():
+    torch = pytest.importorskip("torch")
+    t, y, tau, freq = _grid_case(n=900, nt=30, nf=25)
+    om = WV.make_omega(t, freq)
+    host = WV._transform(y, t, tau, om, 1 / (8 * np.pi ** 2), 3, psd_threshold=3)
+    dev = torch.device("cuda:0")
+    d = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in dict(t=t, y=y, tau=tau, om=om).items()}
+    outs = [torch.empty((tau.size, freq.size), dtype=torch.float64, device=dev) for _ in range(6)]
+    psd = torch.empty(freq.size, dtype=torch.float64, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    rc = _lib.lib().wwzb200_kirchner_dev(d["t"].data_ptr(), d["y"].data_ptr(), t.size, d["tau"].data_ptr(), tau.size,
+                                         d["om"].data_ptr(), freq.size, 1 / (8 * np.pi ** 2), 3, 3, 0,
+                                         *[o.data_ptr() for o in outs], psd.data_ptr(), 0, st)
+    _lib.check(rc)
+    torch.cuda.synchronize()
+    neffs, a0, a1, a2, wwa, phase = [o.cpu().numpy() for o in outs]
+    assert np.array_equal(wwa.view(np.uint64), host[0].view(np.uint64))
+    assert np.array_equal(neffs.view(np.uint64), host[2].view(np.uint64))
+    assert np.array_equal(phase.view(np.uint64), host[1].view(np.uint64))
+    assert max_rel(psd.cpu().numpy(), host[4]) < 1e-14
+
+
+def test_pinned_outputs_and_launch_counter():
+    t, y, tau, freq = _grid_case()
+    om = WV.make_omega(t, freq)
+    before = _lib.launch_count()
+    a = WV._transform(y, t, tau, om, 0.0126, 3, pinned=True)
+    assert _lib.launch_count() - before >= 5
+    b = WV._transform(y, t, tau, om, 0.0126, 3)
+    assert np.array_equal(a[0].view(np.uint64), b[0].view(np.uint64))

@@ -1,0 +1,117 @@
+"""Host-side mirror of the reference interface (pyleoclim_util_b200.wavelet) on the CPU:
+everything around the kernel, checked against the reference-generated fixtures."""
+import types
+
+import numpy as np
+import pytest
+
+from conftest import golden
+from pyleoclim_util_b200 import wavelet as WV
+from pyleoclim_util_b200 import dispatch as REG
+from pyleoclim_util_b200 import synth
+
+
+def test_prepare_wwz_matches_reference():
+    g = golden("cleaning")
+    ys_cut, ts_cut, freq, tau = WV.prepare_wwz(g["ys"], g["ts"], tau=g["tau_in"])
+    assert np.array_equal(ts_cut, g["ts_cut"]) and np.allclose(ys_cut, g["ys_cut"], rtol=1e-15, atol=0)
+    assert np.array_equal(tau, g["tau_out"]) and np.array_equal(freq, g["freq_out"])
+    _, ts2, freq2, tau2 = WV.prepare_wwz(g["ys"], g["ts"])
+    assert np.array_equal(ts2, g["ts_cut_default"])
+    assert np.array_equal(freq2, g["freq_default"]) and np.array_equal(tau2, g["tau_default"])
+
+
+def test_default_grids_match_reference_on_soi():
+    g = golden("soi")
+    _, ts_cut, freq, tau = WV.prepare_wwz(g["ys"], g["ts"])
+    assert np.array_equal(freq, g["freq"]) and np.array_equal(tau, g["tau"])
+    assert np.allclose(WV.make_coi(tau), g["coi"], rtol=1e-15)
+    g = golden("benthic")
+    assert np.array_equal(WV.make_coi(g["tau_in"]), g["file_coi"])
+
+
+def test_make_omega_nyquist_nan():
+    t = np.arange(20.0)
+    om = WV.make_omega(t, np.array([0.1, 0.5, 0.50001, 2.0]))
+    assert np.array_equal(np.isnan(om), [False, False, True, True])
+    assert om[0] == 2 * np.pi * 0.1
+
+
+def test_standardize_semantics():
+    rng = np.random.default_rng(0)
+    y = 3 * rng.standard_normal(100) + 5
+    z, mu, sig = WV.standardize(y)
+    assert abs(z.mean()) < 1e-14 and abs(z.std() - 1) < 1e-14 and mu == np.mean(y) and sig == np.std(y)
+    with pytest.warns(UserWarning):
+        z, _, _ = WV.standardize(np.full(10, 2.0) + 1e-5 * rng.standard_normal(10))
+    assert np.all(np.abs(z - 2.0) < 1e-3)   # (nearly) constant series left unscaled
+
+
+def test_argument_errors_mirror_reference():
+    t, y = synth.uneven_ar1(50, 1)
+    with pytest.raises(AssertionError):
+        WV.kirchner_cuda(y, t, np.array([0.1]), np.array([1.0]), Neff_threshold=0)
+    with pytest.raises(AssertionError):
+        WV.kirchner_cuda(y, t, np.array([0.1]), np.array([1.0]), Neff_threshold=2.5)
+    with pytest.raises(ValueError):
+        WV.get_wwz_func(1, "Kirchner_numba")
+    with pytest.raises(ValueError):
+        WV.make_freq_vector(t, method="bogus")
+    assert WV.get_wwz_func(8, "Kirchner_cuda") is WV.kirchner_cuda
+
+
+def test_register_patches_the_reference_dispatch():
+    calls = []
+
+    def ref_get(nproc, method):
+        calls.append(method)
+        if method == "Kirchner_numba":
+            return "numba"
+        raise ValueError("Wrong specific method name for WWZ.")
+
+    fake = types.SimpleNamespace(get_wwz_func=ref_get, preprocess=lambda ys, ts, **k: ys,
+                                 make_omega=WV.make_omega, assertPositiveInt=WV.assertPositiveInt)
+    REG.register(fake)
+    assert fake.get_wwz_func(1, "Kirchner_numba") == "numba"
+    k = fake.get_wwz_func(1, "Kirchner_cuda")
+    assert callable(k) and k is fake.kirchner_cuda
+    with pytest.raises(ValueError):
+        fake.get_wwz_func(1, "nope")
+    REG.register(fake)                      # idempotent
+    assert fake.get_wwz_func(1, "Kirchner_numba") == "numba"
+    REG.unregister()
+    assert fake.get_wwz_func is ref_get
+
+
+def test_register_inside_live_reference_if_present():
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    import ref_shim
+    if not ref_shim.available():
+        pytest.skip("reference tree not mounted (expected on the GPU box)")
+    W = ref_shim.load()["wavelet"]
+    REG.register(W)
+    try:
+        assert W.get_wwz_func(1, "Kirchner_numba") is W.kirchner_numba
+        assert W.get_wwz_func(1, "Kirchner_cuda") is W.kirchner_cuda
+    finally:
+        REG.unregister()
+    assert not hasattr(W, "kirchner_cuda")
+
+
+def test_library_missing_fails_loudly(monkeypatch):
+    from pyleoclim_util_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libwwz_b200.so")
+    with pytest.raises(_lib.WwzB200Error):
+        _lib.lib()
+
+
+def test_no_gpu_means_error_not_fallback():
+    from conftest import has_cuda
+    if has_cuda():
+        pytest.skip("a CUDA device is present")
+    t, y = synth.uneven_ar1(50, 1)
+    from pyleoclim_util_b200 import _lib
+    with pytest.raises(_lib.WwzB200Error):
+        WV.wwz(y, t)

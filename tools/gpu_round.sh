@@ -1,0 +1,9 @@
+set -x
+python -m pytest tests -m gpu -x -q 2>&1 | tail -5
+python -c "import __graft_entry__ as g; g.smoke()"
+python bench.py --steps 20 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -3 gpurun_out/bench.err; cat gpurun_out/bench.json
+python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2>> gpurun_out/bench.err; cat gpurun_out/bench_ref.json
+python bench.py --steps 5 --warmup 3 > gpurun_out/plain.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 5 --warmup 3 > gpurun_out/ncu.log 2>&1
+tail -2 gpurun_out/ncu.log
+python tools/ncu_one.py > gpurun_out/plain2.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:wwz_cells -s 2 -c 2 -o gpurun_out/prof_cells -f python tools/ncu_one.py > gpurun_out/ncu2.log 2>&1
+tail -3 gpurun_out/ncu2.log
