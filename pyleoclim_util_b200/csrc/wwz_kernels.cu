@@ -600,42 +600,50 @@ cudaError_t launch_faithful(const double *d_ts, const double *d_ys, int64_t n, c
 // ------------------------------------------------------------------------------------------------
 // wwa2psd (utils/wavelet.py:1270-1278): same operation order as the reference expression
 //   power = wwa**2 * 0.5 * (max(ts)-min(ts))/size(ts) * Neffs ;  d = max(Neffs - thr, 0)
-//   psd = nansum(power*d, axis=0) / nansum(d, axis=0), rows added in order j = 0..nt-1.
+//   psd = nansum(power*d, axis=0) / nansum(d, axis=0).
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ double psd_column(const double *__restrict__ wwa, const double *__restrict__ neffs,
-                                             int64_t nt, int64_t row_stride, int64_t k, double tspan,
-                                             double n_d, double thr)
+// One CTA = 32 frequency columns x 32 row lanes: lane y of a column adds rows y, y+32, ... in order,
+// the 32 partial sums of a column are then added in lane order (fixed, deterministic association).
+__global__ void __launch_bounds__(1024)
+    psd_kernel(const double *__restrict__ wwa, const double *__restrict__ neffs, int64_t nt, int64_t nf,
+               int64_t row_stride, double tspan, const double *__restrict__ minmax, double n_d, double thr,
+               double *__restrict__ psd)
 {
-    double sp = 0.0, se = 0.0;
-    for (int64_t j = 0; j < nt; ++j) {
-        const double a = wwa[j * row_stride + k];
-        const double ne = neffs[j * row_stride + k];
-        const double power = a * a * 0.5 * tspan / n_d * ne;
-        double d = ne - thr;
-        if (d < 0.0) d = 0.0;
-        const double pd = power * d;
-        if (!isnan(pd)) sp += pd;
-        if (!isnan(d)) se += d;
-    }
-    return sp / se;
-}
-
-__global__ void psd_kernel(const double *__restrict__ wwa, const double *__restrict__ neffs, int64_t nt,
-                           int64_t nf, int64_t row_stride, double tspan, const double *__restrict__ minmax,
-                           double n_d, double thr, double *__restrict__ psd)
-{
-    const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (k >= nf) return;
+    __shared__ double s_sp[32][33], s_se[32][33];
+    const int64_t k = blockIdx.x * 32 + threadIdx.x;
     if (minmax) tspan = minmax[1] - minmax[0];
-    psd[k] = psd_column(wwa, neffs, nt, row_stride, k, tspan, n_d, thr);
+    double sp = 0.0, se = 0.0;
+    if (k < nf) {
+        for (int64_t j = threadIdx.y; j < nt; j += 32) {
+            const double a = wwa[j * row_stride + k];
+            const double ne = neffs[j * row_stride + k];
+            const double power = a * a * 0.5 * tspan / n_d * ne;
+            double d = ne - thr;
+            if (d < 0.0) d = 0.0;
+            const double pd = power * d;
+            if (!isnan(pd)) sp += pd;     // np.nansum skips NaN terms
+            if (!isnan(d)) se += d;
+        }
+    }
+    s_sp[threadIdx.y][threadIdx.x] = sp;
+    s_se[threadIdx.y][threadIdx.x] = se;
+    __syncthreads();
+    if (threadIdx.y == 0 && k < nf) {
+        double tp = 0.0, te = 0.0;
+        for (int y = 0; y < 32; ++y) {
+            tp += s_sp[y][threadIdx.x];
+            te += s_se[y][threadIdx.x];
+        }
+        psd[k] = tp / te;
+    }
 }
 
 cudaError_t launch_psd(const double *d_wwa, const double *d_neffs, int64_t nt, int64_t nf, int64_t row_stride,
                        double tspan, int64_t n, double neff_thr, double *d_psd, cudaStream_t st)
 {
     if (nf <= 0) return cudaSuccess;
-    psd_kernel<<<(unsigned)((nf + 63) / 64), 64, 0, st>>>(d_wwa, d_neffs, nt, nf, row_stride, tspan, nullptr,
-                                                          (double)n, neff_thr, d_psd);
+    psd_kernel<<<(unsigned)((nf + 31) / 32), dim3(32, 32), 0, st>>>(d_wwa, d_neffs, nt, nf, row_stride, tspan, nullptr,
+                                                                    (double)n, neff_thr, d_psd);
     bump_launch_counter();
     return cudaGetLastError();
 }
@@ -645,8 +653,8 @@ cudaError_t launch_psd_devspan(const double *d_wwa, const double *d_neffs, int64
                                double *d_psd, cudaStream_t st)
 {
     if (nf <= 0) return cudaSuccess;
-    psd_kernel<<<(unsigned)((nf + 63) / 64), 64, 0, st>>>(d_wwa, d_neffs, nt, nf, row_stride, 0.0, d_minmax,
-                                                          (double)n, neff_thr, d_psd);
+    psd_kernel<<<(unsigned)((nf + 31) / 32), dim3(32, 32), 0, st>>>(d_wwa, d_neffs, nt, nf, row_stride, 0.0,
+                                                                    d_minmax, (double)n, neff_thr, d_psd);
     bump_launch_counter();
     return cudaGetLastError();
 }
