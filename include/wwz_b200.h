@@ -130,6 +130,17 @@ int wwzb200_ar1_surrogates(const double *ts, int64_t nts, double tau_est, double
 int wwzb200_quantiles(const double *X, int64_t S, int64_t ncell, const double *probs, int64_t nq,
                       double *q);
 
+/* The whole AR(1)-surrogate significance test of a scalogram / PSD on the device
+ * (Scalogram.signif_test core/scalograms.py:515-522, PSD.signif_test core/psds.py:246-282):
+ * (5) S surrogates on the target's time axis -> z-score each (Series.wavelet / .spectral standardise
+ * by default, core/series.py:3559, utils/wavelet.py:976) -> (3) shared-axis transform -> per-cell
+ * quantiles.  Returns Neffs[nt,nf], q_wwa[nq,nt,nf] and, when q_psd != NULL, the quantiles of the
+ * surrogate spectra q_psd[nq,nf] (wwa2psd with psd_Neff_threshold).  Only these leave the device. */
+int wwzb200_ar1_signif(const double *ts, int64_t nts, double tau_est, double sigma, double mu, int64_t S,
+                       uint64_t seed, const double *taus, int64_t nt, const double *omegas, int64_t nf,
+                       double c, int64_t Neff_threshold, int64_t psd_Neff_threshold, uint32_t flags,
+                       const double *probs, int64_t nq, double *Neffs, double *q_wwa, double *q_psd);
+
 /* ---- device-pointer entry points (inputs/outputs resident in HBM; async on `stream`) ---- */
 int wwzb200_kirchner_dev(const double *d_ts, const double *d_pd_ys, int64_t nts, const double *d_taus,
                          int64_t nt, const double *d_omegas, int64_t nf, double c,

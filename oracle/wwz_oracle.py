@@ -302,3 +302,44 @@ def mquantiles(a, prob, axis=0, alphap=0.4, betap=0.4):
     gamma = (aleph - k).clip(0, 1)
     out = np.stack([(1.0 - g) * x[kk - 1] + g * x[kk] for kk, g in zip(k, gamma)], axis=0)
     return out
+
+
+# --------------------------------------------------------------------------- GPU surrogate stream
+def philox_normals(seed, series, n):
+    """The standard-normal draws the CUDA surrogate generator consumes for one series, restated in
+    NumPy: Philox4x32-10 (Salmon et al., SC'11; counter = (pair lo, pair hi, series lo, series hi),
+    key = (seed lo, seed hi)), two 53-bit uniforms per counter, Box-Muller.  Step i (1 <= i < n) of the
+    recurrence uses z0 of pair i//2 when i is even and z1 of pair i//2 when i is odd.
+    Returns z[n] with z[0] = 0 (unused), ready for ``ar1_model(..., z=z)``."""
+    M0, M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
+    W0, W1 = 0x9E3779B9, 0xBB67AE85
+    npair = n // 2 + 1
+    pair = np.arange(npair, dtype=np.uint64)
+    mask = np.uint64(0xFFFFFFFF)
+    c0 = pair & mask
+    c1 = pair >> np.uint64(32)
+    c2 = np.full(npair, series & 0xFFFFFFFF, dtype=np.uint64)
+    c3 = np.full(npair, (series >> 32) & 0xFFFFFFFF, dtype=np.uint64)
+    k0, k1 = seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF
+    for _ in range(10):
+        p0 = M0 * c0
+        p1 = M1 * c2
+        hi0, lo0 = p0 >> np.uint64(32), p0 & mask
+        hi1, lo1 = p1 >> np.uint64(32), p1 & mask
+        n0 = hi1 ^ c1 ^ np.uint64(k0)
+        n2 = hi0 ^ c3 ^ np.uint64(k1)
+        c0, c1, c2, c3 = n0, lo1, n2, lo0
+        k0 = (k0 + W0) & 0xFFFFFFFF
+        k1 = (k1 + W1) & 0xFFFFFFFF
+
+    def u01(a, b):
+        return ((a >> np.uint64(5)).astype(np.float64) * 67108864.0 + (b >> np.uint64(6)).astype(np.float64) + 0.5) \
+            / 9007199254740992.0
+
+    u1, u2 = u01(c0, c1), u01(c2, c3)
+    rad = np.sqrt(-2.0 * np.log(u1))
+    z0, z1 = rad * np.cos(2 * np.pi * u2), rad * np.sin(2 * np.pi * u2)
+    z = np.zeros(n)
+    i = np.arange(1, n)
+    z[1:] = np.where(i % 2 == 0, z0[i // 2], z1[i // 2])
+    return z

@@ -50,6 +50,8 @@ _SIGS = {
                                                _u32, _dp, _dp, _dp, _dp, _dp, _dp, _dp]),
     "wwzb200_ar1_surrogates": (ctypes.c_int, [_dp, _i64, _dbl, _dbl, _dbl, _i64, _u64, _dp]),
     "wwzb200_quantiles": (ctypes.c_int, [_dp, _i64, _i64, _dp, _i64, _dp]),
+    "wwzb200_ar1_signif": (ctypes.c_int, [_dp, _i64, _dbl, _dbl, _dbl, _i64, _u64, _dp, _i64, _dp, _i64, _dbl, _i64,
+                                          _i64, _u32, _dp, _i64, _dp, _dp, _dp]),
     "wwzb200_kirchner_dev": (ctypes.c_int, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _dbl, _i64, _i64, _u32,
                                             _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "wwzb200_wwa2psd_dev": (ctypes.c_int, [_vp, _vp, _i64, _i64, _dbl, _i64, _i64, _vp, _vp]),

@@ -1,0 +1,175 @@
+"""Batched entry points: AR(1) surrogates, shared-time-axis transforms, ragged ensembles, per-cell
+quantiles and the fused significance test.  Thin NumPy wrappers over the C ABI (include/wwz_b200.h);
+reference semantics are cited per function (paths relative to pyleoclim/).
+"""
+import collections
+
+import numpy as np
+
+from . import _lib
+from . import wavelet as _wv
+
+__all__ = ["tau_estimation", "ar1_surrogates", "ar1_sim", "wwz_shared_axis", "wwz_ragged", "quantiles",
+           "wwz_signif", "SharedAxisResults", "SignifResults"]
+
+SharedAxisResults = collections.namedtuple(
+    "SharedAxisResults", ["amplitude", "Neffs", "phase", "coeff", "psd", "freq", "time", "coi", "scale"])
+SignifResults = collections.namedtuple("SignifResults", ["qs", "amplitude_qs", "psd_qs", "Neffs", "freq", "time"])
+
+
+def tau_estimation(y, t):
+    """utils/tsmodel.py:243-275: persistence of an unevenly sampled AR(1) process (TAUEST),
+    a bounded scalar minimisation on the host (scipy, the same third-party call as the reference)."""
+    from scipy import optimize
+    y = np.asarray(y, dtype=float)
+    dt = np.diff(np.asarray(t, dtype=float))
+
+    def ar1_fun(a):
+        return np.sum((y[1:] - y[:-1] * a ** dt) ** 2)
+
+    a_est = optimize.minimize_scalar(ar1_fun, bounds=[0, 1], method="bounded").x
+    return -1 / np.log(a_est)
+
+
+def ar1_surrogates(t, tau_est, sigma=1.0, mu=0.0, number=1, seed=0):
+    """S realisations of ``ar1_model`` (utils/tsmodel.py:59-69) on the time axis ``t``, generated on
+    the device (Philox4x32-10 + Box-Muller).  Returns ``Y[number, n]``; ``mu`` is added like
+    ``SurrogateSeries.from_series`` does (core/surrogateseries.py:139)."""
+    t = _lib.f64(t)
+    Y = np.empty((int(number), t.size))
+    _lib.check(_lib.lib().wwzb200_ar1_surrogates(_lib.ptr(t), t.size, float(tau_est), float(sigma), float(mu),
+                                                 int(number), int(seed) & 0xFFFFFFFFFFFFFFFF, _lib.ptr(Y)))
+    return Y
+
+
+def ar1_sim(y, p, t=None, seed=0):
+    """utils/tsmodel.py:110-170, uneven-axis branch: ``ysim[n, p]`` (``[n]`` when p == 1).
+    The evenly spaced branch of the reference is a statsmodels ARIMA fit and is not on this path."""
+    y = np.asarray(y, dtype=float)
+    if t is None:
+        raise ValueError("the CUDA surrogate generator needs the (uneven) time axis t")
+    sig = np.std(y)
+    tau_est = tau_estimation(y, t)
+    ysim = ar1_surrogates(t, tau_est, sigma=sig, number=p, seed=seed).T
+    return ysim[:, 0] if p == 1 else np.ascontiguousarray(ysim)
+
+
+def wwz_shared_axis(Y, ts, tau, freq, c=1 / (8 * np.pi ** 2), Neff_threshold=3, standardize=True,
+                    outputs=("amplitude",), psd_Neff_threshold=None, flags=0):
+    """Transform ``S`` series that share the time axis ``ts`` in one batched launch
+    (what ``MultipleSeries.wavelet`` does member by member through a process pool,
+    core/multipleseries.py:1520-1532, for the surrogates of core/scalograms.py:515-517).
+
+    Y : [S, n].  ``outputs`` selects among 'amplitude', 'phase', 'coeff'; ``psd_Neff_threshold`` adds
+    the per-series ``wwa2psd`` (psd [S, nf]).  ts must already be clean (sorted, no NaN) and the grid
+    final: call ``prepare_wwz`` first, as ``wwz`` does."""
+    _wv.assertPositiveInt(Neff_threshold)
+    ts, tau, freq = _lib.f64(ts), _lib.f64(tau), _lib.f64(freq)
+    Y = _lib.f64(Y)
+    if Y.ndim != 2 or Y.shape[1] != ts.size:
+        raise ValueError("Y must be [S, len(ts)]")
+    S, nt, nf = Y.shape[0], tau.size, freq.size
+    omega = _wv.make_omega(ts, freq)
+    Neffs = np.empty((nt, nf))
+    want = set(outputs)
+    amp = np.empty((S, nt, nf)) if "amplitude" in want else None
+    phase = np.empty((S, nt, nf)) if "phase" in want else None
+    a0 = a1 = a2 = None
+    if "coeff" in want:
+        a0, a1, a2 = (np.empty((S, nt, nf)) for _ in range(3))
+    psd = np.empty((S, nf)) if psd_Neff_threshold is not None else None
+    fl = int(flags) | (_lib.STANDARDIZE if standardize else 0)
+    _lib.check(_lib.lib().wwzb200_kirchner_shared_axis(
+        _lib.ptr(ts), _lib.ptr(Y), ts.size, S, _lib.ptr(tau), nt, _lib.ptr(omega), nf, float(c),
+        int(Neff_threshold), int(psd_Neff_threshold or 0), fl, _lib.ptr(Neffs), _lib.ptr(amp), _lib.ptr(phase),
+        _lib.ptr(a0), _lib.ptr(a1), _lib.ptr(a2), _lib.ptr(psd)))
+    coi = _wv.make_coi(tau) if nt > 1 else None
+    return SharedAxisResults(amplitude=amp, Neffs=Neffs, phase=phase, coeff=(a0, a1, a2) if a0 is not None else None,
+                             psd=psd, freq=freq, time=tau, coi=coi, scale=1 / freq)
+
+
+def wwz_ragged(members, c=1 / (8 * np.pi ** 2), Neff_threshold=3, standardize=True, psd_Neff_threshold=None,
+               flags=0):
+    """Transform M series with their own time axes and grids (age ensembles:
+    core/ensembleseries.py:169-173 -> core/multipleseries.py:1520-1532) in one call.
+
+    members : iterable of ``(ys, ts, tau, freq)`` (already prepared with ``prepare_wwz``).
+    Returns a list of ``wavelet.wwz``-style Results (plus ``.psd`` lists when requested)."""
+    _wv.assertPositiveInt(Neff_threshold)
+    ys_l, ts_l, tau_l, om_l, fr_l = [], [], [], [], []
+    for ys, ts, tau, freq in members:
+        ts = _lib.f64(ts)
+        ys = _wv.preprocess(_lib.f64(ys), ts, standardize=standardize)
+        ys_l.append(_lib.f64(ys))
+        ts_l.append(ts)
+        tau_l.append(_lib.f64(tau))
+        fr_l.append(_lib.f64(freq))
+        om_l.append(_wv.make_omega(ts, fr_l[-1]))
+    M = len(ts_l)
+    off = lambda xs: np.concatenate([[0], np.cumsum([x.size for x in xs])]).astype(np.int64)
+    ts_off, tau_off, om_off = off(ts_l), off(tau_l), off(om_l)
+    out_off = np.concatenate([[0], np.cumsum([a.size * b.size for a, b in zip(tau_l, om_l)])]).astype(np.int64)
+    cat = lambda xs: np.concatenate(xs) if xs else np.empty(0)
+    ts_p, ys_p, tau_p, om_p = cat(ts_l), cat(ys_l), cat(tau_l), cat(om_l)
+    outs = [np.empty(int(out_off[-1])) for _ in range(6)]
+    psd = np.empty(int(om_off[-1])) if psd_Neff_threshold is not None else None
+    _lib.check(_lib.lib().wwzb200_kirchner_ragged(
+        _lib.ptr(ts_p), _lib.ptr(ys_p), _lib.iptr(ts_off), _lib.ptr(tau_p), _lib.iptr(tau_off), _lib.ptr(om_p),
+        _lib.iptr(om_off), _lib.iptr(out_off), M, float(c), int(Neff_threshold), int(psd_Neff_threshold or 0),
+        int(flags), *[_lib.ptr(o) for o in outs], _lib.ptr(psd)))
+    res = []
+    for m in range(M):
+        nt, nf = tau_l[m].size, om_l[m].size
+        sl = slice(int(out_off[m]), int(out_off[m + 1]))
+        Neffs, a0, a1, a2, wwa, phase = (o[sl].reshape(nt, nf) for o in outs)
+        r = _wv.WwzResults(amplitude=wwa, phase=phase, coi=_wv.make_coi(tau_l[m]) if nt > 1 else None, freq=fr_l[m],
+                           time=tau_l[m], Neffs=Neffs, coeff=(a0, a1, a2), scale=1 / fr_l[m])
+        res.append(r)
+    if psd is not None:
+        return res, [psd[int(om_off[m]):int(om_off[m + 1])] for m in range(M)]
+    return res
+
+
+def quantiles(X, qs):
+    """Per-cell quantiles over a batch with ``scipy.stats.mstats.mquantiles(alphap=betap=0.4)``
+    semantics (MultipleScalogram.quantiles core/scalograms.py:635-641, MultiplePSD.quantiles
+    core/psds.py:913).  X : [S, ...]; returns [len(qs), ...]."""
+    X = _lib.f64(X)
+    S = X.shape[0]
+    cell_shape = X.shape[1:]
+    ncell = int(np.prod(cell_shape, dtype=np.int64))
+    probs = _lib.f64(np.atleast_1d(qs))
+    q = np.empty((probs.size, ncell))
+    _lib.check(_lib.lib().wwzb200_quantiles(_lib.ptr(X.reshape(S, ncell)), S, ncell, _lib.ptr(probs), probs.size,
+                                            _lib.ptr(q)))
+    return q.reshape((probs.size,) + cell_shape)
+
+
+def wwz_signif(ys, ts, tau=None, freq=None, number=200, qs=(0.95,), seed=0, c=1 / (8 * np.pi ** 2),
+               Neff_threshold=3, psd=False, psd_c=None, psd_Neff_threshold=3, freq_method="log", freq_kwargs=None,
+               flags=0):
+    """AR(1)-surrogate significance levels of a WWZ scalogram (and optionally of the WWZ spectrum) with
+    everything between the time axis and the quantiles on the device (C-ABI ``wwzb200_ar1_signif``).
+
+    Follows Scalogram.signif_test (core/scalograms.py:515-522): surrogates of the target from
+    ``ar1_sim`` (+ target mean, core/surrogateseries.py:137-139), each transformed like the target
+    (standardised, same tau/freq), per-cell ``mquantiles`` over the surrogates.  ``number`` surrogates,
+    probabilities ``qs``.  With ``psd=True`` the quantiles of the surrogate spectra are returned too
+    (PSD.signif_test core/psds.py:246-282), computed with decay constant ``psd_c`` (default ``c``)."""
+    ys_cut, ts_cut, freq, tau = _wv.prepare_wwz(ys, ts, freq=freq, freq_method=freq_method, freq_kwargs=freq_kwargs,
+                                                tau=tau)
+    sig = float(np.std(ys_cut))
+    mu = float(np.mean(ys_cut))
+    tau_est = float(tau_estimation(ys_cut, ts_cut))
+    omega = _wv.make_omega(ts_cut, freq)
+    probs = _lib.f64(np.atleast_1d(qs))
+    nt, nf = tau.size, freq.size
+    Neffs = np.empty((nt, nf))
+    q_wwa = np.empty((probs.size, nt, nf))
+    q_psd = np.empty((probs.size, nf)) if psd else None
+    cc = float(c if not psd or psd_c is None else psd_c)
+    _lib.check(_lib.lib().wwzb200_ar1_signif(
+        _lib.ptr(_lib.f64(ts_cut)), ts_cut.size, tau_est, sig, mu, int(number), int(seed) & 0xFFFFFFFFFFFFFFFF,
+        _lib.ptr(_lib.f64(tau)), nt, _lib.ptr(omega), nf, cc, int(Neff_threshold), int(psd_Neff_threshold), int(flags),
+        _lib.ptr(probs), probs.size, _lib.ptr(Neffs), _lib.ptr(q_wwa), _lib.ptr(q_psd)))
+    return SignifResults(qs=probs, amplitude_qs=q_wwa, psd_qs=q_psd, Neffs=Neffs, freq=freq, time=tau)

@@ -259,6 +259,96 @@ int host_transform(const double *ts, const double *ys, int64_t n, const double *
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Shared-time-axis batch on device-resident inputs.  d_Y is [S][n] row-major.
+// Outputs: d_neffs [nt*nf]; d_wwa and the optional d_phase/d_a0/d_a1/d_a2 are [S][nt*nf];
+// d_psd [S][nf].  amp_cells_out / S_pad_out (optional) receive the cell-major amplitudes
+// [ncell][S_pad] left in the workspace (the layout the quantile kernel consumes).
+// ---------------------------------------------------------------------------------------------
+int shared_axis_device(Workspace *w, const double *d_ts, const double *d_Y, int64_t n, int64_t S, const double *d_tau,
+                       int64_t nt, const double *d_omega, int64_t nf, double c, int64_t thr, int64_t psd_thr,
+                       uint32_t flags, double *d_neffs, double *d_wwa, double *d_phase, double *d_a0, double *d_a1,
+                       double *d_a2, double *d_psd, double tspan, double **amp_cells_out, int64_t *S_pad_out,
+                       cudaStream_t st)
+{
+    using namespace wwz;
+    const int64_t ncell = nt * nf;
+    if (ncell == 0 || S == 0) return 0;
+    if (ncell >= ((int64_t)1 << 32)) return fail(WWZB200_ERR_ARG, "nt*nf exceeds 2^32 cells");
+    const SharedPlan plan = plan_shared(n, nt, nf);
+    const int64_t S_pad = ((S + kSurrBlock - 1) / kSurrBlock) * kSurrBlock;
+    if (S_pad / kSurrBlock > 65535) return fail(WWZB200_ERR_ARG, "more than 65535*16 series in one batch");
+    if ((size_t)nf * (size_t)plan.n_pad * 16 > ((size_t)16 << 30))
+        return fail(WWZB200_ERR_NOMEM, "basis rows of the shared-axis batch exceed 16 GiB");
+    int rc;
+    double *d_kappa, *d_dcut, *d_mu, *d_sig, *d_Yt, *d_wq, *d_amp_t, *d_ph_t = nullptr, *d_a0_t = nullptr,
+           *d_a1_t = nullptr, *d_a2_t = nullptr, *d_ne;
+    double2 *d_ty, *d_basis, *d_rot;
+    unsigned int *d_fix;
+    if ((rc = wsbuf(w, "kappa", (size_t)nf, &d_kappa))) return rc;
+    if ((rc = wsbuf(w, "dcut", (size_t)nf, &d_dcut))) return rc;
+    if ((rc = wsbuf(w, "ty", (size_t)plan.n_pad, &d_ty))) return rc;
+    if ((rc = wsbuf(w, "basis", (size_t)nf * (size_t)plan.n_pad, &d_basis))) return rc;
+    if ((rc = wsbuf(w, "rot", (size_t)ncell, &d_rot))) return rc;
+    if ((rc = wsbuf(w, "mu", (size_t)S_pad, &d_mu))) return rc;
+    if ((rc = wsbuf(w, "sig", (size_t)S_pad, &d_sig))) return rc;
+    if ((rc = wsbuf(w, "Yt", (size_t)S_pad * (size_t)plan.n_pad, &d_Yt))) return rc;
+    if ((rc = wsbuf(w, "wq", (size_t)2 * ncell, &d_wq))) return rc;
+    if ((rc = wsbuf(w, "amp_t", (size_t)ncell * (size_t)S_pad, &d_amp_t))) return rc;
+    if (d_phase && (rc = wsbuf(w, "ph_t", (size_t)ncell * (size_t)S_pad, &d_ph_t))) return rc;
+    if (d_a0 && (rc = wsbuf(w, "a0_t", (size_t)ncell * (size_t)S_pad, &d_a0_t))) return rc;
+    if (d_a1 && (rc = wsbuf(w, "a1_t", (size_t)ncell * (size_t)S_pad, &d_a1_t))) return rc;
+    if (d_a2 && (rc = wsbuf(w, "a2_t", (size_t)ncell * (size_t)S_pad, &d_a2_t))) return rc;
+    if ((rc = wsbuf(w, "fix_list", (size_t)ncell + 1, &d_fix))) return rc;
+    d_ne = d_neffs;
+    if (!d_ne && (rc = wsbuf(w, "ne_t", (size_t)ncell, &d_ne))) return rc;
+
+    CU(launch_freq_setup(d_omega, nf, c, d_kappa, d_dcut, st));
+    CU(launch_basis_sc(d_ts, n, plan.n_pad, d_omega, nf, d_ty, d_basis, st));
+    CU(launch_rotation(d_tau, d_omega, nt, nf, d_rot, st));
+    CU(launch_standardize_retile(d_Y, n, plan.n_pad, S, (flags & WWZB200_STANDARDIZE) != 0, d_mu, d_sig, d_Yt, st));
+    EventPair ev{nullptr, nullptr, (double)n * (double)ncell * (double)S};
+    if (g_profile) {
+        CU(cudaEventCreate(&ev.a));
+        CU(cudaEventCreate(&ev.b));
+        CU(cudaEventRecord(ev.a, st));
+    }
+    CU(launch_shared(plan, d_ty, d_basis, d_Yt, n, S_pad, d_tau, nt, d_kappa, nf, d_rot, (double)thr, d_ne, d_wq,
+                     d_amp_t, d_ph_t, d_a0_t, d_a1_t, d_a2_t, st));
+    if (g_profile) {
+        CU(cudaEventRecord(ev.b, st));
+        g_events.push_back(ev);
+    }
+    CU(launch_shared_fixup(d_ts, d_Yt, n, plan.n_pad, S, S_pad, d_tau, d_omega, nt, nf, c, (double)thr, d_wq, d_fix,
+                           d_fix + 1, d_ne, d_amp_t, d_ph_t, d_a0_t, d_a1_t, d_a2_t, w->sms, st));
+    // cell-major [ncell][S_pad] -> series-major [S][ncell]
+    if (d_wwa) CU(launch_transpose(d_amp_t, ncell, S, S_pad, d_wwa, ncell, st));
+    if (d_phase) CU(launch_transpose(d_ph_t, ncell, S, S_pad, d_phase, ncell, st));
+    if (d_a0) CU(launch_transpose(d_a0_t, ncell, S, S_pad, d_a0, ncell, st));
+    if (d_a1) CU(launch_transpose(d_a1_t, ncell, S, S_pad, d_a1, ncell, st));
+    if (d_a2) CU(launch_transpose(d_a2_t, ncell, S, S_pad, d_a2, ncell, st));
+    if (d_psd) CU(launch_psd_batch(d_amp_t, d_ne, nt, nf, S, S_pad, tspan, n, (double)psd_thr, d_psd, st));
+    if (amp_cells_out) *amp_cells_out = d_amp_t;
+    if (S_pad_out) *S_pad_out = S_pad;
+    return 0;
+}
+
+int quantiles_device(Workspace *w, const double *d_Xcells, int64_t S, int64_t stride, int64_t ncell,
+                     const double *d_probs, int64_t nq, double *d_q, cudaStream_t st)
+{
+    int npow2 = 2;
+    while (npow2 < S) npow2 <<= 1;
+    unsigned long long *d_scr = nullptr;
+    int64_t ctas = 0;
+    if ((size_t)npow2 * 8 > 200 * 1024) {
+        ctas = (int64_t)w->sms * 2;
+        int rc = wsbuf(w, "qscratch", (size_t)ctas * (size_t)npow2, &d_scr);
+        if (rc) return rc;
+    }
+    CU(wwz::launch_quantiles(d_Xcells, S, stride, ncell, d_probs, nq, d_q, d_scr, ctas, w->sms, st));
+    return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -391,6 +481,287 @@ int wwzb200_wwa2psd_dev(const double *d_wwa, const double *d_Neffs, int64_t nt, 
     if (!d_wwa || !d_Neffs || !d_psd) return fail(WWZB200_ERR_ARG, "null pointer");
     CU(wwz::launch_psd(d_wwa, d_Neffs, nt, nf, nf, tspan, nts, (double)Neff_threshold, d_psd,
                        static_cast<cudaStream_t>(stream)));
+    return 0;
+}
+
+int wwzb200_kirchner_shared_axis_dev(const double *d_ts, const double *d_Y, int64_t nts, int64_t S,
+                                     const double *d_taus, int64_t nt, const double *d_omegas, int64_t nf, double c,
+                                     int64_t Neff_threshold, int64_t psd_Neff_threshold, uint32_t flags,
+                                     double *d_Neffs, double *d_wwa, double *d_phase, double *d_a0, double *d_a1,
+                                     double *d_a2, double *d_psd, void *stream)
+{
+    int rc = check_grid_args(d_ts, d_Y, nts, d_taus, nt, d_omegas, nf, c, Neff_threshold);
+    if (rc) return rc;
+    if (S < 0) return fail(WWZB200_ERR_ARG, "S must be >= 0");
+    std::lock_guard<std::mutex> lock(g_mu);
+    Workspace *w;
+    if ((rc = workspace(&w))) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    double tspan = 0;
+    if (d_psd) {   // span of the (device) time axis, needed by wwa2psd
+        double *d_mm, mm[2];
+        if ((rc = wsbuf(w, "minmax", 2, &d_mm))) return rc;
+        CU(wwz::launch_minmax(d_ts, nts, d_mm, st));
+        CU(cudaMemcpyAsync(mm, d_mm, sizeof mm, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        tspan = mm[1] - mm[0];
+    }
+    return shared_axis_device(w, d_ts, d_Y, nts, S, d_taus, nt, d_omegas, nf, c, Neff_threshold, psd_Neff_threshold,
+                              flags, d_Neffs, d_wwa, d_phase, d_a0, d_a1, d_a2, d_psd, tspan, nullptr, nullptr, st);
+}
+
+int wwzb200_kirchner_shared_axis(const double *ts, const double *Y, int64_t nts, int64_t S, const double *taus,
+                                 int64_t nt, const double *omegas, int64_t nf, double c, int64_t Neff_threshold,
+                                 int64_t psd_Neff_threshold, uint32_t flags, double *Neffs, double *wwa,
+                                 double *phase, double *a0, double *a1, double *a2, double *psd)
+{
+    int rc = check_grid_args(ts, Y, nts, taus, nt, omegas, nf, c, Neff_threshold);
+    if (rc) return rc;
+    if (S < 0) return fail(WWZB200_ERR_ARG, "S must be >= 0");
+    std::lock_guard<std::mutex> lock(g_mu);
+    Workspace *w;
+    if ((rc = workspace(&w))) return rc;
+    cudaStream_t st = w->stream;
+    const int64_t ncell = nt * nf;
+    double *d_in, *d_Y, *d_ne, *d_psd = nullptr;
+    if ((rc = wsbuf(w, "in", (size_t)(2 * nts + nt + nf), &d_in))) return rc;
+    if ((rc = wsbuf(w, "Y", (size_t)S * (size_t)nts, &d_Y))) return rc;
+    if ((rc = wsbuf(w, "ne_out", (size_t)ncell, &d_ne))) return rc;
+    if (psd && (rc = wsbuf(w, "psd_out", (size_t)S * (size_t)nf, &d_psd))) return rc;
+    double *d_ts = d_in, *d_tau = d_in + 2 * nts, *d_om = d_tau + nt;
+    CU(cudaMemcpyAsync(d_ts, ts, sizeof(double) * nts, cudaMemcpyHostToDevice, st));
+    if (nt) CU(cudaMemcpyAsync(d_tau, taus, sizeof(double) * nt, cudaMemcpyHostToDevice, st));
+    if (nf) CU(cudaMemcpyAsync(d_om, omegas, sizeof(double) * nf, cudaMemcpyHostToDevice, st));
+    if (S) CU(cudaMemcpyAsync(d_Y, Y, sizeof(double) * (size_t)S * (size_t)nts, cudaMemcpyHostToDevice, st));
+    const auto mm = std::minmax_element(ts, ts + nts);
+    const size_t ob = (size_t)S * (size_t)ncell;
+    double *d_o[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    double *h_o[5] = {wwa, phase, a0, a1, a2};
+    const char *names[5] = {"o_wwa", "o_ph", "o_a0", "o_a1", "o_a2"};
+    for (int i = 0; i < 5; ++i)
+        if (h_o[i] && (rc = wsbuf(w, names[i], ob, &d_o[i]))) return rc;
+    rc = shared_axis_device(w, d_ts, d_Y, nts, S, d_tau, nt, d_om, nf, c, Neff_threshold, psd_Neff_threshold, flags,
+                            d_ne, d_o[0], d_o[1], d_o[2], d_o[3], d_o[4], d_psd, *mm.second - *mm.first, nullptr,
+                            nullptr, st);
+    if (rc) return rc;
+    if (Neffs && ncell) CU(cudaMemcpyAsync(Neffs, d_ne, sizeof(double) * ncell, cudaMemcpyDeviceToHost, st));
+    for (int i = 0; i < 5; ++i)
+        if (h_o[i] && ob) CU(cudaMemcpyAsync(h_o[i], d_o[i], sizeof(double) * ob, cudaMemcpyDeviceToHost, st));
+    if (psd && S * nf) CU(cudaMemcpyAsync(psd, d_psd, sizeof(double) * (size_t)S * nf, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int wwzb200_ar1_surrogates_dev(const double *d_ts, int64_t nts, double tau_est, double sigma, double mu, int64_t S,
+                               uint64_t seed, double *d_Y, void *stream)
+{
+    if (nts < 1 || S < 0) return fail(WWZB200_ERR_ARG, "bad sizes");
+    if (!d_ts || (S && !d_Y)) return fail(WWZB200_ERR_ARG, "null pointer");
+    if (!(tau_est > 0)) return fail(WWZB200_ERR_ARG, "tau_est must be positive");
+    std::lock_guard<std::mutex> lock(g_mu);
+    Workspace *w;
+    int rc;
+    if ((rc = workspace(&w))) return rc;
+    double *d_rq;
+    if ((rc = wsbuf(w, "ar1_rq", (size_t)2 * nts, &d_rq))) return rc;
+    CU(wwz::launch_ar1(d_ts, nts, tau_est, sigma, mu, S, seed, d_rq, d_rq + nts, d_Y, static_cast<cudaStream_t>(stream)));
+    return 0;
+}
+
+int wwzb200_ar1_surrogates(const double *ts, int64_t nts, double tau_est, double sigma, double mu, int64_t S,
+                           uint64_t seed, double *Y)
+{
+    if (nts < 1 || S < 0) return fail(WWZB200_ERR_ARG, "bad sizes");
+    if (!ts || (S && !Y)) return fail(WWZB200_ERR_ARG, "null pointer");
+    if (!(tau_est > 0)) return fail(WWZB200_ERR_ARG, "tau_est must be positive");
+    Workspace *w;
+    int rc;
+    double *d_ts, *d_Y;
+    {
+        std::lock_guard<std::mutex> lock(g_mu);
+        if ((rc = workspace(&w))) return rc;
+        if ((rc = wsbuf(w, "in", (size_t)nts, &d_ts))) return rc;
+        if ((rc = wsbuf(w, "Y", (size_t)S * (size_t)nts, &d_Y))) return rc;
+        CU(cudaMemcpyAsync(d_ts, ts, sizeof(double) * nts, cudaMemcpyHostToDevice, w->stream));
+    }
+    if ((rc = wwzb200_ar1_surrogates_dev(d_ts, nts, tau_est, sigma, mu, S, seed, d_Y, w->stream))) return rc;
+    if (S) CU(cudaMemcpyAsync(Y, d_Y, sizeof(double) * (size_t)S * (size_t)nts, cudaMemcpyDeviceToHost, w->stream));
+    CU(cudaStreamSynchronize(w->stream));
+    return 0;
+}
+
+int wwzb200_quantiles_dev(const double *d_X, int64_t S, int64_t ncell, const double *d_probs, int64_t nq, double *d_q,
+                          void *stream)
+{
+    if (S < 1 || ncell < 0 || nq < 0) return fail(WWZB200_ERR_ARG, "bad sizes");
+    if (ncell == 0 || nq == 0) return 0;
+    if (!d_X || !d_probs || !d_q) return fail(WWZB200_ERR_ARG, "null pointer");
+    if (S > ((int64_t)1 << 24)) return fail(WWZB200_ERR_ARG, "S too large for the quantile kernel");
+    std::lock_guard<std::mutex> lock(g_mu);
+    Workspace *w;
+    int rc;
+    if ((rc = workspace(&w))) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    double *d_Xc;
+    if ((rc = wsbuf(w, "q_cells", (size_t)S * (size_t)ncell, &d_Xc))) return rc;
+    CU(wwz::launch_transpose(d_X, S, ncell, ncell, d_Xc, S, st));   // [S][ncell] -> [ncell][S]
+    return quantiles_device(w, d_Xc, S, S, ncell, d_probs, nq, d_q, st);
+}
+
+int wwzb200_quantiles(const double *X, int64_t S, int64_t ncell, const double *probs, int64_t nq, double *q)
+{
+    if (S < 1 || ncell < 0 || nq < 0) return fail(WWZB200_ERR_ARG, "bad sizes");
+    if (ncell == 0 || nq == 0) return 0;
+    if (!X || !probs || !q) return fail(WWZB200_ERR_ARG, "null pointer");
+    Workspace *w;
+    int rc;
+    double *d_X, *d_p, *d_q;
+    {
+        std::lock_guard<std::mutex> lock(g_mu);
+        if ((rc = workspace(&w))) return rc;
+        if ((rc = wsbuf(w, "q_in", (size_t)S * (size_t)ncell, &d_X))) return rc;
+        if ((rc = wsbuf(w, "q_out", (size_t)nq * (size_t)ncell + (size_t)nq, &d_q))) return rc;
+        d_p = d_q + (size_t)nq * (size_t)ncell;
+        CU(cudaMemcpyAsync(d_X, X, sizeof(double) * (size_t)S * (size_t)ncell, cudaMemcpyHostToDevice, w->stream));
+        CU(cudaMemcpyAsync(d_p, probs, sizeof(double) * nq, cudaMemcpyHostToDevice, w->stream));
+    }
+    if ((rc = wwzb200_quantiles_dev(d_X, S, ncell, d_p, nq, d_q, w->stream))) return rc;
+    CU(cudaMemcpyAsync(q, d_q, sizeof(double) * (size_t)nq * (size_t)ncell, cudaMemcpyDeviceToHost, w->stream));
+    CU(cudaStreamSynchronize(w->stream));
+    return 0;
+}
+
+// Ragged batch: members are independent transforms on their own axes and grids.  The packed inputs
+// go to the device once, every member is transformed in stream order with the workspace pre-sized
+// for the largest member, the packed outputs come back once.
+int wwzb200_kirchner_ragged(const double *ts, const double *pd_ys, const int64_t *ts_off, const double *taus,
+                            const int64_t *tau_off, const double *omegas, const int64_t *om_off,
+                            const int64_t *out_off, int64_t M, double c, int64_t Neff_threshold,
+                            int64_t psd_Neff_threshold, uint32_t flags, double *Neffs, double *a0, double *a1,
+                            double *a2, double *wwa, double *phase, double *psd)
+{
+    if (M < 0) return fail(WWZB200_ERR_ARG, "M must be >= 0");
+    if (M == 0) return 0;
+    if (!ts || !pd_ys || !ts_off || !taus || !tau_off || !omegas || !om_off || !out_off)
+        return fail(WWZB200_ERR_ARG, "null pointer");
+    if (Neff_threshold < 1) return fail(WWZB200_ERR_ARG, "Neff_threshold must be a positive integer");
+    if (!(c > 0) || !std::isfinite(c)) return fail(WWZB200_ERR_ARG, "decay constant c must be positive and finite");
+    int64_t max_cells = 0, max_n = 0, max_nf = 0, max_basis = 0;
+    for (int64_t m = 0; m < M; ++m) {
+        const int64_t n = ts_off[m + 1] - ts_off[m], nt = tau_off[m + 1] - tau_off[m], nf = om_off[m + 1] - om_off[m];
+        if (n < 1 || nt < 0 || nf < 0 || out_off[m + 1] - out_off[m] != nt * nf)
+            return fail(WWZB200_ERR_ARG, "member %lld: inconsistent offsets", (long long)m);
+        max_cells = std::max(max_cells, nt * nf);
+        max_n = std::max(max_n, n);
+        max_nf = std::max(max_nf, nf);
+        max_basis = std::max(max_basis, nf * (n + wwz::kMaxPointsPerStage));
+    }
+    std::lock_guard<std::mutex> lock(g_mu);
+    Workspace *w;
+    int rc;
+    if ((rc = workspace(&w))) return rc;
+    cudaStream_t st = w->stream;
+    const int64_t NT = ts_off[M] - ts_off[0], NTAU = tau_off[M] - tau_off[0], NOM = om_off[M] - om_off[0];
+    const int64_t NOUT = out_off[M] - out_off[0];
+    double *d_in, *d_out;
+    if ((rc = wsbuf(w, "rag_in", (size_t)(2 * NT + NTAU + NOM), &d_in))) return rc;
+    if ((rc = wsbuf(w, "rag_out", (size_t)(6 * NOUT + NOM), &d_out))) return rc;
+    double *d_ts = d_in, *d_ys = d_in + NT, *d_tau = d_ys + NT, *d_om = d_tau + NTAU;
+    CU(cudaMemcpyAsync(d_ts, ts + ts_off[0], sizeof(double) * NT, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_ys, pd_ys + ts_off[0], sizeof(double) * NT, cudaMemcpyHostToDevice, st));
+    if (NTAU) CU(cudaMemcpyAsync(d_tau, taus + tau_off[0], sizeof(double) * NTAU, cudaMemcpyHostToDevice, st));
+    if (NOM) CU(cudaMemcpyAsync(d_om, omegas + om_off[0], sizeof(double) * NOM, cudaMemcpyHostToDevice, st));
+    double *o[6];
+    for (int i = 0; i < 6; ++i) o[i] = d_out + (size_t)i * NOUT;
+    double *o_psd = d_out + (size_t)6 * NOUT;
+    {   // pre-size the per-transform scratch for the largest member: no re-allocation mid-stream
+        double *dd;
+        double2 *d2;
+        unsigned int *du;
+        if ((rc = wsbuf(w, "kappa", (size_t)max_nf, &dd))) return rc;
+        if ((rc = wsbuf(w, "dcut", (size_t)max_nf, &dd))) return rc;
+        if ((rc = wsbuf(w, "ty", (size_t)(max_n + wwz::kMaxPointsPerStage), &d2))) return rc;
+        if ((rc = wsbuf(w, "basis", (size_t)std::min<int64_t>(max_basis, (int64_t)(basis_budget_bytes() / 16)) * 2, &d2)))
+            return rc;
+        if ((rc = wsbuf(w, "sums", (size_t)wwz::kNumSums * (size_t)max_cells, &dd))) return rc;
+        if ((rc = wsbuf(w, "fix_list", (size_t)max_cells + 1, &du))) return rc;
+        if (psd && (rc = wsbuf(w, "psd_wwa", (size_t)max_cells, &dd))) return rc;
+    }
+    for (int64_t m = 0; m < M; ++m) {
+        const int64_t n = ts_off[m + 1] - ts_off[m], nt = tau_off[m + 1] - tau_off[m], nf = om_off[m + 1] - om_off[m];
+        const int64_t t0 = ts_off[m] - ts_off[0], u0 = tau_off[m] - tau_off[0], f0 = om_off[m] - om_off[0];
+        const int64_t c0 = out_off[m] - out_off[0];
+        double tspan = 0;
+        if (psd) {
+            const auto mm = std::minmax_element(ts + ts_off[m], ts + ts_off[m + 1]);
+            tspan = *mm.second - *mm.first;
+        }
+        rc = transform_device(w, d_ts + t0, d_ys + t0, n, d_tau + u0, nt, d_om + f0, nf, c, Neff_threshold,
+                              psd_Neff_threshold, flags, o[0] + c0, o[1] + c0, o[2] + c0, o[3] + c0, o[4] + c0,
+                              o[5] + c0, psd ? o_psd + f0 : nullptr, nf, tspan, st);
+        if (rc) return rc;
+    }
+    double *h[6] = {Neffs, a0, a1, a2, wwa, phase};
+    for (int i = 0; i < 6; ++i)
+        if (h[i] && NOUT) CU(cudaMemcpyAsync(h[i] + out_off[0], o[i], sizeof(double) * NOUT, cudaMemcpyDeviceToHost, st));
+    if (psd && NOM) CU(cudaMemcpyAsync(psd + om_off[0], o_psd, sizeof(double) * NOM, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return 0;
+}
+
+// AR(1)-surrogate significance test, everything on the device: generate S surrogates on the target's
+// time axis, z-score each (Series.wavelet standardises by default), transform them as one
+// shared-axis batch, reduce to per-cell quantiles.  Only Neffs, the [nq, nt, nf] quantiles and the
+// optional [nq, nf] PSD quantiles return to the host.
+int wwzb200_ar1_signif(const double *ts, int64_t nts, double tau_est, double sigma, double mu, int64_t S,
+                       uint64_t seed, const double *taus, int64_t nt, const double *omegas, int64_t nf, double c,
+                       int64_t Neff_threshold, int64_t psd_Neff_threshold, uint32_t flags, const double *probs,
+                       int64_t nq, double *Neffs, double *q_wwa, double *q_psd)
+{
+    int rc = check_grid_args(ts, ts, nts, taus, nt, omegas, nf, c, Neff_threshold);
+    if (rc) return rc;
+    if (S < 1 || nq < 1 || !probs) return fail(WWZB200_ERR_ARG, "need S >= 1 surrogates and nq >= 1 probabilities");
+    if (!(tau_est > 0)) return fail(WWZB200_ERR_ARG, "tau_est must be positive");
+    std::lock_guard<std::mutex> lock(g_mu);
+    Workspace *w;
+    if ((rc = workspace(&w))) return rc;
+    cudaStream_t st = w->stream;
+    const int64_t ncell = nt * nf;
+    double *d_in, *d_Y, *d_rq, *d_ne, *d_q, *d_psd = nullptr, *d_psd_t = nullptr;
+    if ((rc = wsbuf(w, "in", (size_t)(2 * nts + nt + nf + nq), &d_in))) return rc;
+    if ((rc = wsbuf(w, "Y", (size_t)S * (size_t)nts, &d_Y))) return rc;
+    if ((rc = wsbuf(w, "ar1_rq", (size_t)2 * nts, &d_rq))) return rc;
+    if ((rc = wsbuf(w, "ne_out", (size_t)ncell, &d_ne))) return rc;
+    if ((rc = wsbuf(w, "q_out", (size_t)nq * (size_t)(ncell + nf), &d_q))) return rc;
+    if (q_psd) {
+        if ((rc = wsbuf(w, "psd_out", (size_t)S * (size_t)nf, &d_psd))) return rc;
+        if ((rc = wsbuf(w, "psd_t", (size_t)S * (size_t)nf, &d_psd_t))) return rc;
+    }
+    double *d_ts = d_in, *d_tau = d_in + 2 * nts, *d_om = d_tau + nt, *d_probs = d_om + nf;
+    CU(cudaMemcpyAsync(d_ts, ts, sizeof(double) * nts, cudaMemcpyHostToDevice, st));
+    if (nt) CU(cudaMemcpyAsync(d_tau, taus, sizeof(double) * nt, cudaMemcpyHostToDevice, st));
+    if (nf) CU(cudaMemcpyAsync(d_om, omegas, sizeof(double) * nf, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_probs, probs, sizeof(double) * nq, cudaMemcpyHostToDevice, st));
+    CU(wwz::launch_ar1(d_ts, nts, tau_est, sigma, mu, S, seed, d_rq, d_rq + nts, d_Y, st));
+    const auto mm = std::minmax_element(ts, ts + nts);
+    double *d_amp_cells = nullptr;
+    int64_t S_pad = 0;
+    rc = shared_axis_device(w, d_ts, d_Y, nts, S, d_tau, nt, d_om, nf, c, Neff_threshold, psd_Neff_threshold,
+                            flags | WWZB200_STANDARDIZE, d_ne, nullptr, nullptr, nullptr, nullptr, nullptr, d_psd,
+                            *mm.second - *mm.first, &d_amp_cells, &S_pad, st);
+    if (rc) return rc;
+    if (ncell && q_wwa) {
+        if ((rc = quantiles_device(w, d_amp_cells, S, S_pad, ncell, d_probs, nq, d_q, st))) return rc;
+        CU(cudaMemcpyAsync(q_wwa, d_q, sizeof(double) * (size_t)nq * ncell, cudaMemcpyDeviceToHost, st));
+    }
+    if (q_psd && nf) {
+        CU(wwz::launch_transpose(d_psd, S, nf, nf, d_psd_t, S, st));   // [S][nf] -> [nf][S]
+        double *d_qp = d_q + (size_t)nq * ncell;
+        if ((rc = quantiles_device(w, d_psd_t, S, S, nf, d_probs, nq, d_qp, st))) return rc;
+        CU(cudaMemcpyAsync(q_psd, d_qp, sizeof(double) * (size_t)nq * nf, cudaMemcpyDeviceToHost, st));
+    }
+    if (Neffs && ncell) CU(cudaMemcpyAsync(Neffs, d_ne, sizeof(double) * ncell, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
     return 0;
 }
 

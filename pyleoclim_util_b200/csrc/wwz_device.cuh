@@ -127,4 +127,76 @@ __device__ __forceinline__ double gauss_weight(double u)
     return __hiloint2double(tiny ? 0 : hi, tiny ? 0 : __double2loint(p));
 }
 
+// ----------------------------------------------------------------------------------------------
+// Faithful evaluation of one cell by one warp: lanes stride over the points, warp-shuffle
+// reductions; the reference's own two-pass expressions (utils/wavelet.py:988-1032) with exp()
+// keeping subnormal weights and w*w rounded separately.  All lanes return the same values.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ void faithful_cell_warp(const double *__restrict__ ts, const double *__restrict__ ys,
+                                                   long long ystride, long long n, double tj, double om, double c,
+                                                   double thr, int lane, double &neff, double &a0, double &a1,
+                                                   double &a2)
+{
+    double sw = 0.0, sw2 = 0.0;
+    for (long long i = lane; i < n; i += 32) {
+        const double dz = om * (ts[i] - tj);                 // :988
+        const double w = exp(-c * (dz * dz));                // :989
+        sw += w;                                             // :991
+        sw2 = __dadd_rn(sw2, __dmul_rn(w, w));               // :992
+    }
+    sw = warp_sum(sw);
+    sw2 = warp_sum(sw2);
+    neff = sw * sw / sw2;
+    a0 = a1 = a2 = __longlong_as_double(0x7ff8000000000000LL);
+    if (!(neff > thr)) return;                               // :994 with numba's NaN semantics
+    double s1 = 0, c1 = 0, sc = 0, ss = 0, cc = 0;
+    for (long long i = lane; i < n; i += 32) {
+        const double t = ts[i];
+        const double dz = om * (t - tj);
+        const double w = exp(-c * (dz * dz));
+        double sb, cb;
+        sincos(om * t, &sb, &cb);                            // :1002-1003
+        s1 += w * sb;
+        c1 += w * cb;
+        sc += w * sb * cb;
+        ss += w * sb * sb;
+        cc += w * cb * cb;
+    }
+    const double sin_one = warp_sum(s1) / sw, cos_one = warp_sum(c1) / sw, sin_cos = warp_sum(sc) / sw;
+    const double sin_sin = warp_sum(ss) / sw, cos_cos = warp_sum(cc) / sw;
+    const double numerator = 2 * (sin_cos - sin_one * cos_one);                               // :1012
+    const double denominator = (cos_cos - cos_one * cos_one) - (sin_sin - sin_one * sin_one); // :1013
+    const double time_shift = atan2(numerator, denominator) / (2 * om);                       // :1014
+    double ycs = 0, yss = 0, y1 = 0, cs1 = 0, ss1 = 0;
+    for (long long i = lane; i < n; i += 32) {
+        const double t = ts[i], y = ys[i * ystride];
+        const double dz = om * (t - tj);
+        const double w = exp(-c * (dz * dz));
+        double sh, ch;
+        sincos(om * (t - time_shift), &sh, &ch);             // :1016-1017
+        ycs += w * y * ch;
+        yss += w * y * sh;
+        y1 += w * y;
+        cs1 += w * ch;
+        ss1 += w * sh;
+    }
+    const double ys_cos_shift = warp_sum(ycs) / sw, ys_sin_shift = warp_sum(yss) / sw;
+    const double ys_one = warp_sum(y1) / sw;
+    const double cos_shift_one = warp_sum(cs1) / sw, sin_shift_one = warp_sum(ss1) / sw;
+    double stc, ctc;
+    sincos(om * (time_shift - tj), &stc, &ctc);              // :1018-1019
+    const double A = 2 * (ys_cos_shift - ys_one * cos_shift_one);   // :1027
+    const double B = 2 * (ys_sin_shift - ys_one * sin_shift_one);   // :1028
+    a0 = ys_one;                                             // :1030
+    a1 = ctc * A - stc * B;                                  // :1031
+    a2 = stc * A + ctc * B;                                  // :1032
+}
+
 }  // namespace wwz

@@ -13,6 +13,7 @@ constexpr int kStages = 3;
 constexpr int kNumSums = 7;  // W, Q, Ws, Wc, Wy, Wys, Wyc
 constexpr int kStageBudget = 32 * 1024;
 constexpr int kMaxPointsPerStage = 512;
+constexpr int kSurrBlock = 16;   // series per CTA in the shared-time-axis kernel
 
 // Geometry of one launch of the cell kernel, derived on the host by plan_cells().
 struct CellPlan {
@@ -72,6 +73,42 @@ cudaError_t launch_minmax(const double *d_x, int64_t n, double *d_out, cudaStrea
 cudaError_t launch_psd_devspan(const double *d_wwa, const double *d_neffs, int64_t nt, int64_t nf,
                                int64_t row_stride, const double *d_minmax, int64_t n, double neff_thr,
                                double *d_psd, cudaStream_t st);
+
+// ---- batched paths (wwz_batch.cu) -------------------------------------------------------------
+struct SharedPlan {
+    int ft_max, points, stage_bytes, smem_bytes;
+    int64_t n_pad, row_stride, y_off;
+};
+SharedPlan plan_shared(int64_t n, int64_t nt, int64_t nf);
+
+// AR(1) surrogates Y[S][n] (row-major); d_rho, d_q are n-element scratch.
+cudaError_t launch_ar1(const double *d_ts, int64_t n, double tau, double sigma, double mu, int64_t S, uint64_t seed,
+                       double *d_rho, double *d_q, double *d_Y, cudaStream_t st);
+// per-series mean/std (identity when !standardize) and the tiled copy Yt[S_pad/16][n_pad][16]
+cudaError_t launch_standardize_retile(const double *d_Y, int64_t n, int64_t n_pad, int64_t S, bool standardize,
+                                      double *d_mu, double *d_sig, double *d_Yt, cudaStream_t st);
+// {sin, cos}(omega_k t_i) records (16 B) + (t, y) pairs
+cudaError_t launch_basis_sc(const double *d_ts, int64_t n, int64_t n_pad, const double *d_omega, int64_t nf,
+                            double2 *d_ty, double2 *d_basis, cudaStream_t st);
+cudaError_t launch_rotation(const double *d_tau, const double *d_omega, int64_t nt, int64_t nf, double2 *d_rot,
+                            cudaStream_t st);
+cudaError_t launch_shared(const SharedPlan &plan, const double2 *d_ty, const double2 *d_basis, const double *d_Yt,
+                          int64_t n, int64_t S_pad, const double *d_tau, int64_t nt, const double *d_kappa,
+                          int64_t nf, const double2 *d_rot, double thr, double *d_neffs, double *d_wq, double *d_amp,
+                          double *d_phase, double *d_a0, double *d_a1, double *d_a2, cudaStream_t st);
+// deep-underflow cells of a shared-axis batch (flagged from W, Q), recomputed faithfully for every series
+cudaError_t launch_shared_fixup(const double *d_ts, const double *d_Yt, int64_t n, int64_t n_pad, int64_t S,
+                                int64_t S_pad, const double *d_tau, const double *d_omega, int64_t nt, int64_t nf,
+                                double c, double thr, const double *d_wq, unsigned int *d_fix_count,
+                                unsigned int *d_fix_list, double *d_neffs, double *d_amp, double *d_phase,
+                                double *d_a0, double *d_a1, double *d_a2, int sms, cudaStream_t st);
+cudaError_t launch_transpose(const double *d_in, int64_t rows, int64_t cols, int64_t in_stride, double *d_out,
+                             int64_t out_stride, cudaStream_t st);
+cudaError_t launch_psd_batch(const double *d_amp, const double *d_neffs, int64_t nt, int64_t nf, int64_t S,
+                             int64_t S_pad, double tspan, int64_t n, double thr, double *d_psd, cudaStream_t st);
+cudaError_t launch_quantiles(const double *d_X, int64_t S, int64_t stride, int64_t ncell, const double *d_probs,
+                             int64_t nq, double *d_q, unsigned long long *d_scratch, int64_t scratch_ctas, int sms,
+                             cudaStream_t st);
 
 // FP64 FMA peak microbenchmark.
 cudaError_t run_fp64_peak(double *tflops, double *ms);

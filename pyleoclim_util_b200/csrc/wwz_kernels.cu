@@ -479,13 +479,6 @@ __global__ void finalize_kernel(const double *__restrict__ sums, const double *_
 // time_shift, then sin/cos(omega*(ts - time_shift)).  Used (a) for the deep-underflow cells the
 // epilogue flags, (b) for every cell when the caller asks for WWZB200_FAITHFUL (validation mode).
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ double warp_sum(double v)
-{
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-
 __global__ void __launch_bounds__(128)
     faithful_cells_kernel(const double *__restrict__ ts, const double *__restrict__ ys, int64_t n,
                           const double *__restrict__ tau, const double *__restrict__ omega, int64_t nt, int64_t nf,
@@ -506,61 +499,8 @@ __global__ void __launch_bounds__(128)
     for (int64_t item = warp0; item < total; item += nwarps) {
         const int64_t idx = fix_list ? (int64_t)fix_list[item] : item;
         const int64_t j = idx / nf, k = idx - j * nf;
-        const double om = omega[k], tj = tau[j];
-        double sw = 0.0, sw2 = 0.0;
-        for (int64_t i = lane; i < n; i += 32) {
-            const double dz = om * (ts[i] - tj);
-            const double w = exp(-c * (dz * dz));
-            sw += w;
-            sw2 = __dadd_rn(sw2, __dmul_rn(w, w));
-        }
-        sw = warp_sum(sw);
-        sw2 = warp_sum(sw2);
-        const double neff = sw * sw / sw2;
-        double a0 = CUDART_NAN, a1 = CUDART_NAN, a2 = CUDART_NAN;
-        if (neff > thr) {
-            double s1 = 0, c1 = 0, sc = 0, ss = 0, cc = 0;
-            for (int64_t i = lane; i < n; i += 32) {
-                const double t = ts[i];
-                const double dz = om * (t - tj);
-                const double w = exp(-c * (dz * dz));
-                double sb, cb;
-                sincos(om * t, &sb, &cb);
-                s1 += w * sb;
-                c1 += w * cb;
-                sc += w * sb * cb;
-                ss += w * sb * sb;
-                cc += w * cb * cb;
-            }
-            const double sin_one = warp_sum(s1) / sw, cos_one = warp_sum(c1) / sw, sin_cos = warp_sum(sc) / sw;
-            const double sin_sin = warp_sum(ss) / sw, cos_cos = warp_sum(cc) / sw;
-            const double numerator = 2 * (sin_cos - sin_one * cos_one);
-            const double denominator = (cos_cos - cos_one * cos_one) - (sin_sin - sin_one * sin_one);
-            const double time_shift = atan2(numerator, denominator) / (2 * om);
-            double ycs = 0, yss = 0, y1 = 0, cs1 = 0, ss1 = 0;
-            for (int64_t i = lane; i < n; i += 32) {
-                const double t = ts[i], y = ys[i];
-                const double dz = om * (t - tj);
-                const double w = exp(-c * (dz * dz));
-                double sh, ch;
-                sincos(om * (t - time_shift), &sh, &ch);
-                ycs += w * y * ch;
-                yss += w * y * sh;
-                y1 += w * y;
-                cs1 += w * ch;
-                ss1 += w * sh;
-            }
-            const double ys_cos_shift = warp_sum(ycs) / sw, ys_sin_shift = warp_sum(yss) / sw;
-            const double ys_one = warp_sum(y1) / sw;
-            const double cos_shift_one = warp_sum(cs1) / sw, sin_shift_one = warp_sum(ss1) / sw;
-            double stc, ctc;
-            sincos(om * (time_shift - tj), &stc, &ctc);
-            const double A = 2 * (ys_cos_shift - ys_one * cos_shift_one);
-            const double B = 2 * (ys_sin_shift - ys_one * sin_shift_one);
-            a0 = ys_one;
-            a1 = ctc * A - stc * B;
-            a2 = stc * A + ctc * B;
-        }
+        double neff, a0, a1, a2;
+        faithful_cell_warp(ts, ys, 1, n, tau[j], omega[k], c, thr, lane, neff, a0, a1, a2);
         if (lane == 0) store_cell(j * row_stride + k, neff, a0, a1, a2, neffs, a0o, a1o, a2o, wwa, phase);
     }
 }

@@ -1,0 +1,170 @@
+"""Batched paths on the GPU: AR(1) surrogates, shared-time-axis transform, ragged ensembles,
+per-cell quantiles, fused significance test -- against the oracle and against the single-series path."""
+import numpy as np
+import pytest
+
+from conftest import assert_scalogram_parity, as_dict, max_rel, assert_same_nan_mask, has_cuda
+
+pytestmark = pytest.mark.gpu
+
+from pyleoclim_util_b200 import wavelet as WV, batch as B, _lib, synth   # noqa: E402
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_gpu():
+    assert has_cuda(), "these tests need a CUDA device and the built libwwz_b200.so (no CPU fallback)"
+
+
+def oracle():
+    from oracle import wwz_oracle as O
+    return O
+
+
+# ------------------------------------------------------------------ surrogates
+def test_ar1_surrogates_match_the_oracle_recurrence():
+    """Same recurrence as ar1_model (utils/tsmodel.py:59-69) driven by the documented Philox stream."""
+    O = oracle()
+    t, _ = synth.uneven_ar1(333, 5)
+    Y = B.ar1_surrogates(t, tau_est=3.7, sigma=1.9, mu=0.25, number=37, seed=12345)
+    assert Y.shape == (37, 333)
+    for s in (0, 1, 17, 36):
+        z = O.philox_normals(12345, s, t.size)
+        ref = O.ar1_model(t, 3.7, output_sigma=1.9, z=z) + 0.25
+        assert np.max(np.abs(Y[s] - ref)) < 1e-11
+    assert np.all(Y[:, 0] == 0.25)                       # y[0] = 0 (+ mu)
+    Y2 = B.ar1_surrogates(t, tau_est=3.7, sigma=1.9, mu=0.25, number=37, seed=12345)
+    assert np.array_equal(Y, Y2)                         # counter-based: reproducible
+    Y3 = B.ar1_surrogates(t, tau_est=3.7, sigma=1.9, mu=0.25, number=37, seed=12346)
+    assert not np.allclose(Y, Y3)
+
+
+def test_ar1_surrogate_statistics():
+    """The reference's own acceptance criterion (tests/test_core_SurrogateSeries.py:90-104): the AR(1)
+    parameters are recovered from the surrogates; here with a tighter tolerance and many series."""
+    t, y = synth.uneven_ar1(2000, 3)
+    tau_true, sigma = 5.0, 2.0
+    Y = B.ar1_surrogates(t, tau_est=tau_true, sigma=sigma, number=256, seed=7)
+    assert abs(Y[:, 500:].std() / sigma - 1) < 0.02
+    assert abs(Y.mean()) < 0.05
+    taus = [B.tau_estimation(Y[s], t) for s in range(0, 256, 8)]
+    assert abs(np.mean(taus) / tau_true - 1) < 0.1
+    sim = B.ar1_sim(y, 5, t, seed=1)
+    assert sim.shape == (2000, 5) and abs(sim.std() / y.std() - 1) < 0.1
+    assert B.ar1_sim(y, 1, t).shape == (2000,)
+
+
+# ------------------------------------------------------------------ shared time axis
+def _shared_case(n=500, nt=21, nf=17, S=37, seed=2):
+    t, y = synth.uneven_ar1(n, seed)
+    tau = np.linspace(t.min(), t.max(), nt)
+    freq = synth.freq_log(t, nf)
+    Y = B.ar1_surrogates(t, 4.0, sigma=1.3, mu=0.7, number=S, seed=seed)
+    return t, Y, tau, freq
+
+
+@pytest.mark.parametrize("standardize", [True, False])
+def test_shared_axis_matches_single_series_path(standardize):
+    t, Y, tau, freq = _shared_case()
+    r = B.wwz_shared_axis(Y, t, tau, freq, standardize=standardize, outputs=("amplitude", "phase", "coeff"),
+                          psd_Neff_threshold=3, c=1e-3)
+    for s in range(Y.shape[0]):
+        one = WV.kirchner_cuda(Y[s], t, freq, tau, c=1e-3, standardize=standardize)
+        got = dict(amplitude=r.amplitude[s], phase=r.phase[s], Neffs=r.Neffs, a0=r.coeff[0][s], a1=r.coeff[1][s],
+                   a2=r.coeff[2][s])
+        assert_scalogram_parity(got, as_dict(*one), amp_rtol=1e-11, phase_atol=1e-11, what="series %d" % s)
+        p = WV.wwz_psd(Y[s], t, freq=freq, tau=tau, c=1e-3, standardize=standardize)
+        assert max_rel(r.psd[s], p.psd) < 1e-11
+
+
+def test_shared_axis_vs_oracle_default_grid_shape():
+    """nt = 50 (the reference's default) with a frequency above Nyquist and Neff-masked cells."""
+    O = oracle()
+    t, Y, tau, freq = _shared_case(n=400, nt=50, nf=12, S=5)
+    freq = np.append(freq, 3.0)                               # > Nyquist: NaN column
+    r = B.wwz_shared_axis(Y, t, tau, freq, outputs=("amplitude", "phase", "coeff"))
+    for s in range(Y.shape[0]):
+        o = O.kirchner(Y[s], t, freq, tau, standardize=True)
+        got = dict(amplitude=r.amplitude[s], phase=r.phase[s], Neffs=r.Neffs, a0=r.coeff[0][s], a1=r.coeff[1][s],
+                   a2=r.coeff[2][s])
+        assert_scalogram_parity(got, as_dict(*o), what="oracle series %d" % s)
+    assert np.isnan(r.amplitude[:, :, -1]).all()
+
+
+def test_shared_axis_gap_series_deep_underflow():
+    O = oracle()
+    rng = np.random.default_rng(8)
+    t = np.concatenate([np.sort(rng.uniform(0, 50, 100)), np.sort(rng.uniform(400, 450, 100))])
+    Y = rng.standard_normal((3, t.size))
+    tau = np.linspace(t.min(), t.max(), 30)
+    freq = np.logspace(-2.5, 0.05, 20)
+    r = B.wwz_shared_axis(Y, t, tau, freq, outputs=("amplitude", "phase"))
+    for s in range(3):
+        o = O.kirchner(Y[s], t, freq, tau, standardize=True)
+        assert_scalogram_parity(dict(amplitude=r.amplitude[s], phase=r.phase[s], Neffs=r.Neffs),
+                                dict(amplitude=o[0], phase=o[1], Neffs=o[2]), what="gap series %d" % s)
+
+
+@pytest.mark.parametrize("S", [1, 15, 16, 17, 100])
+def test_shared_axis_series_count_padding(S):
+    t, Y, tau, freq = _shared_case(n=200, nt=9, nf=7, S=S)
+    r = B.wwz_shared_axis(Y, t, tau, freq)
+    assert r.amplitude.shape == (S, 9, 7)
+    one = WV.kirchner_cuda(Y[S - 1], t, freq, tau, standardize=True)
+    assert max_rel(r.amplitude[S - 1], one[0]) < 1e-11
+
+
+# ------------------------------------------------------------------ ragged ensembles
+def test_ragged_members_match_single_calls():
+    axes, y = synth.age_ensemble(300, 7)
+    members = []
+    for m, t in enumerate(axes):
+        ys_cut, ts_cut, freq, tau = WV.prepare_wwz(y, t, tau=np.linspace(t.min(), t.max(), 10 + m))
+        members.append((ys_cut, ts_cut, tau, freq[: 20 + m]))
+    res, psds = B.wwz_ragged(members, psd_Neff_threshold=3)
+    assert len(res) == 7
+    for (ys, ts, tau, freq), r, p in zip(members, res, psds):
+        one = WV.kirchner_cuda(ys, ts, freq, tau, standardize=True)
+        assert r.amplitude.shape == (tau.size, freq.size)
+        assert np.array_equal(r.amplitude.view(np.uint64), one[0].view(np.uint64))
+        assert np.array_equal(r.Neffs.view(np.uint64), one[2].view(np.uint64))
+        ps = WV.wwa2psd(one[0], ts, one[2], Neff_threshold=3)
+        assert max_rel(p, ps) < 1e-13
+
+
+# ------------------------------------------------------------------ quantiles
+@pytest.mark.parametrize("S", [1, 2, 3, 10, 200, 1000, 20000])
+def test_quantiles_match_scipy_mquantiles(S):
+    from scipy.stats.mstats import mquantiles
+    rng = np.random.default_rng(S)
+    ncell = 13 if S > 5000 else 57
+    X = rng.standard_normal((S, ncell))
+    X[:, 3] = np.nan                                    # a masked cell: NaN for every series
+    qs = [0.05, 0.5, 0.9, 0.95, 0.99]
+    got = B.quantiles(X, qs)
+    ref = np.asarray(mquantiles(X, qs, axis=0).filled(np.nan))
+    assert got.shape == ref.shape == (5, ncell)
+    assert_same_nan_mask(got, ref)
+    m = ~np.isnan(ref)
+    assert np.max(np.abs(got[m] - ref[m])) < 1e-14
+    got3 = B.quantiles(X.reshape(S, 1, ncell), [0.9])
+    assert got3.shape == (1, 1, ncell)
+
+
+# ------------------------------------------------------------------ fused significance test
+def test_wwz_signif_equals_the_unfused_pipeline():
+    from scipy.stats.mstats import mquantiles
+    t, y = synth.uneven_ar1(400, 11)
+    y = 2.0 * y + 3.0
+    number, qs, seed = 48, [0.9, 0.95], 77
+    sg = B.wwz_signif(y, t, number=number, qs=qs, seed=seed, psd=True, c=1e-3)
+    ys_cut, ts_cut, freq, tau = WV.prepare_wwz(y, t)
+    assert np.array_equal(sg.freq, freq) and np.array_equal(sg.time, tau)
+    tau_est = B.tau_estimation(ys_cut, ts_cut)
+    Y = B.ar1_surrogates(ts_cut, tau_est, sigma=np.std(ys_cut), mu=np.mean(ys_cut), number=number, seed=seed)
+    amps = np.stack([WV.kirchner_cuda(Y[s], ts_cut, freq, tau, c=1e-3, standardize=True)[0] for s in range(number)])
+    ref = np.asarray(mquantiles(amps.reshape(number, -1), qs, axis=0).filled(np.nan)).reshape(2, tau.size, freq.size)
+    assert_same_nan_mask(sg.amplitude_qs, ref)
+    assert max_rel(sg.amplitude_qs, ref) < 1e-10
+    psds = np.stack([WV.wwz_psd(Y[s], ts_cut, freq=freq, tau=tau, c=1e-3).psd for s in range(number)])
+    pref = np.asarray(mquantiles(psds, qs, axis=0))
+    assert max_rel(sg.psd_qs, pref) < 1e-10
