@@ -10,7 +10,7 @@ from . import _lib
 from . import wavelet as _wv
 
 __all__ = ["tau_estimation", "ar1_surrogates", "ar1_sim", "wwz_shared_axis", "wwz_ragged", "quantiles",
-           "wwz_signif", "SharedAxisResults", "SignifResults"]
+           "wwz_signif", "signif_prepared", "SharedAxisResults", "SignifResults"]
 
 SharedAxisResults = collections.namedtuple(
     "SharedAxisResults", ["amplitude", "Neffs", "phase", "coeff", "psd", "freq", "time", "coi", "scale"])
@@ -158,18 +158,32 @@ def wwz_signif(ys, ts, tau=None, freq=None, number=200, qs=(0.95,), seed=0, c=1 
     (PSD.signif_test core/psds.py:246-282), computed with decay constant ``psd_c`` (default ``c``)."""
     ys_cut, ts_cut, freq, tau = _wv.prepare_wwz(ys, ts, freq=freq, freq_method=freq_method, freq_kwargs=freq_kwargs,
                                                 tau=tau)
-    sig = float(np.std(ys_cut))
-    mu = float(np.mean(ys_cut))
-    tau_est = float(tau_estimation(ys_cut, ts_cut))
-    omega = _wv.make_omega(ts_cut, freq)
     probs = _lib.f64(np.atleast_1d(qs))
+    cc = float(c if not psd or psd_c is None else psd_c)
+    q_wwa, q_psd, Neffs = signif_prepared(ys_cut, ts_cut, tau, freq, number=number, probs=probs, seed=seed, c=cc,
+                                          Neff_threshold=Neff_threshold, psd=psd,
+                                          psd_Neff_threshold=psd_Neff_threshold, flags=flags)
+    return SignifResults(qs=probs, amplitude_qs=q_wwa, psd_qs=q_psd, Neffs=Neffs, freq=freq, time=tau)
+
+
+def signif_prepared(ys_cut, ts_cut, tau, freq, number, probs, seed=0, c=1 / (8 * np.pi ** 2), Neff_threshold=3,
+                    psd=False, psd_Neff_threshold=3, flags=0):
+    """The fused significance pipeline on an already prepared series / grid (no prepare_wwz: `tau`
+    may be a row block of the full grid, as in distributed.wwz_signif_tau_sharded).
+    Returns (q_wwa [nq, nt, nf], q_psd [nq, nf] or None, Neffs [nt, nf])."""
+    ts_cut, tau, freq = _lib.f64(ts_cut), _lib.f64(tau), _lib.f64(freq)
+    ys_cut = np.asarray(ys_cut, dtype=float)
+    sig = float(np.std(ys_cut))                     # utils/tsmodel.py:147
+    mu = float(np.mean(ys_cut))                     # core/surrogateseries.py:137-139 (removed again by the z-score)
+    tau_est = float(tau_estimation(ys_cut, ts_cut))  # utils/tsmodel.py:161
+    omega = _wv.make_omega(ts_cut, freq)
+    probs = _lib.f64(np.atleast_1d(probs))
     nt, nf = tau.size, freq.size
     Neffs = np.empty((nt, nf))
     q_wwa = np.empty((probs.size, nt, nf))
     q_psd = np.empty((probs.size, nf)) if psd else None
-    cc = float(c if not psd or psd_c is None else psd_c)
     _lib.check(_lib.lib().wwzb200_ar1_signif(
-        _lib.ptr(_lib.f64(ts_cut)), ts_cut.size, tau_est, sig, mu, int(number), int(seed) & 0xFFFFFFFFFFFFFFFF,
-        _lib.ptr(_lib.f64(tau)), nt, _lib.ptr(omega), nf, cc, int(Neff_threshold), int(psd_Neff_threshold), int(flags),
+        _lib.ptr(ts_cut), ts_cut.size, tau_est, sig, mu, int(number), int(seed) & 0xFFFFFFFFFFFFFFFF,
+        _lib.ptr(tau), nt, _lib.ptr(omega), nf, float(c), int(Neff_threshold), int(psd_Neff_threshold), int(flags),
         _lib.ptr(probs), probs.size, _lib.ptr(Neffs), _lib.ptr(q_wwa), _lib.ptr(q_psd)))
-    return SignifResults(qs=probs, amplitude_qs=q_wwa, psd_qs=q_psd, Neffs=Neffs, freq=freq, time=tau)
+    return q_wwa, q_psd, Neffs

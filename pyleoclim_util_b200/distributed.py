@@ -1,0 +1,136 @@
+"""One process per GPU: tau-block sharding of the (tau, f) grid with a single all-gather of the
+output shards.  Cells are independent, so there is no data-path exchange inside
+the transform; `torch.distributed` (NCCL on GPUs, gloo in the CPU tests) is plumbing only.
+
+The surrogate significance test is sharded the same way -- every rank draws the same counter-based
+surrogate streams (same seed) and evaluates all S surrogates on its own tau rows, so the per-cell
+quantiles need no exchange either; only the [nq, rows, nf] quantile tiles are gathered.
+"""
+import numpy as np
+
+from . import wavelet as _wv
+
+
+def row_blocks(n, world):
+    """Contiguous balanced partition of range(n) into `world` blocks: [(start, stop), ...]."""
+    base, extra = divmod(int(n), int(world))
+    out, start = [], 0
+    for r in range(world):
+        stop = start + base + (1 if r < extra else 0)
+        out.append((start, stop))
+        start = stop
+    return out
+
+
+def _dist():
+    import torch.distributed as dist
+    if not dist.is_available() or not dist.is_initialized():
+        raise RuntimeError("torch.distributed is not initialised (launch with torchrun, one rank per GPU)")
+    return dist
+
+
+def all_gather_rows(local, counts, group=None):
+    """Gather row blocks of different heights: local is [counts[rank], ...]; returns the
+    concatenation [sum(counts), ...] on every rank (one all-gather on blocks padded to the tallest)."""
+    import torch
+    dist = _dist()
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    local = np.ascontiguousarray(local, dtype=np.float64)
+    assert local.shape[0] == counts[rank], "row count of this rank does not match the partition"
+    tail = local.shape[1:]
+    hmax = max(max(counts), 1)
+    backend = dist.get_backend(group)
+    device = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    pad = torch.zeros((hmax,) + tail, dtype=torch.float64, device=device)
+    if local.shape[0]:
+        pad[: local.shape[0]] = torch.from_numpy(local).to(device)
+    out = torch.empty((world, hmax) + tail, dtype=torch.float64, device=device)
+    dist.all_gather_into_tensor(out.view(-1), pad.view(-1), group=group)
+    out = out.cpu().numpy()
+    return np.concatenate([out[r, : counts[r]] for r in range(world)], axis=0)
+
+
+def wwz_tau_sharded(ys, ts, tau=None, freq=None, freq_method="log", freq_kwargs=None, c=1 / (8 * np.pi ** 2),
+                    Neff_threshold=3, Neff_coi=3, standardize=True, group=None, kernel=None, flags=0):
+    """`wavelet.wwz` with the tau rows sharded over the ranks of `group`.  Every rank returns the
+    full Results (amplitude, phase, coi, freq, time, Neffs, coeff, scale), like the reference's wwz
+    (utils/wavelet.py:1294-1494).  `kernel` defaults to `wavelet.kirchner_cuda`."""
+    dist = _dist()
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    kernel = _wv.kirchner_cuda if kernel is None else kernel
+    ys_cut, ts_cut, freq, tau = _wv.prepare_wwz(ys, ts, freq=freq, freq_method=freq_method, freq_kwargs=freq_kwargs,
+                                                tau=tau)
+    pd_ys = _wv.preprocess(ys_cut, ts_cut, standardize=standardize)
+    blocks = row_blocks(tau.size, world)
+    counts = [b - a for a, b in blocks]
+    a, b = blocks[rank]
+    kw = dict(c=c, Neff_threshold=Neff_threshold, standardize=False)
+    if kernel is _wv.kirchner_cuda:
+        kw["flags"] = flags
+    wwa, phase, Neffs, (a0, a1, a2) = kernel(pd_ys, ts_cut, freq, tau[a:b], **kw)
+    stacked = np.stack([wwa, phase, Neffs, a0, a1, a2], axis=1) if b > a else np.zeros((0, 6, freq.size))
+    full = all_gather_rows(stacked, counts, group)
+    wwa, phase, Neffs, a0, a1, a2 = (np.ascontiguousarray(full[:, i]) for i in range(6))
+    return _wv.WwzResults(amplitude=wwa, phase=phase, coi=_wv.make_coi(tau, Neff_threshold=Neff_coi), freq=freq,
+                          time=tau, Neffs=Neffs, coeff=(a0, a1, a2), scale=1 / freq)
+
+
+def wwz_psd_tau_sharded(ys, ts, tau=None, freq=None, freq_method="log", freq_kwargs=None, c=1e-3, standardize=True,
+                        Neff_threshold=3, group=None, kernel=None, flags=0):
+    """`wavelet.wwz_psd` (utils/spectral.py:728-900) with the tau rows sharded.  The tau-reduction of
+    wwa2psd (utils/wavelet.py:1275-1278) is a ratio of two column sums, so the ranks all-reduce their
+    partial numerators and denominators ([2, nf]) before the divide."""
+    import torch
+    dist = _dist()
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    kernel = _wv.kirchner_cuda if kernel is None else kernel
+    ys_cut, ts_cut, freq, tau = _wv.prepare_wwz(ys, ts, freq=freq, freq_method=freq_method, freq_kwargs=freq_kwargs,
+                                                tau=tau)
+    pd_ys = _wv.preprocess(ys_cut, ts_cut, standardize=standardize)
+    a, b = row_blocks(tau.size, world)[rank]
+    kw = dict(c=c, Neff_threshold=3, standardize=False)
+    if kernel is _wv.kirchner_cuda:
+        kw["flags"] = flags
+    part = np.zeros((2, freq.size))
+    if b > a:
+        wwa, _, Neffs, _ = kernel(pd_ys, ts_cut, freq, tau[a:b], **kw)
+        power = wwa ** 2 * 0.5 * (np.max(ts_cut) - np.min(ts_cut)) / np.size(ts_cut) * Neffs   # utils/wavelet.py:1270
+        Neff_diff = Neffs - Neff_threshold
+        Neff_diff[Neff_diff < 0] = 0
+        part[0] = np.nansum(power * Neff_diff, axis=0)
+        part[1] = np.nansum(Neff_diff, axis=0)
+    backend = dist.get_backend(group)
+    device = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    tot = torch.from_numpy(part).to(device)
+    dist.all_reduce(tot, group=group)
+    tot = tot.cpu().numpy()
+    with np.errstate(invalid="ignore", divide="ignore"):
+        psd = tot[0] / tot[1]
+    return _wv.PsdResults(psd=psd, freq=freq)
+
+
+def wwz_signif_tau_sharded(ys, ts, tau=None, freq=None, number=200, qs=(0.95,), seed=0, c=1 / (8 * np.pi ** 2),
+                           Neff_threshold=3, freq_method="log", freq_kwargs=None, group=None, signif=None):
+    """Scalogram significance levels with the tau rows sharded: each rank runs the fused device
+    pipeline (`batch.signif_prepared`) for all `number` surrogates on its rows; the same seed gives
+    every rank the same surrogates, so quantiles are exchange-free.  Returns `batch.SignifResults`."""
+    from . import batch
+    dist = _dist()
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    signif = batch.signif_prepared if signif is None else signif
+    ys_cut, ts_cut, freq, tau = _wv.prepare_wwz(ys, ts, freq=freq, freq_method=freq_method, freq_kwargs=freq_kwargs,
+                                                tau=tau)
+    blocks = row_blocks(tau.size, world)
+    counts = [b - a for a, b in blocks]
+    a, b = blocks[rank]
+    probs = np.atleast_1d(np.asarray(qs, dtype=float))
+    if b > a:
+        q_wwa, _, Neffs = signif(ys_cut, ts_cut, tau[a:b], freq, number=number, probs=probs, seed=seed, c=c,
+                                 Neff_threshold=Neff_threshold)
+        local = np.concatenate([np.moveaxis(q_wwa, 0, 1), Neffs[:, None, :]], axis=1)    # [rows, nq+1, nf]
+    else:
+        local = np.zeros((0, probs.size + 1, freq.size))
+    full = all_gather_rows(local, counts, group)
+    return batch.SignifResults(qs=probs, amplitude_qs=np.ascontiguousarray(np.moveaxis(full[:, :-1], 1, 0)),
+                               psd_qs=None, Neffs=np.ascontiguousarray(full[:, -1]), freq=freq, time=tau)
