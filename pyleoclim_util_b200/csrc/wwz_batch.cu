@@ -214,10 +214,10 @@ cudaError_t launch_standardize_retile(const double *d_Y, int64_t n, int64_t n_pa
 // ------------------------------------------------------------------------------------------------
 // Shared-time-axis transform.  One lane = one cell (as in wwz_cells_kernel with M = 1); a CTA owns
 // 256 consecutive cells and a block of NS = 16 series.  Per (cell, point) the weight is evaluated
-// once (15 FP64 instructions + 6 for W, Q, Ws, Wc and the products w*s, w*c) and contracted
+// once (12 FP64 instructions + 6 for W, Q, Ws, Wc and the products w*s, w*c) and contracted
 // against the 16 series values of that point (3 DFMA each, broadcast LDS from the staged
-// Yt tile): 69 FP64 instructions per (cell, point, 16 series) = 4.3 per (cell, point, series)
-// against the 22 of a full transform per series.
+// Yt tile): 66 FP64 instructions per (cell, point, 16 series) = 4.1 per (cell, point, series)
+// against the 19 of a full transform per series.
 // Staging: TMA producer warp as in wwz_cells_kernel; per chunk one bulk copy of (t,y) pairs, one per
 // frequency row of {s, c} records, one for the [P][NS] tile of series values.
 // Epilogue in registers: Neff / mask once per cell, then per series the coefficients through the
@@ -248,6 +248,7 @@ __global__ void __launch_bounds__(kCellThreads, 1) wwz_shared_kernel(const Share
     unsigned char *const tail = smem_raw + (size_t)kStages * (size_t)a.stage_stride2 * sizeof(double2);
     uint64_t *const full = reinterpret_cast<uint64_t *>(tail);
     uint64_t *const empty = full + kStages;
+    double *const tbl = reinterpret_cast<double *>(empty + kStages);   // [16] 2^(j/16)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const bool consumer = warp < kConsumerWarps;
@@ -267,6 +268,7 @@ __global__ void __launch_bounds__(kCellThreads, 1) wwz_shared_kernel(const Share
         }
         mbar_fence_init();
     }
+    load_exp2_table(tbl, tid);
     __syncthreads();
 
     if (!consumer) {
@@ -321,7 +323,7 @@ __global__ void __launch_bounds__(kCellThreads, 1) wwz_shared_kernel(const Share
             for (int p = 0; p < cnt; ++p) {
                 const double t = st[p].x;
                 const double2 sc = row[p];
-                const double w = gauss_weight(kap * (t - tj));
+                const double w = gauss_weight(kap * (t - tj), tbl);
                 const double ws = w * sc.x, wc = w * sc.y;
                 W += w;
                 Q = fma(w, w, Q);
@@ -504,7 +506,7 @@ SharedPlan plan_shared(int64_t n, int64_t nt, int64_t nf)
     y_off = (y_off + 15) & ~(int64_t)15;
     p.y_off = y_off;
     p.stage_bytes = (int)(y_off + P * kSurrBlock * 8);
-    p.smem_bytes = kStages * p.stage_bytes + 2 * kStages * 8 + 16;
+    p.smem_bytes = kStages * p.stage_bytes + 2 * kStages * 8 + 16 * 8 + 16;
     return p;
 }
 

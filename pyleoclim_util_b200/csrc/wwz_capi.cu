@@ -118,6 +118,23 @@ size_t basis_budget_bytes()
     return (size_t)2 << 30;
 }
 
+// Number of point-axis segments: enough that (cells x segments) fills the machine for ~16 waves
+// (2.4e6 cell-slots = 16 waves x 296 CTAs x 512 cells), each segment at least 256 points.
+// It depends on the problem size only, never on the tile geometry, so every kernel variant adds
+// the same partial sums.
+int point_segments(int64_t n, int64_t ncell)
+{
+    const char *e = getenv("WWZB200_POINT_SEGMENTS");
+    int64_t s;
+    if (e && *e) {
+        s = atoll(e);
+    } else {
+        s = (2400000 + ncell - 1) / std::max<int64_t>(ncell, 1);
+        s = std::min<int64_t>(s, n / 256);
+    }
+    return (int)std::max<int64_t>(1, std::min<int64_t>(s, 4096));
+}
+
 int cells_per_lane_hint(int64_t nt, int64_t nf, int sms)
 {
     const char *e = getenv("WWZB200_CELLS_PER_LANE");
@@ -158,14 +175,16 @@ int transform_device(Workspace *w, const double *d_ts, const double *d_ys, int64
         CU(launch_faithful(d_ts, d_ys, n, d_tau, d_omega, nt, nf, c, (double)thr, nullptr, nullptr, 0, d_neffs, d_a0,
                            d_a1, d_a2, d_wwa, d_phase, row_stride, w->sms, st));
     } else {
-        const CellPlan plan = plan_cells(n, nt, nf, cells_per_lane_hint(nt, nf, w->sms));
+        const int segs = point_segments(n, ncell);
+        const int64_t seg_len = (((n + segs - 1) / segs + 15) / 16) * 16;
+        const CellPlan plan = plan_cells(n, nt, nf, cells_per_lane_hint(nt, nf, w->sms), seg_len);
         size_t per_row = (size_t)plan.n_pad * 32;
         int64_t nf_batch = (int64_t)std::max<size_t>(1, basis_budget_bytes() / per_row);
         nf_batch = std::min<int64_t>(std::min<int64_t>(nf_batch, nf), 65535);
         double2 *d_ty, *d_basis;
         if ((rc = wsbuf(w, "ty", (size_t)plan.n_pad, &d_ty))) return rc;
         if ((rc = wsbuf(w, "basis", (size_t)nf_batch * (size_t)plan.n_pad * 2, &d_basis))) return rc;
-        if ((rc = wsbuf(w, "sums", (size_t)kNumSums * (size_t)ncell, &d_sums))) return rc;
+        if ((rc = wsbuf(w, "sums", (size_t)segs * (size_t)kNumSums * (size_t)ncell, &d_sums))) return rc;
 
         CU(launch_freq_setup(d_omega, nf, c, d_kappa, d_dcut, st));
         CU(launch_unsorted_check(d_ts, n, d_unsorted, st));
@@ -181,14 +200,14 @@ int transform_device(Workspace *w, const double *d_ts, const double *d_ys, int64
                 CU(cudaEventRecord(ev.a, st));
             }
             CU(launch_cells(plan, d_ty, d_basis, d_ts, n, d_tau, nt, d_kappa, d_dcut, d_unsorted, k0, nb, nf, dense,
-                            d_sums, st));
+                            segs, seg_len, d_sums, st));
             if (g_profile) {
                 CU(cudaEventRecord(ev.b, st));
                 g_events.push_back(ev);
             }
         }
         CU(launch_finalize(d_sums, d_tau, d_omega, nt, nf, (double)thr, d_neffs, d_a0, d_a1, d_a2, d_wwa, d_phase,
-                           row_stride, d_fix_count, d_fix_list, (unsigned int)ncell, st));
+                           row_stride, d_fix_count, d_fix_list, (unsigned int)ncell, segs, st));
         CU(launch_faithful(d_ts, d_ys, n, d_tau, d_omega, nt, nf, c, (double)thr, d_fix_count, d_fix_list,
                            (unsigned int)ncell, d_neffs, d_a0, d_a1, d_a2, d_wwa, d_phase, row_stride, w->sms, st));
     }
@@ -646,7 +665,7 @@ int wwzb200_kirchner_ragged(const double *ts, const double *pd_ys, const int64_t
         return fail(WWZB200_ERR_ARG, "null pointer");
     if (Neff_threshold < 1) return fail(WWZB200_ERR_ARG, "Neff_threshold must be a positive integer");
     if (!(c > 0) || !std::isfinite(c)) return fail(WWZB200_ERR_ARG, "decay constant c must be positive and finite");
-    int64_t max_cells = 0, max_n = 0, max_nf = 0, max_basis = 0;
+    int64_t max_cells = 0, max_n = 0, max_nf = 0, max_basis = 0, max_sums = 0;
     for (int64_t m = 0; m < M; ++m) {
         const int64_t n = ts_off[m + 1] - ts_off[m], nt = tau_off[m + 1] - tau_off[m], nf = om_off[m + 1] - om_off[m];
         if (n < 1 || nt < 0 || nf < 0 || out_off[m + 1] - out_off[m] != nt * nf)
@@ -654,7 +673,8 @@ int wwzb200_kirchner_ragged(const double *ts, const double *pd_ys, const int64_t
         max_cells = std::max(max_cells, nt * nf);
         max_n = std::max(max_n, n);
         max_nf = std::max(max_nf, nf);
-        max_basis = std::max(max_basis, nf * (n + wwz::kMaxPointsPerStage));
+        max_basis = std::max(max_basis, nf * (n + wwz::kMaxPointsPerStage + 16));
+        max_sums = std::max(max_sums, (int64_t)point_segments(n, nt * nf) * wwz::kNumSums * nt * nf);
     }
     std::lock_guard<std::mutex> lock(g_mu);
     Workspace *w;
@@ -680,10 +700,10 @@ int wwzb200_kirchner_ragged(const double *ts, const double *pd_ys, const int64_t
         unsigned int *du;
         if ((rc = wsbuf(w, "kappa", (size_t)max_nf, &dd))) return rc;
         if ((rc = wsbuf(w, "dcut", (size_t)max_nf, &dd))) return rc;
-        if ((rc = wsbuf(w, "ty", (size_t)(max_n + wwz::kMaxPointsPerStage), &d2))) return rc;
+        if ((rc = wsbuf(w, "ty", (size_t)(max_n + wwz::kMaxPointsPerStage + 16), &d2))) return rc;
         if ((rc = wsbuf(w, "basis", (size_t)std::min<int64_t>(max_basis, (int64_t)(basis_budget_bytes() / 16)) * 2, &d2)))
             return rc;
-        if ((rc = wsbuf(w, "sums", (size_t)wwz::kNumSums * (size_t)max_cells, &dd))) return rc;
+        if ((rc = wsbuf(w, "sums", (size_t)max_sums, &dd))) return rc;
         if ((rc = wsbuf(w, "fix_list", (size_t)max_cells + 1, &du))) return rc;
         if (psd && (rc = wsbuf(w, "psd_wwa", (size_t)max_cells, &dd))) return rc;
     }

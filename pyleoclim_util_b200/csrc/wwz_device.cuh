@@ -76,55 +76,58 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t
 // ----------------------------------------------------------------------------------------------
 // Gaussian weight on the FP64 pipe.
 //
-//   w = 2^(-u*u),  u = kappa*(t - tau),  kappa = omega*sqrt(c*log2(e))
+//   w = exp(-c*omega^2*(t-tau)^2) = 2^(-u*u),  u = omega*sqrt(c*log2(e))*(t - tau)
 //
-// -u*u is split as n + f with n = rint(-u*u), |f| <= 1/2, using the 1.5*2^52 shift trick; both
-// the shift and the remainder are single FMAs on the *unrounded* product u*u, so f carries no
-// error from squaring.  2^f is a degree-10 minimax polynomial (rel. error 2.1e-16, see
-// tools/gen_exp2_poly.py) in Horner form: 10 DFMA.  2^n is applied with one integer add on the
-// exponent field.
-// FP64-pipe cost: 1 DFMA + 1 DADD + 1 DFMA + 10 DFMA = 13 (plus DADD + DMUL for u).
+// The kernels carry v = 4u (kappa4 = 4*omega*sqrt(c*log2 e)), so that -v*v = -16 u*u = N + g with
+// N = rint(-v*v) = 16 n + j (j = 0..15) and |g| <= 1/2:
+//
+//   w = 2^n * 2^(j/16) * 2^(g/16)
+//
+// N and g come from the 1.5*2^52 shift trick; both the shift and the remainder are single FMAs
+// on the *unrounded* product v*v, so g carries no error from squaring.  2^(g/16) is a degree-6
+// minimax polynomial (rel. error 7e-18, tools/gen_exp2_poly.py) in Horner form with its
+// coefficients in the constant bank; 2^(j/16) is a 16-entry table in shared memory (16 doubles =
+// exactly the 32 banks: distinct entries never conflict); 2^n is one integer add on the exponent
+// field.  FP64-pipe cost: DFMA + DADD + DFMA + 6 DFMA + DMUL = 10 (plus DADD + DMUL for v).
 // ----------------------------------------------------------------------------------------------
 constexpr double kShift = 6755399441055744.0;  // 1.5 * 2^52
 
-// Polynomial coefficients live in the constant bank so that every Horner step is a single DFMA
-// with a c[][] operand (literal doubles would cost two extra UMOV issue slots per step).
-__constant__ double c_exp2[11] = {WWZ_EXP2_C0, WWZ_EXP2_C1, WWZ_EXP2_C2, WWZ_EXP2_C3, WWZ_EXP2_C4, WWZ_EXP2_C5,
-                                  WWZ_EXP2_C6, WWZ_EXP2_C7, WWZ_EXP2_C8, WWZ_EXP2_C9, WWZ_EXP2_C10};
+__constant__ double c_exp2t[7] = {WWZ_EXP2T_C0, WWZ_EXP2T_C1, WWZ_EXP2T_C2, WWZ_EXP2T_C3,
+                                  WWZ_EXP2T_C4, WWZ_EXP2T_C5, WWZ_EXP2T_C6};
+__constant__ double c_exp2_table[16] = WWZ_EXP2_TABLE16;
 
-__device__ __forceinline__ double exp2_frac_poly(double f)
-{
-    double p = c_exp2[10];
-    p = fma(p, f, c_exp2[9]);
-    p = fma(p, f, c_exp2[8]);
-    p = fma(p, f, c_exp2[7]);
-    p = fma(p, f, c_exp2[6]);
-    p = fma(p, f, c_exp2[5]);
-    p = fma(p, f, c_exp2[4]);
-    p = fma(p, f, c_exp2[3]);
-    p = fma(p, f, c_exp2[2]);
-    p = fma(p, f, c_exp2[1]);
-    p = fma(p, f, c_exp2[0]);
-    return p;
-}
-
-// bits(kShift - 1021): z below this (as a signed 64-bit pattern) means n < -1021, i.e. the weight is
-// below the normal range; the same test catches u*u beyond the int32 range and u = +-inf.
-constexpr long long kTinyBits = 0x4337FFFFFFFFFC03LL;
+// bits(kShift - 16336): z below this (as a signed 64-bit pattern) means N < -16336, i.e. n < -1021
+// and the weight is below the normal range; the same test catches v*v beyond the int32 range and
+// v = +-inf.
+constexpr long long kTinyBits = 0x4337FFFFFFFFC030LL;
 
 // Branch-free: weights below 2^-1021 are flushed to +0.0 here.  Cells whose weight sums are small
 // enough for that to matter (or for w*w to underflow) are detected in the epilogue and recomputed
 // by the faithful warp-per-cell kernel, which keeps subnormals like the reference's libm exp.
-__device__ __forceinline__ double gauss_weight(double u)
+__device__ __forceinline__ double gauss_weight(double v, const double *__restrict__ tbl)
 {
-    const double z = fma(-u, u, kShift);   // kShift + rint(-u*u)
-    const double nf = z - kShift;          // rint(-u*u) as a double
-    const double f = fma(-u, u, -nf);      // (-u*u) - n, |f| <= 1/2
-    const double p = exp2_frac_poly(f);
-    const int n = __double2loint(z);
+    const double z = fma(-v, v, kShift);   // kShift + rint(-v*v)
+    const double Nf = z - kShift;          // rint(-v*v) as a double
+    const double g = fma(-v, v, -Nf);      // (-v*v) - N, |g| <= 1/2
+    const int N = __double2loint(z);
+    const double T = tbl[N & 15];
+    double p = c_exp2t[6];
+    p = fma(p, g, c_exp2t[5]);
+    p = fma(p, g, c_exp2t[4]);
+    p = fma(p, g, c_exp2t[3]);
+    p = fma(p, g, c_exp2t[2]);
+    p = fma(p, g, c_exp2t[1]);
+    p = fma(p, g, c_exp2t[0]);
+    p *= T;
     const bool tiny = __double_as_longlong(z) < kTinyBits;
-    const int hi = __double2hiint(p) + (n << 20);
+    const int hi = __double2hiint(p) + ((N >> 4) << 20);
     return __hiloint2double(tiny ? 0 : hi, tiny ? 0 : __double2loint(p));
+}
+
+// The table lives in shared memory; call from the first 16 threads of a CTA before a barrier.
+__device__ __forceinline__ void load_exp2_table(double *tbl, int tid)
+{
+    if (tid < 16) tbl[tid] = c_exp2_table[tid];
 }
 
 // ----------------------------------------------------------------------------------------------

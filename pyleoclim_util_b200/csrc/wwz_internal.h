@@ -28,7 +28,7 @@ struct CellPlan {
     int64_t tiles;        // grid size for nf rows
 };
 
-CellPlan plan_cells(int64_t n, int64_t nt, int64_t nf, int cells_per_lane_hint);
+CellPlan plan_cells(int64_t n, int64_t nt, int64_t nf, int cells_per_lane_hint, int64_t seg_len);
 
 // Per-frequency constants: kappa = omega*sqrt(c*log2 e), dcut = underflow distance (windowing).
 cudaError_t launch_freq_setup(const double *d_omega, int64_t nf, double c, double *d_kappa, double *d_dcut,
@@ -40,11 +40,12 @@ cudaError_t launch_basis(const double *d_ts, const double *d_ys, int64_t n, int6
                          bool write_ty, cudaStream_t st);
 
 // The hot kernel: weighted sums for every (tau, f) cell of a frequency batch.
-// sums is [7][nt * nf_total] laid out like the outputs (cell = j*nf_total + k).
+// sums is [segs][7][nt * nf_total], each slab laid out like the outputs (cell = j*nf_total + k);
+// segment s covers points [s*seg_len, (s+1)*seg_len).
 cudaError_t launch_cells(const CellPlan &plan, const double2 *d_ty, const double2 *d_basis, const double *d_ts,
                          int64_t n, const double *d_tau, int64_t nt, const double *d_kappa,
                          const double *d_dcut, const int *d_unsorted, int64_t k0, int64_t nf_batch,
-                         int64_t nf_total, bool dense, double *d_sums, cudaStream_t st);
+                         int64_t nf_total, bool dense, int segs, int64_t seg_len, double *d_sums, cudaStream_t st);
 
 // *d_flag = 1 if d_x is not ascending (the windowed path needs a sorted time axis).
 cudaError_t launch_unsorted_check(const double *d_x, int64_t n, int *d_flag, cudaStream_t st);
@@ -53,7 +54,7 @@ cudaError_t launch_unsorted_check(const double *d_x, int64_t n, int *d_flag, cud
 cudaError_t launch_finalize(const double *d_sums, const double *d_tau, const double *d_omega, int64_t nt,
                             int64_t nf, double neff_thr, double *d_neffs, double *d_a0, double *d_a1,
                             double *d_a2, double *d_wwa, double *d_phase, int64_t out_row_stride,
-                            unsigned int *d_fix_count, unsigned int *d_fix_list, unsigned int fix_cap,
+                            unsigned int *d_fix_count, unsigned int *d_fix_list, unsigned int fix_cap, int segs,
                             cudaStream_t st);
 
 // Faithful two-pass evaluation (one warp per cell) of the cells in fix_list (count read on the

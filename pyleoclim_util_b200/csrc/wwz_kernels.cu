@@ -38,8 +38,8 @@ void bump_launch_counter(int64_t k) { g_launches.fetch_add(k); }
 
 // ------------------------------------------------------------------------------------------------
 // Per-frequency constants.
-//   kappa = omega * sqrt(c*log2(e))          so that  exp(-c*omega^2*d^2) = 2^(-(kappa*d)^2)
-//   dcut  = sqrt(1081)/|kappa|               |d| > dcut  =>  weight < 2^-1081, i.e. exactly 0.0
+//   kappa4 = 4*omega*sqrt(c*log2(e))         so that  exp(-c*omega^2*d^2) = 2^(-(kappa4*d)^2/16)
+//   dcut   = 4*sqrt(1081)/|kappa4|           |d| > dcut  =>  weight < 2^-1081, i.e. exactly 0.0
 //                                            (used only to window the point range of a tile)
 // omega = NaN (frequency above Nyquist, utils/wavelet.py:1229-1232): kappa = NaN is kept; NaN then
 // flows through every sum of the column and the epilogue yields NaN Neff / coefficients, exactly
@@ -53,14 +53,14 @@ __global__ void freq_setup_kernel(const double *__restrict__ omega, int64_t nf, 
     const double om = omega[k];
     const double ka = om * kscale;
     kappa[k] = ka;
-    dcut[k] = isnan(om) ? -1.0 : sqrt(1081.0) / fabs(ka);  // +inf for omega == 0
+    dcut[k] = isnan(om) ? -1.0 : 4.0 * sqrt(1081.0) / fabs(ka);  // +inf for omega == 0
 }
 
 cudaError_t launch_freq_setup(const double *d_omega, int64_t nf, double c, double *d_kappa, double *d_dcut,
                               cudaStream_t st)
 {
     if (nf <= 0) return cudaSuccess;
-    const double kscale = std::sqrt(c * 1.4426950408889634074);  // sqrt(c*log2(e))
+    const double kscale = 4.0 * std::sqrt(c * 1.4426950408889634074);  // 4*sqrt(c*log2(e))
     freq_setup_kernel<<<(unsigned)((nf + 127) / 128), 128, 0, st>>>(d_omega, nf, kscale, d_kappa, d_dcut);
     bump_launch_counter();
     return cudaGetLastError();
@@ -123,8 +123,14 @@ cudaError_t launch_basis(const double *d_ts, const double *d_ys, int64_t n, int6
 // through empty[] (one arrive per consumer warp).  Consumers read a point's (t, y) and its basis
 // record as warp-broadcast LDS.128.
 //
-// Arithmetic per (cell, point) on the FP64 pipe: DADD (t - tau), DMUL (kappa*d), 13 for the weight
-// (see gauss_weight), 7 accumulations = 22 instructions.
+// Arithmetic per (cell, point) on the FP64 pipe: DADD (t - tau), DMUL (kappa4*d), 10 for the weight
+// (see gauss_weight), 7 accumulations = 19 instructions.
+//
+// Point splitting.  Small grids have too few tiles to fill 148 SMs (config 1: 38 tiles), and even
+// config 2 has only 3.3 waves.  blockIdx.y selects a segment of the point axis (seg_len points,
+// fixed by n and the number of segments only); segment s accumulates into its own slab
+// sums[s][7][ncell] and the epilogue adds the slabs in order, so the result is deterministic and
+// independent of the tile geometry.
 //
 // Windowing (flag dense == 0).  ts is sorted, so the points whose weight is not exactly 0.0 for
 // any cell of the tile form one index range; chunks outside it are skipped.  Skipped points
@@ -139,8 +145,8 @@ struct CellArgs {
     const double *dcut;
     const int *unsorted;  // device flag: 1 if ts is not ascending (forces the dense path)
     double *sums;
-    long long n, n_pad, nslots, ncell_total;
-    int nt, G, P, nchunks, k0, nf_total;
+    long long n, n_pad, nslots, ncell_total, seg_len;
+    int nt, G, P, k0, nf_total;
     int row_stride2;    // basis row stride inside a stage, in double2 units
     int stage_stride2;  // stage stride in double2 units
     int dense;
@@ -155,7 +161,8 @@ __global__ void __launch_bounds__(kCellThreads, 2) wwz_cells_kernel(const CellAr
     uint64_t *const full = reinterpret_cast<uint64_t *>(tail);
     uint64_t *const empty = full + kStages;
     double *const red = reinterpret_cast<double *>(empty + kStages);  // [2][9]
-    int *const win = reinterpret_cast<int *>(red + 18);               // [2]
+    double *const tbl = red + 18;                                      // [16] 2^(j/16)
+    int *const win = reinterpret_cast<int *>(tbl + 16);               // [2]
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
@@ -168,6 +175,9 @@ __global__ void __launch_bounds__(kCellThreads, 2) wwz_cells_kernel(const CellAr
     const int k_last = (int)(qlast / a.G);
     const int Ft = k_last - k_first + 1;
     const int P = a.P;
+    // this CTA's segment of the point axis
+    const long long p0 = (long long)blockIdx.y * a.seg_len;
+    const long long p1 = min(a.n, p0 + a.seg_len);
 
     if (tid == 0) {
 #pragma unroll
@@ -177,6 +187,7 @@ __global__ void __launch_bounds__(kCellThreads, 2) wwz_cells_kernel(const CellAr
         }
         mbar_fence_init();
     }
+    load_exp2_table(tbl, tid);
 
     // ---- lane-slot parameters
     const long long q = q0 + tid;
@@ -208,8 +219,8 @@ __global__ void __launch_bounds__(kCellThreads, 2) wwz_cells_kernel(const CellAr
         }
     }
 
-    // ---- point window of the tile
-    int c_lo = 0, c_hi = a.nchunks;
+    // ---- point window of the tile, in chunks of P points counted from p0
+    int c_lo = 0, c_hi = (int)((p1 - p0 + P - 1) / P);
     const bool dense = a.dense || (a.unsorted && *a.unsorted);
     if (!dense) {
 #pragma unroll
@@ -243,8 +254,10 @@ __global__ void __launch_bounds__(kCellThreads, 2) wwz_cells_kernel(const CellAr
                 }
                 i1 = l;
             }
-            win[0] = (int)(i0 / P);
-            win[1] = (i1 > i0) ? (int)((i1 + P - 1) / P) : (int)(i0 / P);
+            i0 = max(i0, p0);
+            i1 = min(i1, p1);
+            win[0] = (i1 > i0) ? (int)((i0 - p0) / P) : 0;
+            win[1] = (i1 > i0) ? (int)((i1 - p0 + P - 1) / P) : 0;
         }
     }
     __syncthreads();
@@ -263,13 +276,13 @@ __global__ void __launch_bounds__(kCellThreads, 2) wwz_cells_kernel(const CellAr
             if (lane == 0) mbar_arrive_expect_tx(&full[s], bytes);
             __syncwarp();
             for (int r = lane; r <= Ft; r += 32) {
+                const size_t start = (size_t)p0 + (size_t)c * P;
                 if (r == 0) {
-                    tma_load_1d(st, a.ty + (size_t)c * P, (uint32_t)P * 16u, &full[s]);
+                    tma_load_1d(st, a.ty + start, (uint32_t)P * 16u, &full[s]);
                 } else {
                     const size_t row = (size_t)(k_first + r - 1);
                     tma_load_1d(st + P + (size_t)(r - 1) * a.row_stride2,
-                                a.basis + (row * (size_t)a.n_pad + (size_t)c * P) * 2, (uint32_t)P * 32u,
-                                &full[s]);
+                                a.basis + (row * (size_t)a.n_pad + start) * 2, (uint32_t)P * 32u, &full[s]);
                 }
             }
             if (++s == kStages) { s = 0; ++use; }
@@ -289,7 +302,7 @@ __global__ void __launch_bounds__(kCellThreads, 2) wwz_cells_kernel(const CellAr
             mbar_wait(&full[s], (uint32_t)use & 1u);
             const double2 *const st = stage_base + (size_t)s * a.stage_stride2;
             const double2 *const row = st + row_off;
-            const int cnt = (int)min((long long)P, a.n - (long long)c * P);
+            const int cnt = (int)min((long long)P, p1 - p0 - (long long)c * P);
 #pragma unroll 2
             for (int p = 0; p < cnt; ++p) {
                 const double2 t_y = st[p];
@@ -297,8 +310,8 @@ __global__ void __launch_bounds__(kCellThreads, 2) wwz_cells_kernel(const CellAr
                 const double2 ysc = row[2 * p + 1];
 #pragma unroll
                 for (int r = 0; r < M; ++r) {
-                    const double u = kap * (t_y.x - tau_r[r]);
-                    const double w = gauss_weight(u);
+                    const double v = kap * (t_y.x - tau_r[r]);
+                    const double w = gauss_weight(v, tbl);
                     W[r] += w;
                     Q[r] = fma(w, w, Q[r]);
                     Ws[r] = fma(w, sc.x, Ws[r]);
@@ -320,8 +333,8 @@ __global__ void __launch_bounds__(kCellThreads, 2) wwz_cells_kernel(const CellAr
         for (int r = 0; r < M; ++r) {
             const int j = g * M + r;
             if (j < a.nt) {
-                const size_t cell = (size_t)j * (size_t)a.nf_total + (size_t)kcol;
                 const size_t nc = (size_t)a.ncell_total;
+                const size_t cell = (size_t)blockIdx.y * (size_t)kNumSums * nc + (size_t)j * (size_t)a.nf_total + (size_t)kcol;
                 a.sums[0 * nc + cell] = W[r];
                 a.sums[1 * nc + cell] = Q[r];
                 a.sums[2 * nc + cell] = Ws[r];
@@ -334,7 +347,7 @@ __global__ void __launch_bounds__(kCellThreads, 2) wwz_cells_kernel(const CellAr
     }
 }
 
-CellPlan plan_cells(int64_t n, int64_t nt, int64_t nf, int cells_per_lane_hint)
+CellPlan plan_cells(int64_t n, int64_t nt, int64_t nf, int cells_per_lane_hint, int64_t seg_len)
 {
     CellPlan p{};
     int M = cells_per_lane_hint;
@@ -348,21 +361,23 @@ CellPlan plan_cells(int64_t n, int64_t nt, int64_t nf, int cells_per_lane_hint)
     p.ft_max = (int)ft;
     int64_t P = (kStageBudget - 32 * ft) / (16 + 32 * ft);
     if (P > kMaxPointsPerStage) P = kMaxPointsPerStage;
-    if (P > n) P = ((n + 7) / 8) * 8;
+    // at least ~4 chunks per point segment so that the 3-stage ring actually overlaps copy and compute
+    const int64_t span = seg_len > 0 ? std::min(seg_len, n) : n;
+    if (P > (span + 3) / 4) P = (((span + 3) / 4 + 7) / 8) * 8;
     if (P < 8) P = 8;
     p.points = (int)P;
-    p.n_pad = ((n + P - 1) / P) * P;
-    if (p.n_pad < P) p.n_pad = P;
+    p.n_pad = ((n + P + 15) / 16) * 16;   // a chunk may start at any segment boundary < n and spans P points
     p.row_stride = (P + 1) * 32;
     p.stage_bytes = (int)(P * 16 + ft * p.row_stride);
-    p.smem_bytes = kStages * p.stage_bytes + 2 * kStages * 8 + 18 * 8 + 16;
+    p.smem_bytes = kStages * p.stage_bytes + 2 * kStages * 8 + 18 * 8 + 16 * 8 + 16;
     const int64_t nslots = nf * (int64_t)p.groups;
     p.tiles = (nslots + kConsumerThreads - 1) / kConsumerThreads;
     return p;
 }
 
 template <int M>
-static cudaError_t launch_cells_m(const CellPlan &plan, const CellArgs &args, int64_t tiles, cudaStream_t st)
+static cudaError_t launch_cells_m(const CellPlan &plan, const CellArgs &args, int64_t tiles, int segs,
+                                  cudaStream_t st)
 {
     static int configured_smem = -1;
     if (plan.smem_bytes > configured_smem) {
@@ -371,7 +386,7 @@ static cudaError_t launch_cells_m(const CellPlan &plan, const CellArgs &args, in
         if (e != cudaSuccess) return e;
         configured_smem = plan.smem_bytes;
     }
-    wwz_cells_kernel<M><<<(unsigned)tiles, kCellThreads, plan.smem_bytes, st>>>(args);
+    wwz_cells_kernel<M><<<dim3((unsigned)tiles, (unsigned)segs), kCellThreads, plan.smem_bytes, st>>>(args);
     bump_launch_counter();
     return cudaGetLastError();
 }
@@ -379,7 +394,7 @@ static cudaError_t launch_cells_m(const CellPlan &plan, const CellArgs &args, in
 cudaError_t launch_cells(const CellPlan &plan, const double2 *d_ty, const double2 *d_basis, const double *d_ts,
                          int64_t n, const double *d_tau, int64_t nt, const double *d_kappa,
                          const double *d_dcut, const int *d_unsorted, int64_t k0, int64_t nf_batch,
-                         int64_t nf_total, bool dense, double *d_sums, cudaStream_t st)
+                         int64_t nf_total, bool dense, int segs, int64_t seg_len, double *d_sums, cudaStream_t st)
 {
     if (nf_batch <= 0 || nt <= 0) return cudaSuccess;
     CellArgs a{};
@@ -398,7 +413,7 @@ cudaError_t launch_cells(const CellPlan &plan, const double2 *d_ty, const double
     a.nt = (int)nt;
     a.G = plan.groups;
     a.P = plan.points;
-    a.nchunks = (int)((n + plan.points - 1) / plan.points);
+    a.seg_len = seg_len;
     a.k0 = (int)k0;
     a.nf_total = (int)nf_total;
     a.row_stride2 = (int)(plan.row_stride / 16);
@@ -406,9 +421,9 @@ cudaError_t launch_cells(const CellPlan &plan, const double2 *d_ty, const double
     a.dense = dense ? 1 : 0;
     const int64_t tiles = (a.nslots + kConsumerThreads - 1) / kConsumerThreads;
     switch (plan.cells_per_lane) {
-        case 1: return launch_cells_m<1>(plan, a, tiles, st);
-        case 4: return launch_cells_m<4>(plan, a, tiles, st);
-        default: return launch_cells_m<2>(plan, a, tiles, st);
+        case 1: return launch_cells_m<1>(plan, a, tiles, segs, st);
+        case 4: return launch_cells_m<4>(plan, a, tiles, segs, st);
+        default: return launch_cells_m<2>(plan, a, tiles, segs, st);
     }
 }
 
@@ -440,13 +455,22 @@ __global__ void finalize_kernel(const double *__restrict__ sums, const double *_
                                 double *__restrict__ neffs, double *__restrict__ a0o, double *__restrict__ a1o,
                                 double *__restrict__ a2o, double *__restrict__ wwa, double *__restrict__ phase,
                                 int64_t row_stride, unsigned int *__restrict__ fix_count,
-                                unsigned int *__restrict__ fix_list, unsigned int fix_cap)
+                                unsigned int *__restrict__ fix_list, unsigned int fix_cap, int segs)
 {
     const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int64_t nc = nt * nf;
     if (idx >= nc) return;
     const int64_t j = idx / nf, k = idx - j * nf;
-    const double W = sums[idx], Q = sums[nc + idx];
+    // add the point-segment slabs in order
+    double acc[kNumSums];
+#pragma unroll
+    for (int x = 0; x < kNumSums; ++x) acc[x] = sums[(size_t)x * nc + idx];
+    for (int sg = 1; sg < segs; ++sg) {
+        const double *slab = sums + (size_t)sg * kNumSums * nc;
+#pragma unroll
+        for (int x = 0; x < kNumSums; ++x) acc[x] += slab[(size_t)x * nc + idx];
+    }
+    const double W = acc[0], Q = acc[1];
     if (fix_list && (W < 0x1p-500 || Q < 0x1p-1000)) {
         const unsigned int slot = atomicAdd(fix_count, 1u);
         if (slot < fix_cap) fix_list[slot] = (unsigned int)idx;
@@ -454,8 +478,7 @@ __global__ void finalize_kernel(const double *__restrict__ sums, const double *_
     const double neff = W * W / Q;
     double a0 = CUDART_NAN, a1 = CUDART_NAN, a2 = CUDART_NAN;
     if (neff > thr) {
-        const double Ws = sums[2 * nc + idx], Wc = sums[3 * nc + idx], Wy = sums[4 * nc + idx];
-        const double Wys = sums[5 * nc + idx], Wyc = sums[6 * nc + idx];
+        const double Ws = acc[2], Wc = acc[3], Wy = acc[4], Wys = acc[5], Wyc = acc[6];
         const double Y = Wy / W, S = Ws / W, C = Wc / W, YS = Wys / W, YC = Wyc / W;
         const double cyc = YC - Y * C;
         const double cys = YS - Y * S;
@@ -508,14 +531,14 @@ __global__ void __launch_bounds__(128)
 cudaError_t launch_finalize(const double *d_sums, const double *d_tau, const double *d_omega, int64_t nt,
                             int64_t nf, double neff_thr, double *d_neffs, double *d_a0, double *d_a1,
                             double *d_a2, double *d_wwa, double *d_phase, int64_t out_row_stride,
-                            unsigned int *d_fix_count, unsigned int *d_fix_list, unsigned int fix_cap,
+                            unsigned int *d_fix_count, unsigned int *d_fix_list, unsigned int fix_cap, int segs,
                             cudaStream_t st)
 {
     const int64_t nc = nt * nf;
     if (nc <= 0) return cudaSuccess;
     finalize_kernel<<<(unsigned)((nc + 255) / 256), 256, 0, st>>>(d_sums, d_tau, d_omega, nt, nf, neff_thr, d_neffs,
                                                                   d_a0, d_a1, d_a2, d_wwa, d_phase, out_row_stride,
-                                                                  d_fix_count, d_fix_list, fix_cap);
+                                                                  d_fix_count, d_fix_list, fix_cap, segs);
     bump_launch_counter();
     return cudaGetLastError();
 }
@@ -651,17 +674,20 @@ cudaError_t launch_minmax(const double *d_x, int64_t n, double *d_out, cudaStrea
 }
 
 // ------------------------------------------------------------------------------------------------
-// FP64 FMA peak: 8 independent register-resident DFMA chains per thread.
+// FP64 FMA peak: 8 independent register-resident DFMA chains per thread.  Each DFMA reads two
+// distinct registers and an immediate: a DFMA with three distinct register operands is limited by
+// register-file bandwidth to 2/3 of the pipe rate on sm_100a (tools/fp64_micro.cu), and even
+// fma(a, m, b) with m, b shared between the chains only reaches 92%.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, int iters, double x0)
 {
     double a0 = x0, a1 = x0 + 1, a2 = x0 + 2, a3 = x0 + 3, a4 = x0 + 4, a5 = x0 + 5, a6 = x0 + 6, a7 = x0 + 7;
-    const double m = 0.999999, b = 1e-9;
+    const double m = 0.999999 + x0 * 1e-12;
     for (int i = 0; i < iters; ++i) {
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-            a0 = fma(a0, m, b); a1 = fma(a1, m, b); a2 = fma(a2, m, b); a3 = fma(a3, m, b);
-            a4 = fma(a4, m, b); a5 = fma(a5, m, b); a6 = fma(a6, m, b); a7 = fma(a7, m, b);
+            a0 = fma(a0, m, 1e-9); a1 = fma(a1, m, 1e-9); a2 = fma(a2, m, 1e-9); a3 = fma(a3, m, 1e-9);
+            a4 = fma(a4, m, 1e-9); a5 = fma(a5, m, 1e-9); a6 = fma(a6, m, 1e-9); a7 = fma(a7, m, 1e-9);
         }
     }
     const double r = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;

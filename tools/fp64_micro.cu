@@ -1,0 +1,58 @@
+// FP64 pipe microbenchmarks (developer tool): which operand forms sustain the DFMA peak on sm_100a?
+#include <cstdio>
+#include <cuda_runtime.h>
+__constant__ double cc[16];
+#define CH 8
+template <int V> __global__ void __launch_bounds__(256) k(double* out, int iters, double x0, const double* g) {
+    double a[CH], x[CH], y[CH];
+    for (int j = 0; j < CH; ++j) { a[j] = x0 + j; x[j] = g[j] + threadIdx.x * 1e-9; y[j] = g[8 + j] - threadIdx.x * 1e-9; }
+    const double m = g[16], b = g[17];
+    int n = (int)g[18];
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+#pragma unroll
+            for (int j = 0; j < CH; ++j) {
+                if (V == 0) a[j] = fma(a[j], m, b);                 // 1 private + 2 shared registers
+                if (V == 1) a[j] = fma(x[j], y[j], a[j]);           // 3 distinct registers
+                if (V == 2) a[j] = fma(a[j], x[j], cc[(j + u) & 15]); // constant-bank operand
+                if (V == 3) a[j] = a[j] + x[j];                     // DADD
+                if (V == 4) a[j] = fma(a[j], x[j], 6755399441055744.0); // immediate operand
+                if (V == 5) { a[j] = fma(x[j], y[j], a[j]); n = n * 1048576 + j; }  // + 1 IMAD per DFMA
+                if (V == 6) { a[j] = fma(x[j], y[j], a[j]); if ((j & 1) == 0) n = n * 1048576 + j; } // + 1 IMAD per 2 DFMA
+                if (V == 7) a[j] = fma(a[j], a[j], a[j]);           // same register thrice
+                if (V == 8) a[j] = a[j] * x[j];                     // DMUL
+            }
+        }
+    }
+    double r = 0; for (int j = 0; j < CH; ++j) r += a[j];
+    if (r == 123.456 || n == 77) out[0] = r + n;
+}
+template <int V> void run(const char* name, double* d_out, double* d_g) {
+    int sms; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    const int blocks = sms * 8, iters = 1 << 12;
+    cudaEvent_t t0, t1; cudaEventCreate(&t0); cudaEventCreate(&t1);
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(t0); k<V><<<blocks, 256>>>(d_out, iters, 1.0 + rep, d_g); cudaEventRecord(t1); cudaEventSynchronize(t1);
+        float t; cudaEventElapsedTime(&t, t0, t1); if (rep >= 1 && t < best) best = t;
+    }
+    double inst = (double)iters * 4 * CH * blocks * 256;
+    printf("%-44s %8.3f ms  %7.2f Tinst/s (lane-ops)  = %.1f%% of 148*64*1.965e9\n", name, best, inst / (best * 1e-3) / 1e12,
+           100.0 * inst / (best * 1e-3) / (148.0 * 64 * 1.965e9));
+}
+int main() {
+    double h[19]; for (int i = 0; i < 19; ++i) h[i] = 0.999 + i * 1e-6; h[16] = 0.999999; h[17] = 1e-9; h[18] = 3;
+    double *d_g, *d_out; cudaMalloc(&d_g, sizeof h); cudaMalloc(&d_out, 8); cudaMemcpy(d_g, h, sizeof h, cudaMemcpyHostToDevice);
+    double hc[16]; for (int i = 0; i < 16; ++i) hc[i] = 1e-9 * i; cudaMemcpyToSymbol(cc, hc, sizeof hc);
+    run<0>("DFMA a=fma(a,m,b) (shared m,b)", d_out, d_g);
+    run<1>("DFMA a=fma(x,y,a) (3 distinct regs)", d_out, d_g);
+    run<2>("DFMA a=fma(a,x,c[]) (constant bank)", d_out, d_g);
+    run<3>("DADD a=a+x", d_out, d_g);
+    run<4>("DFMA a=fma(a,x,imm)", d_out, d_g);
+    run<5>("DFMA 3 regs + 1 IMAD each", d_out, d_g);
+    run<6>("DFMA 3 regs + 1 IMAD per 2", d_out, d_g);
+    run<7>("DFMA a=fma(a,a,a)", d_out, d_g);
+    run<8>("DMUL a=a*x", d_out, d_g);
+    return 0;
+}
