@@ -44,10 +44,13 @@ extern "C" {
 #define WWZB200_ERR_NOMEM (-3) /* host or device allocation failure */
 
 /* flags */
-#define WWZB200_DENSE 1u        /* evaluate every (cell, point) pair; default skips point chunks \
-                                   whose weights are all exactly 0.0 in fp64 (bit-identical) */
+#define WWZB200_DENSE 1u        /* evaluate every (cell, point) pair with its own exp2: no windowing  \
+                                   (the default skips point chunks whose weights are all exactly 0.0, \
+                                   bit-identical) and no tau-recurrence */
 #define WWZB200_STANDARDIZE 2u  /* batched entry points: z-score every series on the device       \
                                    (utils/tsutils.py:1134-1154, ddof=0, eps=1e-3 guard) */
+#define WWZB200_NO_RECURRENCE 8u /* keep one exp2 per (cell, point): do not use the tau-recurrence kernel \
+                                   (equally spaced tau, frequency rows with kappa*dtau small) */
 #define WWZB200_FAITHFUL 4u     /* validation mode: evaluate every cell with the reference's own    \
                                    two-pass expressions (utils/wavelet.py:988-1032), one warp per   \
                                    cell; ~10x slower, agrees with kirchner_numba to ~1e-12 */

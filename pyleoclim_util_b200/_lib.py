@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libwwz_b200.so")
 DENSE = 1
 STANDARDIZE = 2
 FAITHFUL = 4
+NO_RECURRENCE = 8
 
 _dp = ctypes.POINTER(ctypes.c_double)
 _ip = ctypes.POINTER(ctypes.c_int64)

@@ -434,7 +434,7 @@ __global__ void flag_cells_kernel(const double *__restrict__ wq, int64_t ncell, 
     const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (idx >= ncell) return;
     const double W = wq[idx], Q = wq[ncell + idx];
-    if (W < 0x1p-500 || Q < 0x1p-1000) list[atomicAdd(count, 1u)] = (unsigned int)idx;
+    if (W < 0x1p-200 || Q < 0x1p-400) list[atomicAdd(count, 1u)] = (unsigned int)idx;
 }
 
 template <int NS>

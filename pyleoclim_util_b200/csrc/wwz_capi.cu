@@ -144,12 +144,39 @@ int cells_per_lane_hint(int64_t nt, int64_t nf, int sms)
     return tiles2 >= 4 * (int64_t)sms ? 2 : 1;
 }
 
+// tau-recurrence applicability (wwz_cells_kernel<8, true>): tau must be equally spaced (to 8 ulp) and
+// long enough, and a frequency row qualifies while D = kappa4*dtau <= 8: the recurrence runs from
+// the first of the lane's 8 cells, so a weight is dropped (w_0 flushed at |a| > 127.8) only when every
+// one of the 8 cells sees it below 2^(-(127.8 - 7*8)^2/16) = 2^-322 -- far below the 2^-200 threshold
+// under which the epilogue hands a cell to the faithful kernel.  Rows are taken as a prefix
+// (frequencies normally ascend); the rest of the rows run the direct kernel.
+// Returns the number of leading rows for the recurrence kernel and the spacing in *dtau.
+int64_t rec_rows_prefix(const double *h_tau, int64_t nt, const double *h_omega, int64_t nf, double c, double *dtau)
+{
+    *dtau = 0.0;
+    if (nt < 2 * wwz::kRecCells || nf < 1) return 0;
+    const char *e = getenv("WWZB200_NO_RECURRENCE");
+    if (e && *e && atoi(e)) return 0;
+    const double d = (h_tau[nt - 1] - h_tau[0]) / (double)(nt - 1);
+    if (!(d > 0) || !std::isfinite(d)) return 0;
+    const double scale = std::max(std::fabs(h_tau[0]), std::fabs(h_tau[nt - 1]));
+    const double tol = 8.0 * std::ldexp(scale > 0 ? scale : 1.0, -52);
+    for (int64_t j = 0; j < nt; ++j)
+        if (!(std::fabs(h_tau[j] - (h_tau[0] + (double)j * d)) <= tol)) return 0;
+    const double kscale = 4.0 * std::sqrt(c * 1.4426950408889634074);
+    int64_t k = 0;
+    while (k < nf && std::fabs(h_omega[k]) * kscale * d <= 8.0) ++k;   // NaN omega stops the prefix
+    *dtau = d;
+    return k;
+}
+
 // The transform on device-resident inputs.  Outputs may alias caller memory (row stride given).
 // d_psd != NULL adds the wwa2psd reduction; tspan < 0 means "take max-min of d_ts on the device".
 int transform_device(Workspace *w, const double *d_ts, const double *d_ys, int64_t n, const double *d_tau,
                      int64_t nt, const double *d_omega, int64_t nf, double c, int64_t thr, int64_t psd_thr,
                      uint32_t flags, double *d_neffs, double *d_a0, double *d_a1, double *d_a2, double *d_wwa,
-                     double *d_phase, double *d_psd, int64_t row_stride, double tspan, cudaStream_t st)
+                     double *d_phase, double *d_psd, int64_t row_stride, double tspan, cudaStream_t st,
+                     const double *h_tau = nullptr, const double *h_omega = nullptr)
 {
     using namespace wwz;
     const int64_t ncell = nt * nf;
@@ -177,7 +204,28 @@ int transform_device(Workspace *w, const double *d_ts, const double *d_ys, int64
     } else {
         const int segs = point_segments(n, ncell);
         const int64_t seg_len = (((n + segs - 1) / segs + 15) / 16) * 16;
-        const CellPlan plan = plan_cells(n, nt, nf, cells_per_lane_hint(nt, nf, w->sms), seg_len);
+        CellPlan plan = plan_cells(n, nt, nf, cells_per_lane_hint(nt, nf, w->sms), seg_len);
+        // rows [0, k_rec) go to the tau-recurrence kernel (needs the grid on the host)
+        int64_t k_rec = 0;
+        double dtau = 0.0;
+        CellPlan rplan = plan;
+        if (!(flags & (WWZB200_DENSE | WWZB200_NO_RECURRENCE)) && nt >= 2 * kRecCells) {
+            std::vector<double> hbuf;
+            if (!h_tau || !h_omega) {
+                hbuf.resize((size_t)(nt + nf));
+                CU(cudaMemcpyAsync(hbuf.data(), d_tau, sizeof(double) * nt, cudaMemcpyDeviceToHost, st));
+                CU(cudaMemcpyAsync(hbuf.data() + nt, d_omega, sizeof(double) * nf, cudaMemcpyDeviceToHost, st));
+                CU(cudaStreamSynchronize(st));
+                h_tau = hbuf.data();
+                h_omega = hbuf.data() + nt;
+            }
+            k_rec = rec_rows_prefix(h_tau, nt, h_omega, nf, c, &dtau);
+            if (k_rec > 0) {
+                rplan = plan_cells(n, nt, nf, kRecCells, seg_len);
+                const int64_t np = std::max(plan.n_pad, rplan.n_pad);   // one row stride for both kernels
+                plan.n_pad = rplan.n_pad = np;
+            }
+        }
         size_t per_row = (size_t)plan.n_pad * 32;
         int64_t nf_batch = (int64_t)std::max<size_t>(1, basis_budget_bytes() / per_row);
         nf_batch = std::min<int64_t>(std::min<int64_t>(nf_batch, nf), 65535);
@@ -199,8 +247,15 @@ int transform_device(Workspace *w, const double *d_ts, const double *d_ys, int64
                 CU(cudaEventCreate(&ev.b));
                 CU(cudaEventRecord(ev.a, st));
             }
-            CU(launch_cells(plan, d_ty, d_basis, d_ts, n, d_tau, nt, d_kappa, d_dcut, d_unsorted, k0, nb, nf, dense,
-                            segs, seg_len, d_sums, st));
+            const int64_t nrec = std::max<int64_t>(0, std::min<int64_t>(k_rec - k0, nb));   // recurrence rows of this batch
+            if (nrec > 0)
+                CU(launch_cells(rplan, d_ty, d_basis, d_ts, n, d_tau, nt, d_kappa, d_dcut, d_unsorted, k0, nrec, nf,
+                                dense, segs, seg_len, dtau, d_sums, st));
+            if (nb > nrec)
+                CU(launch_cells(plan, d_ty, d_basis + (size_t)nrec * (size_t)plan.n_pad * 2, d_ts, n, d_tau, nt,
+                                d_kappa, d_dcut, d_unsorted, k0 + nrec, nb - nrec, nf, dense, segs, seg_len, 0.0,
+                                d_sums, st));
+
             if (g_profile) {
                 CU(cudaEventRecord(ev.b, st));
                 g_events.push_back(ev);
@@ -262,7 +317,7 @@ int host_transform(const double *ts, const double *ys, int64_t n, const double *
         const auto mm = std::minmax_element(ts, ts + n);
         tspan = *mm.second - *mm.first;   // utils/wavelet.py:1270 (np.max(ts)-np.min(ts))
     }
-    rc = transform_device(w, d_ts, d_ys, n, d_tau, nt, d_om, nf, c, thr, psd_thr, flags, o_neff, o_a0, o_a1, o_a2, o_wwa, o_ph, psd ? o_psd : nullptr, nf, tspan, st);
+    rc = transform_device(w, d_ts, d_ys, n, d_tau, nt, d_om, nf, c, thr, psd_thr, flags, o_neff, o_a0, o_a1, o_a2, o_wwa, o_ph, psd ? o_psd : nullptr, nf, tspan, st, tau, om);
     if (rc) return rc;
     const size_t cb = sizeof(double) * (size_t)ncell;
     if (ncell) {
@@ -718,7 +773,8 @@ int wwzb200_kirchner_ragged(const double *ts, const double *pd_ys, const int64_t
         }
         rc = transform_device(w, d_ts + t0, d_ys + t0, n, d_tau + u0, nt, d_om + f0, nf, c, Neff_threshold,
                               psd_Neff_threshold, flags, o[0] + c0, o[1] + c0, o[2] + c0, o[3] + c0, o[4] + c0,
-                              o[5] + c0, psd ? o_psd + f0 : nullptr, nf, tspan, st);
+                              o[5] + c0, psd ? o_psd + f0 : nullptr, nf, tspan, st, taus + tau_off[m],
+                              omegas + om_off[m]);
         if (rc) return rc;
     }
     double *h[6] = {Neffs, a0, a1, a2, wwa, phase};

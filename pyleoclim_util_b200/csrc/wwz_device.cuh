@@ -124,6 +124,44 @@ __device__ __forceinline__ double gauss_weight(double v, const double *__restric
     return __hiloint2double(tiny ? 0 : hi, tiny ? 0 : __double2loint(p));
 }
 
+// Weight of the first of M tau-adjacent cells and the ratio between neighbours (tau-recurrence).
+//
+// For equally spaced tau_m = tau_0 + m*dtau:  v_m = a - m*D  with a = kappa4*(t - tau_0), D = kappa4*dtau,
+//   w_m = 2^(-v_m^2/16) = w_0 * rho^m * h_m,   rho = 2^(a*D/8) = 2^(b/16) with b = 2*D*a,
+//   h_m = 2^(-m^2 D^2/16)  (depends on the cell only: applied once in the epilogue).
+// rho costs a second exp2 per (lane, point) but then every further cell of the lane costs one DMUL
+// instead of an exp2.  When w_0 is flushed (|a| > 127.8) rho is forced to 0 as well, so that the
+// products stay 0 instead of 0*inf; with D <= 8 and M <= 8 every weight dropped that way is below
+// 2^-320 (see rec_rows_prefix in wwz_capi.cu).
+__device__ __forceinline__ void gauss_weight_ratio(double a, double step16, const double *__restrict__ tbl,
+                                                   double &w0, double &rho)
+{
+    const double z = fma(-a, a, kShift);
+    const double Nf = z - kShift;
+    const double g = fma(-a, a, -Nf);
+    const int N = __double2loint(z);
+    const double b = a * step16;
+    const double zr = b + kShift;
+    const double Nrf = zr - kShift;
+    const double gr = b - Nrf;
+    const int Nr = __double2loint(zr);
+    const double T = tbl[N & 15], Tr = tbl[Nr & 15];
+    double p = c_exp2t[6], pr = c_exp2t[6];
+    p = fma(p, g, c_exp2t[5]);  pr = fma(pr, gr, c_exp2t[5]);
+    p = fma(p, g, c_exp2t[4]);  pr = fma(pr, gr, c_exp2t[4]);
+    p = fma(p, g, c_exp2t[3]);  pr = fma(pr, gr, c_exp2t[3]);
+    p = fma(p, g, c_exp2t[2]);  pr = fma(pr, gr, c_exp2t[2]);
+    p = fma(p, g, c_exp2t[1]);  pr = fma(pr, gr, c_exp2t[1]);
+    p = fma(p, g, c_exp2t[0]);  pr = fma(pr, gr, c_exp2t[0]);
+    p *= T;
+    pr *= Tr;
+    const bool tiny = __double_as_longlong(z) < kTinyBits;
+    const int hi = __double2hiint(p) + ((N >> 4) << 20);
+    const int hir = __double2hiint(pr) + ((Nr >> 4) << 20);
+    w0 = __hiloint2double(tiny ? 0 : hi, tiny ? 0 : __double2loint(p));
+    rho = __hiloint2double(tiny ? 0 : hir, tiny ? 0 : __double2loint(pr));
+}
+
 // The table lives in shared memory; call from the first 16 threads of a CTA before a barrier.
 __device__ __forceinline__ void load_exp2_table(double *tbl, int tid)
 {

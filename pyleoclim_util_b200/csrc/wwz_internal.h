@@ -13,6 +13,7 @@ constexpr int kStages = 3;
 constexpr int kNumSums = 7;  // W, Q, Ws, Wc, Wy, Wys, Wyc
 constexpr int kStageBudget = 32 * 1024;
 constexpr int kMaxPointsPerStage = 512;
+constexpr int kRecCells = 8;     // tau-adjacent cells per lane in the tau-recurrence kernel
 constexpr int kSurrBlock = 16;   // series per CTA in the shared-time-axis kernel
 
 // Geometry of one launch of the cell kernel, derived on the host by plan_cells().
@@ -45,7 +46,8 @@ cudaError_t launch_basis(const double *d_ts, const double *d_ys, int64_t n, int6
 cudaError_t launch_cells(const CellPlan &plan, const double2 *d_ty, const double2 *d_basis, const double *d_ts,
                          int64_t n, const double *d_tau, int64_t nt, const double *d_kappa,
                          const double *d_dcut, const int *d_unsorted, int64_t k0, int64_t nf_batch,
-                         int64_t nf_total, bool dense, int segs, int64_t seg_len, double *d_sums, cudaStream_t st);
+                         int64_t nf_total, bool dense, int segs, int64_t seg_len, double dtau, double *d_sums,
+                         cudaStream_t st);
 
 // *d_flag = 1 if d_x is not ascending (the windowed path needs a sorted time axis).
 cudaError_t launch_unsorted_check(const double *d_x, int64_t n, int *d_flag, cudaStream_t st);

@@ -150,10 +150,15 @@ struct CellArgs {
     int row_stride2;    // basis row stride inside a stage, in double2 units
     int stage_stride2;  // stage stride in double2 units
     int dense;
+    double dtau;        // REC kernels: the (uniform) tau spacing
 };
 
-template <int M>
-__global__ void __launch_bounds__(kCellThreads, 2) wwz_cells_kernel(const CellArgs a)
+// REC = true: tau-recurrence flavour.  The lane's M tau-adjacent cells share one exp2 for the first
+// cell and one for the neighbour ratio per point (gauss_weight_ratio); the sums are accumulated with
+// the unscaled weights w_0*rho^m and multiplied by the per-cell constant h_m (h_m^2 for Q) when
+// they are stored.  Only for equally spaced tau and rows with kappa4*dtau <= 8 (host decides).
+template <int M, bool REC>
+__global__ void __launch_bounds__(kCellThreads, REC ? 1 : 2) wwz_cells_kernel(const CellArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double2 *const stage_base = reinterpret_cast<double2 *>(smem_raw);
@@ -303,22 +308,45 @@ __global__ void __launch_bounds__(kCellThreads, 2) wwz_cells_kernel(const CellAr
             const double2 *const st = stage_base + (size_t)s * a.stage_stride2;
             const double2 *const row = st + row_off;
             const int cnt = (int)min((long long)P, p1 - p0 - (long long)c * P);
-#pragma unroll 2
-            for (int p = 0; p < cnt; ++p) {
-                const double2 t_y = st[p];
-                const double2 sc = row[2 * p];
-                const double2 ysc = row[2 * p + 1];
+            if (REC) {
+                const double step16 = 2.0 * kap * a.dtau;
+#pragma unroll 1
+                for (int p = 0; p < cnt; ++p) {
+                    const double2 t_y = st[p];
+                    const double2 sc = row[2 * p];
+                    const double2 ysc = row[2 * p + 1];
+                    double w, rho;
+                    gauss_weight_ratio(kap * (t_y.x - tau_r[0]), step16, tbl, w, rho);
 #pragma unroll
-                for (int r = 0; r < M; ++r) {
-                    const double v = kap * (t_y.x - tau_r[r]);
-                    const double w = gauss_weight(v, tbl);
-                    W[r] += w;
-                    Q[r] = fma(w, w, Q[r]);
-                    Ws[r] = fma(w, sc.x, Ws[r]);
-                    Wc[r] = fma(w, sc.y, Wc[r]);
-                    Wy[r] = fma(w, t_y.y, Wy[r]);
-                    Wys[r] = fma(w, ysc.x, Wys[r]);
-                    Wyc[r] = fma(w, ysc.y, Wyc[r]);
+                    for (int r = 0; r < M; ++r) {
+                        W[r] += w;
+                        Q[r] = fma(w, w, Q[r]);
+                        Ws[r] = fma(w, sc.x, Ws[r]);
+                        Wc[r] = fma(w, sc.y, Wc[r]);
+                        Wy[r] = fma(w, t_y.y, Wy[r]);
+                        Wys[r] = fma(w, ysc.x, Wys[r]);
+                        Wyc[r] = fma(w, ysc.y, Wyc[r]);
+                        w *= rho;
+                    }
+                }
+            } else {
+#pragma unroll 2
+                for (int p = 0; p < cnt; ++p) {
+                    const double2 t_y = st[p];
+                    const double2 sc = row[2 * p];
+                    const double2 ysc = row[2 * p + 1];
+#pragma unroll
+                    for (int r = 0; r < M; ++r) {
+                        const double v = kap * (t_y.x - tau_r[r]);
+                        const double w = gauss_weight(v, tbl);
+                        W[r] += w;
+                        Q[r] = fma(w, w, Q[r]);
+                        Ws[r] = fma(w, sc.x, Ws[r]);
+                        Wc[r] = fma(w, sc.y, Wc[r]);
+                        Wy[r] = fma(w, t_y.y, Wy[r]);
+                        Wys[r] = fma(w, ysc.x, Wys[r]);
+                        Wyc[r] = fma(w, ysc.y, Wyc[r]);
+                    }
                 }
             }
             __syncwarp();
@@ -329,19 +357,22 @@ __global__ void __launch_bounds__(kCellThreads, 2) wwz_cells_kernel(const CellAr
 
     if (slot_ok) {
         const long long kcol = (long long)a.k0 + k_first + k_loc;
+        const double D = kap * a.dtau;
 #pragma unroll
         for (int r = 0; r < M; ++r) {
             const int j = g * M + r;
             if (j < a.nt) {
                 const size_t nc = (size_t)a.ncell_total;
                 const size_t cell = (size_t)blockIdx.y * (size_t)kNumSums * nc + (size_t)j * (size_t)a.nf_total + (size_t)kcol;
-                a.sums[0 * nc + cell] = W[r];
-                a.sums[1 * nc + cell] = Q[r];
-                a.sums[2 * nc + cell] = Ws[r];
-                a.sums[3 * nc + cell] = Wc[r];
-                a.sums[4 * nc + cell] = Wy[r];
-                a.sums[5 * nc + cell] = Wys[r];
-                a.sums[6 * nc + cell] = Wyc[r];
+                // REC: undo the per-cell scale h_r = 2^(-(r D)^2/16) that was factored out of the weights
+                const double h = REC ? exp2(-(double)(r * r) * D * D * 0.0625) : 1.0;
+                a.sums[0 * nc + cell] = W[r] * h;
+                a.sums[1 * nc + cell] = Q[r] * h * h;
+                a.sums[2 * nc + cell] = Ws[r] * h;
+                a.sums[3 * nc + cell] = Wc[r] * h;
+                a.sums[4 * nc + cell] = Wy[r] * h;
+                a.sums[5 * nc + cell] = Wys[r] * h;
+                a.sums[6 * nc + cell] = Wyc[r] * h;
             }
         }
     }
@@ -351,8 +382,8 @@ CellPlan plan_cells(int64_t n, int64_t nt, int64_t nf, int cells_per_lane_hint, 
 {
     CellPlan p{};
     int M = cells_per_lane_hint;
-    if (M != 1 && M != 2 && M != 4) M = 2;
-    if (nt < M) M = 1;
+    if (M != 1 && M != 2 && M != 4 && M != kRecCells) M = 2;
+    if (nt < M && M != kRecCells) M = 1;
     p.cells_per_lane = M;
     p.groups = (int)((nt + M - 1) / M);
     int64_t ft = (kConsumerThreads + p.groups - 1) / p.groups + 1;
@@ -375,18 +406,18 @@ CellPlan plan_cells(int64_t n, int64_t nt, int64_t nf, int cells_per_lane_hint, 
     return p;
 }
 
-template <int M>
+template <int M, bool REC>
 static cudaError_t launch_cells_m(const CellPlan &plan, const CellArgs &args, int64_t tiles, int segs,
                                   cudaStream_t st)
 {
     static int configured_smem = -1;
     if (plan.smem_bytes > configured_smem) {
-        cudaError_t e = cudaFuncSetAttribute(wwz_cells_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(wwz_cells_kernel<M, REC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              plan.smem_bytes);
         if (e != cudaSuccess) return e;
         configured_smem = plan.smem_bytes;
     }
-    wwz_cells_kernel<M><<<dim3((unsigned)tiles, (unsigned)segs), kCellThreads, plan.smem_bytes, st>>>(args);
+    wwz_cells_kernel<M, REC><<<dim3((unsigned)tiles, (unsigned)segs), kCellThreads, plan.smem_bytes, st>>>(args);
     bump_launch_counter();
     return cudaGetLastError();
 }
@@ -394,7 +425,8 @@ static cudaError_t launch_cells_m(const CellPlan &plan, const CellArgs &args, in
 cudaError_t launch_cells(const CellPlan &plan, const double2 *d_ty, const double2 *d_basis, const double *d_ts,
                          int64_t n, const double *d_tau, int64_t nt, const double *d_kappa,
                          const double *d_dcut, const int *d_unsorted, int64_t k0, int64_t nf_batch,
-                         int64_t nf_total, bool dense, int segs, int64_t seg_len, double *d_sums, cudaStream_t st)
+                         int64_t nf_total, bool dense, int segs, int64_t seg_len, double dtau, double *d_sums,
+                         cudaStream_t st)
 {
     if (nf_batch <= 0 || nt <= 0) return cudaSuccess;
     CellArgs a{};
@@ -419,11 +451,13 @@ cudaError_t launch_cells(const CellPlan &plan, const double2 *d_ty, const double
     a.row_stride2 = (int)(plan.row_stride / 16);
     a.stage_stride2 = plan.stage_bytes / 16;
     a.dense = dense ? 1 : 0;
+    a.dtau = dtau;
     const int64_t tiles = (a.nslots + kConsumerThreads - 1) / kConsumerThreads;
     switch (plan.cells_per_lane) {
-        case 1: return launch_cells_m<1>(plan, a, tiles, segs, st);
-        case 4: return launch_cells_m<4>(plan, a, tiles, segs, st);
-        default: return launch_cells_m<2>(plan, a, tiles, segs, st);
+        case 1: return launch_cells_m<1, false>(plan, a, tiles, segs, st);
+        case 4: return launch_cells_m<4, false>(plan, a, tiles, segs, st);
+        case kRecCells: return launch_cells_m<kRecCells, true>(plan, a, tiles, segs, st);
+        default: return launch_cells_m<2, false>(plan, a, tiles, segs, st);
     }
 }
 
@@ -434,7 +468,7 @@ cudaError_t launch_cells(const CellPlan &plan, const double2 *d_ty, const double
 //
 // Deep-underflow cells.  The hot kernel flushes weights below 2^-1021 and accumulates w*w with an
 // FMA.  Where the sums are so small that subnormal weights or the underflow of w*w could matter
-// (W < 2^-500 or Q < 2^-1000: tau inside a long data gap at high frequency), the cell index is
+// (W < 2^-200 or Q < 2^-400: tau inside a long data gap at high frequency), the cell index is
 // appended to `fix_list` and the cell is recomputed by faithful_cells_kernel.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void store_cell(int64_t o, double neff, double a0, double a1, double a2,
@@ -471,7 +505,7 @@ __global__ void finalize_kernel(const double *__restrict__ sums, const double *_
         for (int x = 0; x < kNumSums; ++x) acc[x] += slab[(size_t)x * nc + idx];
     }
     const double W = acc[0], Q = acc[1];
-    if (fix_list && (W < 0x1p-500 || Q < 0x1p-1000)) {
+    if (fix_list && (W < 0x1p-200 || Q < 0x1p-400)) {
         const unsigned int slot = atomicAdd(fix_count, 1u);
         if (slot < fix_cap) fix_list[slot] = (unsigned int)idx;
     }

@@ -127,10 +127,30 @@ def _bits(out):
 
 def test_windowed_is_bit_identical_to_dense():
     t, y, tau, freq = _grid_case(n=3000, nt=64, nf=48)
-    a = WV.kirchner_cuda(y, t, freq, tau)
+    a = WV.kirchner_cuda(y, t, freq, tau, flags=_lib.NO_RECURRENCE)
     b = WV.kirchner_cuda(y, t, freq, tau, flags=_lib.DENSE)
     for x, z in zip(_bits(a), _bits(b)):
         assert np.array_equal(x, z)
+
+
+def test_tau_recurrence_kernel_agrees_with_direct_kernel():
+    """Equally spaced tau: rows with kappa*dtau small run the tau-recurrence kernel (one exp2 pair per
+    8 cells); it must agree with the direct kernel far inside the parity bar, cell for cell, and keep the
+    mask.  Covers a partial last group (nt % 8 != 0), both decay constants and a gap series."""
+    for (n, nt, nf, c) in [(3000, 101, 48, 1 / (8 * np.pi ** 2)), (1500, 64, 40, 1e-3), (800, 333, 25, 0.0126)]:
+        t, y, tau, freq = _grid_case(n=n, nt=nt, nf=nf)
+        a = WV.kirchner_cuda(y, t, freq, tau, c=c)
+        b = WV.kirchner_cuda(y, t, freq, tau, c=c, flags=_lib.NO_RECURRENCE)
+        assert_scalogram_parity(as_dict(*a), as_dict(*b), amp_rtol=1e-11, phase_atol=1e-11, neff_rtol=1e-12,
+                                what="recurrence vs direct %s" % ((n, nt, nf),))
+    rng = np.random.default_rng(8)
+    t = np.concatenate([np.sort(rng.uniform(0, 50, 150)), np.sort(rng.uniform(400, 450, 150))])
+    y = rng.standard_normal(t.size)
+    tau = np.linspace(t.min(), t.max(), 200)
+    freq = np.logspace(-2.5, 0.05, 40)
+    a = WV.kirchner_cuda(y, t, freq, tau, standardize=True)
+    o = oracle().kirchner(y, t, freq, tau, standardize=True)
+    assert_scalogram_parity(as_dict(*a), as_dict(*o), what="recurrence on a gap series")
 
 
 @pytest.mark.parametrize("m", ["1", "2", "4"])
