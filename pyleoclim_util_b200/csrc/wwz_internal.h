@@ -14,11 +14,14 @@ constexpr int kNumSums = 7;  // W, Q, Ws, Wc, Wy, Wys, Wyc
 constexpr int kStageBudget = 32 * 1024;
 constexpr int kMaxPointsPerStage = 512;
 constexpr int kRecCells = 8;     // tau-adjacent cells per lane in the tau-recurrence kernel
+constexpr int kRecConsumerWarps = 8;    // consumer warps of its CTA (11 warps, 384 threads, measured slower)
+constexpr int kMaxWarps = 16;
 constexpr int kSurrBlock = 16;   // series per CTA in the shared-time-axis kernel
 
 // Geometry of one launch of the cell kernel, derived on the host by plan_cells().
 struct CellPlan {
-    int cells_per_lane;   // M: tau-adjacent cells owned by one lane (1, 2 or 4)
+    int cells_per_lane;   // M: tau-adjacent cells owned by one lane (1, 2, 4; 8 = recurrence kernel)
+    int consumer_warps;   // consumer warps per CTA
     int groups;           // G = ceil(nt / M) lane slots per frequency row
     int ft_max;           // max number of frequency rows a 256-slot tile can touch
     int points;           // P: points per smem stage

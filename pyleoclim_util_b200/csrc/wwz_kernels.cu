@@ -157,16 +157,21 @@ struct CellArgs {
 // cell and one for the neighbour ratio per point (gauss_weight_ratio); the sums are accumulated with
 // the unscaled weights w_0*rho^m and multiplied by the per-cell constant h_m (h_m^2 for Q) when
 // they are stored.  Only for equally spaced tau and rows with kappa4*dtau <= 8 (host decides).
-template <int M, bool REC>
-__global__ void __launch_bounds__(kCellThreads, REC ? 1 : 2) wwz_cells_kernel(const CellArgs a)
+// CW = consumer warps per CTA (the CTA has CW + 1 warps): 8 everywhere (the direct kernels then fit
+// 2 CTAs/SM at <= 113 registers; the recurrence kernel needs 168 registers, 1 CTA/SM -- 11 consumer
+// warps were measured slower on config 2 because the wider tile touches more frequency rows).
+template <int M, bool REC, int CW>
+__global__ void __launch_bounds__((CW + 1) * 32, REC ? 1 : 2) wwz_cells_kernel(const CellArgs a)
 {
+    constexpr int kConsumerWarps = CW;                 // shadows the namespace-level default
+    constexpr int kConsumerThreads = CW * 32;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double2 *const stage_base = reinterpret_cast<double2 *>(smem_raw);
     unsigned char *const tail = smem_raw + (size_t)kStages * (size_t)a.stage_stride2 * sizeof(double2);
     uint64_t *const full = reinterpret_cast<uint64_t *>(tail);
     uint64_t *const empty = full + kStages;
-    double *const red = reinterpret_cast<double *>(empty + kStages);  // [2][9]
-    double *const tbl = red + 18;                                      // [16] 2^(j/16)
+    double *const red = reinterpret_cast<double *>(empty + kStages);  // [2][kMaxWarps]
+    double *const tbl = red + 2 * kMaxWarps;                          // [16] 2^(j/16)
     int *const win = reinterpret_cast<int *>(tbl + 16);               // [2]
 
     const int tid = threadIdx.x;
@@ -235,14 +240,14 @@ __global__ void __launch_bounds__(kCellThreads, REC ? 1 : 2) wwz_cells_kernel(co
         }
         if (lane == 0) {
             red[warp] = wlo;
-            red[9 + warp] = whi;
+            red[kMaxWarps + warp] = whi;
         }
         __syncthreads();
         if (tid == 0) {
-            double lo = red[0], hi = red[9];
-            for (int w = 1; w < 9; ++w) {
+            double lo = red[0], hi = red[kMaxWarps];
+            for (int w = 1; w <= CW; ++w) {
                 lo = fmin(lo, red[w]);
-                hi = fmax(hi, red[9 + w]);
+                hi = fmax(hi, red[kMaxWarps + w]);
             }
             long long i0 = 0, i1 = 0;
             if (lo <= hi) {
@@ -308,17 +313,30 @@ __global__ void __launch_bounds__(kCellThreads, REC ? 1 : 2) wwz_cells_kernel(co
             const double2 *const st = stage_base + (size_t)s * a.stage_stride2;
             const double2 *const row = st + row_off;
             const int cnt = (int)min((long long)P, p1 - p0 - (long long)c * P);
-            if (REC) {
+            if constexpr (REC) {
                 const double step16 = 2.0 * kap * a.dtau;
-#pragma unroll 1
+#pragma unroll 2
                 for (int p = 0; p < cnt; ++p) {
                     const double2 t_y = st[p];
                     const double2 sc = row[2 * p];
                     const double2 ysc = row[2 * p + 1];
-                    double w, rho;
-                    gauss_weight_ratio(kap * (t_y.x - tau_r[0]), step16, tbl, w, rho);
+                    double w0, rho;
+                    gauss_weight_ratio(kap * (t_y.x - tau_r[0]), step16, tbl, w0, rho);
+                    // w_m = w_0 * rho^m through a product tree (depth 3 instead of a chain of 7 multiplies)
+                    double wv[M];
+                    static_assert(M == 8, "the power tree below is written for 8 cells per lane");
+                    const double rho2 = rho * rho, rho4 = rho2 * rho2;
+                    wv[0] = w0;
+                    wv[1] = w0 * rho;
+                    wv[2] = w0 * rho2;
+                    wv[3] = wv[1] * rho2;
+                    wv[4] = w0 * rho4;
+                    wv[5] = wv[1] * rho4;
+                    wv[6] = wv[2] * rho4;
+                    wv[7] = wv[3] * rho4;
 #pragma unroll
                     for (int r = 0; r < M; ++r) {
+                        const double w = wv[r];
                         W[r] += w;
                         Q[r] = fma(w, w, Q[r]);
                         Ws[r] = fma(w, sc.x, Ws[r]);
@@ -326,7 +344,6 @@ __global__ void __launch_bounds__(kCellThreads, REC ? 1 : 2) wwz_cells_kernel(co
                         Wy[r] = fma(w, t_y.y, Wy[r]);
                         Wys[r] = fma(w, ysc.x, Wys[r]);
                         Wyc[r] = fma(w, ysc.y, Wyc[r]);
-                        w *= rho;
                     }
                 }
             } else {
@@ -386,7 +403,9 @@ CellPlan plan_cells(int64_t n, int64_t nt, int64_t nf, int cells_per_lane_hint, 
     if (nt < M && M != kRecCells) M = 1;
     p.cells_per_lane = M;
     p.groups = (int)((nt + M - 1) / M);
-    int64_t ft = (kConsumerThreads + p.groups - 1) / p.groups + 1;
+    p.consumer_warps = (M == kRecCells) ? kRecConsumerWarps : kConsumerWarps;
+    const int64_t cthreads = (int64_t)p.consumer_warps * 32;
+    int64_t ft = (cthreads + p.groups - 1) / p.groups + 1;
     if (ft > nf) ft = nf;
     if (ft < 1) ft = 1;
     p.ft_max = (int)ft;
@@ -400,24 +419,24 @@ CellPlan plan_cells(int64_t n, int64_t nt, int64_t nf, int cells_per_lane_hint, 
     p.n_pad = ((n + P + 15) / 16) * 16;   // a chunk may start at any segment boundary < n and spans P points
     p.row_stride = (P + 1) * 32;
     p.stage_bytes = (int)(P * 16 + ft * p.row_stride);
-    p.smem_bytes = kStages * p.stage_bytes + 2 * kStages * 8 + 18 * 8 + 16 * 8 + 16;
+    p.smem_bytes = kStages * p.stage_bytes + 2 * kStages * 8 + 2 * kMaxWarps * 8 + 16 * 8 + 16;
     const int64_t nslots = nf * (int64_t)p.groups;
-    p.tiles = (nslots + kConsumerThreads - 1) / kConsumerThreads;
+    p.tiles = (nslots + cthreads - 1) / cthreads;
     return p;
 }
 
-template <int M, bool REC>
+template <int M, bool REC, int CW>
 static cudaError_t launch_cells_m(const CellPlan &plan, const CellArgs &args, int64_t tiles, int segs,
                                   cudaStream_t st)
 {
     static int configured_smem = -1;
     if (plan.smem_bytes > configured_smem) {
-        cudaError_t e = cudaFuncSetAttribute(wwz_cells_kernel<M, REC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             plan.smem_bytes);
+        cudaError_t e = cudaFuncSetAttribute(wwz_cells_kernel<M, REC, CW>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem_bytes);
         if (e != cudaSuccess) return e;
         configured_smem = plan.smem_bytes;
     }
-    wwz_cells_kernel<M, REC><<<dim3((unsigned)tiles, (unsigned)segs), kCellThreads, plan.smem_bytes, st>>>(args);
+    wwz_cells_kernel<M, REC, CW><<<dim3((unsigned)tiles, (unsigned)segs), (CW + 1) * 32, plan.smem_bytes, st>>>(args);
     bump_launch_counter();
     return cudaGetLastError();
 }
@@ -452,12 +471,13 @@ cudaError_t launch_cells(const CellPlan &plan, const double2 *d_ty, const double
     a.stage_stride2 = plan.stage_bytes / 16;
     a.dense = dense ? 1 : 0;
     a.dtau = dtau;
-    const int64_t tiles = (a.nslots + kConsumerThreads - 1) / kConsumerThreads;
+    const int64_t cthreads = (int64_t)plan.consumer_warps * 32;
+    const int64_t tiles = (a.nslots + cthreads - 1) / cthreads;
     switch (plan.cells_per_lane) {
-        case 1: return launch_cells_m<1, false>(plan, a, tiles, segs, st);
-        case 4: return launch_cells_m<4, false>(plan, a, tiles, segs, st);
-        case kRecCells: return launch_cells_m<kRecCells, true>(plan, a, tiles, segs, st);
-        default: return launch_cells_m<2, false>(plan, a, tiles, segs, st);
+        case 1: return launch_cells_m<1, false, kConsumerWarps>(plan, a, tiles, segs, st);
+        case 4: return launch_cells_m<4, false, kConsumerWarps>(plan, a, tiles, segs, st);
+        case kRecCells: return launch_cells_m<kRecCells, true, kRecConsumerWarps>(plan, a, tiles, segs, st);
+        default: return launch_cells_m<2, false, kConsumerWarps>(plan, a, tiles, segs, st);
     }
 }
 
