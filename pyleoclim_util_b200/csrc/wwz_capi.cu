@@ -52,14 +52,20 @@ struct EventPair {
 std::vector<EventPair> g_events;
 
 // Grow-only named device buffers, one set per device.
+constexpr int kLanes = 8;   // concurrent streams of the ragged batch, each with its own scratch set
+
 struct Workspace {
     std::map<std::string, std::pair<void *, size_t>> bufs;
     cudaStream_t stream = nullptr;
+    cudaStream_t lanes[kLanes] = {};
+    cudaEvent_t lane_ev[kLanes] = {};
+    cudaEvent_t fork_ev = nullptr;
+    std::string prefix;   // scratch namespace of the stream currently being enqueued on
     int sms = 0;
 
     int get(const char *name, size_t bytes, void **out)
     {
-        auto &b = bufs[name];
+        auto &b = bufs[prefix + name];
         if (b.second < bytes || b.first == nullptr) {
             if (b.first) cudaFree(b.first);
             b.first = nullptr;
@@ -94,6 +100,11 @@ int workspace(Workspace **out)
     if (!w.stream) {
         CU(cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking));
         CU(cudaDeviceGetAttribute(&w.sms, cudaDevAttrMultiProcessorCount, dev));
+        CU(cudaEventCreateWithFlags(&w.fork_ev, cudaEventDisableTiming));
+        for (int i = 0; i < kLanes; ++i) {
+            CU(cudaStreamCreateWithFlags(&w.lanes[i], cudaStreamNonBlocking));
+            CU(cudaEventCreateWithFlags(&w.lane_ev[i], cudaEventDisableTiming));
+        }
     }
     *out = &w;
     return 0;
@@ -144,39 +155,12 @@ int cells_per_lane_hint(int64_t nt, int64_t nf, int sms)
     return tiles2 >= 4 * (int64_t)sms ? 2 : 1;
 }
 
-// tau-recurrence applicability (wwz_cells_kernel<8, true>): tau must be equally spaced (to 8 ulp) and
-// long enough, and a frequency row qualifies while D = kappa4*dtau <= 8: the recurrence runs from
-// the first of the lane's 8 cells, so a weight is dropped (w_0 flushed at |a| > 127.8) only when every
-// one of the 8 cells sees it below 2^(-(127.8 - 7*8)^2/16) = 2^-322 -- far below the 2^-200 threshold
-// under which the epilogue hands a cell to the faithful kernel.  Rows are taken as a prefix
-// (frequencies normally ascend); the rest of the rows run the direct kernel.
-// Returns the number of leading rows for the recurrence kernel and the spacing in *dtau.
-int64_t rec_rows_prefix(const double *h_tau, int64_t nt, const double *h_omega, int64_t nf, double c, double *dtau)
-{
-    *dtau = 0.0;
-    if (nt < 2 * wwz::kRecCells || nf < 1) return 0;
-    const char *e = getenv("WWZB200_NO_RECURRENCE");
-    if (e && *e && atoi(e)) return 0;
-    const double d = (h_tau[nt - 1] - h_tau[0]) / (double)(nt - 1);
-    if (!(d > 0) || !std::isfinite(d)) return 0;
-    const double scale = std::max(std::fabs(h_tau[0]), std::fabs(h_tau[nt - 1]));
-    const double tol = 8.0 * std::ldexp(scale > 0 ? scale : 1.0, -52);
-    for (int64_t j = 0; j < nt; ++j)
-        if (!(std::fabs(h_tau[j] - (h_tau[0] + (double)j * d)) <= tol)) return 0;
-    const double kscale = 4.0 * std::sqrt(c * 1.4426950408889634074);
-    int64_t k = 0;
-    while (k < nf && std::fabs(h_omega[k]) * kscale * d <= 8.0) ++k;   // NaN omega stops the prefix
-    *dtau = d;
-    return k;
-}
-
 // The transform on device-resident inputs.  Outputs may alias caller memory (row stride given).
 // d_psd != NULL adds the wwa2psd reduction; tspan < 0 means "take max-min of d_ts on the device".
 int transform_device(Workspace *w, const double *d_ts, const double *d_ys, int64_t n, const double *d_tau,
                      int64_t nt, const double *d_omega, int64_t nf, double c, int64_t thr, int64_t psd_thr,
                      uint32_t flags, double *d_neffs, double *d_a0, double *d_a1, double *d_a2, double *d_wwa,
-                     double *d_phase, double *d_psd, int64_t row_stride, double tspan, cudaStream_t st,
-                     const double *h_tau = nullptr, const double *h_omega = nullptr)
+                     double *d_phase, double *d_psd, int64_t row_stride, double tspan, cudaStream_t st)
 {
     using namespace wwz;
     const int64_t ncell = nt * nf;
@@ -205,27 +189,24 @@ int transform_device(Workspace *w, const double *d_ts, const double *d_ys, int64
         const int segs = point_segments(n, ncell);
         const int64_t seg_len = (((n + segs - 1) / segs + 15) / 16) * 16;
         CellPlan plan = plan_cells(n, nt, nf, cells_per_lane_hint(nt, nf, w->sms), seg_len);
-        // rows [0, k_rec) go to the tau-recurrence kernel (needs the grid on the host)
-        int64_t k_rec = 0;
-        double dtau = 0.0;
-        CellPlan rplan = plan;
-        if (!(flags & (WWZB200_DENSE | WWZB200_NO_RECURRENCE)) && nt >= 2 * kRecCells) {
-            std::vector<double> hbuf;
-            if (!h_tau || !h_omega) {
-                hbuf.resize((size_t)(nt + nf));
-                CU(cudaMemcpyAsync(hbuf.data(), d_tau, sizeof(double) * nt, cudaMemcpyDeviceToHost, st));
-                CU(cudaMemcpyAsync(hbuf.data() + nt, d_omega, sizeof(double) * nf, cudaMemcpyDeviceToHost, st));
-                CU(cudaStreamSynchronize(st));
-                h_tau = hbuf.data();
-                h_omega = hbuf.data() + nt;
-            }
-            k_rec = rec_rows_prefix(h_tau, nt, h_omega, nf, c, &dtau);
-            if (k_rec > 0) {
-                rplan = plan_cells(n, nt, nf, kRecCells, seg_len);
-                const int64_t np = std::max(plan.n_pad, rplan.n_pad);   // one row stride for both kernels
-                plan.n_pad = rplan.n_pad = np;
-            }
+        // rows with kappa4*dtau <= 8 on an equally spaced tau axis go to the tau-recurrence kernel; the
+        // decision is taken per row on the device (freq_setup), both flavours are launched over all rows
+        // and every CTA keeps only the rows that are its own
+        bool allow_rec = !(flags & (WWZB200_DENSE | WWZB200_NO_RECURRENCE)) && nt >= 2 * kRecCells;
+        {
+            const char *e = getenv("WWZB200_NO_RECURRENCE");
+            if (e && *e && atoi(e)) allow_rec = false;
         }
+        CellPlan rplan = plan;
+        if (allow_rec) {
+            rplan = plan_cells(n, nt, nf, kRecCells, seg_len);
+            const int64_t np = std::max(plan.n_pad, rplan.n_pad);   // one row stride for both kernels
+            plan.n_pad = rplan.n_pad = np;
+        }
+        double *d_grid;
+        unsigned char *d_rec_row;
+        if ((rc = wsbuf(w, "grid", 2, &d_grid))) return rc;
+        if ((rc = wsbuf(w, "rec_row", (size_t)nf, &d_rec_row))) return rc;
         size_t per_row = (size_t)plan.n_pad * 32;
         int64_t nf_batch = (int64_t)std::max<size_t>(1, basis_budget_bytes() / per_row);
         nf_batch = std::min<int64_t>(std::min<int64_t>(nf_batch, nf), 65535);
@@ -234,7 +215,7 @@ int transform_device(Workspace *w, const double *d_ts, const double *d_ys, int64
         if ((rc = wsbuf(w, "basis", (size_t)nf_batch * (size_t)plan.n_pad * 2, &d_basis))) return rc;
         if ((rc = wsbuf(w, "sums", (size_t)segs * (size_t)kNumSums * (size_t)ncell, &d_sums))) return rc;
 
-        CU(launch_freq_setup(d_omega, nf, c, d_kappa, d_dcut, st));
+        CU(launch_freq_setup(d_omega, nf, d_tau, nt, c, allow_rec, d_kappa, d_dcut, d_grid, d_rec_row, st));
         CU(launch_unsorted_check(d_ts, n, d_unsorted, st));
         CU(cudaMemsetAsync(d_fix_count, 0, sizeof(unsigned int), st));
         const bool dense = (flags & WWZB200_DENSE) != 0;
@@ -247,15 +228,11 @@ int transform_device(Workspace *w, const double *d_ts, const double *d_ys, int64
                 CU(cudaEventCreate(&ev.b));
                 CU(cudaEventRecord(ev.a, st));
             }
-            const int64_t nrec = std::max<int64_t>(0, std::min<int64_t>(k_rec - k0, nb));   // recurrence rows of this batch
-            if (nrec > 0)
-                CU(launch_cells(rplan, d_ty, d_basis, d_ts, n, d_tau, nt, d_kappa, d_dcut, d_unsorted, k0, nrec, nf,
-                                dense, segs, seg_len, dtau, d_sums, st));
-            if (nb > nrec)
-                CU(launch_cells(plan, d_ty, d_basis + (size_t)nrec * (size_t)plan.n_pad * 2, d_ts, n, d_tau, nt,
-                                d_kappa, d_dcut, d_unsorted, k0 + nrec, nb - nrec, nf, dense, segs, seg_len, 0.0,
-                                d_sums, st));
-
+            if (allow_rec)
+                CU(launch_cells(rplan, d_ty, d_basis, d_ts, n, d_tau, nt, d_kappa, d_dcut, d_unsorted, k0, nb, nf, dense,
+                                segs, seg_len, d_rec_row, d_grid, d_sums, st));
+            CU(launch_cells(plan, d_ty, d_basis, d_ts, n, d_tau, nt, d_kappa, d_dcut, d_unsorted, k0, nb, nf, dense, segs,
+                            seg_len, allow_rec ? d_rec_row : nullptr, d_grid, d_sums, st));
             if (g_profile) {
                 CU(cudaEventRecord(ev.b, st));
                 g_events.push_back(ev);
@@ -317,7 +294,7 @@ int host_transform(const double *ts, const double *ys, int64_t n, const double *
         const auto mm = std::minmax_element(ts, ts + n);
         tspan = *mm.second - *mm.first;   // utils/wavelet.py:1270 (np.max(ts)-np.min(ts))
     }
-    rc = transform_device(w, d_ts, d_ys, n, d_tau, nt, d_om, nf, c, thr, psd_thr, flags, o_neff, o_a0, o_a1, o_a2, o_wwa, o_ph, psd ? o_psd : nullptr, nf, tspan, st, tau, om);
+    rc = transform_device(w, d_ts, d_ys, n, d_tau, nt, d_om, nf, c, thr, psd_thr, flags, o_neff, o_a0, o_a1, o_a2, o_wwa, o_ph, psd ? o_psd : nullptr, nf, tspan, st);
     if (rc) return rc;
     const size_t cb = sizeof(double) * (size_t)ncell;
     if (ncell) {
@@ -377,7 +354,11 @@ int shared_axis_device(Workspace *w, const double *d_ts, const double *d_Y, int6
     d_ne = d_neffs;
     if (!d_ne && (rc = wsbuf(w, "ne_t", (size_t)ncell, &d_ne))) return rc;
 
-    CU(launch_freq_setup(d_omega, nf, c, d_kappa, d_dcut, st));
+    double *d_grid;
+    unsigned char *d_rec_row;
+    if ((rc = wsbuf(w, "grid", 2, &d_grid))) return rc;
+    if ((rc = wsbuf(w, "rec_row", (size_t)nf, &d_rec_row))) return rc;
+    CU(launch_freq_setup(d_omega, nf, d_tau, nt, c, false, d_kappa, d_dcut, d_grid, d_rec_row, st));
     CU(launch_basis_sc(d_ts, n, plan.n_pad, d_omega, nf, d_ty, d_basis, st));
     CU(launch_rotation(d_tau, d_omega, nt, nf, d_rot, st));
     CU(launch_standardize_retile(d_Y, n, plan.n_pad, S, (flags & WWZB200_STANDARDIZE) != 0, d_mu, d_sig, d_Yt, st));
@@ -749,20 +730,33 @@ int wwzb200_kirchner_ragged(const double *ts, const double *pd_ys, const int64_t
     double *o[6];
     for (int i = 0; i < 6; ++i) o[i] = d_out + (size_t)i * NOUT;
     double *o_psd = d_out + (size_t)6 * NOUT;
-    {   // pre-size the per-transform scratch for the largest member: no re-allocation mid-stream
+    // Members are independent: they are enqueued round-robin on kLanes streams, each with its own scratch
+    // set (pre-sized for the largest member so that nothing is re-allocated while work is in flight).
+    const int nl = (int)std::min<int64_t>(kLanes, M);
+    for (int l = 0; l < nl; ++l) {
         double *dd;
         double2 *d2;
         unsigned int *du;
-        if ((rc = wsbuf(w, "kappa", (size_t)max_nf, &dd))) return rc;
-        if ((rc = wsbuf(w, "dcut", (size_t)max_nf, &dd))) return rc;
-        if ((rc = wsbuf(w, "ty", (size_t)(max_n + wwz::kMaxPointsPerStage + 16), &d2))) return rc;
+        int *di;
+        w->prefix = "lane" + std::to_string(l) + "_";
+        if ((rc = wsbuf(w, "kappa", (size_t)max_nf, &dd))) break;
+        if ((rc = wsbuf(w, "dcut", (size_t)max_nf, &dd))) break;
+        if ((rc = wsbuf(w, "flags", 4, &di))) break;
+        if ((rc = wsbuf(w, "grid", 2, &dd))) break;
+        { unsigned char *dc; if ((rc = wsbuf(w, "rec_row", (size_t)max_nf, &dc))) break; }
+        if ((rc = wsbuf(w, "ty", (size_t)(max_n + wwz::kMaxPointsPerStage + 16), &d2))) break;
         if ((rc = wsbuf(w, "basis", (size_t)std::min<int64_t>(max_basis, (int64_t)(basis_budget_bytes() / 16)) * 2, &d2)))
-            return rc;
-        if ((rc = wsbuf(w, "sums", (size_t)max_sums, &dd))) return rc;
-        if ((rc = wsbuf(w, "fix_list", (size_t)max_cells + 1, &du))) return rc;
-        if (psd && (rc = wsbuf(w, "psd_wwa", (size_t)max_cells, &dd))) return rc;
+            break;
+        if ((rc = wsbuf(w, "sums", (size_t)max_sums, &dd))) break;
+        if ((rc = wsbuf(w, "fix_list", (size_t)max_cells + 1, &du))) break;
+        if (psd && (rc = wsbuf(w, "psd_wwa", (size_t)max_cells, &dd))) break;
     }
-    for (int64_t m = 0; m < M; ++m) {
+    w->prefix.clear();
+    if (rc) return rc;
+    CU(cudaEventRecord(w->fork_ev, st));
+    for (int l = 0; l < nl; ++l) CU(cudaStreamWaitEvent(w->lanes[l], w->fork_ev, 0));
+    for (int64_t m = 0; m < M && !rc; ++m) {
+        const int l = (int)(m % nl);
         const int64_t n = ts_off[m + 1] - ts_off[m], nt = tau_off[m + 1] - tau_off[m], nf = om_off[m + 1] - om_off[m];
         const int64_t t0 = ts_off[m] - ts_off[0], u0 = tau_off[m] - tau_off[0], f0 = om_off[m] - om_off[0];
         const int64_t c0 = out_off[m] - out_off[0];
@@ -771,11 +765,16 @@ int wwzb200_kirchner_ragged(const double *ts, const double *pd_ys, const int64_t
             const auto mm = std::minmax_element(ts + ts_off[m], ts + ts_off[m + 1]);
             tspan = *mm.second - *mm.first;
         }
+        w->prefix = "lane" + std::to_string(l) + "_";
         rc = transform_device(w, d_ts + t0, d_ys + t0, n, d_tau + u0, nt, d_om + f0, nf, c, Neff_threshold,
                               psd_Neff_threshold, flags, o[0] + c0, o[1] + c0, o[2] + c0, o[3] + c0, o[4] + c0,
-                              o[5] + c0, psd ? o_psd + f0 : nullptr, nf, tspan, st, taus + tau_off[m],
-                              omegas + om_off[m]);
-        if (rc) return rc;
+                              o[5] + c0, psd ? o_psd + f0 : nullptr, nf, tspan, w->lanes[l]);
+    }
+    w->prefix.clear();
+    if (rc) return rc;
+    for (int l = 0; l < nl; ++l) {
+        CU(cudaEventRecord(w->lane_ev[l], w->lanes[l]));
+        CU(cudaStreamWaitEvent(st, w->lane_ev[l], 0));
     }
     double *h[6] = {Neffs, a0, a1, a2, wwa, phase};
     for (int i = 0; i < 6; ++i)

@@ -35,8 +35,11 @@ struct CellPlan {
 CellPlan plan_cells(int64_t n, int64_t nt, int64_t nf, int cells_per_lane_hint, int64_t seg_len);
 
 // Per-frequency constants: kappa = omega*sqrt(c*log2 e), dcut = underflow distance (windowing).
-cudaError_t launch_freq_setup(const double *d_omega, int64_t nf, double c, double *d_kappa, double *d_dcut,
-                              cudaStream_t st);
+// Also decides on the device which rows the tau-recurrence kernel may take (d_rec_row) and the tau
+// spacing (d_grid[0]); allow_rec = false marks every row for the direct kernel.
+cudaError_t launch_freq_setup(const double *d_omega, int64_t nf, const double *d_tau, int64_t nt, double c,
+                              bool allow_rec, double *d_kappa, double *d_dcut, double *d_grid,
+                              unsigned char *d_rec_row, cudaStream_t st);
 
 // (t, y) interleaved + per-frequency basis rows (sin, cos, y sin, y cos), zero padded to n_pad.
 cudaError_t launch_basis(const double *d_ts, const double *d_ys, int64_t n, int64_t n_pad,
@@ -49,8 +52,8 @@ cudaError_t launch_basis(const double *d_ts, const double *d_ys, int64_t n, int6
 cudaError_t launch_cells(const CellPlan &plan, const double2 *d_ty, const double2 *d_basis, const double *d_ts,
                          int64_t n, const double *d_tau, int64_t nt, const double *d_kappa,
                          const double *d_dcut, const int *d_unsorted, int64_t k0, int64_t nf_batch,
-                         int64_t nf_total, bool dense, int segs, int64_t seg_len, double dtau, double *d_sums,
-                         cudaStream_t st);
+                         int64_t nf_total, bool dense, int segs, int64_t seg_len, const unsigned char *d_rec_row,
+                         const double *d_grid, double *d_sums, cudaStream_t st);
 
 // *d_flag = 1 if d_x is not ascending (the windowed path needs a sorted time axis).
 cudaError_t launch_unsorted_check(const double *d_x, int64_t n, int *d_flag, cudaStream_t st);

@@ -45,8 +45,39 @@ void bump_launch_counter(int64_t k) { g_launches.fetch_add(k); }
 // flows through every sum of the column and the epilogue yields NaN Neff / coefficients, exactly
 // what NaN arithmetic gives in the reference.  dcut = -1 marks the row as "no window constraint".
 // ------------------------------------------------------------------------------------------------
+// tau-recurrence applicability (wwz_cells_kernel<8, true, .>), decided on the device so that no
+// entry point has to synchronise: tau must be equally spaced (to 8 ulp) with at least 16 points, and
+// a frequency row qualifies while D = kappa4*dtau <= 8.  The recurrence runs from the first of the
+// lane's 8 cells, so a weight is dropped (w_0 flushed at |a| > 127.8) only when every one of the 8
+// cells sees it below 2^(-(127.8 - 7*8)^2/16) = 2^-322 -- far below the 2^-200 threshold under
+// which the epilogue hands a cell to the faithful kernel.
+// grid[0] = dtau, grid[1] = 1.0 if tau is equally spaced else 0.0.
+__global__ void tau_uniform_kernel(const double *__restrict__ tau, int64_t nt, double *__restrict__ grid)
+{
+    __shared__ int bad;
+    if (threadIdx.x == 0) bad = 0;
+    __syncthreads();
+    double d = 0.0;
+    if (nt >= 2 * kRecCells) {
+        d = (tau[nt - 1] - tau[0]) / (double)(nt - 1);
+        const double scale = fmax(fabs(tau[0]), fabs(tau[nt - 1]));
+        const double tol = 8.0 * (scale > 0 ? scale : 1.0) * 0x1p-52;
+        if (!(d > 0) || isinf(d)) bad = 1;
+        for (int64_t j = threadIdx.x; j < nt; j += blockDim.x)
+            if (!(fabs(tau[j] - (tau[0] + (double)j * d)) <= tol)) bad = 1;
+    } else if (threadIdx.x == 0) {
+        bad = 1;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        grid[0] = d;
+        grid[1] = bad ? 0.0 : 1.0;
+    }
+}
+
 __global__ void freq_setup_kernel(const double *__restrict__ omega, int64_t nf, double kscale,
-                                  double *__restrict__ kappa, double *__restrict__ dcut)
+                                  const double *__restrict__ grid, int allow_rec, double *__restrict__ kappa,
+                                  double *__restrict__ dcut, unsigned char *__restrict__ rec_row)
 {
     int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (k >= nf) return;
@@ -54,15 +85,19 @@ __global__ void freq_setup_kernel(const double *__restrict__ omega, int64_t nf, 
     const double ka = om * kscale;
     kappa[k] = ka;
     dcut[k] = isnan(om) ? -1.0 : 4.0 * sqrt(1081.0) / fabs(ka);  // +inf for omega == 0
+    rec_row[k] = (allow_rec && grid[1] != 0.0 && fabs(ka) * grid[0] <= 8.0) ? 1 : 0;   // NaN omega -> 0
 }
 
-cudaError_t launch_freq_setup(const double *d_omega, int64_t nf, double c, double *d_kappa, double *d_dcut,
-                              cudaStream_t st)
+cudaError_t launch_freq_setup(const double *d_omega, int64_t nf, const double *d_tau, int64_t nt, double c,
+                              bool allow_rec, double *d_kappa, double *d_dcut, double *d_grid,
+                              unsigned char *d_rec_row, cudaStream_t st)
 {
     if (nf <= 0) return cudaSuccess;
     const double kscale = 4.0 * std::sqrt(c * 1.4426950408889634074);  // 4*sqrt(c*log2(e))
-    freq_setup_kernel<<<(unsigned)((nf + 127) / 128), 128, 0, st>>>(d_omega, nf, kscale, d_kappa, d_dcut);
-    bump_launch_counter();
+    tau_uniform_kernel<<<1, 256, 0, st>>>(d_tau, nt, d_grid);
+    freq_setup_kernel<<<(unsigned)((nf + 127) / 128), 128, 0, st>>>(d_omega, nf, kscale, d_grid, allow_rec ? 1 : 0,
+                                                                    d_kappa, d_dcut, d_rec_row);
+    bump_launch_counter(2);
     return cudaGetLastError();
 }
 
@@ -144,13 +179,14 @@ struct CellArgs {
     const double *kappa;
     const double *dcut;
     const int *unsorted;  // device flag: 1 if ts is not ascending (forces the dense path)
+    const unsigned char *rec_row;   // per frequency row: 1 = handled by the recurrence kernel (null: all direct)
+    const double *grid;             // [0] = dtau of the equally spaced tau axis
     double *sums;
     long long n, n_pad, nslots, ncell_total, seg_len;
     int nt, G, P, k0, nf_total;
     int row_stride2;    // basis row stride inside a stage, in double2 units
     int stage_stride2;  // stage stride in double2 units
     int dense;
-    double dtau;        // REC kernels: the (uniform) tau spacing
 };
 
 // REC = true: tau-recurrence flavour.  The lane's M tau-adjacent cells share one exp2 for the first
@@ -201,13 +237,16 @@ __global__ void __launch_bounds__((CW + 1) * 32, REC ? 1 : 2) wwz_cells_kernel(c
 
     // ---- lane-slot parameters
     const long long q = q0 + tid;
-    const bool slot_ok = consumer && q < a.nslots;
+    bool slot_ok = consumer && q < a.nslots;
     int k_loc = 0, g = 0;
     if (slot_ok) {
         const int k = (int)(q / a.G);
         k_loc = k - k_first;
         g = (int)(q - (long long)k * a.G);
+        // each frequency row belongs to exactly one kernel flavour
+        if (a.rec_row) slot_ok = (a.rec_row[a.k0 + k] != 0) == REC;
     }
+    if (!__syncthreads_or(slot_ok ? 1 : 0)) return;   // nothing in this tile is ours
     double kap = 0.0;
     double tau_r[M];
     double wlo = CUDART_INF, whi = -CUDART_INF;
@@ -314,7 +353,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, REC ? 1 : 2) wwz_cells_kernel(c
             const double2 *const row = st + row_off;
             const int cnt = (int)min((long long)P, p1 - p0 - (long long)c * P);
             if constexpr (REC) {
-                const double step16 = 2.0 * kap * a.dtau;
+                const double step16 = 2.0 * kap * a.grid[0];
 #pragma unroll 2
                 for (int p = 0; p < cnt; ++p) {
                     const double2 t_y = st[p];
@@ -374,7 +413,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, REC ? 1 : 2) wwz_cells_kernel(c
 
     if (slot_ok) {
         const long long kcol = (long long)a.k0 + k_first + k_loc;
-        const double D = kap * a.dtau;
+        const double D = REC ? kap * a.grid[0] : 0.0;
 #pragma unroll
         for (int r = 0; r < M; ++r) {
             const int j = g * M + r;
@@ -444,8 +483,8 @@ static cudaError_t launch_cells_m(const CellPlan &plan, const CellArgs &args, in
 cudaError_t launch_cells(const CellPlan &plan, const double2 *d_ty, const double2 *d_basis, const double *d_ts,
                          int64_t n, const double *d_tau, int64_t nt, const double *d_kappa,
                          const double *d_dcut, const int *d_unsorted, int64_t k0, int64_t nf_batch,
-                         int64_t nf_total, bool dense, int segs, int64_t seg_len, double dtau, double *d_sums,
-                         cudaStream_t st)
+                         int64_t nf_total, bool dense, int segs, int64_t seg_len, const unsigned char *d_rec_row,
+                         const double *d_grid, double *d_sums, cudaStream_t st)
 {
     if (nf_batch <= 0 || nt <= 0) return cudaSuccess;
     CellArgs a{};
@@ -470,7 +509,8 @@ cudaError_t launch_cells(const CellPlan &plan, const double2 *d_ty, const double
     a.row_stride2 = (int)(plan.row_stride / 16);
     a.stage_stride2 = plan.stage_bytes / 16;
     a.dense = dense ? 1 : 0;
-    a.dtau = dtau;
+    a.rec_row = d_rec_row;
+    a.grid = d_grid;
     const int64_t cthreads = (int64_t)plan.consumer_warps * 32;
     const int64_t tiles = (a.nslots + cthreads - 1) / cthreads;
     switch (plan.cells_per_lane) {
