@@ -168,3 +168,34 @@ def test_wwz_signif_equals_the_unfused_pipeline():
     psds = np.stack([WV.wwz_psd(Y[s], ts_cut, freq=freq, tau=tau, c=1e-3).psd for s in range(number)])
     pref = np.asarray(mquantiles(psds, qs, axis=0))
     assert max_rel(sg.psd_qs, pref) < 1e-10
+
+
+def test_config3_size_significance_test():
+    """Config 3 at full size: 10,000 AR(1) surrogates of an n=5,000 series on the default 50 x 501 grid, fused on
+    the device.  Size-independent properties: quantiles ordered, mask equal to the target's, reproducible for a
+    seed, and the fused result equals the unfused pipeline (same surrogates, scipy mquantiles) on a tau block."""
+    from scipy.stats.mstats import mquantiles
+    t, y, tau, freq = synth.config_grid("C3")
+    qs = [0.5, 0.9, 0.95]
+    sg = B.wwz_signif(y, t, tau=tau, freq=freq, number=10000, qs=qs, seed=5)
+    assert sg.amplitude_qs.shape == (3, 50, freq.size)
+    target = WV.wwz(y, t, tau=tau, freq=freq)
+    for q in sg.amplitude_qs:
+        assert_same_nan_mask(q, target.amplitude)
+    m = ~np.isnan(target.amplitude)
+    assert (sg.amplitude_qs[1][m] >= sg.amplitude_qs[0][m]).all() and (sg.amplitude_qs[2][m] >= sg.amplitude_qs[1][m]).all()
+    assert_same_nan_mask(sg.Neffs, target.Neffs) and None
+    assert max_rel(sg.Neffs, target.Neffs) < 1e-12
+    sg2 = B.wwz_signif(y, t, tau=tau, freq=freq, number=10000, qs=qs, seed=5)
+    assert np.array_equal(sg.amplitude_qs, sg2.amplitude_qs, equal_nan=True)
+    # unfused pipeline on 4 tau rows: same surrogates, single-batch transform, scipy quantiles
+    ys_cut, ts_cut, freq_c, tau_c = WV.prepare_wwz(y, t, tau=tau, freq=freq)
+    Y = B.ar1_surrogates(ts_cut, B.tau_estimation(ys_cut, ts_cut), sigma=np.std(ys_cut), mu=np.mean(ys_cut),
+                         number=10000, seed=5)
+    rows = slice(20, 24)
+    r = B.wwz_shared_axis(Y, ts_cut, tau_c[rows], freq_c)
+    ref = np.asarray(mquantiles(r.amplitude.reshape(10000, -1), qs, axis=0).filled(np.nan)).reshape(3, 4, freq_c.size)
+    assert max_rel(sg.amplitude_qs[:, rows], ref) < 1e-10
+    # about 5% of the target's cells exceed the 95% level of red noise of the same persistence
+    frac = np.mean(target.amplitude[m] > sg.amplitude_qs[2][m])
+    assert 0.0 < frac < 0.5

@@ -295,3 +295,37 @@ def test_pinned_outputs_and_launch_counter():
     assert _lib.launch_count() - before >= 5
     b = WV._transform(y, t, tau, om, 0.0126, 3)
     assert np.array_equal(a[0].view(np.uint64), b[0].view(np.uint64))
+
+
+# ------------------------------------------------------------------ BASELINE.json's full sizes
+def test_config5_full_grid_properties_and_golden_sample():
+    """Config 5 at full size (n=100,000, 4096 tau x 2047 f = 8.4e6 cells, 8.4e11 cell-points): the cells the
+    reference was run on (tests/golden/c5_sample.npz) are picked out of the full-grid result, the three-state
+    mask is consistent, Neff does not depend on y, and the default path (windowing + tau-recurrence, frequency
+    batches) agrees with the direct kernel on a tau block."""
+    g = golden("c5_sample")
+    t, y, tau, freq = synth.config_grid("C5")
+    ys = (y - y.mean()) / y.std()
+    wwa, phase, Neffs, (a0, a1, a2) = WV.kirchner_cuda(ys, t, freq, tau)
+    assert wwa.shape == (4096, freq.size)
+    sub = np.ix_(g["jt"], g["kf"])
+    got = dict(amplitude=wwa[sub], phase=phase[sub], Neffs=Neffs[sub], a0=a0[sub], a1=a1[sub], a2=a2[sub])
+    assert_scalogram_parity(got, g, what="C5 full grid, golden cells")
+    # mask consistency over all 8.4e6 cells
+    masked = ~(Neffs > 3)
+    assert np.array_equal(np.isnan(wwa), masked) and np.array_equal(np.isnan(a0), masked)
+    assert np.isfinite(wwa[~masked]).all() and (wwa[~masked] >= 0).all()
+    # amplitude / phase are consistent with the coefficients everywhere
+    m = ~masked
+    assert np.max(np.abs(wwa[m] - np.hypot(a1[m], a2[m])) / wwa[m]) < 1e-14
+    # a tau block through the direct kernel (one exp2 per (cell, point), dense) against the default path
+    blk = slice(1024, 1024 + 64)
+    d = WV.kirchner_cuda(ys, t, freq, tau[blk], flags=_lib.DENSE)
+    assert_same_nan_mask(d[0], wwa[blk])
+    assert max_rel(wwa[blk], d[0]) < 1e-10 and max_rel(Neffs[blk], d[2]) < 1e-12
+    # Neff is a property of the time axis alone
+    y2 = np.random.default_rng(0).standard_normal(t.size)
+    e = WV.kirchner_cuda(y2, t, freq, tau[blk])
+    f = WV.kirchner_cuda(ys, t, freq, tau[blk])
+    assert np.array_equal(e[2].view(np.uint64), f[2].view(np.uint64))
+    assert max_rel(f[2], Neffs[blk]) < 1e-12       # (the full grid uses a different point segmentation)
