@@ -149,14 +149,60 @@ def _free_pinned(addr):
         _lib.wwzb200_free_pinned(_vp(addr))
 
 
+class _PinnedPool:
+    """Recycles page-locked output buffers.  A result array handed to the caller is backed by pinned
+    memory (the device-to-host copy is then a plain DMA: ~0.5 ms instead of ~10 ms for the 24 MB of a
+    1000 x 500 grid); when the caller drops the array its buffer returns to the pool, so steady-state
+    loops neither re-allocate nor alias live results."""
+
+    def __init__(self, cap_bytes=2 << 30, max_item=512 << 20):
+        self.free = {}
+        self.pooled = 0
+        self.cap, self.max_item = cap_bytes, max_item
+
+    def take(self, nbytes):
+        lst = self.free.get(nbytes)
+        if lst:
+            self.pooled -= nbytes
+            return lst.pop()
+        p = _vp()
+        check(lib().wwzb200_alloc_pinned(max(nbytes, 1), ctypes.byref(p)))
+        return p.value
+
+    def give(self, addr, nbytes):
+        if self.pooled + nbytes <= self.cap:
+            self.free.setdefault(nbytes, []).append(addr)
+            self.pooled += nbytes
+        else:
+            _free_pinned(addr)
+
+    def clear(self):
+        for lst in self.free.values():
+            for addr in lst:
+                _free_pinned(addr)
+        self.free.clear()
+        self.pooled = 0
+
+
+_pool = _PinnedPool()
+
+
 def pinned_empty(shape, dtype=np.float64):
-    """NumPy array backed by page-locked host memory (freed when the array is collected)."""
+    """NumPy array backed by page-locked host memory; the buffer goes back to a pool when the array
+    (and every view of it) has been collected."""
     shape = tuple(int(s) for s in np.atleast_1d(shape))
     dt = np.dtype(dtype)
-    nbytes = int(np.prod(shape, dtype=np.int64)) * dt.itemsize
-    p = _vp()
-    check(lib().wwzb200_alloc_pinned(max(nbytes, 1), ctypes.byref(p)))
-    buf = (ctypes.c_char * max(nbytes, 1)).from_address(p.value)
-    arr = np.frombuffer(buf, dtype=dt, count=int(np.prod(shape, dtype=np.int64))).reshape(shape)
-    weakref.finalize(buf, _free_pinned, p.value)
-    return arr
+    count = int(np.prod(shape, dtype=np.int64))
+    nbytes = max(count * dt.itemsize, 1)
+    addr = _pool.take(nbytes)
+    buf = (ctypes.c_char * nbytes).from_address(addr)
+    weakref.finalize(buf, _pool.give, addr, nbytes)
+    return np.frombuffer(buf, dtype=dt, count=count).reshape(shape)
+
+
+def output_empty(shape):
+    """Result buffer: pinned (pooled) for anything worth a DMA, plain NumPy for tiny or huge arrays."""
+    nbytes = int(np.prod(shape, dtype=np.int64)) * 8
+    if (64 << 10) <= nbytes <= _pool.max_item:
+        return pinned_empty(shape)
+    return np.empty(shape)

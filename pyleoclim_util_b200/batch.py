@@ -72,11 +72,11 @@ def wwz_shared_axis(Y, ts, tau, freq, c=1 / (8 * np.pi ** 2), Neff_threshold=3, 
     omega = _wv.make_omega(ts, freq)
     Neffs = np.empty((nt, nf))
     want = set(outputs)
-    amp = np.empty((S, nt, nf)) if "amplitude" in want else None
-    phase = np.empty((S, nt, nf)) if "phase" in want else None
+    amp = _lib.output_empty((S, nt, nf)) if "amplitude" in want else None
+    phase = _lib.output_empty((S, nt, nf)) if "phase" in want else None
     a0 = a1 = a2 = None
     if "coeff" in want:
-        a0, a1, a2 = (np.empty((S, nt, nf)) for _ in range(3))
+        a0, a1, a2 = (_lib.output_empty((S, nt, nf)) for _ in range(3))
     psd = np.empty((S, nf)) if psd_Neff_threshold is not None else None
     fl = int(flags) | (_lib.STANDARDIZE if standardize else 0)
     _lib.check(_lib.lib().wwzb200_kirchner_shared_axis(
@@ -111,7 +111,7 @@ def wwz_ragged(members, c=1 / (8 * np.pi ** 2), Neff_threshold=3, standardize=Tr
     out_off = np.concatenate([[0], np.cumsum([a.size * b.size for a, b in zip(tau_l, om_l)])]).astype(np.int64)
     cat = lambda xs: np.concatenate(xs) if xs else np.empty(0)
     ts_p, ys_p, tau_p, om_p = cat(ts_l), cat(ys_l), cat(tau_l), cat(om_l)
-    outs = [np.empty(int(out_off[-1])) for _ in range(6)]
+    outs = [_lib.output_empty((int(out_off[-1]),)) for _ in range(6)]
     psd = np.empty(int(om_off[-1])) if psd_Neff_threshold is not None else None
     _lib.check(_lib.lib().wwzb200_kirchner_ragged(
         _lib.ptr(ts_p), _lib.ptr(ys_p), _lib.iptr(ts_off), _lib.ptr(tau_p), _lib.iptr(tau_off), _lib.ptr(om_p),

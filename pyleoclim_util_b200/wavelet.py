@@ -184,15 +184,20 @@ def prepare_wwz(ys, ts, freq=None, freq_method="log", freq_kwargs=None, tau=None
 
 
 # ------------------------------------------------------------------------------ the kernel
-def _transform(pd_ys, ts, tau, omega, c, Neff_threshold, flags=0, psd_threshold=None, pinned=False):
-    """One call into the C ABI: (1) wwzb200_kirchner or (2) wwzb200_kirchner_psd."""
+def _transform(pd_ys, ts, tau, omega, c, Neff_threshold, flags=0, psd_threshold=None, pinned=True, psd_only=False):
+    """One call into the C ABI: (1) wwzb200_kirchner or (2) wwzb200_kirchner_psd.
+    Returns (wwa, phase, Neffs, (a0, a1, a2), psd); with psd_only the per-cell arrays stay on the device
+    and come back as None."""
     L = _lib.lib()
     ts, pd_ys, tau, omega = _lib.f64(ts), _lib.f64(pd_ys), _lib.f64(tau), _lib.f64(omega)
     if ts.ndim != 1 or pd_ys.shape != ts.shape:
         raise ValueError("ys and ts must be vectors of equal length")
     nt, nf = tau.size, omega.size
-    alloc = _lib.pinned_empty if pinned else np.empty
-    Neffs, a0, a1, a2, wwa, phase = (alloc((nt, nf)) for _ in range(6))
+    alloc = _lib.output_empty if pinned else np.empty
+    if psd_only and psd_threshold is not None:
+        Neffs = a0 = a1 = a2 = wwa = phase = None
+    else:
+        Neffs, a0, a1, a2, wwa, phase = (alloc((nt, nf)) for _ in range(6))
     if psd_threshold is None:
         _lib.check(L.wwzb200_kirchner(_lib.ptr(ts), _lib.ptr(pd_ys), ts.size, _lib.ptr(tau), nt, _lib.ptr(omega),
                                       nf, float(c), int(Neff_threshold), int(flags), _lib.ptr(Neffs), _lib.ptr(a0),
@@ -288,7 +293,7 @@ def wwz_psd(ys, ts, freq=None, freq_method="log", freq_kwargs=None, tau=None, c=
         omega = make_omega(ts2, freq2)
         # wwa2psd takes its span and count from ts_cut (:896)
         if ts2.size == ts_cut.size:
-            psd = _transform(pd_ys, ts2, tau2, omega, c, 3, flags, psd_threshold=Neff_threshold)[4]
+            psd = _transform(pd_ys, ts2, tau2, omega, c, 3, flags, psd_threshold=Neff_threshold, psd_only=True)[4]
         else:
             amp, _, ne, _, _ = _transform(pd_ys, ts2, tau2, omega, c, 3, flags)
             psd = wwa2psd(amp, ts_cut, ne, freq=freq2, Neff_threshold=Neff_threshold)

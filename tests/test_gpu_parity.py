@@ -293,8 +293,11 @@ def test_pinned_outputs_and_launch_counter():
     before = _lib.launch_count()
     a = WV._transform(y, t, tau, om, 0.0126, 3, pinned=True)
     assert _lib.launch_count() - before >= 5
-    b = WV._transform(y, t, tau, om, 0.0126, 3)
+    b = WV._transform(y, t, tau, om, 0.0126, 3, pinned=False)
     assert np.array_equal(a[0].view(np.uint64), b[0].view(np.uint64))
+    del a
+    c = WV._transform(y, t, tau, om, 0.0126, 3, pinned=True)      # recycled buffers, same values
+    assert np.array_equal(c[0].view(np.uint64), b[0].view(np.uint64))
 
 
 # ------------------------------------------------------------------ BASELINE.json's full sizes

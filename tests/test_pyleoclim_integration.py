@@ -69,7 +69,7 @@ def cuda_standins(monkeypatch, pyleo):
         return B.SignifResults(qs=np.asarray(qs), amplitude_qs=quantiles(r.amplitude, list(qs)),
                                psd_qs=quantiles(r.psd, list(qs)) if psd else None, Neffs=r.Neffs, freq=freq, time=tau)
 
-    def single(pd_ys, ts, tau, omega, c, Neff_threshold, flags=0, psd_threshold=None, pinned=False):
+    def single(pd_ys, ts, tau, omega, c, Neff_threshold, flags=0, psd_threshold=None, pinned=False, psd_only=False):
         calls["single"] += 1
         ne, a0, a1, a2 = O.kirchner_cells(ts, pd_ys, tau, omega, c, Neff_threshold)
         wwa, ph = np.sqrt(a1 ** 2 + a2 ** 2), np.arctan2(a2, a1)
