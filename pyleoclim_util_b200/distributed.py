@@ -51,6 +51,45 @@ def all_gather_rows(local, counts, group=None):
     return np.concatenate([out[r, : counts[r]] for r in range(world)], axis=0)
 
 
+def _device_blocks(pd_ys, ts_cut, tau, omega, c, Neff_threshold, flags, group, want, to_host=True):
+    """NCCL fast path: this rank's tau block is transformed into a device buffer (C-ABI *_dev entry point on
+    torch's current stream), the row blocks are all-gathered on the device and only the assembled
+    [len(want), nt, nf] result crosses PCIe, into page-locked host memory.  `want` indexes the library's output
+    order (0 Neffs, 1 a0, 2 a1, 3 a2, 4 wwa, 5 phase)."""
+    import torch
+    from . import _lib
+    dist = _dist()
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    nt, nf = tau.size, omega.size
+    blocks = row_blocks(nt, world)
+    counts = [b - a for a, b in blocks]
+    a, b = blocks[rank]
+    hmax = max(max(counts), 1)
+    up = lambda x: torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64)).to(dev, non_blocking=True)
+    d_ts, d_ys, d_om = up(ts_cut), up(pd_ys), up(omega)
+    d_tau = up(tau[a:b]) if b > a else torch.zeros(1, dtype=torch.float64, device=dev)
+    loc = torch.zeros((6, hmax, nf), dtype=torch.float64, device=dev)
+    if b > a:
+        ptrs = [loc[i].data_ptr() for i in range(6)]
+        _lib.check(_lib.lib().wwzb200_kirchner_dev(d_ts.data_ptr(), d_ys.data_ptr(), ts_cut.size, d_tau.data_ptr(), b - a,
+                                                   d_om.data_ptr(), nf, float(c), int(Neff_threshold), 0, int(flags),
+                                                   *ptrs, None, nf, torch.cuda.current_stream().cuda_stream))
+    k = len(want)
+    sel = loc[list(want)].contiguous()
+    g = torch.empty((world, k, hmax, nf), dtype=torch.float64, device=dev)
+    dist.all_gather_into_tensor(g.view(-1), sel.view(-1), group=group)
+    if len(set(counts)) == 1:
+        full = g.permute(1, 0, 2, 3).reshape(k, nt, nf)
+    else:
+        full = torch.cat([g[r, :, : counts[r]] for r in range(world)], dim=1)
+    host = None
+    if to_host:
+        host = _lib.output_empty((k, nt, nf))
+        torch.from_numpy(host).copy_(full)      # one D2H of the assembled result
+    return host, full
+
+
 def wwz_tau_sharded(ys, ts, tau=None, freq=None, freq_method="log", freq_kwargs=None, c=1 / (8 * np.pi ** 2),
                     Neff_threshold=3, Neff_coi=3, standardize=True, group=None, kernel=None, flags=0):
     """`wavelet.wwz` with the tau rows sharded over the ranks of `group`.  Every rank returns the
@@ -62,6 +101,13 @@ def wwz_tau_sharded(ys, ts, tau=None, freq=None, freq_method="log", freq_kwargs=
     ys_cut, ts_cut, freq, tau = _wv.prepare_wwz(ys, ts, freq=freq, freq_method=freq_method, freq_kwargs=freq_kwargs,
                                                 tau=tau)
     pd_ys = _wv.preprocess(ys_cut, ts_cut, standardize=standardize)
+    if kernel is _wv.kirchner_cuda and dist.get_backend(group) == "nccl":
+        _wv.assertPositiveInt(Neff_threshold)
+        host, _ = _device_blocks(pd_ys, ts_cut, tau, _wv.make_omega(ts_cut, freq), c, Neff_threshold, flags, group,
+                                 want=(4, 5, 0, 1, 2, 3))
+        wwa, phase, Neffs, a0, a1, a2 = host
+        return _wv.WwzResults(amplitude=wwa, phase=phase, coi=_wv.make_coi(tau, Neff_threshold=Neff_coi), freq=freq,
+                              time=tau, Neffs=Neffs, coeff=(a0, a1, a2), scale=1 / freq)
     blocks = row_blocks(tau.size, world)
     counts = [b - a for a, b in blocks]
     a, b = blocks[rank]
@@ -88,6 +134,18 @@ def wwz_psd_tau_sharded(ys, ts, tau=None, freq=None, freq_method="log", freq_kwa
     ys_cut, ts_cut, freq, tau = _wv.prepare_wwz(ys, ts, freq=freq, freq_method=freq_method, freq_kwargs=freq_kwargs,
                                                 tau=tau)
     pd_ys = _wv.preprocess(ys_cut, ts_cut, standardize=standardize)
+    if kernel is _wv.kirchner_cuda and dist.get_backend(group) == "nccl":
+        # gather amplitude and Neffs on the device, reduce the gathered scalogram there (wwzb200_wwa2psd_dev)
+        from . import _lib
+        _, full = _device_blocks(pd_ys, ts_cut, tau, _wv.make_omega(ts_cut, freq), c, 3, flags, group, want=(4, 0),
+                                 to_host=False)
+        full = full.contiguous()
+        d_psd = torch.empty(freq.size, dtype=torch.float64, device=full.device)
+        _lib.check(_lib.lib().wwzb200_wwa2psd_dev(full[0].data_ptr(), full[1].data_ptr(), tau.size, freq.size,
+                                                  float(np.max(ts_cut) - np.min(ts_cut)), int(np.size(ts_cut)),
+                                                  int(Neff_threshold), d_psd.data_ptr(),
+                                                  torch.cuda.current_stream().cuda_stream))
+        return _wv.PsdResults(psd=d_psd.cpu().numpy(), freq=freq)
     a, b = row_blocks(tau.size, world)[rank]
     kw = dict(c=c, Neff_threshold=3, standardize=False)
     if kernel is _wv.kirchner_cuda:
