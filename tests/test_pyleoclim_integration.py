@@ -197,3 +197,37 @@ def test_fused_and_unfused_signif_test(pyleo, cuda_standins):
         ps = psd.signif_test(number=5, qs=[0.95])
     assert cuda_standins["signif"] == 2 and type(ps.signif_qs).__name__ == "MultiplePSD"
     assert ps.signif_qs.psd_list[0].amplitude.shape == psd.amplitude.shape and ps.signif_qs.psd_list[0].label == "95%"
+
+
+def test_wwz_coherence_uses_the_registered_kernel(pyleo, cuda_standins):
+    """wwz_coherence (utils/wavelet.py:1497-1687) makes two wwz() calls on a common grid
+    (:1660-1665); with the dispatch patched both go through the CUDA kernel, the smoothing stays Pyleoclim's."""
+    W = pyleo.utils.wavelet
+    t1, y1 = synth.uneven_ar1(150, 1)
+    t2, y2 = synth.uneven_ar1(150, 2)
+    tau = np.linspace(max(t1.min(), t2.min()), min(t1.max(), t2.max()), 12)
+    kw = dict(tau=tau, freq=FREQ, nproc=1, standardize=True)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        got = W.wwz_coherence(y1, t1, y2, t2, method="Kirchner_cuda", **kw)
+        ref = W.wwz_coherence(y1, t1, y2, t2, method="Kirchner", **kw)
+    assert cuda_standins["single"] == 2
+    assert max_rel(got.xw_coherence, ref.xw_coherence) < 1e-8 and max_rel(got.xw_amplitude, ref.xw_amplitude) < 1e-8
+
+
+def test_surrogates_option_routes_ar1_sim_to_the_device(pyleo, monkeypatch):
+    calls = []
+
+    def fake_ar1_sim(y, p, t, seed=0):
+        calls.append((p, seed))
+        return np.zeros((np.size(y), p)) if p > 1 else np.zeros(np.size(y))
+
+    monkeypatch.setattr(B, "ar1_sim", fake_ar1_sim)
+    D.register(surrogates=True)
+    try:
+        t, y = synth.uneven_ar1(80, 4)
+        out = pyleo.utils.tsmodel.ar1_sim(y, 3, t)
+        assert out.shape == (80, 3) and calls and calls[0][0] == 3
+    finally:
+        D.unregister()
+    assert pyleo.utils.tsmodel.ar1_sim.__module__.endswith("tsmodel")
