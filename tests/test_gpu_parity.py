@@ -332,3 +332,26 @@ def test_config5_full_grid_properties_and_golden_sample():
     f = WV.kirchner_cuda(ys, t, freq, tau[blk])
     assert np.array_equal(e[2].view(np.uint64), f[2].view(np.uint64))
     assert max_rel(f[2], Neffs[blk]) < 1e-12       # (the full grid uses a different point segmentation)
+
+
+def test_arbitrary_tau_axes_use_the_direct_kernel_and_match_the_oracle():
+    """tau need not be np.linspace: unequal spacing, descending order and nearly-but-not equally spaced axes
+    (the tau-recurrence kernel must not take those) all match the oracle."""
+    t, y = synth.uneven_ar1(900, 12)
+    y = (y - y.mean()) / y.std()
+    freq = synth.freq_log(t, 19)
+    rng = np.random.default_rng(4)
+    lin = np.linspace(t.min(), t.max(), 48)
+    cases = {
+        "random sorted": np.sort(rng.uniform(t.min(), t.max(), 48)),
+        "descending": lin[::-1].copy(),
+        "jittered by 1e-9": lin + 1e-9 * rng.standard_normal(48) * np.arange(48),
+        "quadratic": t.min() + (t.max() - t.min()) * np.linspace(0, 1, 48) ** 2,
+    }
+    for name, tau in cases.items():
+        a = WV.kirchner_cuda(y, t, freq, tau)
+        o = oracle().kirchner(y, t, freq, tau)
+        assert_scalogram_parity(as_dict(*a), as_dict(*o), what=name)
+        b = WV.kirchner_cuda(y, t, freq, tau, flags=_lib.NO_RECURRENCE)
+        for x, z in zip(_bits(a), _bits(b)):          # the recurrence kernel was not used
+            assert np.array_equal(x, z), name
