@@ -31,156 +31,145 @@ def assertPositiveInt(*args):
 
 
 def clean_ts(ys, ts, verbose=False):
-    """utils/tsbase.py:316-352: drop NaNs, sort ascending, average duplicated time stamps."""
+    """What utils/tsbase.py:316-352 does to a series before WWZ: entries with a NaN value or stamp are
+    dropped, the rest is put in ascending time order, and samples sharing a stamp are replaced by their mean."""
     ys = np.asarray(ys, dtype=float)
     ts = np.asarray(ts, dtype=float)
     assert ys.size == ts.size, "The size of time axis and data value should be equal!"
-    good = ~np.isnan(ys)
-    ys, ts = ys[good], ts[good]
-    good = ~np.isnan(ts)
-    ys, ts = ys[good], ts[good]
+    keep = ~(np.isnan(ys) | np.isnan(ts))
+    ys, ts = ys[keep], ts[keep]
     order = np.argsort(ts)
     ys, ts = ys[order], ts[order]
-    if ts.size != np.unique(ts).size:
-        uts, start, counts = np.unique(ts, return_index=True, return_counts=True)
-        ys = np.array([np.mean(ys[s:s + c]) for s, c in zip(start, counts)])
-        ts = uts
+    stamps, first, count = np.unique(ts, return_index=True, return_counts=True)
+    if stamps.size != ts.size:
+        ys = np.array([ys[i:i + c].mean() for i, c in zip(first, count)])
+        ts = stamps
     return ys, ts
 
 
 def standardize(x, scale=1, axis=0, ddof=0, eps=1e-3):
-    """utils/tsutils.py:1096-1156: z-score; (nearly) constant series are left unscaled."""
+    """z-score with the conventions of utils/tsutils.py:1096-1156: NaN-aware mean and standard deviation
+    (``ddof`` = 0), ``scale`` divides the deviation, and a series whose deviation is below ``eps`` is returned
+    unshifted and unscaled with a warning.  Returns ``(z, mean, std)``."""
     x = np.asanyarray(x)
     assert x.ndim <= 2, "The time series x should be a vector or 2-D array!"
     mu = np.nanmean(x, axis=axis)
     sig = np.nanstd(x, axis=axis, ddof=ddof)
-    mu2 = np.asarray(np.copy(mu))
-    sig2 = np.asarray(np.copy(sig) / scale)
-    if np.any(np.abs(sig) < eps):
+    flat = np.abs(sig) < eps
+    shift = np.where(flat, 0.0, mu)
+    spread = np.where(flat, 1.0, sig / scale)
+    if np.any(flat):
         warnings.warn("Constant or nearly constant time series not rescaled.", stacklevel=2)
-        where_const = np.abs(sig) < eps
-        mu2[where_const] = 0
-        sig2[where_const] = 1
-    if axis and mu.ndim < x.ndim:
-        z = (x - np.expand_dims(mu2, axis=axis)) / np.expand_dims(sig2, axis=axis)
-    else:
-        z = (x - mu2) / sig2
-    return z, mu, sig
+    if axis and np.ndim(mu) < x.ndim:
+        shift, spread = np.expand_dims(shift, axis=axis), np.expand_dims(spread, axis=axis)
+    return (x - shift) / spread, mu, sig
 
 
 def preprocess(ys, ts, detrend=False, sg_kwargs=None, gaussianize=False, standardize=True):
-    """utils/tsutils.py:1757-1825.  Detrending and gaussianization are optional preprocessing that
-    is off by default on the WWZ path (utils/wavelet.py:1296-1297) and stays with Pyleoclim: when
-    the package is registered inside Pyleoclim, ``register()`` routes through the reference's own
-    ``preprocess``; standalone only the default (z-score) is provided."""
-    if not (detrend == "none" or detrend is False or detrend is None) or gaussianize:
+    """The default branch of utils/tsutils.py:1757-1825 (z-score only).  Detrending and gaussianization are
+    optional Pyleoclim preprocessing that is off by default on the WWZ path (utils/wavelet.py:1296-1297); when this
+    package is registered inside Pyleoclim, ``register()`` routes through Pyleoclim's own ``preprocess`` so those
+    options keep working."""
+    if detrend not in ("none", False, None) or gaussianize:
         raise NotImplementedError(
             "detrend/gaussianize are Pyleoclim preprocessing options; use pyleoclim_util_b200.register() "
             "inside Pyleoclim to have its preprocess() applied before the CUDA kernel")
-    if standardize:
-        return globals()["standardize"](ys)[0]
-    return ys
+    return globals()["standardize"](ys)[0] if standardize else ys
 
 
 def make_omega(ts, freq):
-    """utils/wavelet.py:1210-1234: omega = 2*pi*freq, NaN above f_Nyquist = 0.5/median(diff(ts))."""
-    f_Nyquist = 0.5 / np.median(np.diff(ts))
-    freq_with_nan = np.array(freq, dtype=float, copy=True)
-    freq_with_nan[freq_with_nan > f_Nyquist] = np.nan
-    return 2 * np.pi * freq_with_nan
+    """Angular frequencies for the kernel (utils/wavelet.py:1210-1234): 2*pi*f, NaN for every f above the Nyquist
+    frequency of the median sampling interval."""
+    freq = np.array(freq, dtype=float, copy=True)
+    nyquist = 0.5 / np.median(np.diff(ts))
+    return 2 * np.pi * np.where(freq > nyquist, np.nan, freq)
 
 
 def make_coi(tau, Neff_threshold=3):
-    """utils/wavelet.py:1168-1208: cone of influence."""
+    """Cone of influence (utils/wavelet.py:1168-1208): a tent over the tau axis, distance (in steps of the median
+    tau spacing) to the nearer end, with 1e-5 at the two ends, times the e-folding constant of the Morlet-like
+    wavelet for ``Neff_threshold``."""
     assert isinstance(Neff_threshold, (int, np.integer)) and Neff_threshold >= 1
     nt = np.size(tau)
-    fourier_factor = 4 * np.pi / (Neff_threshold + np.sqrt(2 + Neff_threshold ** 2))
-    coi_const = fourier_factor / np.sqrt(2)
-    dt = np.median(np.diff(tau))
-    nt_half = (nt + 1) // 2 - 1
-    A = np.append(0.00001, np.arange(nt_half) + 1)
-    B = A[::-1]
-    C = np.append(A, B) if nt % 2 == 0 else np.append(A, B[1:])
-    return coi_const * dt * C
+    efold = 4 * np.pi / (Neff_threshold + np.sqrt(2 + Neff_threshold ** 2)) / np.sqrt(2)
+    step = np.median(np.diff(tau))
+    idx = np.arange(nt)
+    tent = np.minimum(idx, nt - 1 - idx).astype(float)
+    tent[tent == 0] = 0.00001
+    return efold * step * tent
 
 
 def freq_vector_log(ts, fmin=None, fmax=None, nf=None):
-    """utils/wavelet.py:1935-1984."""
-    nt = np.size(ts)
-    dt = np.median(np.diff(ts))
-    if nf is None:
-        nf = nt // 10 + 1
-    if fmin is None:
-        fmin = 1 / np.ptp(ts)
-    if fmax is None:
-        fmax = (1 / dt) / 2
-    return np.logspace(np.log2(fmin), np.log2(fmax), nf, base=2)
+    """Log-spaced frequency axis (utils/wavelet.py:1935-1984): nf = n//10 + 1 points from the Rayleigh
+    frequency 1/span to the Nyquist frequency of the median sampling interval, unless given."""
+    n = np.size(ts)
+    lo = 1 / np.ptp(ts) if fmin is None else fmin
+    hi = 0.5 / np.median(np.diff(ts)) if fmax is None else fmax
+    return np.logspace(np.log2(lo), np.log2(hi), n // 10 + 1 if nf is None else nf, base=2)
 
 
 def make_freq_vector(ts, method="log", rayleigh_bound=True, **kwargs):
-    """utils/wavelet.py:1986-2049.  Only the 'log' generator (the default of wwz / wwz_psd) is
-    mirrored; the other generators belong to estimators outside this path."""
-    if method == "log":
-        fr = freq_vector_log(ts, **kwargs)
-    elif method in ("lomb_scargle", "welch", "nfft", "scale"):
+    """utils/wavelet.py:1986-2049.  Only the 'log' generator (the default of wwz / wwz_psd) is mirrored; the
+    other generators belong to estimators outside this path."""
+    if method in ("lomb_scargle", "welch", "nfft", "scale"):
         raise NotImplementedError("freq_method=%r is not on the WWZ hot path; pass freq explicitly" % method)
-    else:
+    if method != "log":
         raise ValueError("This method is not supported")
-    if rayleigh_bound:
-        return fr[fr >= 1 / np.ptp(ts)]
-    return fr
+    fr = freq_vector_log(ts, **kwargs)
+    return fr[fr >= 1 / np.ptp(ts)] if rayleigh_bound else fr
+
+
+def _repair_tau(tau, ts):
+    """tau as wwz will use it (utils/wavelet.py:2147-2169): default 50 points over the series, regenerated over
+    the series span when it holds NaNs or overhangs both ends, and pulled onto time-axis points when its ends
+    are not samples of the series."""
+    t_lo, t_hi = np.min(ts), np.max(ts)
+    if tau is None:
+        return np.linspace(t_lo, t_hi, min(np.size(ts), 50))
+    tau = np.asarray(tau, dtype=float)
+    if np.isnan(tau).any():
+        warnings.warn("The input tau contains some NaNs; it is regenerated over the time span of the series "
+                      "(NaNs deleted) with the same number of points.")
+        return np.linspace(t_lo, t_hi, tau.size)
+    if np.min(tau) < t_lo and np.max(tau) > t_hi:
+        warnings.warn("tau should lie within the time span of the series (leading NaNs of the series are deleted "
+                      "first); a new tau with the same number of points is generated over the series span.")
+        return np.linspace(t_lo, t_hi, tau.size)
+    if np.min(tau) not in ts or np.max(tau) not in ts:
+        warnings.warn("The ends of tau are not points of the time axis; tau is adjusted so that they are.")
+        return np.linspace(np.min(ts[ts > np.min(tau)]), np.max(ts[ts < np.max(tau)]), tau.size)
+    return tau
+
+
+def _ghost_pad(ys, ts, tau, len_bd, bc_mode, reflect_type):
+    """``len_bd`` ghost points on both sides of the series and the matching extension of tau
+    (utils/wavelet.py:2172-2189)."""
+    dt, dtau = np.median(np.diff(ts)), np.median(np.diff(tau))
+    n_tau = int(len_bd * dt // dtau)
+    pad_kw = {"reflect_type": reflect_type} if bc_mode in ("reflect", "symmetric") else {}
+    ys = np.pad(ys, (len_bd, len_bd), bc_mode, **pad_kw)
+    ts = np.concatenate((np.linspace(ts[0] - dt * len_bd, ts[0] - dt, len_bd), ts,
+                         np.linspace(ts[-1] + dt, ts[-1] + dt * len_bd, len_bd)))
+    warnings.warn("The tau will be regenerated to fit the boundary condition.")
+    tau = np.concatenate((np.linspace(tau[0] - dtau * n_tau, tau[0] - dtau, n_tau), tau,
+                          np.linspace(tau[-1] + dtau, tau[-1] + dtau * n_tau, n_tau)))
+    return ys, ts, tau
 
 
 def prepare_wwz(ys, ts, freq=None, freq_method="log", freq_kwargs=None, tau=None, len_bd=0,
                 bc_mode="reflect", reflect_type="odd", **kwargs):
-    """utils/wavelet.py:2094-2202: clean the series, build / repair tau, optional ghost padding,
-    truncate the series to the tau span, build freq, drop f == 0."""
+    """utils/wavelet.py:2094-2202: clean the series, build or repair tau, optional ghost padding, cut the series to
+    the tau span, build freq when it is not given, drop f == 0.  Returns ``ys_cut, ts_cut, freq, tau``."""
     ys, ts = clean_ts(ys, ts)
-    if tau is None:
-        ntau = np.min([np.size(ts), 50])
-        tau = np.linspace(np.min(ts), np.max(ts), ntau)
-    elif np.isnan(tau).any():
-        warnings.warn("The input tau contains some NaNs." +
-                      "It will be regenerated using the boundarys of the time axis of the time series with NaNs deleted," +
-                      "with the length of the size of the input tau.")
-        tau = np.linspace(np.min(ts), np.max(ts), np.size(tau))
-    elif np.min(tau) < np.min(ts) and np.max(tau) > np.max(ts):
-        warnings.warn("tau should be within the time span of the time series." +
-                      "Note that sometimes if the leading points of the time series are NaNs," +
-                      "they will be deleted and cause np.min(tau) < np.min(ts)." +
-                      "A new tau with the same size of the input tau will be generated.")
-        tau = np.linspace(np.min(ts), np.max(ts), np.size(tau))
-    elif np.min(tau) not in ts or np.max(tau) not in ts:
-        warnings.warn("The boundaries of tau are not exactly on two of the time axis points," +
-                      "and it will be adjusted to be so.")
-        tau_lb = np.min(ts[ts > np.min(tau)])
-        tau_ub = np.max(ts[ts < np.max(tau)])
-        tau = np.linspace(tau_lb, tau_ub, np.size(tau))
-
-    if len_bd > 0:                                               # :2172-2189
-        dt = np.median(np.diff(ts))
-        dtau = np.median(np.diff(tau))
-        len_bd_tau = int(len_bd * dt // dtau)
-        if bc_mode in ["reflect", "symmetric"]:
-            ys = np.pad(ys, (len_bd, len_bd), bc_mode, reflect_type=reflect_type)
-        else:
-            ys = np.pad(ys, (len_bd, len_bd), bc_mode)
-        ts_left_bd = np.linspace(ts[0] - dt * len_bd, ts[0] - dt, len_bd)
-        ts_right_bd = np.linspace(ts[-1] + dt, ts[-1] + dt * len_bd, len_bd)
-        ts = np.concatenate((ts_left_bd, ts, ts_right_bd))
-        warnings.warn("The tau will be regenerated to fit the boundary condition.")
-        tau_left_bd = np.linspace(tau[0] - dtau * len_bd_tau, tau[0] - dtau, len_bd_tau)
-        tau_right_bd = np.linspace(tau[-1] + dtau, tau[-1] + dtau * len_bd_tau, len_bd_tau)
-        tau = np.concatenate((tau_left_bd, tau, tau_right_bd))
-
-    sel = (np.min(tau) <= ts) & (ts <= np.max(tau))
-    ts_cut, ys_cut = ts[sel], ys[sel]
+    tau = _repair_tau(tau, ts)
+    if len_bd > 0:
+        ys, ts, tau = _ghost_pad(ys, ts, tau, len_bd, bc_mode, reflect_type)
+    inside = (np.min(tau) <= ts) & (ts <= np.max(tau))
+    ts_cut, ys_cut = ts[inside], ys[inside]
     if freq is None:
-        freq_kwargs = {} if freq_kwargs is None else freq_kwargs.copy()
-        freq = make_freq_vector(ts_cut, method=freq_method, **freq_kwargs)
+        freq = make_freq_vector(ts_cut, method=freq_method, **({} if freq_kwargs is None else dict(freq_kwargs)))
     freq = np.asarray(freq, dtype=float)
-    freq = freq[freq != 0]
-    return ys_cut, ts_cut, freq, np.asarray(tau, dtype=float)
+    return ys_cut, ts_cut, freq[freq != 0], np.asarray(tau, dtype=float)
 
 
 # ------------------------------------------------------------------------------ the kernel
