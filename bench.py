@@ -321,24 +321,74 @@ def run_ours(args):
     e2e_value = world * cells_step_local * args.steps / api_s
 
     # ---------------------------------------------------------------- the other half of the metric: surrogate tests/s
+    # config 3: n=5000, default 50 x 501 grid; surrogates generated, z-scored, transformed and reduced to the 95%
+    # quantile on the device, host to host.  N > 1: the grid is sharded by frequency block over the ranks.
     extras = {}
-    if rank == 0:
-        from pyleoclim_util_b200 import batch as B, synth
-        t3, y3, tau3, freq3 = synth.config_grid("C3")          # n=5000, default 50 x 501 grid
-        S3 = 2048
-        B.wwz_signif(y3, t3, tau=tau3, freq=freq3, number=256, qs=[0.95], seed=1)
-        _lib.profile(True)
-        s0 = time.perf_counter()
-        B.wwz_signif(y3, t3, tau=tau3, freq=freq3, number=S3, qs=[0.95], seed=1)
-        s1 = time.perf_counter() - s0
-        sh_ms, sh_n, sh_cp = _lib.profile_read()
-        _lib.profile(False)
-        extras["signif_test"] = {
-            "workload": "C3: n=5000, 50 tau x %d f, %d AR(1) surrogates generated, z-scored, transformed and reduced "
-                        "to the 95%% quantile on the device (wwzb200_ar1_signif), host to host" % (freq3.size, S3),
-            "surrogates_per_s": S3 / s1, "seconds": s1,
-            "shared_axis_kernel_ms": sh_ms, "contraction_tflops": 6.0 * sh_cp / (sh_ms * 1e-3) / 1e12 if sh_ms else None,
-            "algorithmic": "6 flop per (cell, point, surrogate) (SURVEY.md 8d)"}
+    from pyleoclim_util_b200 import batch as B, synth, distributed as D
+    t3, y3, tau3, freq3 = synth.config_grid("C3")
+    S3 = 2048 * world
+
+    def signif_run(number):
+        if world == 1:
+            return B.wwz_signif(y3, t3, tau=tau3, freq=freq3, number=number, qs=[0.95], seed=1)
+        return D.wwz_signif_sharded(y3, t3, tau=tau3, freq=freq3, number=number, qs=[0.95], seed=1)
+
+    signif_run(256)
+    barrier()
+    _lib.profile(True)
+    s0 = time.perf_counter()
+    signif_run(S3)
+    barrier()
+    s1 = time.perf_counter() - s0
+    sh_ms, sh_n, sh_cp = _lib.profile_read()
+    _lib.profile(False)
+    if dist is not None:
+        tmax = torch.tensor([s1], dtype=torch.float64, device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        s1 = float(tmax.item())
+    extras["signif_test"] = {
+        "workload": "C3: n=5000, 50 tau x %d f, %d AR(1) surrogates (2048 per GPU), generated, z-scored, transformed and "
+                    "reduced to the 95%% quantile on the device (wwzb200_ar1_signif), host to host%s"
+                    % (freq3.size, S3, "" if world == 1 else "; frequency blocks sharded over the ranks"),
+        "surrogates_per_s": S3 / s1, "seconds": s1, "n_gpus": world,
+        "shared_axis_kernel_ms_rank0": sh_ms,
+        "contraction_tflops_rank0": 6.0 * sh_cp / (sh_ms * 1e-3) / 1e12 if sh_ms else None,
+        "algorithmic": "6 flop per (cell, point, surrogate) (SURVEY.md 8d)"}
+
+    # config 5 (n=100,000, 4096 tau x 2047 f = 8.4e11 cell-points), device resident, rank 0 at N = 1 only:
+    # once dense (the FP64-pipe statement BASELINE.json asks for) and once with the default path
+    if world == 1:
+        t5, y5, tau5, freq5 = synth.config_grid("C5")
+        d5 = [torch.from_numpy(np.ascontiguousarray(v)).to(dev) for v in
+              (t5, WV.standardize(y5)[0], tau5, WV.make_omega(t5, freq5))]
+        o5 = torch.empty((6, tau5.size, freq5.size), dtype=torch.float64, device=dev)
+
+        def run5(flags):
+            _lib.check(L.wwzb200_kirchner_dev(d5[0].data_ptr(), d5[1].data_ptr(), t5.size, d5[2].data_ptr(), tau5.size,
+                                              d5[3].data_ptr(), freq5.size, C_WWZ, 3, 3, flags,
+                                              *[o5[i].data_ptr() for i in range(6)], None, freq5.size, stream))
+
+        c5 = {}
+        for name, fl in (("default", 0), ("dense", _lib.DENSE)):
+            run5(fl)
+            torch.cuda.synchronize()
+            _lib.profile(True)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            run5(fl)
+            e1.record()
+            torch.cuda.synchronize()
+            k_ms, k_n, k_cp = _lib.profile_read()
+            _lib.profile(False)
+            tot = e0.elapsed_time(e1)
+            c5[name] = {"ms": tot, "cells_per_s": tau5.size * freq5.size / (tot * 1e-3), "cell_kernel_ms": k_ms,
+                        "cell_kernel_launches": k_n,
+                        "cell_kernel_algorithmic_tflops": FLOP_PER_CELL_POINT * k_cp / (k_ms * 1e-3) / 1e12}
+        c5["dense"]["frac_of_fp64_peak"] = c5["dense"]["cell_kernel_algorithmic_tflops"] / fp64_tf
+        c5["workload"] = "C5: n=100000, 4096 tau x %d f, one transform, device resident (basis rows in %d frequency batches)" \
+                         % (freq5.size, c5["dense"]["cell_kernel_launches"])
+        extras["config5"] = c5
+        del d5, o5
 
     clocks = sampler.stop()
 

@@ -168,27 +168,48 @@ def wwz_psd_tau_sharded(ys, ts, tau=None, freq=None, freq_method="log", freq_kwa
     return _wv.PsdResults(psd=psd, freq=freq)
 
 
-def wwz_signif_tau_sharded(ys, ts, tau=None, freq=None, number=200, qs=(0.95,), seed=0, c=1 / (8 * np.pi ** 2),
-                           Neff_threshold=3, freq_method="log", freq_kwargs=None, group=None, signif=None):
-    """Scalogram significance levels with the tau rows sharded: each rank runs the fused device
-    pipeline (`batch.signif_prepared`) for all `number` surrogates on its rows; the same seed gives
-    every rank the same surrogates, so quantiles are exchange-free.  Returns `batch.SignifResults`."""
+def wwz_signif_sharded(ys, ts, tau=None, freq=None, number=200, qs=(0.95,), seed=0, c=1 / (8 * np.pi ** 2),
+                       Neff_threshold=3, freq_method="log", freq_kwargs=None, group=None, signif=None, axis="auto"):
+    """Scalogram significance levels with the (tau, f) grid sharded over the ranks: each rank runs the fused
+    device pipeline (`batch.signif_prepared`) for all `number` surrogates on its block of tau rows
+    (axis='tau') or of frequency columns (axis='freq'; 'auto' takes the longer axis, which balances better --
+    the reference's default grid is 50 tau x n/10 frequencies).  The same seed gives every rank the same
+    surrogates, so the per-cell quantiles are exchange-free; only the quantile tiles are gathered.
+    Returns `batch.SignifResults`."""
     from . import batch
     dist = _dist()
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     signif = batch.signif_prepared if signif is None else signif
     ys_cut, ts_cut, freq, tau = _wv.prepare_wwz(ys, ts, freq=freq, freq_method=freq_method, freq_kwargs=freq_kwargs,
                                                 tau=tau)
-    blocks = row_blocks(tau.size, world)
-    counts = [b - a for a, b in blocks]
-    a, b = blocks[rank]
+    if axis == "auto":
+        axis = "freq" if freq.size >= tau.size else "tau"
     probs = np.atleast_1d(np.asarray(qs, dtype=float))
-    if b > a:
-        q_wwa, _, Neffs = signif(ys_cut, ts_cut, tau[a:b], freq, number=number, probs=probs, seed=seed, c=c,
-                                 Neff_threshold=Neff_threshold)
-        local = np.concatenate([np.moveaxis(q_wwa, 0, 1), Neffs[:, None, :]], axis=1)    # [rows, nq+1, nf]
+    nq = probs.size
+    if axis == "tau":
+        blocks = row_blocks(tau.size, world)
+        a, b = blocks[rank]
+        tau_loc, freq_loc = tau[a:b], freq
+    elif axis == "freq":
+        blocks = row_blocks(freq.size, world)
+        a, b = blocks[rank]
+        tau_loc, freq_loc = tau, freq[a:b]
     else:
-        local = np.zeros((0, probs.size + 1, freq.size))
-    full = all_gather_rows(local, counts, group)
-    return batch.SignifResults(qs=probs, amplitude_qs=np.ascontiguousarray(np.moveaxis(full[:, :-1], 1, 0)),
-                               psd_qs=None, Neffs=np.ascontiguousarray(full[:, -1]), freq=freq, time=tau)
+        raise ValueError("axis must be 'tau', 'freq' or 'auto'")
+    counts = [y - x for x, y in blocks]
+    if b > a:
+        q_wwa, _, Neffs = signif(ys_cut, ts_cut, tau_loc, freq_loc, number=number, probs=probs, seed=seed, c=c,
+                                 Neff_threshold=Neff_threshold)
+        local = np.concatenate([q_wwa, Neffs[None]], axis=0)                 # [nq+1, nt_loc, nf_loc]
+        local = np.moveaxis(local, 1 if axis == "tau" else 2, 0)             # sharded axis first
+    else:
+        local = np.zeros((0, nq + 1, freq.size if axis == "tau" else tau.size))
+    full = all_gather_rows(np.ascontiguousarray(local), counts, group)
+    full = np.moveaxis(full, 0, 1 if axis == "tau" else 2)                   # back to [nq+1, nt, nf]
+    return batch.SignifResults(qs=probs, amplitude_qs=np.ascontiguousarray(full[:nq]), psd_qs=None,
+                               Neffs=np.ascontiguousarray(full[nq]), freq=freq, time=tau)
+
+
+def wwz_signif_tau_sharded(ys, ts, **kw):
+    """`wwz_signif_sharded` with axis='tau'."""
+    return wwz_signif_sharded(ys, ts, axis="tau", **kw)

@@ -60,6 +60,9 @@ def _worker(rank, world, port, nt, out_dir):
         r = D.wwz_tau_sharded(y, t, tau=tau, freq=freq, kernel=kernel)
         p = D.wwz_psd_tau_sharded(y, t, tau=tau, freq=freq, kernel=kernel)
         s = D.wwz_signif_tau_sharded(y, t, tau=tau, freq=freq, number=4, qs=[0.5, 0.9], seed=5, signif=signif)
+        sf = D.wwz_signif_sharded(y, t, tau=tau, freq=freq, number=4, qs=[0.5, 0.9], seed=5, signif=signif, axis="freq")
+        assert np.array_equal(s.amplitude_qs, sf.amplitude_qs, equal_nan=True)      # either axis, same quantiles
+        assert np.array_equal(s.Neffs, sf.Neffs, equal_nan=True)
         g = D.all_gather_rows(np.full((rank + 1, 2), float(rank)), [1, 2])
         g0 = D.all_gather_rows(np.full((2 * rank, 3), 7.0), [0, 2])            # rank 0 holds an empty block
         np.savez(os.path.join(out_dir, "rank%d.npz" % rank), amp=r.amplitude, phase=r.phase, Neffs=r.Neffs, a0=r.coeff[0],
