@@ -68,6 +68,10 @@ int wwzb200_release(void);
 /* Page-locked host buffers (so that the host-pointer entry points move data by DMA). */
 int wwzb200_alloc_pinned(size_t bytes, void **ptr);
 int wwzb200_free_pinned(void *ptr);
+/* Device-to-host copy on `stream` (a cudaStream_t), synchronised before returning; a plain DMA when
+ * dst is page-locked (wwzb200_alloc_pinned).  For callers that keep results in HBM (the *_dev entry
+ * points) and bring an assembled result to the host once. */
+int wwzb200_copy_to_host(void *dst, const void *d_src, size_t bytes, void *stream);
 
 /* (1) Single-series Kirchner transform.  Replaces f2py_wwz.wwa (f2py_wwz.f90:13-44) and the cell
  * loop of kirchner_numba (utils/wavelet.py:985-1042), plus wwa/phase (:1044-1045).

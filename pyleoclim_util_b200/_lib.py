@@ -40,6 +40,7 @@ _SIGS = {
     "wwzb200_release": (ctypes.c_int, []),
     "wwzb200_alloc_pinned": (ctypes.c_int, [ctypes.c_size_t, ctypes.POINTER(_vp)]),
     "wwzb200_free_pinned": (ctypes.c_int, [_vp]),
+    "wwzb200_copy_to_host": (ctypes.c_int, [_vp, _vp, ctypes.c_size_t, _vp]),
     "wwzb200_kirchner": (ctypes.c_int, [_dp, _dp, _i64, _dp, _i64, _dp, _i64, _dbl, _i64, _u32,
                                         _dp, _dp, _dp, _dp, _dp, _dp]),
     "wwzb200_kirchner_psd": (ctypes.c_int, [_dp, _dp, _i64, _dp, _i64, _dp, _i64, _dbl, _i64, _i64, _u32,

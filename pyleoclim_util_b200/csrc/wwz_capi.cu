@@ -466,6 +466,16 @@ int wwzb200_free_pinned(void *ptr)
     return 0;
 }
 
+int wwzb200_copy_to_host(void *dst, const void *d_src, size_t bytes, void *stream)
+{
+    if (bytes == 0) return 0;
+    if (!dst || !d_src) return fail(WWZB200_ERR_ARG, "null pointer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CU(cudaMemcpyAsync(dst, d_src, bytes, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return 0;
+}
+
 int wwzb200_kirchner(const double *ts, const double *pd_ys, int64_t nts, const double *taus, int64_t nt,
                      const double *omegas, int64_t nf, double c, int64_t Neff_threshold, uint32_t flags,
                      double *Neffs, double *a0, double *a1, double *a2, double *wwa, double *phase)

@@ -86,7 +86,10 @@ def _device_blocks(pd_ys, ts_cut, tau, omega, c, Neff_threshold, flags, group, w
     host = None
     if to_host:
         host = _lib.output_empty((k, nt, nf))
-        torch.from_numpy(host).copy_(full)      # one D2H of the assembled result
+        full = full.contiguous()
+        # one D2H of the assembled result, straight into the page-locked result buffer
+        _lib.check(_lib.lib().wwzb200_copy_to_host(host.ctypes.data, full.data_ptr(), host.nbytes,
+                                                   torch.cuda.current_stream().cuda_stream))
     return host, full
 
 
