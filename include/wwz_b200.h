@@ -45,8 +45,12 @@ extern "C" {
 
 /* flags */
 #define WWZB200_DENSE 1u        /* evaluate every (cell, point) pair with its own exp2: no windowing  \
-                                   (the default skips point chunks whose weights are all exactly 0.0, \
-                                   bit-identical) and no tau-recurrence */
+                                   and no tau-recurrence.  The default walks, per tile of cells, only \
+                                   the points whose weight reaches 2^-300 for some cell of the tile:  \
+                                   skipped terms are < 2^-100 of any sum that is not recomputed by    \
+                                   the faithful kernel (cells with sum(w) < 2^-200) */
+#define WWZB200_EXACT_WINDOW 16u /* window only on weights that are exactly 0.0 in the kernel (below   \
+                                   2^-1081): bit-identical to WWZB200_DENSE for the direct kernel */
 #define WWZB200_STANDARDIZE 2u  /* batched entry points: z-score every series on the device       \
                                    (utils/tsutils.py:1134-1154, ddof=0, eps=1e-3 guard) */
 #define WWZB200_NO_RECURRENCE 8u /* keep one exp2 per (cell, point): do not use the tau-recurrence kernel \

@@ -15,6 +15,7 @@ DENSE = 1
 STANDARDIZE = 2
 FAITHFUL = 4
 NO_RECURRENCE = 8
+EXACT_WINDOW = 16
 
 _dp = ctypes.POINTER(ctypes.c_double)
 _ip = ctypes.POINTER(ctypes.c_int64)

@@ -129,8 +129,9 @@ size_t basis_budget_bytes()
     return (size_t)2 << 30;
 }
 
-// Number of point-axis segments: enough that (cells x segments) fills the machine for ~16 waves
-// (2.4e6 cell-slots = 16 waves x 296 CTAs x 512 cells), each segment at least 256 points.
+// Number of point-axis segments: enough that (cells x segments) fills the machine for several waves
+// (1.5e6 cell-slots = 10 waves x 296 CTAs x 512 cells of the direct kernel, 3.3 waves x 1776 warp tiles x 256
+// cells of the recurrence kernel -- measured best on config 2), each segment at least 256 points.
 // It depends on the problem size only, never on the tile geometry, so every kernel variant adds
 // the same partial sums.
 int point_segments(int64_t n, int64_t ncell)
@@ -140,7 +141,7 @@ int point_segments(int64_t n, int64_t ncell)
     if (e && *e) {
         s = atoll(e);
     } else {
-        s = (2400000 + ncell - 1) / std::max<int64_t>(ncell, 1);
+        s = (1500000 + ncell - 1) / std::max<int64_t>(ncell, 1);
         s = std::min<int64_t>(s, n / 256);
     }
     return (int)std::max<int64_t>(1, std::min<int64_t>(s, 4096));
@@ -197,12 +198,13 @@ int transform_device(Workspace *w, const double *d_ts, const double *d_ys, int64
             const char *e = getenv("WWZB200_NO_RECURRENCE");
             if (e && *e && atoi(e)) allow_rec = false;
         }
-        CellPlan rplan = plan;
+        RecPlan rplan{};
         if (allow_rec) {
-            rplan = plan_cells(n, nt, nf, kRecCells, seg_len);
+            rplan = plan_rec(n, nt, nf, seg_len);
             const int64_t np = std::max(plan.n_pad, rplan.n_pad);   // one row stride for both kernels
             plan.n_pad = rplan.n_pad = np;
         }
+        const double cut_bits = (flags & WWZB200_EXACT_WINDOW) ? 1081.0 : 300.0;
         double *d_grid;
         unsigned char *d_rec_row;
         if ((rc = wsbuf(w, "grid", 2, &d_grid))) return rc;
@@ -215,7 +217,7 @@ int transform_device(Workspace *w, const double *d_ts, const double *d_ys, int64
         if ((rc = wsbuf(w, "basis", (size_t)nf_batch * (size_t)plan.n_pad * 2, &d_basis))) return rc;
         if ((rc = wsbuf(w, "sums", (size_t)segs * (size_t)kNumSums * (size_t)ncell, &d_sums))) return rc;
 
-        CU(launch_freq_setup(d_omega, nf, d_tau, nt, c, allow_rec, d_kappa, d_dcut, d_grid, d_rec_row, st));
+        CU(launch_freq_setup(d_omega, nf, d_tau, nt, c, allow_rec, cut_bits, d_kappa, d_dcut, d_grid, d_rec_row, st));
         CU(launch_unsorted_check(d_ts, n, d_unsorted, st));
         CU(cudaMemsetAsync(d_fix_count, 0, sizeof(unsigned int), st));
         const bool dense = (flags & WWZB200_DENSE) != 0;
@@ -229,8 +231,8 @@ int transform_device(Workspace *w, const double *d_ts, const double *d_ys, int64
                 CU(cudaEventRecord(ev.a, st));
             }
             if (allow_rec)
-                CU(launch_cells(rplan, d_ty, d_basis, d_ts, n, d_tau, nt, d_kappa, d_dcut, d_unsorted, k0, nb, nf, dense,
-                                segs, seg_len, d_rec_row, d_grid, d_sums, st));
+                CU(launch_rec(rplan, d_ty, d_basis, d_ts, n, d_tau, nt, d_kappa, d_dcut, d_unsorted, k0, nb, nf, segs,
+                              seg_len, d_rec_row, d_grid, d_sums, st));
             CU(launch_cells(plan, d_ty, d_basis, d_ts, n, d_tau, nt, d_kappa, d_dcut, d_unsorted, k0, nb, nf, dense, segs,
                             seg_len, allow_rec ? d_rec_row : nullptr, d_grid, d_sums, st));
             if (g_profile) {
@@ -358,7 +360,7 @@ int shared_axis_device(Workspace *w, const double *d_ts, const double *d_Y, int6
     unsigned char *d_rec_row;
     if ((rc = wsbuf(w, "grid", 2, &d_grid))) return rc;
     if ((rc = wsbuf(w, "rec_row", (size_t)nf, &d_rec_row))) return rc;
-    CU(launch_freq_setup(d_omega, nf, d_tau, nt, c, false, d_kappa, d_dcut, d_grid, d_rec_row, st));
+    CU(launch_freq_setup(d_omega, nf, d_tau, nt, c, false, 300.0, d_kappa, d_dcut, d_grid, d_rec_row, st));
     CU(launch_basis_sc(d_ts, n, plan.n_pad, d_omega, nf, d_ty, d_basis, st));
     CU(launch_rotation(d_tau, d_omega, nt, nf, d_rot, st));
     CU(launch_standardize_retile(d_Y, n, plan.n_pad, S, (flags & WWZB200_STANDARDIZE) != 0, d_mu, d_sig, d_Yt, st));

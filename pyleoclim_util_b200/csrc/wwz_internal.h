@@ -34,11 +34,30 @@ struct CellPlan {
 
 CellPlan plan_cells(int64_t n, int64_t nt, int64_t nf, int cells_per_lane_hint, int64_t seg_len);
 
+// Geometry of the warp-tile tau-recurrence kernel (wwz_rec.cu), derived on the host by plan_rec().
+struct RecPlan {
+    int groups;           // G = ceil(nt / 8) tau-groups per frequency row
+    int tg_log2;          // a warp tile is 2^tg_log2 tau-groups x (32 >> tg_log2) frequency rows
+    int points;           // P: points per stage of a warp's ring
+    int64_t n_pad;
+    int64_t row_stride;   // smem basis row stride in bytes ((P+1)*32)
+    int stage_bytes;      // bytes of one stage
+    int warp_bytes;       // shared memory per warp (ring + mbarriers)
+    int smem_bytes;       // dynamic shared memory of the CTA
+};
+RecPlan plan_rec(int64_t n, int64_t nt, int64_t nf, int64_t seg_len);
+cudaError_t launch_rec(const RecPlan &plan, const double2 *d_ty, const double2 *d_basis, const double *d_ts, int64_t n,
+                       const double *d_tau, int64_t nt, const double *d_kappa, const double *d_dcut,
+                       const int *d_unsorted, int64_t k0, int64_t nf_batch, int64_t nf_total, int segs,
+                       int64_t seg_len, const unsigned char *d_rec_row, const double *d_grid, double *d_sums,
+                       cudaStream_t st);
+
 // Per-frequency constants: kappa = omega*sqrt(c*log2 e), dcut = underflow distance (windowing).
 // Also decides on the device which rows the tau-recurrence kernel may take (d_rec_row) and the tau
 // spacing (d_grid[0]); allow_rec = false marks every row for the direct kernel.
+// cut_bits: weights below 2^-cut_bits are outside the point window of a tile (1081 = exactly zero weights only).
 cudaError_t launch_freq_setup(const double *d_omega, int64_t nf, const double *d_tau, int64_t nt, double c,
-                              bool allow_rec, double *d_kappa, double *d_dcut, double *d_grid,
+                              bool allow_rec, double cut_bits, double *d_kappa, double *d_dcut, double *d_grid,
                               unsigned char *d_rec_row, cudaStream_t st);
 
 // (t, y) interleaved + per-frequency basis rows (sin, cos, y sin, y cos), zero padded to n_pad.

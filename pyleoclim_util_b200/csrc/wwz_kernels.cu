@@ -39,8 +39,9 @@ void bump_launch_counter(int64_t k) { g_launches.fetch_add(k); }
 // ------------------------------------------------------------------------------------------------
 // Per-frequency constants.
 //   kappa4 = 4*omega*sqrt(c*log2(e))         so that  exp(-c*omega^2*d^2) = 2^(-(kappa4*d)^2/16)
-//   dcut   = 4*sqrt(1081)/|kappa4|           |d| > dcut  =>  weight < 2^-1081, i.e. exactly 0.0
-//                                            (used only to window the point range of a tile)
+//   dcut   = 4*sqrt(cut_bits)/|kappa4|       |d| > dcut  =>  weight < 2^-cut_bits (default 300; 1081 with
+//                                            WWZB200_EXACT_WINDOW: exactly 0.0 in the direct kernel);
+//                                            used only to window the point range of a tile
 // omega = NaN (frequency above Nyquist, utils/wavelet.py:1229-1232): kappa = NaN is kept; NaN then
 // flows through every sum of the column and the epilogue yields NaN Neff / coefficients, exactly
 // what NaN arithmetic gives in the reference.  dcut = -1 marks the row as "no window constraint".
@@ -75,7 +76,7 @@ __global__ void tau_uniform_kernel(const double *__restrict__ tau, int64_t nt, d
     }
 }
 
-__global__ void freq_setup_kernel(const double *__restrict__ omega, int64_t nf, double kscale,
+__global__ void freq_setup_kernel(const double *__restrict__ omega, int64_t nf, double kscale, double vcut,
                                   const double *__restrict__ grid, int allow_rec, double *__restrict__ kappa,
                                   double *__restrict__ dcut, unsigned char *__restrict__ rec_row)
 {
@@ -84,18 +85,18 @@ __global__ void freq_setup_kernel(const double *__restrict__ omega, int64_t nf, 
     const double om = omega[k];
     const double ka = om * kscale;
     kappa[k] = ka;
-    dcut[k] = isnan(om) ? -1.0 : 4.0 * sqrt(1081.0) / fabs(ka);  // +inf for omega == 0
+    dcut[k] = isnan(om) ? -1.0 : vcut / fabs(ka);  // |kappa4*d| > vcut => weight < 2^-cut_bits; +inf for omega == 0
     rec_row[k] = (allow_rec && grid[1] != 0.0 && fabs(ka) * grid[0] <= 8.0) ? 1 : 0;   // NaN omega -> 0
 }
 
 cudaError_t launch_freq_setup(const double *d_omega, int64_t nf, const double *d_tau, int64_t nt, double c,
-                              bool allow_rec, double *d_kappa, double *d_dcut, double *d_grid,
+                              bool allow_rec, double cut_bits, double *d_kappa, double *d_dcut, double *d_grid,
                               unsigned char *d_rec_row, cudaStream_t st)
 {
     if (nf <= 0) return cudaSuccess;
     const double kscale = 4.0 * std::sqrt(c * 1.4426950408889634074);  // 4*sqrt(c*log2(e))
     tau_uniform_kernel<<<1, 256, 0, st>>>(d_tau, nt, d_grid);
-    freq_setup_kernel<<<(unsigned)((nf + 127) / 128), 128, 0, st>>>(d_omega, nf, kscale, d_grid, allow_rec ? 1 : 0,
+    freq_setup_kernel<<<(unsigned)((nf + 127) / 128), 128, 0, st>>>(d_omega, nf, kscale, 4.0 * std::sqrt(cut_bits), d_grid, allow_rec ? 1 : 0,
                                                                     d_kappa, d_dcut, d_rec_row);
     bump_launch_counter(2);
     return cudaGetLastError();

@@ -126,11 +126,25 @@ def _bits(out):
 
 
 def test_windowed_is_bit_identical_to_dense():
+    """WWZB200_EXACT_WINDOW skips only points whose weight is exactly +0.0 in the kernel: same bits as dense."""
     t, y, tau, freq = _grid_case(n=3000, nt=64, nf=48)
-    a = WV.kirchner_cuda(y, t, freq, tau, flags=_lib.NO_RECURRENCE)
+    a = WV.kirchner_cuda(y, t, freq, tau, flags=_lib.NO_RECURRENCE | _lib.EXACT_WINDOW)
     b = WV.kirchner_cuda(y, t, freq, tau, flags=_lib.DENSE)
     for x, z in zip(_bits(a), _bits(b)):
         assert np.array_equal(x, z)
+
+
+def test_default_window_is_invisible():
+    """The default window drops weights below 2^-300 (less than 2^-100 of any sum that is kept): against the
+    dense run the results agree to rounding, with the same mask, for both kernels and both decay constants."""
+    for c in (1 / (8 * np.pi ** 2), 1e-3):
+        t, y, tau, freq = _grid_case(n=3000, nt=64, nf=48)
+        d = WV.kirchner_cuda(y, t, freq, tau, c=c, flags=_lib.DENSE)
+        for fl in (_lib.NO_RECURRENCE, 0):
+            a = WV.kirchner_cuda(y, t, freq, tau, c=c, flags=fl)
+            assert_scalogram_parity(as_dict(*a), as_dict(*d), amp_rtol=1e-11 if fl == 0 else 1e-14,
+                                    phase_atol=1e-11 if fl == 0 else 1e-14, neff_rtol=1e-12 if fl == 0 else 1e-15,
+                                    what="default window vs dense (flags=%d, c=%g)" % (fl, c))
 
 
 def test_tau_recurrence_kernel_agrees_with_direct_kernel():
