@@ -177,19 +177,22 @@ __global__ void __launch_bounds__(256)
 }
 
 template <int NS>
-__global__ void retile_kernel(const double *__restrict__ Y, int64_t n, int64_t n_pad, int64_t S,
-                              const double *__restrict__ mu, const double *__restrict__ sig, double *__restrict__ Yt)
+__global__ void __launch_bounds__(256)
+    retile_kernel(const double *__restrict__ Y, int64_t n, int64_t n_pad, int64_t S, const double *__restrict__ mu,
+                  const double *__restrict__ sig, double *__restrict__ Yt)
 {
-    // thread -> (block b, point i, lane j): Yt[(b*n_pad + i)*NS + j] = (Y[(b*NS+j)*n + i] - mu)/sig
+    // block (b, 32 points): Yt[(b*n_pad + i)*NS + j] = (Y[(b*NS+j)*n + i] - mu_j)/sig_j, zero beyond n and S
     __shared__ double tile[NS][33];
     const int64_t b = blockIdx.y;
     const int64_t i0 = (int64_t)blockIdx.x * 32;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // blockDim = 32 x NS
-    const int64_t s = b * NS + ty;
-    const int64_t i = i0 + tx;
-    double v = 0.0;
-    if (s < S && i < n) v = (Y[s * n + i] - mu[s]) / sig[s];
-    tile[ty][tx] = v;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // blockDim = 32 x 8
+    for (int jj = ty; jj < NS; jj += 8) {
+        const int64_t s = b * NS + jj;
+        const int64_t i = i0 + tx;
+        double v = 0.0;
+        if (s < S && i < n) v = (Y[s * n + i] - mu[s]) / sig[s];
+        tile[jj][tx] = v;
+    }
     __syncthreads();
     // write: NS contiguous doubles per point
     for (int idx = threadIdx.x; idx < 32 * NS; idx += blockDim.x) {
@@ -199,182 +202,19 @@ __global__ void retile_kernel(const double *__restrict__ Y, int64_t n, int64_t n
     }
 }
 
-cudaError_t launch_standardize_retile(const double *d_Y, int64_t n, int64_t n_pad, int64_t S, bool standardize,
-                                      double *d_mu, double *d_sig, double *d_Yt, cudaStream_t st)
+cudaError_t launch_standardize_retile(const double *d_Y, int64_t n, int64_t n_pad, int64_t S, int series_block,
+                                      bool standardize, double *d_mu, double *d_sig, double *d_Yt, cudaStream_t st)
 {
     if (S <= 0 || n <= 0) return cudaSuccess;
     row_stats_kernel<<<(unsigned)S, 256, 0, st>>>(d_Y, n, standardize ? 1 : 0, d_mu, d_sig);
-    const int64_t blocks = (S + kSurrBlock - 1) / kSurrBlock;
+    const int64_t blocks = (S + series_block - 1) / series_block;
     dim3 grid((unsigned)((n_pad + 31) / 32), (unsigned)blocks);
-    retile_kernel<kSurrBlock><<<grid, 32 * kSurrBlock, 0, st>>>(d_Y, n, n_pad, S, d_mu, d_sig, d_Yt);
+    if (series_block == 64)
+        retile_kernel<64><<<grid, 256, 0, st>>>(d_Y, n, n_pad, S, d_mu, d_sig, d_Yt);
+    else
+        retile_kernel<16><<<grid, 256, 0, st>>>(d_Y, n, n_pad, S, d_mu, d_sig, d_Yt);
     bump_launch_counter(2);
     return cudaGetLastError();
-}
-
-// ------------------------------------------------------------------------------------------------
-// Shared-time-axis transform.  One lane = one cell (as in wwz_cells_kernel with M = 1); a CTA owns
-// 256 consecutive cells and a block of NS = 16 series.  Per (cell, point) the weight is evaluated
-// once (12 FP64 instructions + 6 for W, Q, Ws, Wc and the products w*s, w*c) and contracted
-// against the 16 series values of that point (3 DFMA each, broadcast LDS from the staged
-// Yt tile): 66 FP64 instructions per (cell, point, 16 series) = 4.1 per (cell, point, series)
-// against the 19 of a full transform per series.
-// Staging: TMA producer warp as in wwz_cells_kernel; per chunk one bulk copy of (t,y) pairs, one per
-// frequency row of {s, c} records, one for the [P][NS] tile of series values.
-// Epilogue in registers: Neff / mask once per cell, then per series the coefficients through the
-// pre-computed rotation (sin, cos)(omega*tau); outputs are written cell-major [ncell][S] (each lane
-// stores 128 contiguous bytes), the layout the quantile kernel consumes.
-// ------------------------------------------------------------------------------------------------
-struct SharedArgs {
-    const double2 *ty;
-    const double2 *basis;   // [nf][n_pad] records {s, c}
-    const double *Yt;       // [S/NS][n_pad][NS]
-    const double *tau;
-    const double *kappa;
-    const double2 *rot;     // [ncell] (sin, cos)(omega*tau)
-    double *neffs;          // [ncell] (written by surrogate block 0)
-    double *wq;             // [2][ncell] W, Q (written by surrogate block 0; deep-underflow detection)
-    double *amp, *phase, *a0, *a1, *a2;   // [ncell][S_pad], any may be null except amp
-    long long n, n_pad, ncell, S_pad;
-    int nt, nf, P, nchunks;
-    int row_stride2, stage_stride2, y_off2;   // double2 units
-    double thr;
-};
-
-template <int NS>
-__global__ void __launch_bounds__(kCellThreads, 1) wwz_shared_kernel(const SharedArgs a)
-{
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    double2 *const stage_base = reinterpret_cast<double2 *>(smem_raw);
-    unsigned char *const tail = smem_raw + (size_t)kStages * (size_t)a.stage_stride2 * sizeof(double2);
-    uint64_t *const full = reinterpret_cast<uint64_t *>(tail);
-    uint64_t *const empty = full + kStages;
-    double *const tbl = reinterpret_cast<double *>(empty + kStages);   // [16] 2^(j/16)
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const bool consumer = warp < kConsumerWarps;
-    const long long q0 = (long long)blockIdx.x * kConsumerThreads;
-    const long long qlast = min(q0 + (long long)kConsumerThreads - 1, a.ncell - 1);
-    // cells are numbered frequency-major here: q = k*nt + j
-    const int k_first = (int)(q0 / a.nt), k_last = (int)(qlast / a.nt);
-    const int Ft = k_last - k_first + 1;
-    const int P = a.P;
-    const long long sb = blockIdx.y;
-
-    if (tid == 0) {
-#pragma unroll
-        for (int s = 0; s < kStages; ++s) {
-            mbar_init(&full[s], 1);
-            mbar_init(&empty[s], kConsumerWarps);
-        }
-        mbar_fence_init();
-    }
-    load_exp2_table(tbl, tid);
-    __syncthreads();
-
-    if (!consumer) {
-        const uint32_t bytes = (uint32_t)P * 16u + (uint32_t)Ft * (uint32_t)P * 16u + (uint32_t)P * NS * 8u;
-        int s = 0, use = 0;
-        for (int c = 0; c < a.nchunks; ++c) {
-            if (use > 0) mbar_wait(&empty[s], (uint32_t)(use - 1) & 1u);
-            double2 *const st = stage_base + (size_t)s * a.stage_stride2;
-            if (lane == 0) mbar_arrive_expect_tx(&full[s], bytes);
-            __syncwarp();
-            for (int r = lane; r <= Ft + 1; r += 32) {
-                if (r == 0) {
-                    tma_load_1d(st, a.ty + (size_t)c * P, (uint32_t)P * 16u, &full[s]);
-                } else if (r == 1) {
-                    tma_load_1d(st + a.y_off2, a.Yt + ((size_t)sb * a.n_pad + (size_t)c * P) * NS,
-                                (uint32_t)P * NS * 8u, &full[s]);
-                } else {
-                    const size_t row = (size_t)(k_first + r - 2);
-                    tma_load_1d(st + P + (size_t)(r - 2) * a.row_stride2, a.basis + row * (size_t)a.n_pad + (size_t)c * P,
-                                (uint32_t)P * 16u, &full[s]);
-                }
-            }
-            if (++s == kStages) { s = 0; ++use; }
-        }
-        return;
-    }
-
-    const long long q = q0 + tid;
-    const bool ok = q < a.ncell;
-    int k = k_first, j = 0;
-    if (ok) {
-        k = (int)(q / a.nt);
-        j = (int)(q - (long long)k * a.nt);
-    }
-    const double kap = a.kappa[k];
-    const double tj = a.tau[j];
-    const int row_off = P + (k - k_first) * a.row_stride2;
-
-    double W = 0.0, Q = 0.0, Ws = 0.0, Wc = 0.0;
-    double Wy[NS], Wys[NS], Wyc[NS];
-#pragma unroll
-    for (int m = 0; m < NS; ++m) Wy[m] = Wys[m] = Wyc[m] = 0.0;
-
-    {
-        int s = 0, use = 0;
-        for (int c = 0; c < a.nchunks; ++c) {
-            mbar_wait(&full[s], (uint32_t)use & 1u);
-            const double2 *const st = stage_base + (size_t)s * a.stage_stride2;
-            const double2 *const row = st + row_off;
-            const double2 *const yv = st + a.y_off2;
-            const int cnt = (int)min((long long)P, a.n - (long long)c * P);
-            for (int p = 0; p < cnt; ++p) {
-                const double t = st[p].x;
-                const double2 sc = row[p];
-                const double w = gauss_weight(kap * (t - tj), tbl);
-                const double ws = w * sc.x, wc = w * sc.y;
-                W += w;
-                Q = fma(w, w, Q);
-                Ws += ws;
-                Wc += wc;
-#pragma unroll
-                for (int m = 0; m < NS / 2; ++m) {
-                    const double2 y2 = yv[p * (NS / 2) + m];
-                    Wy[2 * m] = fma(w, y2.x, Wy[2 * m]);
-                    Wys[2 * m] = fma(ws, y2.x, Wys[2 * m]);
-                    Wyc[2 * m] = fma(wc, y2.x, Wyc[2 * m]);
-                    Wy[2 * m + 1] = fma(w, y2.y, Wy[2 * m + 1]);
-                    Wys[2 * m + 1] = fma(ws, y2.y, Wys[2 * m + 1]);
-                    Wyc[2 * m + 1] = fma(wc, y2.y, Wyc[2 * m + 1]);
-                }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[s]);
-            if (++s == kStages) { s = 0; ++use; }
-        }
-    }
-
-    if (!ok) return;
-    const size_t cell = (size_t)j * (size_t)a.nf + (size_t)k;   // output order: tau-major rows
-    const double neff = W * W / Q;
-    if (sb == 0) {
-        a.neffs[cell] = neff;
-        a.wq[cell] = W;
-        a.wq[(size_t)a.ncell + cell] = Q;
-    }
-    const bool valid = neff > a.thr;
-    const double S1 = Ws / W, C1 = Wc / W;
-    const double2 rt = a.rot[cell];
-    const size_t o = cell * (size_t)a.S_pad + (size_t)sb * NS;
-#pragma unroll
-    for (int m = 0; m < NS; ++m) {
-        double c0 = CUDART_NAN, c1 = CUDART_NAN, c2 = CUDART_NAN;
-        if (valid) {
-            const double Yb = Wy[m] / W;
-            const double cyc = Wyc[m] / W - Yb * C1;
-            const double cys = Wys[m] / W - Yb * S1;
-            c0 = Yb;
-            c1 = 2.0 * (rt.y * cyc + rt.x * cys);
-            c2 = 2.0 * (rt.y * cys - rt.x * cyc);
-        }
-        a.amp[o + m] = sqrt(c1 * c1 + c2 * c2);
-        if (a.phase) a.phase[o + m] = atan2(c2, c1);
-        if (a.a0) a.a0[o + m] = c0;
-        if (a.a1) a.a1[o + m] = c1;
-        if (a.a2) a.a2[o + m] = c2;
-    }
 }
 
 // (sin, cos)(omega_k * tau_j) per cell, same residual folding as finalize_kernel.
@@ -437,10 +277,9 @@ __global__ void flag_cells_kernel(const double *__restrict__ wq, int64_t ncell, 
     if (W < 0x1p-200 || Q < 0x1p-400) list[atomicAdd(count, 1u)] = (unsigned int)idx;
 }
 
-template <int NS>
 __global__ void __launch_bounds__(128)
     faithful_batch_kernel(const double *__restrict__ ts, const double *__restrict__ Yt, int64_t n, int64_t n_pad,
-                          int64_t S, int64_t S_pad, const double *__restrict__ tau, const double *__restrict__ omega,
+                          int64_t S, int64_t S_pad, int NS, const double *__restrict__ tau, const double *__restrict__ omega,
                           int64_t nf, double c, double thr, const unsigned int *__restrict__ count,
                           const unsigned int *__restrict__ list, double *__restrict__ neffs, double *__restrict__ amp,
                           double *__restrict__ phase, double *__restrict__ a0o, double *__restrict__ a1o,
@@ -469,7 +308,7 @@ __global__ void __launch_bounds__(128)
 }
 
 cudaError_t launch_shared_fixup(const double *d_ts, const double *d_Yt, int64_t n, int64_t n_pad, int64_t S,
-                                int64_t S_pad, const double *d_tau, const double *d_omega, int64_t nt, int64_t nf,
+                                int64_t S_pad, int series_block, const double *d_tau, const double *d_omega, int64_t nt, int64_t nf,
                                 double c, double thr, const double *d_wq, unsigned int *d_fix_count,
                                 unsigned int *d_fix_list, double *d_neffs, double *d_amp, double *d_phase,
                                 double *d_a0, double *d_a1, double *d_a2, int sms, cudaStream_t st)
@@ -479,35 +318,11 @@ cudaError_t launch_shared_fixup(const double *d_ts, const double *d_Yt, int64_t 
     cudaError_t e = cudaMemsetAsync(d_fix_count, 0, sizeof(unsigned int), st);
     if (e != cudaSuccess) return e;
     flag_cells_kernel<<<(unsigned)((ncell + 255) / 256), 256, 0, st>>>(d_wq, ncell, d_fix_count, d_fix_list);
-    faithful_batch_kernel<kSurrBlock><<<(unsigned)(sms * 8), 128, 0, st>>>(d_ts, d_Yt, n, n_pad, S, S_pad, d_tau, d_omega,
+    faithful_batch_kernel<<<(unsigned)(sms * 8), 128, 0, st>>>(d_ts, d_Yt, n, n_pad, S, S_pad, series_block, d_tau, d_omega,
                                                                             nf, c, thr, d_fix_count, d_fix_list, d_neffs,
                                                                             d_amp, d_phase, d_a0, d_a1, d_a2);
     bump_launch_counter(2);
     return cudaGetLastError();
-}
-
-SharedPlan plan_shared(int64_t n, int64_t nt, int64_t nf)
-{
-    SharedPlan p{};
-    int64_t ft = (kConsumerThreads + nt - 1) / nt + 1;
-    if (ft > nf) ft = nf;
-    if (ft < 1) ft = 1;
-    p.ft_max = (int)ft;
-    // stage = P*16 (t,y) + ft*(P+1)*16 ({s,c} rows) + P*NS*8 (series tile)
-    int64_t P = (kStageBudget - 16 * ft) / (16 + 16 * ft + 8 * kSurrBlock);
-    P &= ~(int64_t)1;   // keep the series tile 16-byte aligned
-    if (P > 256) P = 256;
-    if (P > n) P = ((n + 7) / 8) * 8;
-    if (P < 8) P = 8;
-    p.points = (int)P;
-    p.n_pad = ((n + P - 1) / P) * P;
-    p.row_stride = (P + 1) * 16;
-    int64_t y_off = P * 16 + ft * p.row_stride;
-    y_off = (y_off + 15) & ~(int64_t)15;
-    p.y_off = y_off;
-    p.stage_bytes = (int)(y_off + P * kSurrBlock * 8);
-    p.smem_bytes = kStages * p.stage_bytes + 2 * kStages * 8 + 16 * 8 + 16;
-    return p;
 }
 
 cudaError_t launch_rotation(const double *d_tau, const double *d_omega, int64_t nt, int64_t nf, double2 *d_rot,
@@ -515,52 +330,6 @@ cudaError_t launch_rotation(const double *d_tau, const double *d_omega, int64_t 
 {
     if (nt * nf <= 0) return cudaSuccess;
     rotation_kernel<<<(unsigned)((nt * nf + 255) / 256), 256, 0, st>>>(d_tau, d_omega, nt, nf, d_rot);
-    bump_launch_counter();
-    return cudaGetLastError();
-}
-
-cudaError_t launch_shared(const SharedPlan &plan, const double2 *d_ty, const double2 *d_basis, const double *d_Yt,
-                          int64_t n, int64_t S_pad, const double *d_tau, int64_t nt, const double *d_kappa,
-                          int64_t nf, const double2 *d_rot, double thr, double *d_neffs, double *d_wq, double *d_amp,
-                          double *d_phase, double *d_a0, double *d_a1, double *d_a2, cudaStream_t st)
-{
-    const int64_t ncell = nt * nf;
-    if (ncell <= 0 || S_pad <= 0) return cudaSuccess;
-    SharedArgs a{};
-    a.ty = d_ty;
-    a.basis = d_basis;
-    a.Yt = d_Yt;
-    a.tau = d_tau;
-    a.kappa = d_kappa;
-    a.rot = d_rot;
-    a.neffs = d_neffs;
-    a.wq = d_wq;
-    a.amp = d_amp;
-    a.phase = d_phase;
-    a.a0 = d_a0;
-    a.a1 = d_a1;
-    a.a2 = d_a2;
-    a.n = n;
-    a.n_pad = plan.n_pad;
-    a.ncell = ncell;
-    a.S_pad = S_pad;
-    a.nt = (int)nt;
-    a.nf = (int)nf;
-    a.P = plan.points;
-    a.nchunks = (int)((n + plan.points - 1) / plan.points);
-    a.row_stride2 = (int)(plan.row_stride / 16);
-    a.stage_stride2 = plan.stage_bytes / 16;
-    a.y_off2 = (int)(plan.y_off / 16);
-    a.thr = thr;
-    static int configured = -1;
-    if (plan.smem_bytes > configured) {
-        cudaError_t e = cudaFuncSetAttribute(wwz_shared_kernel<kSurrBlock>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             plan.smem_bytes);
-        if (e != cudaSuccess) return e;
-        configured = plan.smem_bytes;
-    }
-    dim3 grid((unsigned)((ncell + kConsumerThreads - 1) / kConsumerThreads), (unsigned)(S_pad / kSurrBlock));
-    wwz_shared_kernel<kSurrBlock><<<grid, kCellThreads, plan.smem_bytes, st>>>(a);
     bump_launch_counter();
     return cudaGetLastError();
 }

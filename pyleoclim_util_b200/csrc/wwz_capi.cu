@@ -328,9 +328,10 @@ int shared_axis_device(Workspace *w, const double *d_ts, const double *d_Y, int6
     const int64_t ncell = nt * nf;
     if (ncell == 0 || S == 0) return 0;
     if (ncell >= ((int64_t)1 << 32)) return fail(WWZB200_ERR_ARG, "nt*nf exceeds 2^32 cells");
-    const SharedPlan plan = plan_shared(n, nt, nf);
-    const int64_t S_pad = ((S + kSurrBlock - 1) / kSurrBlock) * kSurrBlock;
-    if (S_pad / kSurrBlock > 65535) return fail(WWZB200_ERR_ARG, "more than 65535*16 series in one batch");
+    const SharedPlan plan = plan_shared(n, nt, nf, S);
+    const int NS = plan.series_block;
+    const int64_t S_pad = ((S + NS - 1) / NS) * NS;
+    if (S_pad / NS > 65535) return fail(WWZB200_ERR_ARG, "more than 65535*%d series in one batch", NS);
     if ((size_t)nf * (size_t)plan.n_pad * 16 > ((size_t)16 << 30))
         return fail(WWZB200_ERR_NOMEM, "basis rows of the shared-axis batch exceed 16 GiB");
     int rc;
@@ -338,6 +339,8 @@ int shared_axis_device(Workspace *w, const double *d_ts, const double *d_Y, int6
            *d_a1_t = nullptr, *d_a2_t = nullptr, *d_ne;
     double2 *d_ty, *d_basis, *d_rot;
     unsigned int *d_fix;
+    int *d_unsorted;
+    if ((rc = wsbuf(w, "flags", 4, &d_unsorted))) return rc;
     if ((rc = wsbuf(w, "kappa", (size_t)nf, &d_kappa))) return rc;
     if ((rc = wsbuf(w, "dcut", (size_t)nf, &d_dcut))) return rc;
     if ((rc = wsbuf(w, "ty", (size_t)plan.n_pad, &d_ty))) return rc;
@@ -360,23 +363,26 @@ int shared_axis_device(Workspace *w, const double *d_ts, const double *d_Y, int6
     unsigned char *d_rec_row;
     if ((rc = wsbuf(w, "grid", 2, &d_grid))) return rc;
     if ((rc = wsbuf(w, "rec_row", (size_t)nf, &d_rec_row))) return rc;
-    CU(launch_freq_setup(d_omega, nf, d_tau, nt, c, false, 300.0, d_kappa, d_dcut, d_grid, d_rec_row, st));
+    // point windows of the cell tiles: 2^-300 cutoff as in the single-series path; WWZB200_DENSE walks every point
+    const double cut_bits = (flags & WWZB200_DENSE) ? HUGE_VAL : (flags & WWZB200_EXACT_WINDOW) ? 1081.0 : 300.0;
+    CU(launch_freq_setup(d_omega, nf, d_tau, nt, c, false, cut_bits, d_kappa, d_dcut, d_grid, d_rec_row, st));
     CU(launch_basis_sc(d_ts, n, plan.n_pad, d_omega, nf, d_ty, d_basis, st));
     CU(launch_rotation(d_tau, d_omega, nt, nf, d_rot, st));
-    CU(launch_standardize_retile(d_Y, n, plan.n_pad, S, (flags & WWZB200_STANDARDIZE) != 0, d_mu, d_sig, d_Yt, st));
+    CU(launch_unsorted_check(d_ts, n, d_unsorted, st));
+    CU(launch_standardize_retile(d_Y, n, plan.n_pad, S, NS, (flags & WWZB200_STANDARDIZE) != 0, d_mu, d_sig, d_Yt, st));
     EventPair ev{nullptr, nullptr, (double)n * (double)ncell * (double)S};
     if (g_profile) {
         CU(cudaEventCreate(&ev.a));
         CU(cudaEventCreate(&ev.b));
         CU(cudaEventRecord(ev.a, st));
     }
-    CU(launch_shared(plan, d_ty, d_basis, d_Yt, n, S_pad, d_tau, nt, d_kappa, nf, d_rot, (double)thr, d_ne, d_wq,
-                     d_amp_t, d_ph_t, d_a0_t, d_a1_t, d_a2_t, st));
+    CU(launch_shared(plan, d_ty, d_basis, d_Yt, d_ts, n, S_pad, d_tau, nt, d_kappa, d_dcut, d_unsorted, nf, d_rot,
+                     (double)thr, d_ne, d_wq, d_amp_t, d_ph_t, d_a0_t, d_a1_t, d_a2_t, st));
     if (g_profile) {
         CU(cudaEventRecord(ev.b, st));
         g_events.push_back(ev);
     }
-    CU(launch_shared_fixup(d_ts, d_Yt, n, plan.n_pad, S, S_pad, d_tau, d_omega, nt, nf, c, (double)thr, d_wq, d_fix,
+    CU(launch_shared_fixup(d_ts, d_Yt, n, plan.n_pad, S, S_pad, NS, d_tau, d_omega, nt, nf, c, (double)thr, d_wq, d_fix,
                            d_fix + 1, d_ne, d_amp_t, d_ph_t, d_a0_t, d_a1_t, d_a2_t, w->sms, st));
     // cell-major [ncell][S_pad] -> series-major [S][ncell]
     if (d_wwa) CU(launch_transpose(d_amp_t, ncell, S, S_pad, d_wwa, ncell, st));

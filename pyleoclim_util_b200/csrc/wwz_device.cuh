@@ -169,6 +169,37 @@ __device__ __forceinline__ void load_exp2_table(double *tbl, int tid)
 }
 
 // ----------------------------------------------------------------------------------------------
+// Warp-cooperative search on the sorted time axis (point windows of a tile of cells).
+// ----------------------------------------------------------------------------------------------
+// First index i in [a, b) with ts[i] >= x (UPPER = false) or ts[i] > x (UPPER = true); b if there is none.
+// All 32 lanes take part: 32 probes per round.
+template <bool UPPER>
+__device__ __forceinline__ long long warp_bound(const double *__restrict__ ts, long long a, long long b, double x,
+                                                int lane)
+{
+    while (b - a > 32) {
+        const long long step = (b - a + 32) / 33;
+        const long long pidx = a + (long long)(lane + 1) * step - 1;
+        bool below = false;
+        if (pidx < b) {
+            const double v = ts[pidx];
+            below = UPPER ? (v <= x) : (v < x);
+        }
+        const int cnt = __popc(__ballot_sync(0xffffffffu, below));
+        const long long na = a + (long long)cnt * step;                 // everything up to probe cnt-1 is below
+        const long long nb = a + (long long)(cnt + 1) * step - 1;       // probe cnt is not below (if it exists)
+        a = na;
+        if (cnt < 32 && nb < b) b = nb;
+    }
+    bool below = false;
+    if (a + lane < b) {
+        const double v = ts[a + lane];
+        below = UPPER ? (v <= x) : (v < x);
+    }
+    return a + __popc(__ballot_sync(0xffffffffu, below));
+}
+
+// ----------------------------------------------------------------------------------------------
 // Faithful evaluation of one cell by one warp: lanes stride over the points, warp-shuffle
 // reductions; the reference's own two-pass expressions (utils/wavelet.py:988-1032) with exp()
 // keeping subnormal weights and w*w rounded separately.  All lanes return the same values.

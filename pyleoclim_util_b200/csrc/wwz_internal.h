@@ -16,7 +16,6 @@ constexpr int kMaxPointsPerStage = 512;
 constexpr int kRecCells = 8;     // tau-adjacent cells per lane in the tau-recurrence kernel
 constexpr int kRecConsumerWarps = 8;    // consumer warps of its CTA (11 warps, 384 threads, measured slower)
 constexpr int kMaxWarps = 16;
-constexpr int kSurrBlock = 16;   // series per CTA in the shared-time-axis kernel
 
 // Geometry of one launch of the cell kernel, derived on the host by plan_cells().
 struct CellPlan {
@@ -104,30 +103,33 @@ cudaError_t launch_psd_devspan(const double *d_wwa, const double *d_neffs, int64
 
 // ---- batched paths (wwz_batch.cu) -------------------------------------------------------------
 struct SharedPlan {
-    int ft_max, points, stage_bytes, smem_bytes;
+    int series_block;     // NS: series per CTA tile of the shared-time-axis kernel (64, or 16 for small batches)
+    int points, stage_bytes, smem_bytes;
     int64_t n_pad, row_stride, y_off;
 };
-SharedPlan plan_shared(int64_t n, int64_t nt, int64_t nf);
+SharedPlan plan_shared(int64_t n, int64_t nt, int64_t nf, int64_t S);
 
 // AR(1) surrogates Y[S][n] (row-major); d_rho, d_q are n-element scratch.
 cudaError_t launch_ar1(const double *d_ts, int64_t n, double tau, double sigma, double mu, int64_t S, uint64_t seed,
                        double *d_rho, double *d_q, double *d_Y, cudaStream_t st);
-// per-series mean/std (identity when !standardize) and the tiled copy Yt[S_pad/16][n_pad][16]
-cudaError_t launch_standardize_retile(const double *d_Y, int64_t n, int64_t n_pad, int64_t S, bool standardize,
-                                      double *d_mu, double *d_sig, double *d_Yt, cudaStream_t st);
+// per-series mean/std (identity when !standardize) and the tiled copy Yt[S_pad/NS][n_pad][NS]
+cudaError_t launch_standardize_retile(const double *d_Y, int64_t n, int64_t n_pad, int64_t S, int series_block,
+                                      bool standardize, double *d_mu, double *d_sig, double *d_Yt, cudaStream_t st);
 // {sin, cos}(omega_k t_i) records (16 B) + (t, y) pairs
 cudaError_t launch_basis_sc(const double *d_ts, int64_t n, int64_t n_pad, const double *d_omega, int64_t nf,
                             double2 *d_ty, double2 *d_basis, cudaStream_t st);
 cudaError_t launch_rotation(const double *d_tau, const double *d_omega, int64_t nt, int64_t nf, double2 *d_rot,
                             cudaStream_t st);
+// the contraction on the FP64 tensor pipe (wwz_mma.cu)
 cudaError_t launch_shared(const SharedPlan &plan, const double2 *d_ty, const double2 *d_basis, const double *d_Yt,
-                          int64_t n, int64_t S_pad, const double *d_tau, int64_t nt, const double *d_kappa,
-                          int64_t nf, const double2 *d_rot, double thr, double *d_neffs, double *d_wq, double *d_amp,
+                          const double *d_ts, int64_t n, int64_t S_pad, const double *d_tau, int64_t nt,
+                          const double *d_kappa, const double *d_dcut, const int *d_unsorted, int64_t nf,
+                          const double2 *d_rot, double thr, double *d_neffs, double *d_wq, double *d_amp,
                           double *d_phase, double *d_a0, double *d_a1, double *d_a2, cudaStream_t st);
 // deep-underflow cells of a shared-axis batch (flagged from W, Q), recomputed faithfully for every series
 cudaError_t launch_shared_fixup(const double *d_ts, const double *d_Yt, int64_t n, int64_t n_pad, int64_t S,
-                                int64_t S_pad, const double *d_tau, const double *d_omega, int64_t nt, int64_t nf,
-                                double c, double thr, const double *d_wq, unsigned int *d_fix_count,
+                                int64_t S_pad, int series_block, const double *d_tau, const double *d_omega, int64_t nt,
+                                int64_t nf, double c, double thr, const double *d_wq, unsigned int *d_fix_count,
                                 unsigned int *d_fix_list, double *d_neffs, double *d_amp, double *d_phase,
                                 double *d_a0, double *d_a1, double *d_a2, int sms, cudaStream_t st);
 cudaError_t launch_transpose(const double *d_in, int64_t rows, int64_t cols, int64_t in_stride, double *d_out,

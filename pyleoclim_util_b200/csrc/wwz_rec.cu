@@ -44,34 +44,6 @@ struct RecArgs {
     int warp_stride;     // bytes of shared memory per warp (ring + barriers)
 };
 
-// First index i in [a, b) with ts[i] >= x (UPPER = false) or ts[i] > x (UPPER = true); b if there is none.
-// All 32 lanes take part: 32 probes per round.
-template <bool UPPER>
-__device__ __forceinline__ long long warp_bound(const double *__restrict__ ts, long long a, long long b, double x,
-                                                int lane)
-{
-    while (b - a > 32) {
-        const long long step = (b - a + 32) / 33;
-        const long long pidx = a + (long long)(lane + 1) * step - 1;
-        bool below = false;
-        if (pidx < b) {
-            const double v = ts[pidx];
-            below = UPPER ? (v <= x) : (v < x);
-        }
-        const int cnt = __popc(__ballot_sync(0xffffffffu, below));
-        const long long na = a + (long long)cnt * step;                 // everything up to probe cnt-1 is below
-        const long long nb = a + (long long)(cnt + 1) * step - 1;       // probe cnt is not below (if it exists)
-        a = na;
-        if (cnt < 32 && nb < b) b = nb;
-    }
-    bool below = false;
-    if (a + lane < b) {
-        const double v = ts[a + lane];
-        below = UPPER ? (v <= x) : (v < x);
-    }
-    return a + __popc(__ballot_sync(0xffffffffu, below));
-}
-
 constexpr int kRecWarps = 4;     // warps per CTA; every warp is an independent worker
 
 __global__ void __launch_bounds__(kRecWarps * 32, 3) wwz_rec_kernel(const RecArgs a)

@@ -1,4 +1,5 @@
 set -x
+mkdir -p gpurun_out
 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
 python -c "import __graft_entry__ as g; g.smoke()"
 python bench.py --steps 20 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -3 gpurun_out/bench.err; cat gpurun_out/bench.json
@@ -7,3 +8,5 @@ python bench.py --steps 5 --warmup 3 > gpurun_out/plain.log 2>&1 && ncu --metric
 tail -2 gpurun_out/ncu.log
 python tools/ncu_one.py > gpurun_out/plain2.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:wwz_cells -s 2 -c 2 -o gpurun_out/prof_cells -f python tools/ncu_one.py > gpurun_out/ncu2.log 2>&1
 tail -3 gpurun_out/ncu2.log
+WWZ_FLAGS=0 python tools/ncu_one.py > gpurun_out/plain3.log 2>&1 && WWZ_FLAGS=0 ncu --set full --clock-control none --import-source on -k regex:wwz_rec -s 2 -c 2 -o gpurun_out/prof_rec -f python tools/ncu_one.py > gpurun_out/ncu3.log 2>&1
+tail -3 gpurun_out/ncu3.log
