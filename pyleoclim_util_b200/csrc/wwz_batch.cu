@@ -477,11 +477,159 @@ __global__ void __launch_bounds__(1024)
     }
 }
 
+// Few quantiles of many values (the significance test: one to three probabilities of 10,000 surrogates per
+// cell): radix select instead of a sort.  One CTA per cell; the keys sit in shared memory (or are re-read from
+// global memory above 25,600 values); per probability the order statistic k-1 is found by an 8-pass MSD radix
+// select on the 64-bit keys (256-bin histogram per pass, warp-aggregated shared-memory atomics), then one more
+// pass yields the order statistic k (the same key if it is repeated, else the smallest larger key).
+// Same key order (NaN last) and the same interpolation arithmetic as quantile_kernel: results are identical.
+template <bool SMEM_KEYS>
+__global__ void __launch_bounds__(512)
+    quantile_select_kernel(const double *__restrict__ X, int64_t S, int64_t stride, int64_t ncell,
+                           const double *__restrict__ probs, int nq, double *__restrict__ q)
+{
+    extern __shared__ unsigned long long keys_sh[];
+    __shared__ unsigned int hist[256];
+    __shared__ unsigned long long sel_prefix;
+    __shared__ unsigned int sel_rank;
+    __shared__ unsigned int cnt_le;
+    __shared__ unsigned long long min_gt;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int N = (int)S;
+    for (int64_t cell = blockIdx.x; cell < ncell; cell += gridDim.x) {
+        const double *const xc = X + cell * stride;
+        if (SMEM_KEYS) {
+            for (int i = tid; i < N; i += blockDim.x) keys_sh[i] = sort_key(xc[i]);
+        }
+        __syncthreads();
+        auto key_at = [&](int i) -> unsigned long long { return SMEM_KEYS ? keys_sh[i] : sort_key(xc[i]); };
+        for (int iq = 0; iq < nq; ++iq) {
+            // every operation rounded separately, in scipy's order (see quantile_kernel)
+            const double p = probs[iq];
+            const double m = __dadd_rn(0.4, __dmul_rn(p, (1.0 - 0.4) - 0.4));
+            const double aleph = __dadd_rn(__dmul_rn((double)S, p), m);
+            const double kc = fmin(fmax(aleph, 1.0), (double)(S - 1));
+            const long long kk = (long long)floor(kc);
+            const double gamma = fmin(fmax(__dadd_rn(aleph, -(double)kk), 0.0), 1.0);
+            const unsigned int r0 = (N == 1) ? 0u : (unsigned int)(kk - 1);   // 0-based rank of x[k-1]
+            if (tid == 0) {
+                sel_prefix = 0ull;
+                sel_rank = r0;
+            }
+            unsigned long long mask = 0ull;
+            for (int shift = 56; shift >= 0; shift -= 8) {
+                if (tid < 256) hist[tid] = 0u;
+                __syncthreads();
+                const unsigned long long prefix = sel_prefix;
+                for (int i0 = 0; i0 < N; i0 += blockDim.x) {
+                    const int i = i0 + tid;
+                    unsigned int digit = 0xFFFFFFFFu;                   // not a candidate
+                    if (i < N) {
+                        const unsigned long long k = key_at(i);
+                        if ((k & mask) == prefix) digit = (unsigned int)(k >> shift) & 255u;
+                    }
+                    const unsigned int peers = __match_any_sync(0xffffffffu, digit);
+                    if (digit != 0xFFFFFFFFu && lane == __ffs(peers) - 1) atomicAdd(&hist[digit], (unsigned int)__popc(peers));
+                }
+                __syncthreads();
+                if (tid < 32) {
+                    // bins 8*lane .. 8*lane+7: find the bin that holds the wanted rank
+                    const unsigned int want = sel_rank;                  // read by all lanes before the shuffles
+                    unsigned int c[8], tot = 0;
+#pragma unroll
+                    for (int b = 0; b < 8; ++b) {
+                        c[b] = hist[8 * lane + b];
+                        tot += c[b];
+                    }
+                    unsigned int incl = tot;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const unsigned int v = __shfl_up_sync(0xffffffffu, incl, o);
+                        if (lane >= o) incl += v;
+                    }
+                    const unsigned int excl = incl - tot;
+                    if (want >= excl && want < incl) {
+                        unsigned int acc = excl;
+#pragma unroll
+                        for (int b = 0; b < 8; ++b) {
+                            if (want >= acc && want < acc + c[b]) {
+                                sel_prefix = prefix | ((unsigned long long)(8 * lane + b) << shift);
+                                sel_rank = want - acc;
+                            }
+                            acc += c[b];
+                        }
+                    }
+                }
+                mask |= 0xFFull << shift;
+                __syncthreads();
+            }
+            const unsigned long long k0 = sel_prefix;                    // key of rank r0
+            if (tid == 0) {
+                cnt_le = 0u;
+                min_gt = 0xFFFFFFFFFFFFFFFFull;
+            }
+            __syncthreads();
+            {
+                unsigned int le = 0;
+                unsigned long long mg = 0xFFFFFFFFFFFFFFFFull;
+                for (int i = tid; i < N; i += blockDim.x) {
+                    const unsigned long long k = key_at(i);
+                    if (k <= k0) ++le;
+                    else if (k < mg) mg = k;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    le += __shfl_xor_sync(0xffffffffu, le, o);
+                    const unsigned long long other = __shfl_xor_sync(0xffffffffu, mg, o);
+                    mg = other < mg ? other : mg;
+                }
+                if (lane == 0) {
+                    atomicAdd(&cnt_le, le);
+                    atomicMin(&min_gt, mg);
+                }
+            }
+            __syncthreads();
+            if (tid == 0) {
+                double r;
+                if (N == 1) {
+                    r = key_value(k0);
+                } else {
+                    const unsigned long long k1 = (cnt_le >= r0 + 2u) ? k0 : min_gt;   // key of rank r0 + 1
+                    const double x0 = key_value(k0), x1 = key_value(k1);
+                    r = __dadd_rn(__dmul_rn(__dadd_rn(1.0, -gamma), x0), __dmul_rn(gamma, x1));
+                }
+                q[(size_t)iq * (size_t)ncell + (size_t)cell] = r;
+            }
+            __syncthreads();
+        }
+    }
+}
+
 cudaError_t launch_quantiles(const double *d_X, int64_t S, int64_t stride, int64_t ncell, const double *d_probs,
                              int64_t nq, double *d_q, unsigned long long *d_scratch, int64_t scratch_ctas, int sms,
                              cudaStream_t st)
 {
     if (ncell <= 0 || nq <= 0 || S <= 0) return cudaSuccess;
+    if (nq <= 16 && S >= 64 && S < ((int64_t)1 << 31)) {
+        // few probabilities: radix select
+        const size_t kb = (size_t)S * 8;
+        if (kb <= 200 * 1024) {
+            static size_t configured_sel = 0;
+            if (kb > configured_sel) {
+                cudaError_t e = cudaFuncSetAttribute(quantile_select_kernel<true>,
+                                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kb);
+                if (e != cudaSuccess) return e;
+                configured_sel = kb;
+            }
+            const int64_t grid = std::min<int64_t>(ncell, (int64_t)sms * 16);
+            quantile_select_kernel<true><<<(unsigned)grid, 512, kb, st>>>(d_X, S, stride, ncell, d_probs, (int)nq, d_q);
+        } else {
+            const int64_t grid = std::min<int64_t>(ncell, (int64_t)sms * 4);
+            quantile_select_kernel<false><<<(unsigned)grid, 512, 0, st>>>(d_X, S, stride, ncell, d_probs, (int)nq, d_q);
+        }
+        bump_launch_counter();
+        return cudaGetLastError();
+    }
     int npow2 = 2;
     while (npow2 < S) npow2 <<= 1;
     const size_t smem = (size_t)npow2 * 8;

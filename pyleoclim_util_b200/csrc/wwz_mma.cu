@@ -20,7 +20,7 @@
 // and frequency, so its Gaussian support is one index range of the sorted time axis: the producer finds it
 // (warp-cooperative search) and only the chunks that intersect it are staged; points below 2^-300 for every
 // cell of the tile are skipped exactly as in wwz_rec.cu.  Per chunk of P points: one bulk copy for (t, .), one
-// per frequency row of {sin, cos} records, one for the [P][NS] series tile; 4-stage ring, full/empty mbarriers.
+// per frequency row of {sin, cos} records, one per point for the [P][NS] series tile (rows skewed by 32 B); 4-stage ring, full/empty mbarriers.
 //
 // Grid: x = cell tiles (low frequencies, i.e. the long windows, first), y = series blocks: CTAs that run
 // together share the series block (streamed from HBM once) and differ in the basis rows (L2 resident).
@@ -134,13 +134,16 @@ __global__ void __launch_bounds__(kMmaThreads, 1) wwz_shared_mma_kernel(const Mm
             __syncwarp();
             if (lane == 0) {
                 tma_load_1d(st, a.ty + start, (uint32_t)P * 16u, &full[s]);
-            } else if (lane == 1) {
-                tma_load_1d(st + a.y_off2, a.Yt + ((size_t)sb * a.n_pad + start) * NS, (uint32_t)P * NS * 8u, &full[s]);
-            } else if (lane - 2 < rows) {
+            } else if (lane - 2 < rows && lane >= 2) {
                 const size_t row = (size_t)(k_base + lane - 2);
                 tma_load_1d(st + P + (size_t)(lane - 2) * a.row_stride2, a.basis + row * (size_t)a.n_pad + start,
                             (uint32_t)P * 16u, &full[s]);
             }
+            // series tile: one copy per point, rows skewed by 32 B in shared memory (conflict-free B fragments)
+            const double *const ysrc = a.Yt + ((size_t)sb * a.n_pad + start) * NS;
+            double *const ydst = reinterpret_cast<double *>(st + a.y_off2);
+            for (int q = lane; q < P; q += 32)
+                tma_load_1d(ydst + (size_t)q * (NS + 4), ysrc + (size_t)q * NS, (uint32_t)NS * 8u, &full[s]);
             if (++s == kMmaStages) { s = 0; ++use; }
         }
         return;
@@ -171,16 +174,15 @@ __global__ void __launch_bounds__(kMmaThreads, 1) wwz_shared_mma_kernel(const Mm
             const long long left = a.n - (long long)(c_lo + i) * P;     // points of this chunk that exist
 #pragma unroll 2
             for (int q = p; q < P; q += 4) {
-                const double t = st[q].x;
                 const double2 sc = row[q];
-                double w = gauss_weight(kap * (t - tj), tbl);
+                double w = gauss_weight_estrin(kap * (st[q].x - tj), tbl);
                 if (q >= left) w = 0.0;
                 const double ws = w * sc.x, wc = w * sc.y;
                 W += w;
                 Q = fma(w, w, Q);
                 Ws += ws;
                 Wc += wc;
-                const double *const yq = yv + q * NS;
+                const double *const yq = yv + q * (NS + 4);
 #pragma unroll
                 for (int m = 0; m < NT; ++m) {
                     const double b = yq[8 * m];
@@ -270,7 +272,7 @@ SharedPlan plan_shared(int64_t n, int64_t nt, int64_t nf, int64_t S)
     int64_t y_off = P * 16 + (int64_t)kMmaRows * p.row_stride;
     y_off = (y_off + 127) & ~(int64_t)127;
     p.y_off = y_off;
-    p.stage_bytes = (int)(y_off + P * p.series_block * 8);
+    p.stage_bytes = (int)(y_off + P * (p.series_block + 4) * 8);   // series rows skewed by 32 B
     p.smem_bytes = kMmaStages * p.stage_bytes + 2 * kMmaStages * 8 + 16 * 8 + 16;
     return p;
 }

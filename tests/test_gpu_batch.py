@@ -150,6 +150,29 @@ def test_quantiles_match_scipy_mquantiles(S):
     assert got3.shape == (1, 1, ncell)
 
 
+@pytest.mark.parametrize("S,nq", [(64, 1), (257, 3), (5000, 2), (30000, 1), (300, 17)])
+def test_quantiles_with_ties_and_scattered_nans(S, nq):
+    """Radix-select path (few probabilities) and sort path (nq > 16) against scipy on data with repeated values,
+    negative values, zeros of both signs, infinities and NaNs scattered through the sample (NaN sorts last)."""
+    from scipy.stats.mstats import mquantiles
+    rng = np.random.default_rng(S + nq)
+    ncell = 9
+    X = np.round(rng.standard_normal((S, ncell)), 1)             # many ties
+    X[rng.random((S, ncell)) < 0.02] = np.nan
+    X[rng.random((S, ncell)) < 0.01] = np.inf
+    X[rng.random((S, ncell)) < 0.01] = -0.0
+    X[:, 1] = 4.25                                               # constant cell
+    X[: S // 2, 2] = np.nan                                      # half NaN: upper quantiles land on NaN
+    qs = list(np.linspace(0.03, 0.97, nq))
+    got = B.quantiles(X, qs)
+    with np.errstate(invalid="ignore"):
+        ref = np.asarray(mquantiles(X, qs, axis=0).filled(np.nan))
+    assert_same_nan_mask(got, ref)
+    m = np.isfinite(ref)
+    assert np.array_equal(np.isinf(got), np.isinf(ref))
+    assert np.max(np.abs(got[m] - ref[m])) < 1e-14
+
+
 # ------------------------------------------------------------------ fused significance test
 def test_wwz_signif_equals_the_unfused_pipeline():
     from scipy.stats.mstats import mquantiles
