@@ -55,6 +55,8 @@ extern "C" {
                                    (utils/tsutils.py:1134-1154, ddof=0, eps=1e-3 guard) */
 #define WWZB200_NO_RECURRENCE 8u /* keep one exp2 per (cell, point): do not use the tau-recurrence kernel \
                                    (equally spaced tau, frequency rows with kappa*dtau small) */
+#define WWZB200_UAR1 32u        /* wwzb200_ar1_signif: surrogates follow uar1_sim (utils/tsmodel.py:673-716) instead  \
+                                   of ar1_model; the `sigma` argument then carries the innovation variance sigma_2 */
 #define WWZB200_FAITHFUL 4u     /* validation mode: evaluate every cell with the reference's own    \
                                    two-pass expressions (utils/wavelet.py:988-1032), one warp per   \
                                    cell; ~10x slower, agrees with kirchner_numba to ~1e-12 */
@@ -135,6 +137,14 @@ int wwzb200_kirchner_ragged(const double *ts, const double *pd_ys, const int64_t
 int wwzb200_ar1_surrogates(const double *ts, int64_t nts, double tau_est, double sigma, double mu,
                            int64_t S, uint64_t seed, double *Y);
 
+/* The 'uar1' surrogates of SurrogateSeries.from_series (core/surrogateseries.py:147-156): S realisations of
+ * uar1_sim (utils/tsmodel.py:673-716) on the time axis ts with the maximum-likelihood parameters of
+ * uar1_fit (:646-671; a Nelder-Mead fit on the host):  y_0 = z_0; phi_i = exp(-(t_i - t_{i-1})/tau);
+ * y_i = phi_i y_{i-1} + sqrt(sigma_2 (1 - phi_i^2)) z_i;  Y[s,i] = y_i + mu.  Same Philox stream as
+ * wwzb200_ar1_surrogates (the reference draws one normal(size=(n,p)) matrix from NumPy's global generator). */
+int wwzb200_uar1_surrogates(const double *ts, int64_t nts, double tau, double sigma_2, double mu, int64_t S,
+                            uint64_t seed, double *Y);
+
 /* Per-cell quantiles over a batch: scipy.stats.mstats.mquantiles(alphap=betap=0.4) semantics as
  * used by MultipleScalogram.quantiles (core/scalograms.py:635-641) and MultiplePSD.quantiles
  * (core/psds.py:913).  X is [S, ncell] row-major, q is [nq, ncell]. */
@@ -171,6 +181,9 @@ int wwzb200_kirchner_shared_axis_dev(const double *d_ts, const double *d_Y, int6
 
 int wwzb200_ar1_surrogates_dev(const double *d_ts, int64_t nts, double tau_est, double sigma,
                                double mu, int64_t S, uint64_t seed, double *d_Y, void *stream);
+
+int wwzb200_uar1_surrogates_dev(const double *d_ts, int64_t nts, double tau, double sigma_2, double mu,
+                                int64_t S, uint64_t seed, double *d_Y, void *stream);
 
 int wwzb200_quantiles_dev(const double *d_X, int64_t S, int64_t ncell, const double *d_probs,
                           int64_t nq, double *d_q, void *stream);

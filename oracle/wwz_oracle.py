@@ -287,6 +287,52 @@ def ar1_sim(y, p, t, rng=None):
     return ysim[:, 0] if p == 1 else ysim
 
 
+def n_ll_unevenly_spaced_ar1(theta, y, t):
+    """utils/tsmodel.py:612-644, term by term (Python ``sum`` over the arrays like the reference)."""
+    n = len(y)
+    log_tau, log_sigma_2 = theta[0], theta[1]
+    tau = np.exp(log_tau)
+    sigma_2 = np.exp(log_sigma_2)
+    delta = np.diff(t)
+    phi = np.exp((-delta / tau))
+    term_1 = y[1:n] - (phi * y[0:(n - 1)])
+    term_2 = pow(term_1, 2)
+    term_3 = term_2 / (1 - pow(phi, 2))
+    term_4 = 1 / (sigma_2 * n) * sum(term_3)
+    term_5 = 1 / n * sum(np.log(1 - pow(phi, 2)))
+    return np.log(2 * np.pi) + np.log(sigma_2) + term_5 + term_4
+
+
+def uar1_fit(y, t):
+    """utils/tsmodel.py:646-671 (scipy Nelder-Mead, third-party, same call and options as the reference)."""
+    from scipy.optimize import minimize
+    y, t = _c(y), _c(t)
+    x0 = [np.log(tau_estimation(y, t)), np.log(np.var(y))]
+    res = minimize(n_ll_unevenly_spaced_ar1, x0=x0, args=(y, t), method="nelder-mead",
+                   options={"xatol": 1e-10, "disp": False, "maxiter": 1000})
+    return np.exp(res.x)
+
+
+def uar1_sim(t, tau, sigma_2=1, z=None):
+    """utils/tsmodel.py:673-716 with the innovations made explicit: ``z`` has the shape of the reference's
+    ``np.random.normal(size=(n, p))`` matrix (``[n]`` for a 1-D ``t``); None draws it from NumPy's legacy
+    global generator exactly like the reference (:702)."""
+    t = np.asarray(t, dtype=float)
+    squeeze = t.ndim == 1
+    if squeeze:
+        t = t[:, np.newaxis]
+    n, p = t.shape
+    z = np.random.normal(loc=0, scale=1, size=(n, p)) if z is None else np.asarray(z, dtype=float).reshape(n, p)
+    y = np.copy(z)
+    for j in range(p):
+        for i in range(1, n):
+            delta_i = t[i, j] - t[i - 1, j]
+            phi = np.exp(-delta_i / tau)
+            sigma_i = np.sqrt(sigma_2 * (1 - phi ** 2))
+            y[i, j] = phi * y[i - 1, j] + sigma_i * z[i, j]
+    return np.squeeze(y) if squeeze or p == 1 else y
+
+
 def mquantiles(a, prob, axis=0, alphap=0.4, betap=0.4):
     """scipy.stats.mstats.mquantiles (scipy 1.18.1, third-party; called at
     core/scalograms.py:641 and core/psds.py:913) restated for NaN-free data:
@@ -310,7 +356,7 @@ def philox_normals(seed, series, n):
     NumPy: Philox4x32-10 (Salmon et al., SC'11; counter = (pair lo, pair hi, series lo, series hi),
     key = (seed lo, seed hi)), two 53-bit uniforms per counter, Box-Muller.  Step i (1 <= i < n) of the
     recurrence uses z0 of pair i//2 when i is even and z1 of pair i//2 when i is odd.
-    Returns z[n] with z[0] = 0 (unused), ready for ``ar1_model(..., z=z)``."""
+    Returns z[n]; z[0] (z0 of pair 0) is the start value of ``uar1_sim`` and is ignored by ``ar1_model``."""
     M0, M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
     W0, W1 = 0x9E3779B9, 0xBB67AE85
     npair = n // 2 + 1
@@ -339,7 +385,5 @@ def philox_normals(seed, series, n):
     u1, u2 = u01(c0, c1), u01(c2, c3)
     rad = np.sqrt(-2.0 * np.log(u1))
     z0, z1 = rad * np.cos(2 * np.pi * u2), rad * np.sin(2 * np.pi * u2)
-    z = np.zeros(n)
-    i = np.arange(1, n)
-    z[1:] = np.where(i % 2 == 0, z0[i // 2], z1[i // 2])
-    return z
+    i = np.arange(n)
+    return np.where(i % 2 == 0, z0[i // 2], z1[i // 2])

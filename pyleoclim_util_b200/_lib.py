@@ -16,6 +16,7 @@ STANDARDIZE = 2
 FAITHFUL = 4
 NO_RECURRENCE = 8
 EXACT_WINDOW = 16
+UAR1 = 32
 
 _dp = ctypes.POINTER(ctypes.c_double)
 _ip = ctypes.POINTER(ctypes.c_int64)
@@ -52,6 +53,7 @@ _SIGS = {
     "wwzb200_kirchner_ragged": (ctypes.c_int, [_dp, _dp, _ip, _dp, _ip, _dp, _ip, _ip, _i64, _dbl, _i64, _i64,
                                                _u32, _dp, _dp, _dp, _dp, _dp, _dp, _dp]),
     "wwzb200_ar1_surrogates": (ctypes.c_int, [_dp, _i64, _dbl, _dbl, _dbl, _i64, _u64, _dp]),
+    "wwzb200_uar1_surrogates": (ctypes.c_int, [_dp, _i64, _dbl, _dbl, _dbl, _i64, _u64, _dp]),
     "wwzb200_quantiles": (ctypes.c_int, [_dp, _i64, _i64, _dp, _i64, _dp]),
     "wwzb200_ar1_signif": (ctypes.c_int, [_dp, _i64, _dbl, _dbl, _dbl, _i64, _u64, _dp, _i64, _dp, _i64, _dbl, _i64,
                                           _i64, _u32, _dp, _i64, _dp, _dp, _dp]),
@@ -61,6 +63,7 @@ _SIGS = {
     "wwzb200_kirchner_shared_axis_dev": (ctypes.c_int, [_vp, _vp, _i64, _i64, _vp, _i64, _vp, _i64, _dbl, _i64,
                                                         _i64, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "wwzb200_ar1_surrogates_dev": (ctypes.c_int, [_vp, _i64, _dbl, _dbl, _dbl, _i64, _u64, _vp, _vp]),
+    "wwzb200_uar1_surrogates_dev": (ctypes.c_int, [_vp, _i64, _dbl, _dbl, _dbl, _i64, _u64, _vp, _vp]),
     "wwzb200_quantiles_dev": (ctypes.c_int, [_vp, _i64, _i64, _vp, _i64, _vp, _vp]),
     "wwzb200_measure_fp64_peak": (ctypes.c_int, [_dp, _dp]),
     "wwzb200_launch_count": (_i64, []),

@@ -9,7 +9,8 @@ import numpy as np
 from . import _lib
 from . import wavelet as _wv
 
-__all__ = ["tau_estimation", "ar1_surrogates", "ar1_sim", "wwz_shared_axis", "wwz_ragged", "quantiles",
+__all__ = ["tau_estimation", "ar1_surrogates", "ar1_sim", "n_ll_unevenly_spaced_ar1", "uar1_fit", "uar1_surrogates",
+           "uar1_sim", "wwz_shared_axis", "wwz_ragged", "quantiles",
            "wwz_signif", "signif_prepared", "SharedAxisResults", "SignifResults"]
 
 SharedAxisResults = collections.namedtuple(
@@ -52,6 +53,55 @@ def ar1_sim(y, p, t=None, seed=0):
     tau_est = tau_estimation(y, t)
     ysim = ar1_surrogates(t, tau_est, sigma=sig, number=p, seed=seed).T
     return ysim[:, 0] if p == 1 else np.ascontiguousarray(ysim)
+
+
+def n_ll_unevenly_spaced_ar1(theta, y, t):
+    """utils/tsmodel.py:612-644: negative log-likelihood of an AR(1) process on an uneven axis,
+    ``theta = (log tau, log sigma_2)``."""
+    y = np.asarray(y, dtype=float)
+    n = len(y)
+    tau, sigma_2 = np.exp(theta[0]), np.exp(theta[1])
+    phi = np.exp(-np.diff(np.asarray(t, dtype=float)) / tau)
+    term_3 = (y[1:n] - phi * y[0:n - 1]) ** 2 / (1 - phi ** 2)
+    term_4 = 1 / (sigma_2 * n) * sum(term_3)
+    term_5 = 1 / n * sum(np.log(1 - phi ** 2))
+    return np.log(2 * np.pi) + np.log(sigma_2) + term_5 + term_4
+
+
+def uar1_fit(y, t):
+    """utils/tsmodel.py:646-671: maximum-likelihood ``(tau, sigma_2)`` of an unevenly sampled AR(1) process
+    (Nelder-Mead on the host from the TAUEST / variance starting point; scipy, the same third-party call as
+    the reference)."""
+    from scipy.optimize import minimize
+    y = np.asarray(y, dtype=float)
+    t = np.asarray(t, dtype=float)
+    x0 = [np.log(tau_estimation(y=y, t=t)), np.log(np.var(y))]
+    res = minimize(n_ll_unevenly_spaced_ar1, x0=x0, args=(y, t), method="nelder-mead",
+                   options={"xatol": 1e-10, "disp": False, "maxiter": 1000})
+    return np.exp(res.x)
+
+
+def uar1_surrogates(t, tau, sigma_2=1.0, mu=0.0, number=1, seed=0):
+    """S realisations of ``uar1_sim`` (utils/tsmodel.py:673-716) on the time axis ``t``, generated on the device:
+    ``y[0] = z[0]``, ``y[i] = phi_i y[i-1] + sqrt(sigma_2 (1 - phi_i^2)) z[i]``.  Returns ``Y[number, n]``;
+    ``mu`` is added like ``SurrogateSeries.from_series`` does (core/surrogateseries.py:156)."""
+    t = _lib.f64(t)
+    Y = np.empty((int(number), t.size))
+    _lib.check(_lib.lib().wwzb200_uar1_surrogates(_lib.ptr(t), t.size, float(tau), float(sigma_2), float(mu),
+                                                  int(number), int(seed) & 0xFFFFFFFFFFFFFFFF, _lib.ptr(Y)))
+    return Y
+
+
+def uar1_sim(t, tau, sigma_2=1, seed=0):
+    """utils/tsmodel.py:673-716 for a time axis shared by all realisations: ``t`` is ``[n]`` (one series, returns
+    ``[n]``) or ``[n, p]`` with identical columns (what SurrogateSeries.from_series passes, core/surrogateseries.py:154;
+    returns ``[n, p]``).  Different axes per column are independent series: call once per axis."""
+    t = np.asarray(t, dtype=float)
+    if t.ndim == 1:
+        return uar1_surrogates(t, tau, sigma_2, number=1, seed=seed)[0]
+    if not (t == t[:, :1]).all():
+        raise ValueError("the batched generator needs one time axis shared by all columns")
+    return np.ascontiguousarray(uar1_surrogates(t[:, 0], tau, sigma_2, number=t.shape[1], seed=seed).T)
 
 
 def wwz_shared_axis(Y, ts, tau, freq, c=1 / (8 * np.pi ** 2), Neff_threshold=3, standardize=True,
@@ -147,7 +197,7 @@ def quantiles(X, qs):
 
 def wwz_signif(ys, ts, tau=None, freq=None, number=200, qs=(0.95,), seed=0, c=1 / (8 * np.pi ** 2),
                Neff_threshold=3, psd=False, psd_c=None, psd_Neff_threshold=3, freq_method="log", freq_kwargs=None,
-               flags=0):
+               flags=0, method="ar1sim"):
     """AR(1)-surrogate significance levels of a WWZ scalogram (and optionally of the WWZ spectrum) with
     everything between the time axis and the quantiles on the device (C-ABI ``wwzb200_ar1_signif``).
 
@@ -155,27 +205,35 @@ def wwz_signif(ys, ts, tau=None, freq=None, number=200, qs=(0.95,), seed=0, c=1 
     ``ar1_sim`` (+ target mean, core/surrogateseries.py:137-139), each transformed like the target
     (standardised, same tau/freq), per-cell ``mquantiles`` over the surrogates.  ``number`` surrogates,
     probabilities ``qs``.  With ``psd=True`` the quantiles of the surrogate spectra are returned too
-    (PSD.signif_test core/psds.py:246-282), computed with decay constant ``psd_c`` (default ``c``)."""
+    (PSD.signif_test core/psds.py:246-282), computed with decay constant ``psd_c`` (default ``c``).
+    ``method='uar1'`` draws the surrogates from the maximum-likelihood AR(1) fit instead
+    (core/surrogateseries.py:147-156: uar1_fit + uar1_sim)."""
     ys_cut, ts_cut, freq, tau = _wv.prepare_wwz(ys, ts, freq=freq, freq_method=freq_method, freq_kwargs=freq_kwargs,
                                                 tau=tau)
     probs = _lib.f64(np.atleast_1d(qs))
     cc = float(c if not psd or psd_c is None else psd_c)
     q_wwa, q_psd, Neffs = signif_prepared(ys_cut, ts_cut, tau, freq, number=number, probs=probs, seed=seed, c=cc,
                                           Neff_threshold=Neff_threshold, psd=psd,
-                                          psd_Neff_threshold=psd_Neff_threshold, flags=flags)
+                                          psd_Neff_threshold=psd_Neff_threshold, flags=flags, method=method)
     return SignifResults(qs=probs, amplitude_qs=q_wwa, psd_qs=q_psd, Neffs=Neffs, freq=freq, time=tau)
 
 
 def signif_prepared(ys_cut, ts_cut, tau, freq, number, probs, seed=0, c=1 / (8 * np.pi ** 2), Neff_threshold=3,
-                    psd=False, psd_Neff_threshold=3, flags=0):
+                    psd=False, psd_Neff_threshold=3, flags=0, method="ar1sim"):
     """The fused significance pipeline on an already prepared series / grid (no prepare_wwz: `tau`
     may be a row block of the full grid, as in distributed.wwz_signif_tau_sharded).
     Returns (q_wwa [nq, nt, nf], q_psd [nq, nf] or None, Neffs [nt, nf])."""
     ts_cut, tau, freq = _lib.f64(ts_cut), _lib.f64(tau), _lib.f64(freq)
     ys_cut = np.asarray(ys_cut, dtype=float)
-    sig = float(np.std(ys_cut))                     # utils/tsmodel.py:147
     mu = float(np.mean(ys_cut))                     # core/surrogateseries.py:137-139 (removed again by the z-score)
-    tau_est = float(tau_estimation(ys_cut, ts_cut))  # utils/tsmodel.py:161
+    if method == "ar1sim":
+        sig = float(np.std(ys_cut))                     # utils/tsmodel.py:147
+        tau_est = float(tau_estimation(ys_cut, ts_cut))  # utils/tsmodel.py:161
+    elif method == "uar1":
+        tau_est, sig = (float(v) for v in uar1_fit(ys_cut, ts_cut))   # core/surrogateseries.py:149; sig = sigma_2
+        flags = int(flags) | _lib.UAR1
+    else:
+        raise ValueError("surrogate method must be 'ar1sim' or 'uar1'")
     omega = _wv.make_omega(ts_cut, freq)
     probs = _lib.f64(np.atleast_1d(probs))
     nt, nf = tau.size, freq.size

@@ -60,15 +60,25 @@ __device__ __forceinline__ void normal_pair(uint64_t pair, uint64_t series, uint
     z1 = rad * s;
 }
 
-// rho_i = exp(-(t_i - t_{i-1})/tau), q_i = sqrt(1 - rho_i^2)*sigma   (utils/tsmodel.py:64-66)
-__global__ void ar1_coeff_kernel(const double *__restrict__ ts, int64_t n, double tau, double sigma,
+// ar1_model (uar1 == 0):  rho_i = exp(-(t_i - t_{i-1})/tau), q_i = sqrt(1 - rho_i^2)*sigma, y_0 = 0
+//                         (utils/tsmodel.py:61-66)
+// uar1_sim  (uar1 == 1):  phi_i = exp(-delta_i/tau), q_i = sqrt(sigma_2*(1 - phi_i^2)), y_0 = z_0
+//                         (utils/tsmodel.py:702-711; `sigma` carries sigma_2, the innovation variance)
+__global__ void ar1_coeff_kernel(const double *__restrict__ ts, int64_t n, double tau, double sigma, int uar1,
                                  double *__restrict__ rho, double *__restrict__ q)
 {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
     if (i == 0) {
         rho[0] = 0.0;
-        q[0] = 0.0;
+        q[0] = uar1 ? 1.0 : 0.0;
+        return;
+    }
+    if (uar1) {
+        const double delta = ts[i] - ts[i - 1];
+        const double phi = exp(-delta / tau);
+        rho[i] = phi;
+        q[i] = sqrt(sigma * (1.0 - phi * phi));
         return;
     }
     const double scaled_dt = (ts[i] - ts[i - 1]) / tau;
@@ -79,8 +89,9 @@ __global__ void ar1_coeff_kernel(const double *__restrict__ ts, int64_t n, doubl
 
 // One warp = 32 surrogates; the recurrence runs 32 steps at a time and the 32x32 tile is written
 // through shared memory so that each surrogate row receives 256 contiguous bytes.
-// y[0] = 0 (:61), y[i] = y[i-1]*rho_i + q_i*z_i (:67); stored value is y + mu
-// (core/surrogateseries.py:139).
+// y[i] = y[i-1]*rho_i + q_i*z_i (:67, uar1: :711) with rho_0 = 0 and q_0 = 0 (ar1_model: y[0] = 0, :61) or
+// q_0 = 1 (uar1_sim: y[0] = z_0, :704-705); stored value is y + mu (core/surrogateseries.py:139, :156).
+// Step i consumes z0 of Philox pair i/2 when i is even and z1 when i is odd.
 __global__ void __launch_bounds__(128)
     ar1_generate_kernel(const double *__restrict__ rho, const double *__restrict__ q, int64_t n, int64_t S,
                         double mu, uint64_t seed, double *__restrict__ Y)
@@ -95,18 +106,16 @@ __global__ void __launch_bounds__(128)
         const int cnt = (int)min((int64_t)32, n - i0);
         for (int j = 0; j < cnt; ++j) {
             const int64_t i = i0 + j;
-            if (i > 0) {
-                double z;
-                if ((i & 1) == 0 || i == 1) {
-                    double z0, z1;
-                    normal_pair((uint64_t)(i >> 1), (uint64_t)s, seed, z0, z1);
-                    zodd = z1;
-                    z = (i & 1) ? z1 : z0;
-                } else {
-                    z = zodd;
-                }
-                y = y * rho[i] + q[i] * z;
+            double z;
+            if ((i & 1) == 0) {
+                double z0, z1;
+                normal_pair((uint64_t)(i >> 1), (uint64_t)s, seed, z0, z1);
+                zodd = z1;
+                z = z0;
+            } else {
+                z = zodd;
             }
+            y = y * rho[i] + q[i] * z;
             tile[wib][lane][j] = y + mu;
         }
         __syncwarp();
@@ -119,10 +128,10 @@ __global__ void __launch_bounds__(128)
 }
 
 cudaError_t launch_ar1(const double *d_ts, int64_t n, double tau, double sigma, double mu, int64_t S, uint64_t seed,
-                       double *d_rho, double *d_q, double *d_Y, cudaStream_t st)
+                       bool uar1, double *d_rho, double *d_q, double *d_Y, cudaStream_t st)
 {
     if (n <= 0 || S <= 0) return cudaSuccess;
-    ar1_coeff_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_ts, n, tau, sigma, d_rho, d_q);
+    ar1_coeff_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_ts, n, tau, sigma, uar1 ? 1 : 0, d_rho, d_q);
     ar1_generate_kernel<<<(unsigned)((S + 127) / 128), 128, 0, st>>>(d_rho, d_q, n, S, mu, seed, d_Y);
     bump_launch_counter(2);
     return cudaGetLastError();

@@ -625,28 +625,29 @@ int wwzb200_kirchner_shared_axis(const double *ts, const double *Y, int64_t nts,
     return 0;
 }
 
-int wwzb200_ar1_surrogates_dev(const double *d_ts, int64_t nts, double tau_est, double sigma, double mu, int64_t S,
-                               uint64_t seed, double *d_Y, void *stream)
+static int surrogates_dev(const double *d_ts, int64_t nts, double tau_est, double sigma, double mu, int64_t S,
+                          uint64_t seed, bool uar1, double *d_Y, void *stream)
 {
     if (nts < 1 || S < 0) return fail(WWZB200_ERR_ARG, "bad sizes");
     if (!d_ts || (S && !d_Y)) return fail(WWZB200_ERR_ARG, "null pointer");
-    if (!(tau_est > 0)) return fail(WWZB200_ERR_ARG, "tau_est must be positive");
+    if (!(tau_est > 0)) return fail(WWZB200_ERR_ARG, "tau must be positive");
+    if (uar1 && !(sigma >= 0)) return fail(WWZB200_ERR_ARG, "sigma_2 must be non-negative");
     std::lock_guard<std::mutex> lock(g_mu);
     Workspace *w;
     int rc;
     if ((rc = workspace(&w))) return rc;
     double *d_rq;
     if ((rc = wsbuf(w, "ar1_rq", (size_t)2 * nts, &d_rq))) return rc;
-    CU(wwz::launch_ar1(d_ts, nts, tau_est, sigma, mu, S, seed, d_rq, d_rq + nts, d_Y, static_cast<cudaStream_t>(stream)));
+    CU(wwz::launch_ar1(d_ts, nts, tau_est, sigma, mu, S, seed, uar1, d_rq, d_rq + nts, d_Y,
+                       static_cast<cudaStream_t>(stream)));
     return 0;
 }
 
-int wwzb200_ar1_surrogates(const double *ts, int64_t nts, double tau_est, double sigma, double mu, int64_t S,
-                           uint64_t seed, double *Y)
+static int surrogates_host(const double *ts, int64_t nts, double tau_est, double sigma, double mu, int64_t S,
+                           uint64_t seed, bool uar1, double *Y)
 {
     if (nts < 1 || S < 0) return fail(WWZB200_ERR_ARG, "bad sizes");
     if (!ts || (S && !Y)) return fail(WWZB200_ERR_ARG, "null pointer");
-    if (!(tau_est > 0)) return fail(WWZB200_ERR_ARG, "tau_est must be positive");
     Workspace *w;
     int rc;
     double *d_ts, *d_Y;
@@ -657,10 +658,34 @@ int wwzb200_ar1_surrogates(const double *ts, int64_t nts, double tau_est, double
         if ((rc = wsbuf(w, "Y", (size_t)S * (size_t)nts, &d_Y))) return rc;
         CU(cudaMemcpyAsync(d_ts, ts, sizeof(double) * nts, cudaMemcpyHostToDevice, w->stream));
     }
-    if ((rc = wwzb200_ar1_surrogates_dev(d_ts, nts, tau_est, sigma, mu, S, seed, d_Y, w->stream))) return rc;
+    if ((rc = surrogates_dev(d_ts, nts, tau_est, sigma, mu, S, seed, uar1, d_Y, w->stream))) return rc;
     if (S) CU(cudaMemcpyAsync(Y, d_Y, sizeof(double) * (size_t)S * (size_t)nts, cudaMemcpyDeviceToHost, w->stream));
     CU(cudaStreamSynchronize(w->stream));
     return 0;
+}
+
+int wwzb200_ar1_surrogates_dev(const double *d_ts, int64_t nts, double tau_est, double sigma, double mu, int64_t S,
+                               uint64_t seed, double *d_Y, void *stream)
+{
+    return surrogates_dev(d_ts, nts, tau_est, sigma, mu, S, seed, false, d_Y, stream);
+}
+
+int wwzb200_ar1_surrogates(const double *ts, int64_t nts, double tau_est, double sigma, double mu, int64_t S,
+                           uint64_t seed, double *Y)
+{
+    return surrogates_host(ts, nts, tau_est, sigma, mu, S, seed, false, Y);
+}
+
+int wwzb200_uar1_surrogates_dev(const double *d_ts, int64_t nts, double tau, double sigma_2, double mu, int64_t S,
+                                uint64_t seed, double *d_Y, void *stream)
+{
+    return surrogates_dev(d_ts, nts, tau, sigma_2, mu, S, seed, true, d_Y, stream);
+}
+
+int wwzb200_uar1_surrogates(const double *ts, int64_t nts, double tau, double sigma_2, double mu, int64_t S,
+                            uint64_t seed, double *Y)
+{
+    return surrogates_host(ts, nts, tau, sigma_2, mu, S, seed, true, Y);
 }
 
 int wwzb200_quantiles_dev(const double *d_X, int64_t S, int64_t ncell, const double *d_probs, int64_t nq, double *d_q,
@@ -835,7 +860,7 @@ int wwzb200_ar1_signif(const double *ts, int64_t nts, double tau_est, double sig
     if (nt) CU(cudaMemcpyAsync(d_tau, taus, sizeof(double) * nt, cudaMemcpyHostToDevice, st));
     if (nf) CU(cudaMemcpyAsync(d_om, omegas, sizeof(double) * nf, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(d_probs, probs, sizeof(double) * nq, cudaMemcpyHostToDevice, st));
-    CU(wwz::launch_ar1(d_ts, nts, tau_est, sigma, mu, S, seed, d_rq, d_rq + nts, d_Y, st));
+    CU(wwz::launch_ar1(d_ts, nts, tau_est, sigma, mu, S, seed, (flags & WWZB200_UAR1) != 0, d_rq, d_rq + nts, d_Y, st));
     const auto mm = std::minmax_element(ts, ts + nts);
     double *d_amp_cells = nullptr;
     int64_t S_pad = 0;

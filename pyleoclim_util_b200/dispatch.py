@@ -219,15 +219,18 @@ def _patch_core(pyleo, wavemod):
                     for i, amp in enumerate(amp_qs)]                  # :915-919
         return MPSD(psd_list=psd_list)
 
-    def _fusable(ts, args):
-        """The fused device pipeline covers the default preprocessing on an uneven axis."""
+    def _fusable(ts, args, method="ar1sim"):
+        """The fused device pipeline covers the default preprocessing; 'ar1sim' on an uneven axis only."""
+        if method not in ("ar1sim", "uar1"):
+            return False
         if ts is None or not isinstance(args, dict) or args.get("method") != CUDA_METHOD:
             return False
         if args.get("detrend", False) not in (False, None, "none") or args.get("gaussianize", False):
             return False
         if args.get("len_bd", 0) or args.get("anti_alias", False) or not args.get("standardize", True):
             return False
-        return not ts.is_evenly_spaced()          # the even branch of ar1_sim is a statsmodels fit
+        # the even branch of ar1_sim is a statsmodels fit; uar1_fit / uar1_sim take any axis (utils/tsmodel.py:646-716)
+        return method == "uar1" or not ts.is_evenly_spaced()
 
     def _surrogate_grid(ts, args):
         """tau / freq exactly as the surrogates' Series.wavelet / Series.spectral would build them
@@ -239,8 +242,8 @@ def _patch_core(pyleo, wavemod):
 
     @functools.wraps(orig["scal_signif"])
     def scal_signif_test(self, method="ar1sim", number=None, seed=None, qs=[0.95], settings=None, export_scal=False):
-        fused = (method == "ar1sim" and self.wave_method == "wwz" and not export_scal
-                 and not getattr(self, "signif_scals", None) and _fusable(self.timeseries, self.wave_args))
+        fused = (self.wave_method == "wwz" and not export_scal
+                 and not getattr(self, "signif_scals", None) and _fusable(self.timeseries, self.wave_args, method))
         if not fused:
             return orig["scal_signif"](self, method=method, number=number, seed=seed, qs=qs, settings=settings,
                                        export_scal=export_scal)
@@ -255,7 +258,7 @@ def _patch_core(pyleo, wavemod):
         ys_cut, ts_cut, freq, tau = _surrogate_grid(ts, args)
         sg = batch.wwz_signif(ys_cut, ts_cut, tau=tau, freq=freq, number=number, qs=qs,
                               seed=0 if seed is None else seed, c=args.get("c", 1 / (8 * np.pi ** 2)),
-                              Neff_threshold=args.get("Neff_threshold", 3))
+                              Neff_threshold=args.get("Neff_threshold", 3), method=method)
         new = self.copy()
         coi = wavemod.make_coi(tau, Neff_threshold=args.get("Neff_coi", 3))
         new.signif_qs = MScal(scalogram_list=[
@@ -267,8 +270,8 @@ def _patch_core(pyleo, wavemod):
 
     @functools.wraps(orig["psd_signif"])
     def psd_signif_test(self, method="ar1sim", number=None, seed=None, qs=[0.95], settings=None, scalogram=None):
-        fused = (method == "ar1sim" and self.spec_method == "wwz" and scalogram is None
-                 and _fusable(self.timeseries, self.spec_args) and "tau" not in self.spec_args)
+        fused = (self.spec_method == "wwz" and scalogram is None
+                 and _fusable(self.timeseries, self.spec_args, method) and "tau" not in self.spec_args)
         if not fused:
             return orig["psd_signif"](self, method=method, number=number, seed=seed, qs=qs, settings=settings,
                                       scalogram=scalogram)
@@ -282,7 +285,7 @@ def _patch_core(pyleo, wavemod):
         ys_cut, ts_cut, freq, tau = wavemod.prepare_wwz(ts.value, ts.time, freq=freq)   # utils/spectral.py:882
         sg = batch.wwz_signif(ys_cut, ts_cut, tau=tau, freq=freq, number=number, qs=qs,
                               seed=0 if seed is None else seed, c=args.get("c", 1e-3), Neff_threshold=3, psd=True,
-                              psd_Neff_threshold=args.get("Neff_threshold", 3))
+                              psd_Neff_threshold=args.get("Neff_threshold", 3), method=method)
         new = self.copy()
         lw = [0.5, 1.5, 0.5] if len(qs) == 3 else [1.0] * len(qs)
         new.signif_qs = MPSD(psd_list=[
@@ -312,7 +315,8 @@ def register(pyleoclim_wavelet=None, core=True, surrogates=False):
     * ``core=True``: when the full package is importable, batches ``MultipleSeries.wavelet`` /
       ``.spectral``, moves the ``quantiles`` of CUDA results to the device and fuses
       ``signif_test`` (class level, see the module docstring);
-    * ``surrogates=True``: additionally routes ``pyleoclim.utils.tsmodel.ar1_sim`` for unevenly spaced
+    * ``surrogates=True``: additionally routes ``pyleoclim.utils.tsmodel.uar1_sim`` (shared time axis) and
+      ``pyleoclim.utils.tsmodel.ar1_sim`` for unevenly spaced
       axes to the device generator (the reference draws from NumPy's unseeded global stream, so only
       the distribution, not the stream, is preserved).
 
@@ -362,6 +366,18 @@ def register(pyleoclim_wavelet=None, core=True, surrogates=False):
 
         tsmodel.ar1_sim = ar1_sim
         undo.append(lambda: setattr(tsmodel, "ar1_sim", orig_sim))
+        orig_usim = tsmodel.uar1_sim
+
+        @functools.wraps(orig_usim)
+        def uar1_sim(t, tau, sigma_2=1):
+            t_arr = np.asarray(t, dtype=float)
+            if t_arr.ndim == 2 and not (t_arr == t_arr[:, :1]).all():
+                return orig_usim(t, tau, sigma_2)                 # per-column axes: not one shared-axis batch
+            from . import batch
+            return batch.uar1_sim(t_arr, tau, sigma_2, seed=int(np.random.randint(0, 2 ** 31 - 1)))
+
+        tsmodel.uar1_sim = uar1_sim
+        undo.append(lambda: setattr(tsmodel, "uar1_sim", orig_usim))
     _state[id(mod)] = undo
     return mod
 

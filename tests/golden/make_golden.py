@@ -144,6 +144,26 @@ def surrogates():
          sim_seed99_p3=sim)
 
 
+def uar1():
+    """uar1_fit / uar1_sim / the likelihood (utils/tsmodel.py:612-716) with NumPy's legacy global RNG; the
+    innovation matrices are stored so that a restatement can be checked draw for draw."""
+    t, y = synth.uneven_ar1(300, 31)
+    y = 1.8 * y + 0.5
+    theta = TM.uar1_fit(y, t)
+    nll = TM.n_ll_unevenly_spaced_ar1([np.log(4.0), np.log(1.3)], y, t)
+    np.random.seed(4321)
+    z1 = np.random.normal(loc=0, scale=1, size=(t.size, 1))
+    np.random.seed(4321)
+    sim1 = TM.uar1_sim(t, tau=theta[0], sigma_2=theta[1])
+    T = np.tile(t, (3, 1)).T
+    np.random.seed(77)
+    z3 = np.random.normal(loc=0, scale=1, size=T.shape)
+    np.random.seed(77)
+    sim3 = TM.uar1_sim(T, tau=3.5, sigma_2=2.2)
+    save("uar1", ts=t, ys=y, theta_hat=np.asarray(theta), nll_tau4_s1p3=np.array([nll]), z_seed4321=z1[:, 0],
+         sim_seed4321=sim1, z_seed77=z3, sim_seed77_tau3p5_s2p2=sim3)
+
+
 def cleaning():
     """prepare_wwz on NaNs, unsorted stamps, duplicates and a tau that is off the time axis."""
     rng = np.random.default_rng(77)
@@ -167,6 +187,6 @@ def cleaning():
 
 if __name__ == "__main__":
     which = sys.argv[1:] or ["benthic", "soi", "synth_small", "edge", "c2_subsample", "c5_sample",
-                             "surrogates", "cleaning"]
+                             "surrogates", "uar1", "cleaning"]
     for name in which:
         globals()[name]()

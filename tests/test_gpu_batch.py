@@ -1,5 +1,7 @@
 """Batched paths on the GPU: AR(1) surrogates, shared-time-axis transform, ragged ensembles,
 per-cell quantiles, fused significance test -- against the oracle and against the single-series path."""
+import os
+
 import numpy as np
 import pytest
 
@@ -51,6 +53,45 @@ def test_ar1_surrogate_statistics():
     sim = B.ar1_sim(y, 5, t, seed=1)
     assert sim.shape == (2000, 5) and abs(sim.std() / y.std() - 1) < 0.1
     assert B.ar1_sim(y, 1, t).shape == (2000,)
+
+
+def test_uar1_surrogates_match_the_oracle_recurrence():
+    """uar1_sim (utils/tsmodel.py:673-716): y[0] = z[0], innovations sqrt(sigma_2 (1 - phi^2)) z, same Philox stream."""
+    O = oracle()
+    t, y = synth.uneven_ar1(301, 9)
+    Y = B.uar1_surrogates(t, tau=2.9, sigma_2=1.7, mu=-0.5, number=40, seed=99)
+    assert Y.shape == (40, 301)
+    for s in (0, 3, 39):
+        z = O.philox_normals(99, s, t.size)
+        ref = O.uar1_sim(t, tau=2.9, sigma_2=1.7, z=z) - 0.5
+        assert np.max(np.abs(Y[s] - ref)) < 1e-11
+        assert abs(Y[s, 0] - (z[0] - 0.5)) < 1e-14              # y[0] = z[0] (+ mu)
+    sim = B.uar1_sim(np.tile(t, (6, 1)).T, tau=2.9, sigma_2=1.7, seed=99)
+    assert sim.shape == (301, 6) and np.max(np.abs(sim - (Y[:6].T + 0.5))) < 1e-14
+    assert B.uar1_sim(t, tau=2.9, sigma_2=1.7, seed=99).shape == (301,)
+    # the fit recovers the parameters of its own surrogates (reference criterion: tests/test_core_SurrogateSeries.py:90-104)
+    t2, _ = synth.uneven_ar1(2000, 4)
+    Y2 = B.uar1_surrogates(t2, tau=5.0, sigma_2=2.0, number=8, seed=1)
+    th = np.array([B.uar1_fit(Y2[s], t2) for s in range(8)])
+    assert abs(th[:, 0].mean() / 5.0 - 1) < 0.15 and abs(th[:, 1].mean() / 2.0 - 1) < 0.1
+    gfit = np.load(os.path.join(os.path.dirname(__file__), "golden", "uar1.npz"))
+    assert np.max(np.abs(B.uar1_fit(gfit["ys"], gfit["ts"]) / gfit["theta_hat"] - 1)) < 1e-6
+
+
+def test_wwz_signif_with_uar1_surrogates():
+    from scipy.stats.mstats import mquantiles
+    t, y = synth.uneven_ar1(350, 13)
+    number, qs, seed = 40, [0.9, 0.95], 5
+    sg = B.wwz_signif(y, t, number=number, qs=qs, seed=seed, method="uar1")
+    ys_cut, ts_cut, freq, tau = WV.prepare_wwz(y, t)
+    tau_hat, s2 = B.uar1_fit(ys_cut, ts_cut)
+    Y = B.uar1_surrogates(ts_cut, tau_hat, s2, mu=np.mean(ys_cut), number=number, seed=seed)
+    amps = np.stack([WV.kirchner_cuda(Y[s], ts_cut, freq, tau, standardize=True)[0] for s in range(number)])
+    ref = np.asarray(mquantiles(amps.reshape(number, -1), qs, axis=0).filled(np.nan)).reshape(2, tau.size, freq.size)
+    assert_same_nan_mask(sg.amplitude_qs, ref)
+    assert max_rel(sg.amplitude_qs, ref) < 1e-10
+    with pytest.raises(ValueError):
+        B.wwz_signif(y, t, number=4, method="phaseran")
 
 
 # ------------------------------------------------------------------ shared time axis

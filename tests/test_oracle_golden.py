@@ -111,6 +111,23 @@ def test_surrogate_generator():
     assert np.max(np.abs(sim - g["sim_seed99_p3"])) < 1e-9
 
 
+def test_uar1_fit_and_sim():
+    """uar1 surrogates: likelihood, Nelder-Mead fit and the recurrence against outputs of the
+    reference's own uar1_fit / uar1_sim (utils/tsmodel.py:612-716), draw for draw."""
+    g = golden("uar1")
+    t, y = g["ts"], g["ys"]
+    assert abs(O.n_ll_unevenly_spaced_ar1([np.log(4.0), np.log(1.3)], y, t) / g["nll_tau4_s1p3"][0] - 1) < 1e-13
+    theta = O.uar1_fit(y, t)
+    assert np.max(np.abs(theta / g["theta_hat"] - 1)) < 1e-6
+    sim1 = O.uar1_sim(t, tau=g["theta_hat"][0], sigma_2=g["theta_hat"][1], z=g["z_seed4321"])
+    assert sim1.shape == g["sim_seed4321"].shape and np.max(np.abs(sim1 - g["sim_seed4321"])) < 1e-13
+    T = np.tile(t, (3, 1)).T
+    sim3 = O.uar1_sim(T, tau=3.5, sigma_2=2.2, z=g["z_seed77"])
+    assert np.max(np.abs(sim3 - g["sim_seed77_tau3p5_s2p2"])) < 1e-13
+    np.random.seed(77)
+    assert np.array_equal(O.uar1_sim(T, tau=3.5, sigma_2=2.2), sim3)      # same draws from the global generator
+
+
 def test_prepare_wwz_cleaning():
     g = golden("cleaning")
     ys_cut, ts_cut, freq, tau = O.prepare_wwz(g["ys"], g["ts"], tau=g["tau_in"])

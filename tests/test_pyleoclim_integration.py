@@ -62,6 +62,7 @@ def cuda_standins(monkeypatch, pyleo):
     def signif(ys, ts, tau=None, freq=None, number=200, qs=(0.95,), seed=0, c=1 / (8 * np.pi ** 2), Neff_threshold=3,
                psd=False, psd_c=None, psd_Neff_threshold=3, **kw):
         calls["signif"] += 1
+        calls["signif_method"] = kw.get("method", "ar1sim")
         rng = np.random.RandomState(seed)
         tau_est = O.tau_estimation(ys, ts)
         Y = np.stack([O.ar1_model(ts, tau_est, output_sigma=np.std(ys), rng=rng) + np.mean(ys) for _ in range(number)])
@@ -231,3 +232,34 @@ def test_surrogates_option_routes_ar1_sim_to_the_device(pyleo, monkeypatch):
     finally:
         D.unregister()
     assert pyleo.utils.tsmodel.ar1_sim.__module__.endswith("tsmodel")
+
+
+def test_uar1_signif_is_fused_and_uar1_sim_is_routed(pyleo, cuda_standins, monkeypatch):
+    """method='uar1' (core/surrogateseries.py:147-156) takes the fused device pipeline, and
+    register(surrogates=True) routes tsmodel.uar1_sim for a shared time axis to the device generator."""
+    s = _series(pyleo, 120, 5, "u")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        scal = s.wavelet(method="wwz", settings=CUDA, freq=FREQ)
+        sig = scal.signif_test(method="uar1", number=4, qs=[0.95], seed=1)
+    assert cuda_standins["signif"] == 1 and cuda_standins["signif_method"] == "uar1"
+    assert sig.signif_method == "uar1" and sig.signif_qs.scalogram_list[0].amplitude.shape == scal.amplitude.shape
+    D.unregister()
+    calls = []
+
+    def fake_uar1_sim(t, tau, sigma_2=1, seed=0):
+        calls.append((np.shape(t), tau, sigma_2))
+        return np.zeros(np.shape(t))
+
+    monkeypatch.setattr(B, "uar1_sim", fake_uar1_sim)
+    D.register(surrogates=True)
+    try:
+        t, _ = synth.uneven_ar1(60, 2)
+        out = pyleo.utils.tsmodel.uar1_sim(np.tile(t, (4, 1)).T, tau=3.0, sigma_2=1.5)
+        assert out.shape == (60, 4) and calls == [((60, 4), 3.0, 1.5)]
+        T = np.stack([t, t * 1.01], axis=1)                      # per-column axes stay with the reference
+        np.random.seed(0)
+        assert pyleo.utils.tsmodel.uar1_sim(T, tau=3.0).shape == (60, 2) and len(calls) == 1
+    finally:
+        D.unregister()
+    assert pyleo.utils.tsmodel.uar1_sim.__module__.endswith("tsmodel")
