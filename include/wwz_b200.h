@@ -57,6 +57,10 @@ extern "C" {
                                    (equally spaced tau, frequency rows with kappa*dtau small) */
 #define WWZB200_UAR1 32u        /* wwzb200_ar1_signif: surrogates follow uar1_sim (utils/tsmodel.py:673-716) instead  \
                                    of ar1_model; the `sigma` argument then carries the innovation variance sigma_2 */
+#define WWZB200_FOSTER 64u      /* single-series and ragged entry points: Foster's weighted projection on            \
+                                   {1, cos w(t-tau), sin w(t-tau)} with the 3x3 pseudo-inverse solve of the           \
+                                   reference's method='Foster' (wwz_basic, utils/wavelet.py:341-374) instead of        \
+                                   Kirchner's centred covariances; a0,a1,a2 then hold ywave_1,2,3 (:372-374) */
 #define WWZB200_FAITHFUL 4u     /* validation mode: evaluate every cell with the reference's own    \
                                    two-pass expressions (utils/wavelet.py:988-1032), one warp per   \
                                    cell; ~10x slower, agrees with kirchner_numba to ~1e-12 */

@@ -137,6 +137,48 @@ def kirchner(ys, ts, freq, tau, c=1 / (8 * np.pi ** 2), Neff_threshold=3, nproc=
     return wwa, phase, Neffs, (a0, a1, a2)
 
 
+def foster(ys, ts, freq, tau, c=1 / (8 * np.pi ** 2), Neff_threshold=3, nproc=1, detrend=False, sg_kwargs=None,
+           gaussianize=False, standardize=False):
+    """wwz_basic (the reference's method='Foster'), utils/wavelet.py:328-381, restated with NumPy: the cell loop
+    :341-374 vectorised over tau for one frequency at a time, the 3x3 pseudo-inverses (:366) as one stacked
+    np.linalg.pinv call (third-party, same function and default rcond as the reference)."""
+    assert nproc == 1 and Neff_threshold >= 1
+    ts, tau, freq = _c(ts), _c(tau), _c(freq)
+    pd_ys = globals()["standardize"](ys)[0] if standardize else _c(ys)   # :334
+    omega = make_omega(ts, freq)                                          # :336
+    nt, nf = tau.size, freq.size
+    Neffs = np.full((nt, nf), np.nan)
+    y1 = np.full((nt, nf), np.nan)
+    y2 = np.full((nt, nf), np.nan)
+    y3 = np.full((nt, nf), np.nan)
+    for k in range(nf):
+        dz = omega[k] * (ts[None, :] - tau[:, None])                      # :343
+        w = np.exp(-c * dz ** 2)                                          # :344
+        sum_w = np.sum(w, axis=1)                                         # :346
+        with np.errstate(invalid="ignore", divide="ignore"):
+            Neffs[:, k] = sum_w ** 2 / np.sum(w ** 2, axis=1)             # :347
+        ok = Neffs[:, k] > Neff_threshold                                 # :349 (NaN Neff: left NaN here)
+        if not ok.any():
+            continue
+        w, dz, sw = w[ok], dz[ok], sum_w[ok, None]
+        phi2, phi3 = np.cos(dz), np.sin(dz)                               # :354-355
+        S = np.empty((w.shape[0], 3, 3))
+        S[:, 0, 0] = 1
+        S[:, 1, 1] = np.sum(w * phi2 * phi2, axis=1) / sw[:, 0]
+        S[:, 2, 2] = np.sum(w * phi3 * phi3, axis=1) / sw[:, 0]
+        S[:, 1, 0] = S[:, 0, 1] = np.sum(w * phi2, axis=1) / sw[:, 0]
+        S[:, 2, 0] = S[:, 0, 2] = np.sum(w * phi3, axis=1) / sw[:, 0]
+        S[:, 2, 1] = S[:, 1, 2] = np.sum(w * phi2 * phi3, axis=1) / sw[:, 0]
+        S_inv = np.linalg.pinv(S)                                         # :366
+        p = np.stack([np.sum(w * pd_ys, axis=1), np.sum(w * phi2 * pd_ys, axis=1),
+                      np.sum(w * phi3 * pd_ys, axis=1)], axis=1) / sw     # :368-370
+        sol = np.einsum("cij,cj->ci", S_inv, p)                           # :372-374
+        y1[ok, k], y2[ok, k], y3[ok, k] = sol[:, 0], sol[:, 1], sol[:, 2]
+    wwa = np.sqrt(y2 ** 2 + y3 ** 2)                                      # :376
+    phase = np.arctan2(y3, y2)                                            # :377
+    return wwa, phase, Neffs, (y1, y2, y3)
+
+
 def wwa2psd(wwa, ts, Neffs, freq=None, Neff_threshold=3, anti_alias=False, avgs=2):
     """utils/wavelet.py:1236-1292 with anti_alias off (the default on this path)."""
     if anti_alias:

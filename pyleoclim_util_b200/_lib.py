@@ -17,6 +17,7 @@ FAITHFUL = 4
 NO_RECURRENCE = 8
 EXACT_WINDOW = 16
 UAR1 = 32
+FOSTER = 64
 
 _dp = ctypes.POINTER(ctypes.c_double)
 _ip = ctypes.POINTER(ctypes.c_int64)

@@ -183,9 +183,14 @@ int transform_device(Workspace *w, const double *d_ts, const double *d_ys, int64
         if (row_stride != nf) return fail(WWZB200_ERR_ARG, "psd without wwa output needs row_stride == nf");
     }
 
+    const bool foster = (flags & WWZB200_FOSTER) != 0;
     if (flags & WWZB200_FAITHFUL) {
-        CU(launch_faithful(d_ts, d_ys, n, d_tau, d_omega, nt, nf, c, (double)thr, nullptr, nullptr, 0, d_neffs, d_a0,
-                           d_a1, d_a2, d_wwa, d_phase, row_stride, w->sms, st));
+        if (foster)
+            CU(launch_foster_faithful(d_ts, d_ys, n, d_tau, d_omega, nt, nf, c, (double)thr, nullptr, nullptr, 0, d_neffs,
+                                      d_a0, d_a1, d_a2, d_wwa, d_phase, row_stride, w->sms, st));
+        else
+            CU(launch_faithful(d_ts, d_ys, n, d_tau, d_omega, nt, nf, c, (double)thr, nullptr, nullptr, 0, d_neffs, d_a0,
+                               d_a1, d_a2, d_wwa, d_phase, row_stride, w->sms, st));
     } else {
         const int segs = point_segments(n, ncell);
         const int64_t seg_len = (((n + segs - 1) / segs + 15) / 16) * 16;
@@ -216,6 +221,8 @@ int transform_device(Workspace *w, const double *d_ts, const double *d_ys, int64
         if ((rc = wsbuf(w, "ty", (size_t)plan.n_pad, &d_ty))) return rc;
         if ((rc = wsbuf(w, "basis", (size_t)nf_batch * (size_t)plan.n_pad * 2, &d_basis))) return rc;
         if ((rc = wsbuf(w, "sums", (size_t)segs * (size_t)kNumSums * (size_t)ncell, &d_sums))) return rc;
+        double *d_sums2 = nullptr;   // Foster: sums of the second pass (y := cos)
+        if (foster && (rc = wsbuf(w, "sums2", (size_t)segs * (size_t)kNumSums * (size_t)ncell, &d_sums2))) return rc;
 
         CU(launch_freq_setup(d_omega, nf, d_tau, nt, c, allow_rec, cut_bits, d_kappa, d_dcut, d_grid, d_rec_row, st));
         CU(launch_unsorted_check(d_ts, n, d_unsorted, st));
@@ -223,7 +230,7 @@ int transform_device(Workspace *w, const double *d_ts, const double *d_ys, int64
         const bool dense = (flags & WWZB200_DENSE) != 0;
         for (int64_t k0 = 0; k0 < nf; k0 += nf_batch) {
             const int64_t nb = std::min<int64_t>(nf_batch, nf - k0);
-            CU(launch_basis(d_ts, d_ys, n, plan.n_pad, d_omega + k0, nb, d_ty, d_basis, k0 == 0, st));
+            CU(launch_basis(d_ts, d_ys, n, plan.n_pad, d_omega + k0, nb, d_ty, d_basis, k0 == 0, false, st));
             EventPair ev{nullptr, nullptr, (double)n * (double)nt * (double)nb};
             if (g_profile) {
                 CU(cudaEventCreate(&ev.a));
@@ -239,11 +246,29 @@ int transform_device(Workspace *w, const double *d_ts, const double *d_ys, int64
                 CU(cudaEventRecord(ev.b, st));
                 g_events.push_back(ev);
             }
+            if (foster) {
+                // second pass of the same kernels over records built with y := cos(omega t): its "y sin" and
+                // "y cos" sums are sum(w c s) and sum(w c c), the two extra entries of Foster's normal matrix
+                CU(launch_basis(d_ts, d_ys, n, plan.n_pad, d_omega + k0, nb, d_ty, d_basis, false, true, st));
+                if (allow_rec)
+                    CU(launch_rec(rplan, d_ty, d_basis, d_ts, n, d_tau, nt, d_kappa, d_dcut, d_unsorted, k0, nb, nf, segs,
+                                  seg_len, d_rec_row, d_grid, d_sums2, st));
+                CU(launch_cells(plan, d_ty, d_basis, d_ts, n, d_tau, nt, d_kappa, d_dcut, d_unsorted, k0, nb, nf, dense,
+                                segs, seg_len, allow_rec ? d_rec_row : nullptr, d_grid, d_sums2, st));
+            }
         }
-        CU(launch_finalize(d_sums, d_tau, d_omega, nt, nf, (double)thr, d_neffs, d_a0, d_a1, d_a2, d_wwa, d_phase,
-                           row_stride, d_fix_count, d_fix_list, (unsigned int)ncell, segs, st));
-        CU(launch_faithful(d_ts, d_ys, n, d_tau, d_omega, nt, nf, c, (double)thr, d_fix_count, d_fix_list,
-                           (unsigned int)ncell, d_neffs, d_a0, d_a1, d_a2, d_wwa, d_phase, row_stride, w->sms, st));
+        if (foster) {
+            CU(launch_finalize_foster(d_sums, d_sums2, d_tau, d_omega, nt, nf, (double)thr, d_neffs, d_a0, d_a1, d_a2,
+                                      d_wwa, d_phase, row_stride, d_fix_count, d_fix_list, (unsigned int)ncell, segs, st));
+            CU(launch_foster_faithful(d_ts, d_ys, n, d_tau, d_omega, nt, nf, c, (double)thr, d_fix_count, d_fix_list,
+                                      (unsigned int)ncell, d_neffs, d_a0, d_a1, d_a2, d_wwa, d_phase, row_stride,
+                                      w->sms, st));
+        } else {
+            CU(launch_finalize(d_sums, d_tau, d_omega, nt, nf, (double)thr, d_neffs, d_a0, d_a1, d_a2, d_wwa, d_phase,
+                               row_stride, d_fix_count, d_fix_list, (unsigned int)ncell, segs, st));
+            CU(launch_faithful(d_ts, d_ys, n, d_tau, d_omega, nt, nf, c, (double)thr, d_fix_count, d_fix_list,
+                               (unsigned int)ncell, d_neffs, d_a0, d_a1, d_a2, d_wwa, d_phase, row_stride, w->sms, st));
+        }
     }
     if (d_psd) {
         if (tspan >= 0) {
@@ -328,6 +353,9 @@ int shared_axis_device(Workspace *w, const double *d_ts, const double *d_Y, int6
     const int64_t ncell = nt * nf;
     if (ncell == 0 || S == 0) return 0;
     if (ncell >= ((int64_t)1 << 32)) return fail(WWZB200_ERR_ARG, "nt*nf exceeds 2^32 cells");
+    if (flags & WWZB200_FOSTER)
+        return fail(WWZB200_ERR_ARG, "WWZB200_FOSTER is not available for the shared-time-axis batch (the 3x3 solve is "
+                                     "not linear in the basis sums alone); use the single-series or ragged entry points");
     const SharedPlan plan = plan_shared(n, nt, nf, S);
     const int NS = plan.series_block;
     const int64_t S_pad = ((S + NS - 1) / NS) * NS;

@@ -60,9 +60,10 @@ cudaError_t launch_freq_setup(const double *d_omega, int64_t nf, const double *d
                               unsigned char *d_rec_row, cudaStream_t st);
 
 // (t, y) interleaved + per-frequency basis rows (sin, cos, y sin, y cos), zero padded to n_pad.
+// cos_as_y: records (sin, cos, cos*sin, cos*cos) -- the second pass of Foster's method (wwz_foster.cu).
 cudaError_t launch_basis(const double *d_ts, const double *d_ys, int64_t n, int64_t n_pad,
                          const double *d_omega, int64_t nf_batch, double2 *d_ty, double2 *d_basis,
-                         bool write_ty, cudaStream_t st);
+                         bool write_ty, bool cos_as_y, cudaStream_t st);
 
 // The hot kernel: weighted sums for every (tau, f) cell of a frequency batch.
 // sums is [segs][7][nt * nf_total], each slab laid out like the outputs (cell = j*nf_total + k);
@@ -90,6 +91,19 @@ cudaError_t launch_faithful(const double *d_ts, const double *d_ys, int64_t n, c
                             const unsigned int *d_fix_count, const unsigned int *d_fix_list, unsigned int fix_cap,
                             double *d_neffs, double *d_a0, double *d_a1, double *d_a2, double *d_wwa,
                             double *d_phase, int64_t out_row_stride, int sms, cudaStream_t st);
+
+// Foster's method (wwz_foster.cu): epilogue over the sums of both passes (3x3 pseudo-inverse solve per cell) and
+// the warp-per-cell evaluator with the reference's own expressions (utils/wavelet.py:343-374).
+cudaError_t launch_finalize_foster(const double *d_sums, const double *d_sums2, const double *d_tau,
+                                   const double *d_omega, int64_t nt, int64_t nf, double neff_thr, double *d_neffs,
+                                   double *d_a0, double *d_a1, double *d_a2, double *d_wwa, double *d_phase,
+                                   int64_t out_row_stride, unsigned int *d_fix_count, unsigned int *d_fix_list,
+                                   unsigned int fix_cap, int segs, cudaStream_t st);
+cudaError_t launch_foster_faithful(const double *d_ts, const double *d_ys, int64_t n, const double *d_tau,
+                                   const double *d_omega, int64_t nt, int64_t nf, double c, double neff_thr,
+                                   const unsigned int *d_fix_count, const unsigned int *d_fix_list,
+                                   unsigned int fix_cap, double *d_neffs, double *d_a0, double *d_a1, double *d_a2,
+                                   double *d_wwa, double *d_phase, int64_t out_row_stride, int sms, cudaStream_t st);
 
 // wwa2psd tau-reduction (one thread per frequency column, rows added in order).
 cudaError_t launch_psd(const double *d_wwa, const double *d_neffs, int64_t nt, int64_t nf, int64_t row_stride,

@@ -110,7 +110,7 @@ cudaError_t launch_freq_setup(const double *d_omega, int64_t nf, const double *d
 // ------------------------------------------------------------------------------------------------
 __global__ void basis_kernel(const double *__restrict__ ts, const double *__restrict__ ys, int64_t n,
                              int64_t n_pad, const double *__restrict__ omega, double2 *__restrict__ ty,
-                             double2 *__restrict__ basis, int write_ty)
+                             double2 *__restrict__ basis, int write_ty, int cos_as_y)
 {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n_pad) return;
@@ -131,16 +131,20 @@ __global__ void basis_kernel(const double *__restrict__ ts, const double *__rest
     }
     double2 *row = basis + ((size_t)k * (size_t)n_pad + (size_t)i) * 2;
     row[0] = make_double2(s, c);
-    row[1] = make_double2(y * s, y * c);
+    // cos_as_y: second pass of Foster's method (wwz_foster.cu), whose "y" sums are sum(w c s) and sum(w c c)
+    const double yy = cos_as_y ? c : y;
+    row[1] = make_double2(yy * s, yy * c);
     if (write_ty && k == 0) ty[i] = make_double2(t, y);
 }
 
 cudaError_t launch_basis(const double *d_ts, const double *d_ys, int64_t n, int64_t n_pad, const double *d_omega,
-                         int64_t nf_batch, double2 *d_ty, double2 *d_basis, bool write_ty, cudaStream_t st)
+                         int64_t nf_batch, double2 *d_ty, double2 *d_basis, bool write_ty, bool cos_as_y,
+                         cudaStream_t st)
 {
     if (nf_batch <= 0 || n_pad <= 0) return cudaSuccess;
     dim3 grid((unsigned)((n_pad + 255) / 256), (unsigned)nf_batch);
-    basis_kernel<<<grid, 256, 0, st>>>(d_ts, d_ys, n, n_pad, d_omega, d_ty, d_basis, write_ty ? 1 : 0);
+    basis_kernel<<<grid, 256, 0, st>>>(d_ts, d_ys, n, n_pad, d_omega, d_ty, d_basis, write_ty ? 1 : 0,
+                                      cos_as_y ? 1 : 0);
     bump_launch_counter();
     return cudaGetLastError();
 }

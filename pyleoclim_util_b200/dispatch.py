@@ -24,18 +24,22 @@ import warnings
 
 import numpy as np
 
+from . import _lib
 from . import wavelet as _wavelet
 
 _state = {}
 _recorder = None          # list collecting kernel requests while a batch is being recorded
 
 CUDA_METHOD = "Kirchner_cuda"
+FOSTER_METHOD = "Foster_cuda"          # the reference's method='Foster' (wwz_basic) on the same kernels
+CUDA_METHODS = (CUDA_METHOD, FOSTER_METHOD)
 
 
 # ----------------------------------------------------------------------------------- kernel level
-def _make_kernel(mod):
+def _make_kernel(mod, foster=False):
     pre = getattr(mod, "preprocess", None)
     mko = getattr(mod, "make_omega", None)
+    flags = _lib.FOSTER if foster else 0
 
     def kirchner_cuda(ys, ts, freq, tau, c=1 / (8 * np.pi ** 2), Neff_threshold=3, nproc=1, detrend=False,
                       sg_kwargs=None, gaussianize=False, standardize=False):
@@ -45,14 +49,16 @@ def _make_kernel(mod):
             _recorder.append(dict(ys=np.asarray(ys, dtype=float), ts=np.asarray(ts, dtype=float),
                                   freq=np.asarray(freq, dtype=float), tau=np.asarray(tau, dtype=float), c=c,
                                   Neff_threshold=Neff_threshold, detrend=detrend, sg_kwargs=sg_kwargs,
-                                  gaussianize=gaussianize, standardize=standardize))
+                                  gaussianize=gaussianize, standardize=standardize, flags=flags))
             hole = np.full((nt, nf), np.nan)
             return hole, hole, hole, (hole, hole, hole)
         return _wavelet.kirchner_cuda(ys, ts, freq, tau, c=c, Neff_threshold=Neff_threshold, nproc=nproc,
                                       detrend=detrend, sg_kwargs=sg_kwargs, gaussianize=gaussianize,
-                                      standardize=standardize, _preprocess=pre, _make_omega=mko)
+                                      standardize=standardize, flags=flags, _preprocess=pre, _make_omega=mko)
 
-    kirchner_cuda.__doc__ = _wavelet.kirchner_cuda.__doc__
+    kirchner_cuda.__doc__ = (_wavelet.foster_cuda if foster else _wavelet.kirchner_cuda).__doc__
+    if foster:
+        kirchner_cuda.__name__ = kirchner_cuda.__qualname__ = "foster_cuda"
     return kirchner_cuda
 
 
@@ -83,11 +89,14 @@ def _replay(requests, mod, psd_threshold=None, batch=None):
         return []
     r0 = requests[0]
     uniform = all(r["c"] == r0["c"] and r["Neff_threshold"] == r0["Neff_threshold"]
-                  and r["standardize"] == r0["standardize"] and _plain(r) == _plain(r0) for r in requests)
+                  and r["standardize"] == r0["standardize"] and _plain(r) == _plain(r0)
+                  and r.get("flags", 0) == r0.get("flags", 0) for r in requests)
     if not uniform:
         raise ValueError("members of one batched WWZ call must share c, Neff_threshold and preprocessing flags")
     pre = getattr(mod, "preprocess", _wavelet.preprocess)
-    same_axis = len(requests) > 1 and _plain(r0) and all(
+    kflags = int(r0.get("flags", 0))
+    # Foster's solve is not linear in the shared basis sums: its batches take the ragged (per-member) entry point
+    same_axis = len(requests) > 1 and _plain(r0) and not (kflags & _lib.FOSTER) and all(
         r["ts"].shape == r0["ts"].shape and np.array_equal(r["ts"], r0["ts"]) and np.array_equal(r["tau"], r0["tau"])
         and np.array_equal(r["freq"], r0["freq"]) for r in requests[1:])
     out = []
@@ -105,7 +114,7 @@ def _replay(requests, mod, psd_threshold=None, batch=None):
                     standardize=r["standardize"])
         members.append((pd_ys, r["ts"], r["tau"], r["freq"]))
     res = batch.wwz_ragged(members, c=r0["c"], Neff_threshold=r0["Neff_threshold"], standardize=False,
-                           psd_Neff_threshold=psd_threshold)
+                           psd_Neff_threshold=psd_threshold, **({"flags": kflags} if kflags else {}))
     if psd_threshold is not None:
         res, psds = res
     else:
@@ -116,7 +125,7 @@ def _replay(requests, mod, psd_threshold=None, batch=None):
 
 
 def _wants_cuda(method, settings):
-    return method == "wwz" and isinstance(settings, dict) and settings.get("method") == CUDA_METHOD
+    return method == "wwz" and isinstance(settings, dict) and settings.get("method") in CUDA_METHODS
 
 
 # ----------------------------------------------------------------------------------- class level
@@ -178,7 +187,7 @@ def _patch_core(pyleo, wavemod):
         return MPSD(psd_list=psd_list)
 
     def _all_cuda(objs, attr):
-        return all(isinstance(getattr(o, attr, None), dict) and getattr(o, attr).get("method") == CUDA_METHOD
+        return all(isinstance(getattr(o, attr, None), dict) and getattr(o, attr).get("method") in CUDA_METHODS
                    for o in objs)
 
     @functools.wraps(orig["mscal_q"])
@@ -307,7 +316,8 @@ def _patch_core(pyleo, wavemod):
 
 
 def register(pyleoclim_wavelet=None, core=True, surrogates=False):
-    """Add ``'Kirchner_cuda'`` to Pyleoclim.
+    """Add ``'Kirchner_cuda'`` (and ``'Foster_cuda'``, the reference's ``method='Foster'`` on the same kernels) to
+    Pyleoclim.
 
     * wraps ``pyleoclim.utils.wavelet.get_wwz_func`` (kernel level); the registered kernel calls the
       reference's own ``preprocess`` and ``make_omega`` exactly as every reference kernel variant
@@ -331,24 +341,27 @@ def register(pyleoclim_wavelet=None, core=True, surrogates=False):
         return mod
     original = mod.get_wwz_func
     kernel = _make_kernel(mod)
+    foster_kernel = _make_kernel(mod, foster=True)
 
     @functools.wraps(original)
     def get_wwz_func(nproc, method):
-        if method == CUDA_METHOD:
+        if method in CUDA_METHODS:
             if hasattr(mod, "assertPositiveInt"):
                 mod.assertPositiveInt(nproc)
-            return kernel
+            return kernel if method == CUDA_METHOD else foster_kernel
         return original(nproc, method)
 
     get_wwz_func._wwz_b200 = True
     undo = []
     mod.get_wwz_func = get_wwz_func
     mod.kirchner_cuda = kernel
+    mod.foster_cuda = foster_kernel
 
     def undo_kernel():
         mod.get_wwz_func = original
-        if hasattr(mod, "kirchner_cuda"):
-            delattr(mod, "kirchner_cuda")
+        for name in ("kirchner_cuda", "foster_cuda"):
+            if hasattr(mod, name):
+                delattr(mod, name)
 
     undo.append(undo_kernel)
     if core and pyleo is not None and hasattr(pyleo, "core"):

@@ -218,13 +218,25 @@ def kirchner_cuda(ys, ts, freq, tau, c=1 / (8 * np.pi ** 2), Neff_threshold=3, n
     return wwa, phase, Neffs, coeff
 
 
+def foster_cuda(ys, ts, freq, tau, c=1 / (8 * np.pi ** 2), Neff_threshold=3, nproc=1, detrend=False,
+                sg_kwargs=None, gaussianize=False, standardize=False, flags=0, _preprocess=None, _make_omega=None):
+    """Foster's original projection (the reference's ``method='Foster'``, ``wwz_basic``, utils/wavelet.py:228-381:
+    3x3 normal equations per cell solved with a pseudo-inverse, :357-374) on the same CUDA kernels.
+    Same signature and return as ``wwz_basic``; the coefficients are ``(ywave_1, ywave_2, ywave_3)``."""
+    return kirchner_cuda(ys, ts, freq, tau, c=c, Neff_threshold=Neff_threshold, nproc=nproc, detrend=detrend,
+                         sg_kwargs=sg_kwargs, gaussianize=gaussianize, standardize=standardize,
+                         flags=int(flags) | _lib.FOSTER, _preprocess=_preprocess, _make_omega=_make_omega)
+
+
 def get_wwz_func(nproc, method):
-    """utils/wavelet.py:2052-2092 restricted to the method this package provides."""
+    """utils/wavelet.py:2052-2092 restricted to the methods this package provides."""
     assertPositiveInt(nproc)
     if method == "Kirchner_cuda":
         return kirchner_cuda
-    raise ValueError('Wrong specific method name for WWZ. pyleoclim_util_b200 provides {"Kirchner_cuda"}; '
-                     'use pyleoclim_util_b200.register() to add it to Pyleoclim\'s own dispatch')
+    if method == "Foster_cuda":
+        return foster_cuda
+    raise ValueError('Wrong specific method name for WWZ. pyleoclim_util_b200 provides {"Kirchner_cuda", "Foster_cuda"}; '
+                     'use pyleoclim_util_b200.register() to add them to Pyleoclim\'s own dispatch')
 
 
 def wwz(ys, ts, tau=None, ntau=None, freq=None, freq_method="log", freq_kwargs={}, c=1 / (8 * np.pi ** 2),
@@ -276,7 +288,8 @@ def wwz_psd(ys, ts, freq=None, freq_method="log", freq_kwargs=None, tau=None, c=
         if standardize == True:  # noqa: E712  (the nested wwz call warns again, utils/wavelet.py:1471)
             warnings.warn("Standardizing the timeseries")
         ys2, ts2, freq2, tau2 = prepare_wwz(ys_cut, ts_cut, freq=freq, tau=tau)
-        get_wwz_func(nproc, method)
+        if get_wwz_func(nproc, method) is foster_cuda:
+            flags = int(flags) | _lib.FOSTER
         pd_ys = preprocess(ys2, ts2, detrend=detrend, sg_kwargs=sg_kwargs, gaussianize=gaussianize,
                            standardize=standardize)
         omega = make_omega(ts2, freq2)

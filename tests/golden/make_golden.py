@@ -144,6 +144,28 @@ def surrogates():
          sim_seed99_p3=sim)
 
 
+def foster():
+    """method='Foster' (wwz_basic, utils/wavelet.py:228-381): kernel-level call and wwz / wwz_psd front ends."""
+    t, y = synth.uneven_ar1(420, 41)
+    y = 1.3 * y - 0.4
+    tau = np.linspace(t.min(), t.max(), 23)
+    freq = synth.freq_log(t, 19)
+    wwa, phase, Neffs, coeff = W.wwz_basic(y, t, freq, tau, c=1 / (8 * np.pi ** 2), Neff_threshold=3, nproc=1,
+                                           standardize=True)
+    ref = run_wwz(y, t, method="Foster", tau=tau, freq=freq)
+    psd = SP.wwz_psd(y, t, freq=freq, tau=tau, method="Foster", nproc=1)
+    # a sparse series: cells with few effective points (ill-conditioned normal matrices)
+    t2, y2 = synth.uneven_ar1(60, 42)
+    tau2 = np.linspace(t2.min(), t2.max(), 11)
+    freq2 = synth.freq_log(t2, 13)
+    k2 = W.wwz_basic(y2, t2, freq2, tau2, c=1 / (8 * np.pi ** 2), Neff_threshold=3, nproc=1, standardize=True)
+    save("foster", ts=t, ys=y, tau_in=tau, freq_in=freq, k_wwa=wwa, k_phase=phase, k_Neffs=Neffs, k_y1=coeff[0],
+         k_y2=coeff[1], k_y3=coeff[2], amplitude=ref["amplitude"], phase=ref["phase"], Neffs=ref["Neffs"],
+         coi=ref["coi"], psd=psd.psd, psd_freq=psd.freq,
+         ts2=t2, ys2=y2, tau2=tau2, freq2=freq2, s_wwa=k2[0], s_phase=k2[1], s_Neffs=k2[2], s_y1=k2[3][0],
+         s_y2=k2[3][1], s_y3=k2[3][2])
+
+
 def uar1():
     """uar1_fit / uar1_sim / the likelihood (utils/tsmodel.py:612-716) with NumPy's legacy global RNG; the
     innovation matrices are stored so that a restatement can be checked draw for draw."""
@@ -187,6 +209,6 @@ def cleaning():
 
 if __name__ == "__main__":
     which = sys.argv[1:] or ["benthic", "soi", "synth_small", "edge", "c2_subsample", "c5_sample",
-                             "surrogates", "uar1", "cleaning"]
+                             "surrogates", "uar1", "foster", "cleaning"]
     for name in which:
         globals()[name]()

@@ -111,6 +111,24 @@ def test_surrogate_generator():
     assert np.max(np.abs(sim - g["sim_seed99_p3"])) < 1e-9
 
 
+def test_foster_restatement_vs_reference_outputs():
+    """method='Foster' (wwz_basic, utils/wavelet.py:228-381)."""
+    g = golden("foster")
+    wwa, ph, ne, co = O.foster(g["ys"], g["ts"], g["freq_in"], g["tau_in"], standardize=True)
+    assert np.array_equal(np.isnan(wwa), np.isnan(g["k_wwa"]))
+    m = ~np.isnan(g["k_wwa"])
+    assert np.max(np.abs(wwa[m] / g["k_wwa"][m] - 1)) < 1e-12 and np.max(np.abs(ne / g["k_Neffs"] - 1)) < 1e-13
+    for c, name in zip(co, ("k_y1", "k_y2", "k_y3")):
+        assert np.nanmax(np.abs(c - g[name])) < 1e-13
+    assert np.array_equal(g["amplitude"], g["k_wwa"], equal_nan=True)       # wwz(method='Foster') is this kernel
+    wwa2 = O.foster(g["ys2"], g["ts2"], g["freq2"], g["tau2"], standardize=True)[0]
+    assert np.array_equal(np.isnan(wwa2), np.isnan(g["s_wwa"]))
+    m2 = ~np.isnan(g["s_wwa"])
+    assert np.max(np.abs(wwa2[m2] / g["s_wwa"][m2] - 1)) < 1e-11
+    psd = O.wwa2psd(g["amplitude"], g["ts"], g["Neffs"], Neff_threshold=3)   # c = 1e-3 in wwz_psd: its own transform
+    assert psd.shape == g["psd"].shape
+
+
 def test_uar1_fit_and_sim():
     """uar1 surrogates: likelihood, Nelder-Mead fit and the recurrence against outputs of the
     reference's own uar1_fit / uar1_sim (utils/tsmodel.py:612-716), draw for draw."""

@@ -72,6 +72,11 @@ def cuda_standins(monkeypatch, pyleo):
 
     def single(pd_ys, ts, tau, omega, c, Neff_threshold, flags=0, psd_threshold=None, pinned=False, psd_only=False):
         calls["single"] += 1
+        if flags & 64:                                            # WWZB200_FOSTER
+            calls["foster"] = calls.get("foster", 0) + 1
+            wwa, ph, ne, co = O.foster(pd_ys, ts, omega / (2 * np.pi), tau, c=c, Neff_threshold=Neff_threshold)
+            psd = None if psd_threshold is None else O.wwa2psd(wwa, ts, ne, Neff_threshold=psd_threshold)
+            return wwa, ph, ne, co, psd
         ne, a0, a1, a2 = O.kirchner_cells(ts, pd_ys, tau, omega, c, Neff_threshold)
         wwa, ph = np.sqrt(a1 ** 2 + a2 ** 2), np.arctan2(a2, a1)
         psd = None if psd_threshold is None else O.wwa2psd(wwa, ts, ne, Neff_threshold=psd_threshold)
@@ -263,3 +268,24 @@ def test_uar1_signif_is_fused_and_uar1_sim_is_routed(pyleo, cuda_standins, monke
     finally:
         D.unregister()
     assert pyleo.utils.tsmodel.uar1_sim.__module__.endswith("tsmodel")
+
+
+def test_foster_cuda_is_registered_next_to_foster(pyleo, cuda_standins):
+    """method='Foster_cuda' goes through Pyleoclim's own wwz() front end (prepare_wwz,
+    preprocess, make_omega, make_coi are the reference's) and matches method='Foster' (wwz_basic)."""
+    W = pyleo.utils.wavelet
+    t, y = synth.uneven_ar1(130, 6)
+    tau = np.linspace(t.min(), t.max(), 9)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        got = W.wwz(y, t, tau=tau, freq=FREQ, method="Foster_cuda", nproc=1)
+        ref = W.wwz(y, t, tau=tau, freq=FREQ, method="Foster", nproc=1)
+    assert cuda_standins.get("foster") == 1
+    assert np.array_equal(np.isnan(got.amplitude), np.isnan(ref.amplitude))
+    assert max_rel(got.amplitude, ref.amplitude) < 1e-8 and np.array_equal(got.coi, ref.coi)
+    assert W.get_wwz_func(1, "Foster_cuda").__name__ == "foster_cuda"
+    s = _series(pyleo, 120, 8, "f")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        scal = s.wavelet(method="wwz", settings={"method": "Foster_cuda", "ntau": 6}, freq=FREQ)
+    assert scal.wave_args["method"] == "Foster_cuda" and cuda_standins["foster"] == 2
