@@ -386,6 +386,11 @@ int shared_axis_device(Workspace *w, const double *d_ts, const double *d_Y, int6
     if ((rc = wsbuf(w, "fix_list", (size_t)ncell + 1, &d_fix))) return rc;
     d_ne = d_neffs;
     if (!d_ne && (rc = wsbuf(w, "ne_t", (size_t)ncell, &d_ne))) return rc;
+    double *d_wfrag = nullptr, *d_cellsums = nullptr;
+    if (plan.stored_weights) {
+        if ((rc = wsbuf(w, "wfrag", plan.weights_count, &d_wfrag))) return rc;
+        if ((rc = wsbuf(w, "cellsums", (size_t)4 * ncell, &d_cellsums))) return rc;
+    }
 
     double *d_grid;
     unsigned char *d_rec_row;
@@ -405,7 +410,7 @@ int shared_axis_device(Workspace *w, const double *d_ts, const double *d_Y, int6
         CU(cudaEventRecord(ev.a, st));
     }
     CU(launch_shared(plan, d_ty, d_basis, d_Yt, d_ts, n, S_pad, d_tau, nt, d_kappa, d_dcut, d_unsorted, nf, d_rot,
-                     (double)thr, d_ne, d_wq, d_amp_t, d_ph_t, d_a0_t, d_a1_t, d_a2_t, st));
+                     (double)thr, d_wfrag, d_cellsums, d_ne, d_wq, d_amp_t, d_ph_t, d_a0_t, d_a1_t, d_a2_t, st));
     if (g_profile) {
         CU(cudaEventRecord(ev.b, st));
         g_events.push_back(ev);

@@ -119,7 +119,9 @@ cudaError_t launch_psd_devspan(const double *d_wwa, const double *d_neffs, int64
 struct SharedPlan {
     int series_block;     // NS: series per CTA tile of the shared-time-axis kernel (64, or 16 for small batches)
     int points, stage_bytes, smem_bytes;
-    int64_t n_pad, row_stride, y_off;
+    int64_t n_pad, row_stride, y_off, w_off;
+    bool stored_weights;  // the A fragments (weights) are evaluated once and streamed to every series block
+    size_t weights_count; // doubles of the fragment store (tiles * n_pad * 64)
 };
 SharedPlan plan_shared(int64_t n, int64_t nt, int64_t nf, int64_t S);
 
@@ -139,8 +141,9 @@ cudaError_t launch_rotation(const double *d_tau, const double *d_omega, int64_t 
 cudaError_t launch_shared(const SharedPlan &plan, const double2 *d_ty, const double2 *d_basis, const double *d_Yt,
                           const double *d_ts, int64_t n, int64_t S_pad, const double *d_tau, int64_t nt,
                           const double *d_kappa, const double *d_dcut, const int *d_unsorted, int64_t nf,
-                          const double2 *d_rot, double thr, double *d_neffs, double *d_wq, double *d_amp,
-                          double *d_phase, double *d_a0, double *d_a1, double *d_a2, cudaStream_t st);
+                          const double2 *d_rot, double thr, double *d_wfrag, double *d_cellsums, double *d_neffs,
+                          double *d_wq, double *d_amp, double *d_phase, double *d_a0, double *d_a1, double *d_a2,
+                          cudaStream_t st);
 // deep-underflow cells of a shared-axis batch (flagged from W, Q), recomputed faithfully for every series
 cudaError_t launch_shared_fixup(const double *d_ts, const double *d_Yt, int64_t n, int64_t n_pad, int64_t S,
                                 int64_t S_pad, int series_block, const double *d_tau, const double *d_omega, int64_t nt,

@@ -55,9 +55,14 @@ struct MmaArgs {
     double *neffs;          // [ncell]
     double *wq;             // [2][ncell] W, Q
     double *amp, *phase, *a0, *a1, *a2;   // [ncell][S_pad]
+    // stored-weights mode (PRE): A fragments written once by wwz_tile_weights_kernel,
+    // wfrag[tile][chunk][warp][step][lane], and the y-independent sums of every cell
+    double *wfrag;
+    double *cellsums;       // [4][ncell] W, Q, Ws, Wc
     long long n, n_pad, ncell, S_pad;
+    long long wf_tile_stride;   // doubles per tile in wfrag = chunks of the whole axis * P * 64
     int nt, nf, P, tiles_t;
-    int row_stride2, stage_stride2, y_off2;   // double2 units
+    int row_stride2, stage_stride2, y_off2, w_off2;   // double2 units
     double thr;
 };
 
@@ -68,7 +73,97 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
                  : "d"(a), "d"(b));
 }
 
-template <int NS>
+// Point window of a cell tile, by one warp: chunks [win[0], win[0] + win[1]) hold every point whose weight reaches
+// the cut-off for some cell of the tile ([min tau - dcut, max tau + dcut] with the widest dcut of its rows).
+__device__ __forceinline__ void tile_window(const MmaArgs &a, int k_base, int rows, int j_base, int lane, int *win)
+{
+    double dc = -1.0, tlo = CUDART_INF, thi = -CUDART_INF;
+    if (lane < rows) dc = a.dcut[k_base + lane];            // -1: NaN row (no constraint of its own)
+    if (lane < kMmaWT && j_base + lane < a.nt) tlo = thi = a.tau[j_base + lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        dc = fmax(dc, __shfl_xor_sync(0xffffffffu, dc, o));
+        tlo = fmin(tlo, __shfl_xor_sync(0xffffffffu, tlo, o));
+        thi = fmax(thi, __shfl_xor_sync(0xffffffffu, thi, o));
+    }
+    long long i0 = 0, i1 = a.n;
+    if (dc < 0.0) {
+        i1 = 0;                                             // every row is NaN: nothing to add, Neff = 0/0
+    } else if (!*a.unsorted && dc < CUDART_INF) {
+        i0 = warp_bound<false>(a.ts, 0, a.n, tlo - dc, lane);
+        i1 = warp_bound<true>(a.ts, i0, a.n, thi + dc, lane);
+    }
+    if (lane == 0) {
+        const int c_lo = (int)(i0 / a.P);
+        win[0] = c_lo;
+        win[1] = i1 > i0 ? (int)((i1 + a.P - 1) / a.P) - c_lo : 0;
+    }
+}
+
+// Stored-weights mode, pass 1: the A fragments of every tile, once for all series blocks.  Same tile geometry,
+// window and lane mapping as the contraction kernel (8 warps, no staging: the operands are read straight from
+// global memory, L2 resident), plus the y-independent sums W, Q, Ws, Wc, Neff of every cell.
+__global__ void __launch_bounds__(kMmaWarps * 32) wwz_tile_weights_kernel(const MmaArgs a)
+{
+    __shared__ double tbl[16];
+    __shared__ int win[2];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int kt = (int)blockIdx.x / a.tiles_t, jt = (int)blockIdx.x - kt * a.tiles_t;
+    const int k_base = kt * kMmaRows, j_base = jt * kMmaWT;
+    const int rows = min(kMmaRows, a.nf - k_base);
+    const int P = a.P;
+    load_exp2_table(tbl, tid);
+    if (warp == 0) tile_window(a, k_base, rows, j_base, lane, win);
+    __syncthreads();
+    const int c_lo = win[0], nchunks = win[1];
+    const int wf = warp % kMmaWF, wt = warp / kMmaWF;
+    const int r = lane >> 2, p = lane & 3;
+    const int k = k_base + wf * 8 + r, j = j_base + wt;
+    const bool ok = k < a.nf && j < a.nt;
+    const int kc = min(k, a.nf - 1), jc = min(j, a.nt - 1);
+    const double kap = a.kappa[kc];
+    const double tj = a.tau[jc];
+    const double2 *const brow = a.basis + (size_t)kc * (size_t)a.n_pad;
+    double *const wout = a.wfrag + (size_t)blockIdx.x * (size_t)a.wf_tile_stride + (size_t)warp * (size_t)(P / 4) * 32 + lane;
+    double W = 0.0, Q = 0.0, Ws = 0.0, Wc = 0.0;
+    for (int i = 0; i < nchunks; ++i) {
+        const long long base = (long long)(c_lo + i) * P;
+        double *const wo = wout + (size_t)(c_lo + i) * (size_t)P * 64;
+#pragma unroll 4
+        for (int q = p; q < P; q += 4) {
+            const long long gi = base + q;
+            const double2 sc = brow[gi];
+            double w = gauss_weight_estrin(kap * (a.ty[gi].x - tj), tbl);
+            if (gi >= a.n) w = 0.0;
+            W += w;
+            Q = fma(w, w, Q);
+            Ws = fma(w, sc.x, Ws);
+            Wc = fma(w, sc.y, Wc);
+            wo[(q >> 2) * 32] = w;
+        }
+    }
+#pragma unroll
+    for (int o = 1; o <= 2; o <<= 1) {
+        W += __shfl_xor_sync(0xffffffffu, W, o);
+        Q += __shfl_xor_sync(0xffffffffu, Q, o);
+        Ws += __shfl_xor_sync(0xffffffffu, Ws, o);
+        Wc += __shfl_xor_sync(0xffffffffu, Wc, o);
+    }
+    if (ok && p == 0) {
+        const size_t cell = (size_t)j * (size_t)a.nf + (size_t)k;
+        const size_t nc = (size_t)a.ncell;
+        a.cellsums[cell] = W;
+        a.cellsums[nc + cell] = Q;
+        a.cellsums[2 * nc + cell] = Ws;
+        a.cellsums[3 * nc + cell] = Wc;
+        a.neffs[cell] = W * W / Q;
+        a.wq[cell] = W;
+        a.wq[nc + cell] = Q;
+    }
+}
+
+// PRE: the A fragments come from wfrag (stored-weights mode) instead of being evaluated in the loop.
+template <int NS, bool PRE>
 __global__ void __launch_bounds__(kMmaThreads, 1) wwz_shared_mma_kernel(const MmaArgs a)
 {
     constexpr int NT = NS / 8;   // n-tiles of 8 series
@@ -96,35 +191,13 @@ __global__ void __launch_bounds__(kMmaThreads, 1) wwz_shared_mma_kernel(const Mm
         mbar_fence_init();
     }
     load_exp2_table(tbl, tid);
-    if (warp == kMmaWarps) {
-        // point window of the tile: [min tau - dcut, max tau + dcut] with the widest dcut of its rows
-        double dc = -1.0, tlo = CUDART_INF, thi = -CUDART_INF;
-        if (lane < rows) dc = a.dcut[k_base + lane];            // -1: NaN row (no constraint of its own)
-        if (lane < kMmaWT && j_base + lane < a.nt) tlo = thi = a.tau[j_base + lane];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            dc = fmax(dc, __shfl_xor_sync(0xffffffffu, dc, o));
-            tlo = fmin(tlo, __shfl_xor_sync(0xffffffffu, tlo, o));
-            thi = fmax(thi, __shfl_xor_sync(0xffffffffu, thi, o));
-        }
-        long long i0 = 0, i1 = a.n;
-        if (dc < 0.0) {
-            i1 = 0;                                             // every row is NaN: nothing to add, Neff = 0/0
-        } else if (!*a.unsorted && dc < CUDART_INF) {
-            i0 = warp_bound<false>(a.ts, 0, a.n, tlo - dc, lane);
-            i1 = warp_bound<true>(a.ts, i0, a.n, thi + dc, lane);
-        }
-        if (lane == 0) {
-            const int c_lo = (int)(i0 / P);
-            win[0] = c_lo;
-            win[1] = i1 > i0 ? (int)((i1 + P - 1) / P) - c_lo : 0;
-        }
-    }
+    if (warp == kMmaWarps) tile_window(a, k_base, rows, j_base, lane, win);
     __syncthreads();
     const int c_lo = win[0], nchunks = win[1];
 
     if (warp == kMmaWarps) {
-        const uint32_t bytes = (uint32_t)P * 16u + (uint32_t)rows * (uint32_t)P * 16u + (uint32_t)P * NS * 8u;
+        const uint32_t bytes = (uint32_t)P * 16u + (uint32_t)rows * (uint32_t)P * 16u + (uint32_t)P * NS * 8u +
+                               (PRE ? (uint32_t)P * 512u : 0u);
         int s = 0, use = 0;
         for (int i = 0; i < nchunks; ++i) {
             if (use > 0) mbar_wait(&empty[s], (uint32_t)(use - 1) & 1u);
@@ -134,6 +207,9 @@ __global__ void __launch_bounds__(kMmaThreads, 1) wwz_shared_mma_kernel(const Mm
             __syncwarp();
             if (lane == 0) {
                 tma_load_1d(st, a.ty + start, (uint32_t)P * 16u, &full[s]);
+            } else if (PRE && lane == 1) {
+                tma_load_1d(st + a.w_off2, a.wfrag + (size_t)blockIdx.x * (size_t)a.wf_tile_stride + start * 64,
+                            (uint32_t)P * 512u, &full[s]);
             } else if (lane - 2 < rows && lane >= 2) {
                 const size_t row = (size_t)(k_base + lane - 2);
                 tma_load_1d(st + P + (size_t)(lane - 2) * a.row_stride2, a.basis + row * (size_t)a.n_pad + start,
@@ -172,16 +248,24 @@ __global__ void __launch_bounds__(kMmaThreads, 1) wwz_shared_mma_kernel(const Mm
             const double2 *const row = st + row_off;
             const double *const yv = reinterpret_cast<const double *>(st + a.y_off2) + r;
             const long long left = a.n - (long long)(c_lo + i) * P;     // points of this chunk that exist
+            const double *const wst = reinterpret_cast<const double *>(st + a.w_off2) + warp * (P / 4) * 32 + lane;
 #pragma unroll 2
             for (int q = p; q < P; q += 4) {
                 const double2 sc = row[q];
-                double w = gauss_weight_estrin(kap * (st[q].x - tj), tbl);
-                if (q >= left) w = 0.0;
+                double w;
+                if (PRE) {
+                    w = wst[(q >> 2) * 32];
+                } else {
+                    w = gauss_weight_estrin(kap * (st[q].x - tj), tbl);
+                    if (q >= left) w = 0.0;
+                }
                 const double ws = w * sc.x, wc = w * sc.y;
-                W += w;
-                Q = fma(w, w, Q);
-                Ws += ws;
-                Wc += wc;
+                if (!PRE) {
+                    W += w;
+                    Q = fma(w, w, Q);
+                    Ws += ws;
+                    Wc += wc;
+                }
                 const double *const yq = yv + q * (NS + 4);
 #pragma unroll
                 for (int m = 0; m < NT; ++m) {
@@ -197,18 +281,27 @@ __global__ void __launch_bounds__(kMmaThreads, 1) wwz_shared_mma_kernel(const Mm
         }
     }
 
-    // quad reduction of the y-independent sums: every lane of a quad then holds the totals of its cell
+    if (!PRE) {
+        // quad reduction of the y-independent sums: every lane of a quad then holds the totals of its cell
 #pragma unroll
-    for (int o = 1; o <= 2; o <<= 1) {
-        W += __shfl_xor_sync(0xffffffffu, W, o);
-        Q += __shfl_xor_sync(0xffffffffu, Q, o);
-        Ws += __shfl_xor_sync(0xffffffffu, Ws, o);
-        Wc += __shfl_xor_sync(0xffffffffu, Wc, o);
+        for (int o = 1; o <= 2; o <<= 1) {
+            W += __shfl_xor_sync(0xffffffffu, W, o);
+            Q += __shfl_xor_sync(0xffffffffu, Q, o);
+            Ws += __shfl_xor_sync(0xffffffffu, Ws, o);
+            Wc += __shfl_xor_sync(0xffffffffu, Wc, o);
+        }
     }
     if (!ok) return;
     const size_t cell = (size_t)j * (size_t)a.nf + (size_t)k;   // output order: tau-major rows
+    if (PRE) {
+        const size_t nc = (size_t)a.ncell;
+        W = a.cellsums[cell];
+        Q = a.cellsums[nc + cell];
+        Ws = a.cellsums[2 * nc + cell];
+        Wc = a.cellsums[3 * nc + cell];
+    }
     const double neff = W * W / Q;
-    if (sb == 0 && p == 0) {
+    if (!PRE && sb == 0 && p == 0) {
         a.neffs[cell] = neff;
         a.wq[cell] = W;
         a.wq[(size_t)a.ncell + cell] = Q;
@@ -254,10 +347,15 @@ int shared_series_block(int64_t S)
     return S > 32 ? 64 : 16;
 }
 
+size_t stored_weights_budget()
+{
+    const char *e = getenv("WWZB200_WEIGHTS_BYTES");
+    if (e && *e) return (size_t)atof(e);
+    return (size_t)8 << 30;
+}
+
 SharedPlan plan_shared(int64_t n, int64_t nt, int64_t nf, int64_t S)
 {
-    (void)nt;
-    (void)nf;
     SharedPlan p{};
     p.series_block = shared_series_block(S);
     int64_t P = 32;
@@ -272,16 +370,42 @@ SharedPlan plan_shared(int64_t n, int64_t nt, int64_t nf, int64_t S)
     int64_t y_off = P * 16 + (int64_t)kMmaRows * p.row_stride;
     y_off = (y_off + 127) & ~(int64_t)127;
     p.y_off = y_off;
-    p.stage_bytes = (int)(y_off + P * (p.series_block + 4) * 8);   // series rows skewed by 32 B
+    int64_t w_off = y_off + P * (p.series_block + 4) * 8;   // series rows skewed by 32 B
+    w_off = (w_off + 127) & ~(int64_t)127;
+    p.w_off = w_off;
+    // stored-weights mode: worth it once several series blocks reuse the weights, if the fragments fit the budget
+    const int64_t tiles = ((nf + kMmaRows - 1) / kMmaRows) * ((nt + kMmaWT - 1) / kMmaWT);
+    p.weights_count = (size_t)tiles * (size_t)p.n_pad * 64;
+    const int64_t blocks = (S + p.series_block - 1) / p.series_block;
+    p.stored_weights = blocks >= 4 && p.weights_count * 8 <= stored_weights_budget();
+    {
+        const char *e = getenv("WWZB200_STORED_WEIGHTS");
+        if (e && *e) p.stored_weights = atoi(e) != 0 && p.weights_count * 8 <= stored_weights_budget();
+    }
+    p.stage_bytes = (int)(p.stored_weights ? w_off + P * 512 : w_off);
     p.smem_bytes = kMmaStages * p.stage_bytes + 2 * kMmaStages * 8 + 16 * 8 + 16;
     return p;
+}
+
+template <int NS, bool PRE>
+static cudaError_t launch_mma(const MmaArgs &a, dim3 grid, int smem, cudaStream_t st)
+{
+    static int configured = -1;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(wwz_shared_mma_kernel<NS, PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    wwz_shared_mma_kernel<NS, PRE><<<grid, kMmaThreads, smem, st>>>(a);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_shared(const SharedPlan &plan, const double2 *d_ty, const double2 *d_basis, const double *d_Yt,
                           const double *d_ts, int64_t n, int64_t S_pad, const double *d_tau, int64_t nt,
                           const double *d_kappa, const double *d_dcut, const int *d_unsorted, int64_t nf,
-                          const double2 *d_rot, double thr, double *d_neffs, double *d_wq, double *d_amp,
-                          double *d_phase, double *d_a0, double *d_a1, double *d_a2, cudaStream_t st)
+                          const double2 *d_rot, double thr, double *d_wfrag, double *d_cellsums, double *d_neffs,
+                          double *d_wq, double *d_amp, double *d_phase, double *d_a0, double *d_a1, double *d_a2,
+                          cudaStream_t st)
 {
     const int64_t ncell = nt * nf;
     if (ncell <= 0 || S_pad <= 0) return cudaSuccess;
@@ -302,10 +426,13 @@ cudaError_t launch_shared(const SharedPlan &plan, const double2 *d_ty, const dou
     a.a0 = d_a0;
     a.a1 = d_a1;
     a.a2 = d_a2;
+    a.wfrag = d_wfrag;
+    a.cellsums = d_cellsums;
     a.n = n;
     a.n_pad = plan.n_pad;
     a.ncell = ncell;
     a.S_pad = S_pad;
+    a.wf_tile_stride = plan.n_pad * 64;
     a.nt = (int)nt;
     a.nf = (int)nf;
     a.P = plan.points;
@@ -313,26 +440,23 @@ cudaError_t launch_shared(const SharedPlan &plan, const double2 *d_ty, const dou
     a.row_stride2 = (int)(plan.row_stride / 16);
     a.stage_stride2 = plan.stage_bytes / 16;
     a.y_off2 = (int)(plan.y_off / 16);
+    a.w_off2 = (int)(plan.w_off / 16);
     a.thr = thr;
     const int NS = plan.series_block;
-    static int configured[2] = {-1, -1};
-    int &conf = configured[NS == 64 ? 1 : 0];
-    if (plan.smem_bytes > conf) {
-        cudaError_t e = NS == 64 ? cudaFuncSetAttribute(wwz_shared_mma_kernel<64>,
-                                                        cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem_bytes)
-                                 : cudaFuncSetAttribute(wwz_shared_mma_kernel<16>,
-                                                        cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem_bytes);
-        if (e != cudaSuccess) return e;
-        conf = plan.smem_bytes;
-    }
     const int64_t tiles_k = (nf + kMmaRows - 1) / kMmaRows;
-    dim3 grid((unsigned)(tiles_k * a.tiles_t), (unsigned)(S_pad / NS));
-    if (NS == 64)
-        wwz_shared_mma_kernel<64><<<grid, kMmaThreads, plan.smem_bytes, st>>>(a);
-    else
-        wwz_shared_mma_kernel<16><<<grid, kMmaThreads, plan.smem_bytes, st>>>(a);
+    const dim3 grid((unsigned)(tiles_k * a.tiles_t), (unsigned)(S_pad / NS));
+    cudaError_t e;
+    if (plan.stored_weights) {
+        if (!d_wfrag || !d_cellsums) return cudaErrorInvalidValue;
+        wwz_tile_weights_kernel<<<grid.x, kMmaWarps * 32, 0, st>>>(a);
+        bump_launch_counter();
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        e = NS == 64 ? launch_mma<64, true>(a, grid, plan.smem_bytes, st) : launch_mma<16, true>(a, grid, plan.smem_bytes, st);
+    } else {
+        e = NS == 64 ? launch_mma<64, false>(a, grid, plan.smem_bytes, st) : launch_mma<16, false>(a, grid, plan.smem_bytes, st);
+    }
     bump_launch_counter();
-    return cudaGetLastError();
+    return e;
 }
 
 }  // namespace wwz
