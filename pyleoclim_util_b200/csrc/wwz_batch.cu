@@ -87,42 +87,58 @@ __global__ void ar1_coeff_kernel(const double *__restrict__ ts, int64_t n, doubl
     q[i] = sqrt(1.0 - r * r) * sigma;
 }
 
-// One warp = 32 surrogates; the recurrence runs 32 steps at a time and the 32x32 tile is written
-// through shared memory so that each surrogate row receives 256 contiguous bytes.
+// Generation in two kernels.  (1) ar1_normals_kernel: the standard-normal draws, fully parallel -- one thread per
+// (series, Philox pair) writes z[2p], z[2p+1] of its series straight into Y.  (2) ar1_recur_kernel: the recurrence
+// in place.  One warp = 32 series; 32 steps at a time, the 32x32 tile goes through shared memory so that global
+// accesses are row-contiguous (256 B per series) while lane = series walks its row; the next tile is prefetched
+// into registers while the current one is processed.
 // y[i] = y[i-1]*rho_i + q_i*z_i (:67, uar1: :711) with rho_0 = 0 and q_0 = 0 (ar1_model: y[0] = 0, :61) or
 // q_0 = 1 (uar1_sim: y[0] = z_0, :704-705); stored value is y + mu (core/surrogateseries.py:139, :156).
 // Step i consumes z0 of Philox pair i/2 when i is even and z1 when i is odd.
+__global__ void __launch_bounds__(256)
+    ar1_normals_kernel(int64_t n, int64_t S, uint64_t seed, double *__restrict__ Y)
+{
+    const int64_t npair = (n + 1) / 2;
+    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (idx >= S * npair) return;
+    const int64_t s = idx / npair, pr = idx - s * npair;
+    double z0, z1;
+    normal_pair((uint64_t)pr, (uint64_t)s, seed, z0, z1);
+    double *row = Y + s * n + 2 * pr;
+    row[0] = z0;
+    if (2 * pr + 1 < n) row[1] = z1;
+}
+
 __global__ void __launch_bounds__(128)
-    ar1_generate_kernel(const double *__restrict__ rho, const double *__restrict__ q, int64_t n, int64_t S,
-                        double mu, uint64_t seed, double *__restrict__ Y)
+    ar1_recur_kernel(const double *__restrict__ rho, const double *__restrict__ q, int64_t n, int64_t S, double mu,
+                     double *__restrict__ Y)
 {
     __shared__ double tile[4][32][33];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int64_t s0 = ((int64_t)blockIdx.x * 4 + wib) * 32;
     if (s0 >= S) return;
-    const int64_t s = s0 + lane;
-    double y = 0.0, zodd = 0.0;
+    const int nrows = (int)min((int64_t)32, S - s0);
+    double (*const tl)[33] = tile[wib];
+    double nxt[32];
+    auto fetch = [&](int64_t i0) {
+#pragma unroll
+        for (int r = 0; r < 32; ++r) nxt[r] = (r < nrows && i0 + lane < n) ? Y[(s0 + r) * n + i0 + lane] : 0.0;
+    };
+    fetch(0);
+    double y = 0.0;
     for (int64_t i0 = 0; i0 < n; i0 += 32) {
         const int cnt = (int)min((int64_t)32, n - i0);
+#pragma unroll
+        for (int r = 0; r < 32; ++r) tl[r][lane] = nxt[r];
+        __syncwarp();
+        if (i0 + 32 < n) fetch(i0 + 32);
         for (int j = 0; j < cnt; ++j) {
-            const int64_t i = i0 + j;
-            double z;
-            if ((i & 1) == 0) {
-                double z0, z1;
-                normal_pair((uint64_t)(i >> 1), (uint64_t)s, seed, z0, z1);
-                zodd = z1;
-                z = z0;
-            } else {
-                z = zodd;
-            }
-            y = y * rho[i] + q[i] * z;
-            tile[wib][lane][j] = y + mu;
+            y = y * rho[i0 + j] + q[i0 + j] * tl[lane][j];
+            tl[lane][j] = y + mu;
         }
         __syncwarp();
-        for (int r = 0; r < 32; ++r) {
-            const int64_t sr = s0 + r;
-            if (sr < S && lane < cnt) Y[sr * n + i0 + lane] = tile[wib][r][lane];
-        }
+        for (int r = 0; r < nrows; ++r)
+            if (lane < cnt) Y[(s0 + r) * n + i0 + lane] = tl[r][lane];
         __syncwarp();
     }
 }
@@ -132,8 +148,10 @@ cudaError_t launch_ar1(const double *d_ts, int64_t n, double tau, double sigma, 
 {
     if (n <= 0 || S <= 0) return cudaSuccess;
     ar1_coeff_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_ts, n, tau, sigma, uar1 ? 1 : 0, d_rho, d_q);
-    ar1_generate_kernel<<<(unsigned)((S + 127) / 128), 128, 0, st>>>(d_rho, d_q, n, S, mu, seed, d_Y);
-    bump_launch_counter(2);
+    const int64_t npair = (n + 1) / 2;
+    ar1_normals_kernel<<<(unsigned)((S * npair + 255) / 256), 256, 0, st>>>(n, S, seed, d_Y);
+    ar1_recur_kernel<<<(unsigned)((S + 127) / 128), 128, 0, st>>>(d_rho, d_q, n, S, mu, d_Y);
+    bump_launch_counter(3);
     return cudaGetLastError();
 }
 

@@ -22,6 +22,38 @@ def row_blocks(n, world):
     return out
 
 
+TILE_ROWS = 16      # frequency rows of one CTA tile of the shared-axis kernel (kMmaRows, csrc/wwz_mma.cu)
+
+
+def balanced_freq_groups(ts_cut, tau, freq, c, world, cut_bits=300.0):
+    """Frequency rows for each rank of a frequency-sharded significance test: [index arrays].
+
+    The shared-axis kernel walks, per tile of TILE_ROWS consecutive frequencies, only the points inside the
+    Gaussian support of the tile (weights above 2^-cut_bits), so a low-frequency row costs up to the whole
+    series and a high-frequency row a few points: equal-count contiguous blocks would leave the first rank with
+    most of the work.  Rows are kept in groups of TILE_ROWS consecutive frequencies (compact windows), the groups
+    are dealt to the ranks by modelled cost (longest-processing-time first), and each rank's groups are put back
+    in ascending order (a short last group stays last, so tiles never straddle two groups)."""
+    freq = np.asarray(freq, dtype=float)
+    nf = freq.size
+    span = float(np.max(ts_cut) - np.min(ts_cut)) or 1.0
+    kappa4 = 4.0 * 2.0 * np.pi * np.abs(freq) * np.sqrt(c * np.log2(np.e))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        dcut = 4.0 * np.sqrt(cut_bits) / kappa4
+    dtau = 3.0 * float(np.median(np.abs(np.diff(tau)))) if np.size(tau) > 1 else 0.0
+    frac = np.clip(np.nan_to_num((2.0 * dcut + dtau) / span, nan=0.0, posinf=1.0), 0.0, 1.0)
+    groups = [np.arange(g, min(g + TILE_ROWS, nf)) for g in range(0, nf, TILE_ROWS)]
+    # a tile costs its widest window for all of its row slots, plus a fixed part per tile
+    cost = np.array([TILE_ROWS * (frac[g].max() + 0.02) for g in groups])
+    load = np.zeros(world)
+    mine = [[] for _ in range(world)]
+    for gi in np.argsort(-cost, kind="stable"):
+        r = int(np.argmin(load))
+        mine[r].append(int(gi))
+        load[r] += cost[gi]
+    return [np.concatenate([groups[g] for g in sorted(m)]) if m else np.zeros(0, dtype=int) for m in mine]
+
+
 def _dist():
     import torch.distributed as dist
     if not dist.is_available() or not dist.is_initialized():
@@ -175,8 +207,9 @@ def wwz_signif_sharded(ys, ts, tau=None, freq=None, number=200, qs=(0.95,), seed
                        Neff_threshold=3, freq_method="log", freq_kwargs=None, group=None, signif=None, axis="auto"):
     """Scalogram significance levels with the (tau, f) grid sharded over the ranks: each rank runs the fused
     device pipeline (`batch.signif_prepared`) for all `number` surrogates on its block of tau rows
-    (axis='tau') or of frequency columns (axis='freq'; 'auto' takes the longer axis, which balances better --
-    the reference's default grid is 50 tau x n/10 frequencies).  The same seed gives every rank the same
+    (axis='tau') or on its share of the frequency columns (axis='freq': groups of 16 consecutive frequencies dealt
+    to the ranks by modelled cost, `balanced_freq_groups`; 'auto' takes the longer axis -- the reference's default
+    grid is 50 tau x n/10 frequencies).  The same seed gives every rank the same
     surrogates, so the per-cell quantiles are exchange-free; only the quantile tiles are gathered.
     Returns `batch.SignifResults`."""
     from . import batch
@@ -194,9 +227,11 @@ def wwz_signif_sharded(ys, ts, tau=None, freq=None, number=200, qs=(0.95,), seed
         a, b = blocks[rank]
         tau_loc, freq_loc = tau[a:b], freq
     elif axis == "freq":
-        blocks = row_blocks(freq.size, world)
+        # cost-balanced groups of consecutive frequencies per rank (not contiguous blocks: see balanced_freq_groups)
+        rows = balanced_freq_groups(ts_cut, tau, freq, c, world)
+        blocks = [(0, r.size) for r in rows]
         a, b = blocks[rank]
-        tau_loc, freq_loc = tau, freq[a:b]
+        tau_loc, freq_loc = tau, freq[rows[rank]]
     else:
         raise ValueError("axis must be 'tau', 'freq' or 'auto'")
     counts = [y - x for x, y in blocks]
@@ -208,6 +243,10 @@ def wwz_signif_sharded(ys, ts, tau=None, freq=None, number=200, qs=(0.95,), seed
     else:
         local = np.zeros((0, nq + 1, freq.size if axis == "tau" else tau.size))
     full = all_gather_rows(np.ascontiguousarray(local), counts, group)
+    if axis == "freq":                                                       # undo the dealing of the frequency rows
+        ordered = np.empty_like(full)
+        ordered[np.concatenate(rows)] = full
+        full = ordered
     full = np.moveaxis(full, 0, 1 if axis == "tau" else 2)                   # back to [nq+1, nt, nf]
     return batch.SignifResults(qs=probs, amplitude_qs=np.ascontiguousarray(full[:nq]), psd_qs=None,
                                Neffs=np.ascontiguousarray(full[nq]), freq=freq, time=tau)
