@@ -334,6 +334,7 @@ def run_ours(args):
         return D.wwz_signif_sharded(y3, t3, tau=tau3, freq=freq3, number=number, qs=[0.95], seed=1)
 
     signif_run(256)
+    signif_run(S3)                     # workspace (series tiles, stored weights) allocated at full size
     barrier()
     _lib.profile(True)
     s0 = time.perf_counter()
@@ -342,6 +343,17 @@ def run_ours(args):
     s1 = time.perf_counter() - s0
     sh_ms, sh_n, sh_cp = _lib.profile_read()
     _lib.profile(False)
+    dense3 = None
+    if world == 1:
+        # the same test with every (cell, point, surrogate) triple evaluated (WWZB200_DENSE: no point windows):
+        # algorithmic flops / kernel time is then a statement about the FP64 (tensor) pipe
+        _lib.profile(True)
+        B.wwz_signif(y3, t3, tau=tau3, freq=freq3, number=S3, qs=[0.95], seed=1, flags=_lib.DENSE)
+        torch.cuda.synchronize()
+        d_ms, d_n, d_cp = _lib.profile_read()
+        _lib.profile(False)
+        dense3 = {"kernel_ms": d_ms, "contraction_tflops": 6.0 * d_cp / (d_ms * 1e-3) / 1e12,
+                  "frac_of_fp64_peak": 6.0 * d_cp / (d_ms * 1e-3) / 1e12 / fp64_tf}
     if dist is not None:
         tmax = torch.tensor([s1], dtype=torch.float64, device=dev)
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -351,8 +363,13 @@ def run_ours(args):
                     "reduced to the 95%% quantile on the device (wwzb200_ar1_signif), host to host%s"
                     % (freq3.size, S3, "" if world == 1 else "; frequency blocks sharded over the ranks"),
         "surrogates_per_s": S3 / s1, "seconds": s1, "n_gpus": world, "scaling": "strong",
+        "kernel": "wwz_tile_weights_kernel + wwz_shared_mma_kernel<64, stored weights> (mma.sync m8n8k4 f64, SASS "
+                  "DMMA.8x8x4): weights once per (cell, point), contracted against 64 surrogates per tile",
         "shared_axis_kernel_ms_rank0": sh_ms,
         "contraction_tflops_rank0": 6.0 * sh_cp / (sh_ms * 1e-3) / 1e12 if sh_ms else None,
+        "contraction_tflops_note": "algorithmic rate over all (cell, point, surrogate) triples, including the points "
+                                   "the tile windows skip (weights below 2^-300)",
+        "dense": dense3,
         "algorithmic": "6 flop per (cell, point, surrogate) (SURVEY.md 8d)"}
 
     # config 5 (n=100,000, 4096 tau x 2047 f = 8.4e11 cell-points), device resident, rank 0 at N = 1 only:
@@ -397,8 +414,9 @@ def run_ours(args):
     windowed_tf = FLOP_PER_CELL_POINT * cell_points / (cell_ms * 1e-3) / 1e12 if cell_ms > 0 else None
     roofline = {"bound": "fp64", "kernel": "wwz_cells_kernel", "achieved": achieved_tf, "peak": fp64_tf,
                 "unit": "TFLOP/s", "frac": (achieved_tf / fp64_tf) if achieved_tf else None,
-                "traffic": 34.3e6, "traffic_note": "dram__bytes_read+write per launch from ncu --set full "
-                "(profiles/r01_cells_kernel_ncu.txt): 33.5 MB read + 0.8 MB write vs 32 MB basis rows + 28 MB sums",
+                "traffic": 63.4e6, "traffic_note": "dram__bytes_read+write per launch from ncu --set full "
+                "(profiles/r01_cells_kernel_ncu.txt): 33.0 MB read (32 MB of basis rows) + 30.4 MB written (partial-sum "
+                "slabs) against 24 MB of algorithmic output (48 B per cell); the kernel is FP64-pipe bound, not HBM bound",
                 "mode": "WWZB200_DENSE launches (nothing skipped), %d launches after the timed region" % dense_launches,
                 "avg_launch_ms": dense_ms / max(dense_launches, 1),
                 "timed_region": {"launches": cell_launches, "avg_launch_ms": cell_ms / max(cell_launches, 1),
@@ -425,7 +443,7 @@ def run_ours(args):
             "config": {"workload": WORKLOAD, "n": n, "ntau_per_gpu": nt_local, "nfreq": nf,
                        "cells_per_step_per_gpu": cells_step_local, "partition": "tau-block per GPU + NCCL all-gather"
                        if world > 1 else "single GPU", "l2": "256 MiB buffer written between timed iterations",
-                       "window": "exact-zero weight chunks skipped (bit-identical to dense)",
+                       "window": "per tile of cells only the points with a weight above 2^-300 are walked",
                        "kernels": "tau-recurrence kernel on rows with kappa*dtau <= 8 (all rows here), direct kernel otherwise"},
             "e2e": {"value": e2e_value, "unit": "cells/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * api_s / args.steps,
