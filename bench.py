@@ -183,10 +183,12 @@ def run_ours(args):
     loc2 = torch.empty((2, nt_local, nf), dtype=torch.float64, device=dev)   # Neffs, wwa of the psd pass
     psd = torch.empty(nf, dtype=torch.float64, device=dev)
     if world > 1:
-        g6 = torch.empty((world, 6, nt_local, nf), dtype=torch.float64, device=dev)
-        g2 = torch.empty((world, 2, nt_local, nf), dtype=torch.float64, device=dev)
+        # the assembled outputs: plane i of full6 is [world, nt_local, nf] = the tau-row blocks of all ranks side by
+        # side, so each output plane is gathered straight into its final place (no re-layout copy)
         full6 = torch.empty((6, nt_total, nf), dtype=torch.float64, device=dev)
         full2 = torch.empty((2, nt_total, nf), dtype=torch.float64, device=dev)
+        comm = torch.cuda.Stream(device=dev)
+        ev_a, ev_b, ev_c = (torch.cuda.Event() for _ in range(3))
     stream = torch.cuda.current_stream().cuda_stream
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)             # > 126 MB L2
     tspan = float(t.max() - t.min())
@@ -196,17 +198,27 @@ def run_ours(args):
         _lib.check(L.wwzb200_kirchner_dev(d_t.data_ptr(), d_y.data_ptr(), n, d_tau.data_ptr(), nt_local,
                                           d_om.data_ptr(), nf, C_WWZ, 3, 3, 0, o[0], o[1], o[2], o[3], o[4], o[5],
                                           None, nf, stream))
+        if world > 1:
+            # tau-row blocks are the shards: NCCL all-gathers of the wwz outputs over NVLink on a side stream,
+            # overlapped with the second transform
+            ev_a.record()
+            with torch.cuda.stream(comm):
+                comm.wait_event(ev_a)
+                for i in range(6):
+                    dist.all_gather_into_tensor(full6[i].view(-1), loc6[i].view(-1))
         _lib.check(L.wwzb200_kirchner_dev(d_t.data_ptr(), d_y.data_ptr(), n, d_tau.data_ptr(), nt_local,
                                           d_om.data_ptr(), nf, C_PSD, 3, 3, 0, loc2[0].data_ptr(), None, None, None,
                                           loc2[1].data_ptr(), None, psd.data_ptr() if world == 1 else None, nf,
                                           stream))
         if world > 1:
-            # tau-row blocks are the shards: one NCCL all-gather per output family over NVLink, then the
-            # row blocks are laid side by side and wwa2psd reduces the gathered scalogram
-            dist.all_gather_into_tensor(g6.view(-1), loc6.view(-1))
-            dist.all_gather_into_tensor(g2.view(-1), loc2.view(-1))
-            full6.view(6, world, nt_local, nf).copy_(g6.permute(1, 0, 2, 3))
-            full2.view(2, world, nt_local, nf).copy_(g2.permute(1, 0, 2, 3))
+            ev_b.record()
+            with torch.cuda.stream(comm):
+                comm.wait_event(ev_b)
+                for i in range(2):
+                    dist.all_gather_into_tensor(full2[i].view(-1), loc2[i].view(-1))
+                ev_c.record()
+            torch.cuda.current_stream().wait_event(ev_c)
+            # wwa2psd reduces the gathered scalogram
             _lib.check(L.wwzb200_wwa2psd_dev(full2[1].data_ptr(), full2[0].data_ptr(), nt_total, nf, tspan, n, 3,
                                              psd.data_ptr(), stream))
 
@@ -290,8 +302,10 @@ def run_ours(args):
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         e2e_s = float(tmax.item())
     cabi_s = e2e_s
-    h2d = 2 * 8 * (2 * n + nt_local + nf)
-    d2h = 8 * (6 * nt_local * nf + nf)
+    # per rank, through the public API: the inputs of both calls go up (the sharded API prepares the full tau axis),
+    # the assembled result of both calls comes back on every rank
+    h2d = 2 * 8 * (2 * n + (nt_local if world == 1 else nt_total) + nf)
+    d2h = 8 * (6 * (nt_local if world == 1 else nt_total) * nf + nf)
 
     # the public Python API: what a user (or Pyleoclim through register()) calls.  Host NumPy arrays in, fresh
     # NumPy result arrays out (page-locked, pooled); prepare_wwz / standardize / make_omega / make_coi on the host,
@@ -372,6 +386,25 @@ def run_ours(args):
         "dense": dense3,
         "algorithmic": "6 flop per (cell, point, surrogate) (SURVEY.md 8d)"}
 
+    # config 4: 1,000 age-ensemble members (n = 1500 each, own time axis, default 50 x 151 grid), one ragged batch,
+    # host to host (wwzb200_kirchner_ragged: packed inputs up once, members over 8 streams, packed outputs back once)
+    if world == 1:
+        axes, y4 = synth.age_ensemble(1500, 1000)
+        members = []
+        for tm in axes:
+            ys_c, ts_c, fr_c, ta_c = WV.prepare_wwz(y4, tm)
+            members.append((ys_c, ts_c, ta_c, fr_c))
+        B.wwz_ragged(members[:64])
+        torch.cuda.synchronize()
+        m0 = time.perf_counter()
+        res4 = B.wwz_ragged(members)
+        m1 = time.perf_counter() - m0
+        cells4 = sum(r.amplitude.size for r in res4)
+        extras["ensemble"] = {"workload": "C4: 1000 age-ensemble members, n=1500, default grid per member (50 tau x ~151 f), "
+                                          "standardised, all six outputs, host to host through batch.wwz_ragged",
+                              "members_per_s": len(members) / m1, "cells_per_s": cells4 / m1, "seconds": m1}
+        del res4
+
     # config 5 (n=100,000, 4096 tau x 2047 f = 8.4e11 cell-points), device resident, rank 0 at N = 1 only:
     # once dense (the FP64-pipe statement BASELINE.json asks for) and once with the default path
     if world == 1:
@@ -441,7 +474,8 @@ def run_ours(args):
             "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "n": n, "ntau_per_gpu": nt_local, "nfreq": nf,
-                       "cells_per_step_per_gpu": cells_step_local, "partition": "tau-block per GPU + NCCL all-gather"
+                       "cells_per_step_per_gpu": cells_step_local, "partition": "tau-block per GPU + NCCL all-gather of every output "
+                       "plane into the assembled grid (side stream, overlapped with the second transform)"
                        if world > 1 else "single GPU", "l2": "256 MiB buffer written between timed iterations",
                        "window": "per tile of cells only the points with a weight above 2^-300 are walked",
                        "kernels": "tau-recurrence kernel on rows with kappa*dtau <= 8 (all rows here), direct kernel otherwise"},

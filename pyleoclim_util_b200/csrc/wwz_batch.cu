@@ -89,9 +89,10 @@ __global__ void ar1_coeff_kernel(const double *__restrict__ ts, int64_t n, doubl
 
 // Generation in two kernels.  (1) ar1_normals_kernel: the standard-normal draws, fully parallel -- one thread per
 // (series, Philox pair) writes z[2p], z[2p+1] of its series straight into Y.  (2) ar1_recur_kernel: the recurrence
-// in place.  One warp = 32 series; 32 steps at a time, the 32x32 tile goes through shared memory so that global
-// accesses are row-contiguous (256 B per series) while lane = series walks its row; the next tile is prefetched
-// into registers while the current one is processed.
+// in place.  One warp = 8 series (the kernel is latency bound: 1,250 narrow warps hide DRAM round trips better than
+// 313 wide ones); 32 steps at a time, the 8x32 tile goes through shared memory so that global accesses are
+// row-contiguous (256 B per series) while lanes 0..7 walk their rows; the next tile is prefetched into registers
+// while the current one is processed.
 // y[i] = y[i-1]*rho_i + q_i*z_i (:67, uar1: :711) with rho_0 = 0 and q_0 = 0 (ar1_model: y[0] = 0, :61) or
 // q_0 = 1 (uar1_sim: y[0] = z_0, :704-705); stored value is y + mu (core/surrogateseries.py:139, :156).
 // Step i consumes z0 of Philox pair i/2 when i is even and z1 when i is odd.
@@ -109,32 +110,42 @@ __global__ void __launch_bounds__(256)
     if (2 * pr + 1 < n) row[1] = z1;
 }
 
+constexpr int kRecurSeries = 8;   // series per warp of ar1_recur_kernel (latency bound: more warps, not wider ones)
+
 __global__ void __launch_bounds__(128)
     ar1_recur_kernel(const double *__restrict__ rho, const double *__restrict__ q, int64_t n, int64_t S, double mu,
                      double *__restrict__ Y)
 {
-    __shared__ double tile[4][32][33];
+    __shared__ double tile[4][kRecurSeries][33];
+    __shared__ double coef[4][2][32];            // rho, q of the 32 steps of the current tile
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int64_t s0 = ((int64_t)blockIdx.x * 4 + wib) * 32;
+    const int64_t s0 = ((int64_t)blockIdx.x * 4 + wib) * kRecurSeries;
     if (s0 >= S) return;
-    const int nrows = (int)min((int64_t)32, S - s0);
+    const int nrows = (int)min((int64_t)kRecurSeries, S - s0);
     double (*const tl)[33] = tile[wib];
-    double nxt[32];
+    double nxt[kRecurSeries];
     auto fetch = [&](int64_t i0) {
 #pragma unroll
-        for (int r = 0; r < 32; ++r) nxt[r] = (r < nrows && i0 + lane < n) ? Y[(s0 + r) * n + i0 + lane] : 0.0;
+        for (int r = 0; r < kRecurSeries; ++r)
+            nxt[r] = (r < nrows && i0 + lane < n) ? Y[(s0 + r) * n + i0 + lane] : 0.0;
     };
     fetch(0);
     double y = 0.0;
     for (int64_t i0 = 0; i0 < n; i0 += 32) {
         const int cnt = (int)min((int64_t)32, n - i0);
 #pragma unroll
-        for (int r = 0; r < 32; ++r) tl[r][lane] = nxt[r];
+        for (int r = 0; r < kRecurSeries; ++r) tl[r][lane] = nxt[r];
+        coef[wib][0][lane] = lane < cnt ? rho[i0 + lane] : 0.0;      // steps beyond n: never stored
+        coef[wib][1][lane] = lane < cnt ? q[i0 + lane] : 0.0;
         __syncwarp();
         if (i0 + 32 < n) fetch(i0 + 32);
-        for (int j = 0; j < cnt; ++j) {
-            y = y * rho[i0 + j] + q[i0 + j] * tl[lane][j];
-            tl[lane][j] = y + mu;
+        if (lane < kRecurSeries) {
+            // fully unrolled: the 96 shared-memory loads are issued ahead of the dependent chain, one FMA per step
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                y = y * coef[wib][0][j] + coef[wib][1][j] * tl[lane][j];
+                tl[lane][j] = y + mu;
+            }
         }
         __syncwarp();
         for (int r = 0; r < nrows; ++r)
@@ -150,7 +161,8 @@ cudaError_t launch_ar1(const double *d_ts, int64_t n, double tau, double sigma, 
     ar1_coeff_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_ts, n, tau, sigma, uar1 ? 1 : 0, d_rho, d_q);
     const int64_t npair = (n + 1) / 2;
     ar1_normals_kernel<<<(unsigned)((S * npair + 255) / 256), 256, 0, st>>>(n, S, seed, d_Y);
-    ar1_recur_kernel<<<(unsigned)((S + 127) / 128), 128, 0, st>>>(d_rho, d_q, n, S, mu, d_Y);
+    const int64_t per_block = 4 * kRecurSeries;
+    ar1_recur_kernel<<<(unsigned)((S + per_block - 1) / per_block), 128, 0, st>>>(d_rho, d_q, n, S, mu, d_Y);
     bump_launch_counter(3);
     return cudaGetLastError();
 }

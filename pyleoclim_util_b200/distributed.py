@@ -108,12 +108,16 @@ def _device_blocks(pd_ys, ts_cut, tau, omega, c, Neff_threshold, flags, group, w
                                                    d_om.data_ptr(), nf, float(c), int(Neff_threshold), 0, int(flags),
                                                    *ptrs, None, nf, torch.cuda.current_stream().cuda_stream))
     k = len(want)
-    sel = loc[list(want)].contiguous()
-    g = torch.empty((world, k, hmax, nf), dtype=torch.float64, device=dev)
-    dist.all_gather_into_tensor(g.view(-1), sel.view(-1), group=group)
     if len(set(counts)) == 1:
-        full = g.permute(1, 0, 2, 3).reshape(k, nt, nf)
+        # equal row blocks: plane i of the result is [world, hmax, nf], so every wanted output plane is gathered
+        # straight into its final place (no selection copy, no re-layout)
+        full = torch.empty((k, nt, nf), dtype=torch.float64, device=dev)
+        for i, w_i in enumerate(want):
+            dist.all_gather_into_tensor(full[i].view(-1), loc[w_i].view(-1), group=group)
     else:
+        sel = loc[list(want)].contiguous()
+        g = torch.empty((world, k, hmax, nf), dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(g.view(-1), sel.view(-1), group=group)
         full = torch.cat([g[r, :, : counts[r]] for r in range(world)], dim=1)
     host = None
     if to_host:
