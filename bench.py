@@ -382,7 +382,7 @@ def run_ours(args):
         "shared_axis_kernel_ms_rank0": sh_ms,
         "contraction_tflops_rank0": 6.0 * sh_cp / (sh_ms * 1e-3) / 1e12 if sh_ms else None,
         "contraction_tflops_note": "algorithmic rate over all (cell, point, surrogate) triples, including the points "
-                                   "the tile windows skip (weights below 2^-300)",
+                                   "the tile windows skip (weights below 2^-100 of a cell's largest weight)",
         "dense": dense3,
         "algorithmic": "6 flop per (cell, point, surrogate) (SURVEY.md 8d)"}
 
@@ -477,7 +477,7 @@ def run_ours(args):
                        "cells_per_step_per_gpu": cells_step_local, "partition": "tau-block per GPU + NCCL all-gather of every output "
                        "plane into the assembled grid (side stream, overlapped with the second transform)"
                        if world > 1 else "single GPU", "l2": "256 MiB buffer written between timed iterations",
-                       "window": "per tile of cells only the points with a weight above 2^-300 are walked",
+                       "window": "per tile of cells only the points whose weight reaches 2^-100 of a cell's largest weight are walked",
                        "kernels": "tau-recurrence kernel on rows with kappa*dtau <= 8 (all rows here), direct kernel otherwise"},
             "e2e": {"value": e2e_value, "unit": "cells/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * api_s / args.steps,

@@ -46,9 +46,9 @@ extern "C" {
 /* flags */
 #define WWZB200_DENSE 1u        /* evaluate every (cell, point) pair with its own exp2: no windowing  \
                                    and no tau-recurrence.  The default walks, per tile of cells, only \
-                                   the points whose weight reaches 2^-300 for some cell of the tile:  \
-                                   skipped terms are < 2^-100 of any sum that is not recomputed by    \
-                                   the faithful kernel (cells with sum(w) < 2^-200) */
+                                   the points whose weight reaches 2^-100 of the largest weight of    \
+                                   some cell of the tile (the window widens with the distance from    \
+                                   tau to the nearest sample): skipped terms are < 2^-100 of sum(w) */
 #define WWZB200_EXACT_WINDOW 16u /* window only on weights that are exactly 0.0 in the kernel (below   \
                                    2^-1081): bit-identical to WWZB200_DENSE for the direct kernel */
 #define WWZB200_STANDARDIZE 2u  /* batched entry points: z-score every series on the device       \

@@ -209,11 +209,13 @@ int transform_device(Workspace *w, const double *d_ts, const double *d_ys, int64
             const int64_t np = std::max(plan.n_pad, rplan.n_pad);   // one row stride for both kernels
             plan.n_pad = rplan.n_pad = np;
         }
-        const double cut_bits = (flags & WWZB200_EXACT_WINDOW) ? 1081.0 : 300.0;
+        const double cut_bits = (flags & WWZB200_EXACT_WINDOW) ? 1081.0 : 100.0;
         double *d_grid;
         unsigned char *d_rec_row;
         if ((rc = wsbuf(w, "grid", 2, &d_grid))) return rc;
         if ((rc = wsbuf(w, "rec_row", (size_t)nf, &d_rec_row))) return rc;
+        double *d_gap;
+        if ((rc = wsbuf(w, "taugap", (size_t)nt, &d_gap))) return rc;
         size_t per_row = (size_t)plan.n_pad * 32;
         int64_t nf_batch = (int64_t)std::max<size_t>(1, basis_budget_bytes() / per_row);
         nf_batch = std::min<int64_t>(std::min<int64_t>(nf_batch, nf), 65535);
@@ -226,6 +228,7 @@ int transform_device(Workspace *w, const double *d_ts, const double *d_ys, int64
 
         CU(launch_freq_setup(d_omega, nf, d_tau, nt, c, allow_rec, cut_bits, d_kappa, d_dcut, d_grid, d_rec_row, st));
         CU(launch_unsorted_check(d_ts, n, d_unsorted, st));
+        CU(launch_tau_gap(d_ts, n, d_tau, nt, d_gap, st));
         CU(cudaMemsetAsync(d_fix_count, 0, sizeof(unsigned int), st));
         const bool dense = (flags & WWZB200_DENSE) != 0;
         for (int64_t k0 = 0; k0 < nf; k0 += nf_batch) {
@@ -238,9 +241,9 @@ int transform_device(Workspace *w, const double *d_ts, const double *d_ys, int64
                 CU(cudaEventRecord(ev.a, st));
             }
             if (allow_rec)
-                CU(launch_rec(rplan, d_ty, d_basis, d_ts, n, d_tau, nt, d_kappa, d_dcut, d_unsorted, k0, nb, nf, segs,
+                CU(launch_rec(rplan, d_ty, d_basis, d_ts, n, d_tau, nt, d_kappa, d_dcut, d_gap, d_unsorted, k0, nb, nf, segs,
                               seg_len, d_rec_row, d_grid, d_sums, st));
-            CU(launch_cells(plan, d_ty, d_basis, d_ts, n, d_tau, nt, d_kappa, d_dcut, d_unsorted, k0, nb, nf, dense, segs,
+            CU(launch_cells(plan, d_ty, d_basis, d_ts, n, d_tau, nt, d_kappa, d_dcut, d_gap, d_unsorted, k0, nb, nf, dense, segs,
                             seg_len, allow_rec ? d_rec_row : nullptr, d_grid, d_sums, st));
             if (g_profile) {
                 CU(cudaEventRecord(ev.b, st));
@@ -251,9 +254,9 @@ int transform_device(Workspace *w, const double *d_ts, const double *d_ys, int64
                 // "y cos" sums are sum(w c s) and sum(w c c), the two extra entries of Foster's normal matrix
                 CU(launch_basis(d_ts, d_ys, n, plan.n_pad, d_omega + k0, nb, d_ty, d_basis, false, true, st));
                 if (allow_rec)
-                    CU(launch_rec(rplan, d_ty, d_basis, d_ts, n, d_tau, nt, d_kappa, d_dcut, d_unsorted, k0, nb, nf, segs,
+                    CU(launch_rec(rplan, d_ty, d_basis, d_ts, n, d_tau, nt, d_kappa, d_dcut, d_gap, d_unsorted, k0, nb, nf, segs,
                                   seg_len, d_rec_row, d_grid, d_sums2, st));
-                CU(launch_cells(plan, d_ty, d_basis, d_ts, n, d_tau, nt, d_kappa, d_dcut, d_unsorted, k0, nb, nf, dense,
+                CU(launch_cells(plan, d_ty, d_basis, d_ts, n, d_tau, nt, d_kappa, d_dcut, d_gap, d_unsorted, k0, nb, nf, dense,
                                 segs, seg_len, allow_rec ? d_rec_row : nullptr, d_grid, d_sums2, st));
             }
         }
@@ -396,12 +399,15 @@ int shared_axis_device(Workspace *w, const double *d_ts, const double *d_Y, int6
     unsigned char *d_rec_row;
     if ((rc = wsbuf(w, "grid", 2, &d_grid))) return rc;
     if ((rc = wsbuf(w, "rec_row", (size_t)nf, &d_rec_row))) return rc;
-    // point windows of the cell tiles: 2^-300 cutoff as in the single-series path; WWZB200_DENSE walks every point
-    const double cut_bits = (flags & WWZB200_DENSE) ? HUGE_VAL : (flags & WWZB200_EXACT_WINDOW) ? 1081.0 : 300.0;
+    // point windows of the cell tiles: same relative 2^-100 cut as the single-series path; WWZB200_DENSE walks every point
+    const double cut_bits = (flags & WWZB200_DENSE) ? HUGE_VAL : (flags & WWZB200_EXACT_WINDOW) ? 1081.0 : 100.0;
     CU(launch_freq_setup(d_omega, nf, d_tau, nt, c, false, cut_bits, d_kappa, d_dcut, d_grid, d_rec_row, st));
     CU(launch_basis_sc(d_ts, n, plan.n_pad, d_omega, nf, d_ty, d_basis, st));
     CU(launch_rotation(d_tau, d_omega, nt, nf, d_rot, st));
     CU(launch_unsorted_check(d_ts, n, d_unsorted, st));
+    double *d_gap;
+    if ((rc = wsbuf(w, "taugap", (size_t)nt, &d_gap))) return rc;
+    CU(launch_tau_gap(d_ts, n, d_tau, nt, d_gap, st));
     CU(launch_standardize_retile(d_Y, n, plan.n_pad, S, NS, (flags & WWZB200_STANDARDIZE) != 0, d_mu, d_sig, d_Yt, st));
     EventPair ev{nullptr, nullptr, (double)n * (double)ncell * (double)S};
     if (g_profile) {
@@ -409,7 +415,7 @@ int shared_axis_device(Workspace *w, const double *d_ts, const double *d_Y, int6
         CU(cudaEventCreate(&ev.b));
         CU(cudaEventRecord(ev.a, st));
     }
-    CU(launch_shared(plan, d_ty, d_basis, d_Yt, d_ts, n, S_pad, d_tau, nt, d_kappa, d_dcut, d_unsorted, nf, d_rot,
+    CU(launch_shared(plan, d_ty, d_basis, d_Yt, d_ts, n, S_pad, d_tau, nt, d_kappa, d_dcut, d_gap, d_unsorted, nf, d_rot,
                      (double)thr, d_wfrag, d_cellsums, d_ne, d_wq, d_amp_t, d_ph_t, d_a0_t, d_a1_t, d_a2_t, st));
     if (g_profile) {
         CU(cudaEventRecord(ev.b, st));

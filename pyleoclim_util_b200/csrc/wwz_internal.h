@@ -47,17 +47,21 @@ struct RecPlan {
 RecPlan plan_rec(int64_t n, int64_t nt, int64_t nf, int64_t seg_len);
 cudaError_t launch_rec(const RecPlan &plan, const double2 *d_ty, const double2 *d_basis, const double *d_ts, int64_t n,
                        const double *d_tau, int64_t nt, const double *d_kappa, const double *d_dcut,
-                       const int *d_unsorted, int64_t k0, int64_t nf_batch, int64_t nf_total, int segs,
+                       const double *d_taugap, const int *d_unsorted, int64_t k0, int64_t nf_batch, int64_t nf_total, int segs,
                        int64_t seg_len, const unsigned char *d_rec_row, const double *d_grid, double *d_sums,
                        cudaStream_t st);
 
 // Per-frequency constants: kappa = omega*sqrt(c*log2 e), dcut = underflow distance (windowing).
 // Also decides on the device which rows the tau-recurrence kernel may take (d_rec_row) and the tau
 // spacing (d_grid[0]); allow_rec = false marks every row for the direct kernel.
-// cut_bits: weights below 2^-cut_bits are outside the point window of a tile (1081 = exactly zero weights only).
+// cut_bits: weights below 2^-cut_bits of a cell's largest weight are outside the point window of a tile
+// (1081 = exactly zero weights only).
 cudaError_t launch_freq_setup(const double *d_omega, int64_t nf, const double *d_tau, int64_t nt, double c,
                               bool allow_rec, double cut_bits, double *d_kappa, double *d_dcut, double *d_grid,
                               unsigned char *d_rec_row, cudaStream_t st);
+
+// gap[j] = distance from tau[j] to the nearest sample of the sorted time axis (windows relative to the largest weight)
+cudaError_t launch_tau_gap(const double *d_ts, int64_t n, const double *d_tau, int64_t nt, double *d_gap, cudaStream_t st);
 
 // (t, y) interleaved + per-frequency basis rows (sin, cos, y sin, y cos), zero padded to n_pad.
 // cos_as_y: records (sin, cos, cos*sin, cos*cos) -- the second pass of Foster's method (wwz_foster.cu).
@@ -70,7 +74,7 @@ cudaError_t launch_basis(const double *d_ts, const double *d_ys, int64_t n, int6
 // segment s covers points [s*seg_len, (s+1)*seg_len).
 cudaError_t launch_cells(const CellPlan &plan, const double2 *d_ty, const double2 *d_basis, const double *d_ts,
                          int64_t n, const double *d_tau, int64_t nt, const double *d_kappa,
-                         const double *d_dcut, const int *d_unsorted, int64_t k0, int64_t nf_batch,
+                         const double *d_dcut, const double *d_taugap, const int *d_unsorted, int64_t k0, int64_t nf_batch,
                          int64_t nf_total, bool dense, int segs, int64_t seg_len, const unsigned char *d_rec_row,
                          const double *d_grid, double *d_sums, cudaStream_t st);
 
@@ -140,8 +144,8 @@ cudaError_t launch_rotation(const double *d_tau, const double *d_omega, int64_t 
 // the contraction on the FP64 tensor pipe (wwz_mma.cu)
 cudaError_t launch_shared(const SharedPlan &plan, const double2 *d_ty, const double2 *d_basis, const double *d_Yt,
                           const double *d_ts, int64_t n, int64_t S_pad, const double *d_tau, int64_t nt,
-                          const double *d_kappa, const double *d_dcut, const int *d_unsorted, int64_t nf,
-                          const double2 *d_rot, double thr, double *d_wfrag, double *d_cellsums, double *d_neffs,
+                          const double *d_kappa, const double *d_dcut, const double *d_taugap, const int *d_unsorted,
+                          int64_t nf, const double2 *d_rot, double thr, double *d_wfrag, double *d_cellsums, double *d_neffs,
                           double *d_wq, double *d_amp, double *d_phase, double *d_a0, double *d_a1, double *d_a2,
                           cudaStream_t st);
 // deep-underflow cells of a shared-axis batch (flagged from W, Q), recomputed faithfully for every series

@@ -102,6 +102,35 @@ cudaError_t launch_freq_setup(const double *d_omega, int64_t nf, const double *d
     return cudaGetLastError();
 }
 
+// Distance from every tau to the nearest sample of the (sorted) time axis.  The point window of a tile is measured
+// relative to the largest weight of its cells: a cell whose nearest sample is gap away has a largest weight of
+// 2^-(kappa4*gap)^2/16, so points beyond sqrt(dcut^2 + gap^2) weigh less than 2^-cut_bits of it -- inside a hiatus the
+// window widens by itself and no cell ever loses a weight that matters relative to its own sums.
+__global__ void tau_gap_kernel(const double *__restrict__ ts, int64_t n, const double *__restrict__ tau, int64_t nt,
+                               double *__restrict__ gap)
+{
+    const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (j >= nt) return;
+    const double tj = tau[j];
+    int64_t l = 0, r = n;   // first index with ts >= tj
+    while (l < r) {
+        const int64_t m = (l + r) >> 1;
+        if (ts[m] < tj) l = m + 1; else r = m;
+    }
+    double g = CUDART_INF;
+    if (l < n) g = fabs(ts[l] - tj);
+    if (l > 0) g = fmin(g, fabs(tj - ts[l - 1]));
+    gap[j] = isnan(g) ? CUDART_INF : g;
+}
+
+cudaError_t launch_tau_gap(const double *d_ts, int64_t n, const double *d_tau, int64_t nt, double *d_gap, cudaStream_t st)
+{
+    if (nt <= 0) return cudaSuccess;
+    tau_gap_kernel<<<(unsigned)((nt + 127) / 128), 128, 0, st>>>(d_ts, n, d_tau, nt, d_gap);
+    bump_launch_counter();
+    return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------------
 // Basis rows.  theta = fl(omega*t) is the argument the reference passes to sin/cos
 // (utils/wavelet.py:1002-1003); the rounding residual of the product is folded back to first
@@ -183,6 +212,7 @@ struct CellArgs {
     const double *tau;
     const double *kappa;
     const double *dcut;
+    const double *taugap; // distance from each tau to the nearest sample (tau_gap_kernel)
     const int *unsorted;  // device flag: 1 if ts is not ascending (forces the dense path)
     const unsigned char *rec_row;   // per frequency row: 1 = handled by the recurrence kernel (null: all direct)
     const double *grid;             // [0] = dtau of the equally spaced tau axis
@@ -267,8 +297,10 @@ __global__ void __launch_bounds__((CW + 1) * 32, REC ? 1 : 2) wwz_cells_kernel(c
             const double tj = a.tau[min(j, a.nt - 1)];
             tau_r[r] = tj;
             if (j < a.nt && dc >= 0.0) {
-                wlo = fmin(wlo, tj - dc);
-                whi = fmax(whi, tj + dc);
+                const double gj = a.taugap[j];
+                const double de = sqrt(fma(gj, gj, dc * dc));     // relative to the cell's own largest weight
+                wlo = fmin(wlo, tj - de);
+                whi = fmax(whi, tj + de);
             }
         }
     }
@@ -487,7 +519,7 @@ static cudaError_t launch_cells_m(const CellPlan &plan, const CellArgs &args, in
 
 cudaError_t launch_cells(const CellPlan &plan, const double2 *d_ty, const double2 *d_basis, const double *d_ts,
                          int64_t n, const double *d_tau, int64_t nt, const double *d_kappa,
-                         const double *d_dcut, const int *d_unsorted, int64_t k0, int64_t nf_batch,
+                         const double *d_dcut, const double *d_taugap, const int *d_unsorted, int64_t k0, int64_t nf_batch,
                          int64_t nf_total, bool dense, int segs, int64_t seg_len, const unsigned char *d_rec_row,
                          const double *d_grid, double *d_sums, cudaStream_t st)
 {
@@ -499,6 +531,7 @@ cudaError_t launch_cells(const CellPlan &plan, const double2 *d_ty, const double
     a.tau = d_tau;
     a.kappa = d_kappa;
     a.dcut = d_dcut;
+    a.taugap = d_taugap;
     a.unsorted = d_unsorted;
     a.sums = d_sums;
     a.n = n;

@@ -18,8 +18,8 @@
 //
 // A CTA = 8 compute warps = 16 frequency rows x 4 taus, + one TMA producer warp.  The tile is compact in tau
 // and frequency, so its Gaussian support is one index range of the sorted time axis: the producer finds it
-// (warp-cooperative search) and only the chunks that intersect it are staged; points below 2^-300 for every
-// cell of the tile are skipped exactly as in wwz_rec.cu.  Per chunk of P points: one bulk copy for (t, .), one
+// (warp-cooperative search) and only the chunks that intersect it are staged; points below 2^-100 of the largest
+// weight of every cell of the tile are skipped exactly as in wwz_rec.cu.  Per chunk of P points: one bulk copy for (t, .), one
 // per frequency row of {sin, cos} records, one per point for the [P][NS] series tile (rows skewed by 32 B); 4-stage ring, full/empty mbarriers.
 //
 // Grid: x = cell tiles (low frequencies, i.e. the long windows, first), y = series blocks: CTAs that run
@@ -50,6 +50,7 @@ struct MmaArgs {
     const double *tau;
     const double *kappa;
     const double *dcut;
+    const double *taugap;   // distance from each tau to the nearest sample
     const int *unsorted;
     const double2 *rot;     // [ncell] (sin, cos)(omega*tau)
     double *neffs;          // [ncell]
@@ -77,11 +78,15 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
 // the cut-off for some cell of the tile ([min tau - dcut, max tau + dcut] with the widest dcut of its rows).
 __device__ __forceinline__ void tile_window(const MmaArgs &a, int k_base, int rows, int j_base, int lane, int *win)
 {
-    double dc = -1.0, tlo = CUDART_INF, thi = -CUDART_INF;
+    double dc = -1.0, tlo = CUDART_INF, thi = -CUDART_INF, gp = 0.0;
     if (lane < rows) dc = a.dcut[k_base + lane];            // -1: NaN row (no constraint of its own)
-    if (lane < kMmaWT && j_base + lane < a.nt) tlo = thi = a.tau[j_base + lane];
+    if (lane < kMmaWT && j_base + lane < a.nt) {
+        tlo = thi = a.tau[j_base + lane];
+        gp = a.taugap[j_base + lane];
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
+        gp = fmax(gp, __shfl_xor_sync(0xffffffffu, gp, o));
         dc = fmax(dc, __shfl_xor_sync(0xffffffffu, dc, o));
         tlo = fmin(tlo, __shfl_xor_sync(0xffffffffu, tlo, o));
         thi = fmax(thi, __shfl_xor_sync(0xffffffffu, thi, o));
@@ -90,8 +95,9 @@ __device__ __forceinline__ void tile_window(const MmaArgs &a, int k_base, int ro
     if (dc < 0.0) {
         i1 = 0;                                             // every row is NaN: nothing to add, Neff = 0/0
     } else if (!*a.unsorted && dc < CUDART_INF) {
-        i0 = warp_bound<false>(a.ts, 0, a.n, tlo - dc, lane);
-        i1 = warp_bound<true>(a.ts, i0, a.n, thi + dc, lane);
+        const double de = sqrt(fma(gp, gp, dc * dc));       // cut relative to the cells' own largest weight
+        i0 = warp_bound<false>(a.ts, 0, a.n, tlo - de, lane);
+        i1 = warp_bound<true>(a.ts, i0, a.n, thi + de, lane);
     }
     if (lane == 0) {
         const int c_lo = (int)(i0 / a.P);
@@ -402,8 +408,8 @@ static cudaError_t launch_mma(const MmaArgs &a, dim3 grid, int smem, cudaStream_
 
 cudaError_t launch_shared(const SharedPlan &plan, const double2 *d_ty, const double2 *d_basis, const double *d_Yt,
                           const double *d_ts, int64_t n, int64_t S_pad, const double *d_tau, int64_t nt,
-                          const double *d_kappa, const double *d_dcut, const int *d_unsorted, int64_t nf,
-                          const double2 *d_rot, double thr, double *d_wfrag, double *d_cellsums, double *d_neffs,
+                          const double *d_kappa, const double *d_dcut, const double *d_taugap, const int *d_unsorted,
+                          int64_t nf, const double2 *d_rot, double thr, double *d_wfrag, double *d_cellsums, double *d_neffs,
                           double *d_wq, double *d_amp, double *d_phase, double *d_a0, double *d_a1, double *d_a2,
                           cudaStream_t st)
 {
@@ -417,6 +423,7 @@ cudaError_t launch_shared(const SharedPlan &plan, const double2 *d_ty, const dou
     a.tau = d_tau;
     a.kappa = d_kappa;
     a.dcut = d_dcut;
+    a.taugap = d_taugap;
     a.unsorted = d_unsorted;
     a.rot = d_rot;
     a.neffs = d_neffs;

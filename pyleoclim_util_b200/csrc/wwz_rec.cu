@@ -8,14 +8,14 @@
 //    a tau-group = 8 adjacent cells of one row), i.e. a tile compact in tau AND in frequency, so that the
 //    support of its Gaussian weights is a short index range of the sorted time axis;
 //  * every warp finds the range of its own tile (warp-cooperative 32-ary search on ts) and walks only
-//    that: points whose weight is below 2^-300 for every cell of the tile are never touched;
+//    that: points whose weight is below 2^-100 of the largest weight of every cell of the tile are never touched;
 //  * every warp stages its own points: a private 3-stage shared-memory ring filled by 1-D TMA bulk copies
 //    (cp.async.bulk + mbarrier complete_tx) that the warp issues itself -- no producer warp, no CTA-wide
 //    barrier in the loop, 12 compute warps per SM (3 CTAs x 4 warps at 168 registers) instead of 8.
 //
-// Skipped weights.  A weight below 2^-300 adds less than 2^-100 relative to any sum of a cell whose
-// W = sum(w) is at least 2^-200, far below one ulp; cells with W < 2^-200 are recomputed by the faithful
-// kernel anyway (finalize_kernel flags them), so the skip is invisible in the results.
+// Skipped weights.  The window of a tile reaches sqrt(dcut^2 + gap^2) beyond its taus, gap = distance from tau to
+// the nearest sample (tau_gap_kernel): a skipped weight is below 2^-100 of the largest weight of the cell, hence of
+// W = sum(w) -- 2^-47 ulp -- wherever tau lies, also inside a hiatus (the window widens by itself there).
 #include <math_constants.h>
 
 #include <algorithm>
@@ -33,6 +33,7 @@ struct RecArgs {
     const double *tau;
     const double *kappa;
     const double *dcut;
+    const double *taugap;
     const int *unsorted;
     const unsigned char *rec_row;
     const double *grid;
@@ -78,8 +79,12 @@ __global__ void __launch_bounds__(kRecWarps * 32, 3) wwz_rec_kernel(const RecArg
         kap = a.kappa[a.k0 + kb];
         const double dc = a.dcut[a.k0 + kb];
         tau0 = a.tau[g * M];
-        wlo = tau0 - dc;
-        whi = a.tau[min(g * M + M - 1, a.nt - 1)] + dc;
+        double gmax = 0.0;                                   // widest sample gap seen by the lane's cells
+#pragma unroll
+        for (int r = 0; r < M; ++r) gmax = fmax(gmax, a.taugap[min(g * M + r, a.nt - 1)]);
+        const double de = sqrt(fma(gmax, gmax, dc * dc));   // cut relative to the cells' own largest weight
+        wlo = tau0 - de;
+        whi = a.tau[min(g * M + M - 1, a.nt - 1)] + de;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -228,7 +233,7 @@ RecPlan plan_rec(int64_t n, int64_t nt, int64_t nf, int64_t seg_len)
 
 cudaError_t launch_rec(const RecPlan &plan, const double2 *d_ty, const double2 *d_basis, const double *d_ts, int64_t n,
                        const double *d_tau, int64_t nt, const double *d_kappa, const double *d_dcut,
-                       const int *d_unsorted, int64_t k0, int64_t nf_batch, int64_t nf_total, int segs,
+                       const double *d_taugap, const int *d_unsorted, int64_t k0, int64_t nf_batch, int64_t nf_total, int segs,
                        int64_t seg_len, const unsigned char *d_rec_row, const double *d_grid, double *d_sums,
                        cudaStream_t st)
 {
@@ -240,6 +245,7 @@ cudaError_t launch_rec(const RecPlan &plan, const double2 *d_ty, const double2 *
     a.tau = d_tau;
     a.kappa = d_kappa;
     a.dcut = d_dcut;
+    a.taugap = d_taugap;
     a.unsorted = d_unsorted;
     a.rec_row = d_rec_row;
     a.grid = d_grid;

@@ -134,9 +134,33 @@ def test_windowed_is_bit_identical_to_dense():
         assert np.array_equal(x, z)
 
 
+def test_relative_window_inside_a_hiatus():
+    """The point window is measured relative to each cell's own largest weight (it widens by the distance from tau
+    to the nearest sample): with tau inside a long hiatus, where every weight of a cell is tiny, the default path
+    still agrees with the dense run to rounding -- single-series kernels and the shared-axis batch."""
+    from pyleoclim_util_b200 import batch as B
+    rng = np.random.default_rng(21)
+    t = np.concatenate([np.sort(rng.uniform(0, 300, 700)), np.sort(rng.uniform(520, 900, 800))])
+    y = rng.standard_normal(t.size)
+    tau = np.linspace(t.min(), t.max(), 96)                 # a quarter of the rows lie inside the 220-wide gap
+    freq = np.logspace(-2.6, -0.4, 36)
+    d = WV.kirchner_cuda(y, t, freq, tau, standardize=True, flags=_lib.DENSE)
+    assert np.sum(~np.isnan(d[0][(tau > 330) & (tau < 490)])) > 200      # valid cells inside the hiatus exist
+    for fl in (_lib.NO_RECURRENCE, 0):
+        a = WV.kirchner_cuda(y, t, freq, tau, standardize=True, flags=fl)
+        assert_scalogram_parity(as_dict(*a), as_dict(*d), amp_rtol=1e-11, phase_atol=1e-11, neff_rtol=1e-12,
+                                what="hiatus, flags=%d" % fl)
+    Y = np.stack([y, rng.standard_normal(t.size), y[::-1].copy()])
+    sa = B.wwz_shared_axis(Y, t, tau, freq, outputs=("amplitude", "phase"))
+    sd = B.wwz_shared_axis(Y, t, tau, freq, outputs=("amplitude", "phase"), flags=_lib.DENSE)
+    assert_same_nan_mask(sa.amplitude, sd.amplitude)
+    assert max_rel(sa.amplitude, sd.amplitude) < 1e-11 and max_rel(sa.Neffs, sd.Neffs) < 1e-12
+    assert max_rel(sa.amplitude[0], d[0]) < 1e-10
+
+
 def test_default_window_is_invisible():
-    """The default window drops weights below 2^-300 (less than 2^-100 of any sum that is kept): against the
-    dense run the results agree to rounding, with the same mask, for both kernels and both decay constants."""
+    """The default window drops weights below 2^-100 of the largest weight of a cell (hence of its sum(w)): against
+    the dense run the results agree to rounding, with the same mask, for both kernels and both decay constants."""
     for c in (1 / (8 * np.pi ** 2), 1e-3):
         t, y, tau, freq = _grid_case(n=3000, nt=64, nf=48)
         d = WV.kirchner_cuda(y, t, freq, tau, c=c, flags=_lib.DENSE)
