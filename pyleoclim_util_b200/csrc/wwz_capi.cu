@@ -62,6 +62,8 @@ struct Workspace {
     cudaEvent_t fork_ev = nullptr;
     std::string prefix;   // scratch namespace of the stream currently being enqueued on
     int sms = 0;
+    double *h_in = nullptr;   // page-locked staging of the single-series inputs
+    size_t h_in_count = 0;
 
     int get(const char *name, size_t bytes, void **out)
     {
@@ -87,6 +89,9 @@ struct Workspace {
         for (auto &kv : bufs)
             if (kv.second.first) cudaFree(kv.second.first);
         bufs.clear();
+        if (h_in) cudaFreeHost(h_in);
+        h_in = nullptr;
+        h_in_count = 0;
     }
 };
 
@@ -313,10 +318,20 @@ int host_transform(const double *ts, const double *ys, int64_t n, const double *
     if ((rc = wsbuf(w, "in", in_count, &d_in))) return rc;
     if ((rc = wsbuf(w, "out", (size_t)(6 * ncell + nf), &d_out))) return rc;
     double *d_ts = d_in, *d_ys = d_in + n, *d_tau = d_ys + n, *d_om = d_tau + nt;
-    CU(cudaMemcpyAsync(d_ts, ts, sizeof(double) * n, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(d_ys, ys, sizeof(double) * n, cudaMemcpyHostToDevice, st));
-    if (nt) CU(cudaMemcpyAsync(d_tau, tau, sizeof(double) * nt, cudaMemcpyHostToDevice, st));
-    if (nf) CU(cudaMemcpyAsync(d_om, om, sizeof(double) * nf, cudaMemcpyHostToDevice, st));
+    // the four input vectors go up as ONE DMA from a page-locked staging buffer (caller memory is usually pageable:
+    // four separate copies would each be staged by the driver)
+    if (w->h_in_count < in_count) {
+        if (w->h_in) cudaFreeHost(w->h_in);
+        w->h_in = nullptr;
+        w->h_in_count = 0;
+        CU(cudaMallocHost(&w->h_in, sizeof(double) * std::max<size_t>(in_count, 4096)));
+        w->h_in_count = std::max<size_t>(in_count, 4096);
+    }
+    memcpy(w->h_in, ts, sizeof(double) * n);
+    memcpy(w->h_in + n, ys, sizeof(double) * n);
+    if (nt) memcpy(w->h_in + 2 * n, tau, sizeof(double) * nt);
+    if (nf) memcpy(w->h_in + 2 * n + nt, om, sizeof(double) * nf);
+    CU(cudaMemcpyAsync(d_in, w->h_in, sizeof(double) * in_count, cudaMemcpyHostToDevice, st));
     double *o_neff = d_out, *o_a0 = d_out + ncell, *o_a1 = d_out + 2 * ncell, *o_a2 = d_out + 3 * ncell;
     double *o_wwa = d_out + 4 * ncell, *o_ph = d_out + 5 * ncell, *o_psd = d_out + 6 * ncell;
     double tspan = 0;

@@ -22,6 +22,7 @@ template <int V> __global__ void __launch_bounds__(256) k(double* out, int iters
                 if (V == 6) { a[j] = fma(x[j], y[j], a[j]); if ((j & 1) == 0) n = n * 1048576 + j; } // + 1 IMAD per 2 DFMA
                 if (V == 7) a[j] = fma(a[j], a[j], a[j]);           // same register thrice
                 if (V == 8) a[j] = a[j] * x[j];                     // DMUL
+                if (V == 9) a[j] = fma(x[j], m, a[j]);              // 2 private + 1 shared register (operand reuse)
             }
         }
     }
@@ -54,5 +55,6 @@ int main() {
     run<6>("DFMA 3 regs + 1 IMAD per 2", d_out, d_g);
     run<7>("DFMA a=fma(a,a,a)", d_out, d_g);
     run<8>("DMUL a=a*x", d_out, d_g);
+    run<9>("DFMA a=fma(x,m,a) (2 private + shared m)", d_out, d_g);
     return 0;
 }
