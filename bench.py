@@ -34,6 +34,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+_REAL_STDOUT = sys.stdout
 
 C_WWZ = 1.0 / (8.0 * np.pi ** 2)
 C_PSD = 1e-3
@@ -147,7 +148,7 @@ def run_reference(args):
             "e2e": {"value": value, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "reference arm = CPU restatement of pyleoclim kirchner_numba (utils/wavelet.py:985-1045) in C with "
                     "OpenMP on all host cores; the reference's numba path adds a ~7-8 s JIT per call (BASELINE.md)"}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_REAL_STDOUT, flush=True)
 
 
 def run_ours(args):
@@ -186,9 +187,9 @@ def run_ours(args):
         # the assembled outputs: plane i of full6 is [world, nt_local, nf] = the tau-row blocks of all ranks side by
         # side, so each output plane is gathered straight into its final place (no re-layout copy)
         full6 = torch.empty((6, nt_total, nf), dtype=torch.float64, device=dev)
-        full2 = torch.empty((2, nt_total, nf), dtype=torch.float64, device=dev)
+        parts = torch.empty((2, nf), dtype=torch.float64, device=dev)
         comm = torch.cuda.Stream(device=dev)
-        ev_a, ev_b, ev_c = (torch.cuda.Event() for _ in range(3))
+        ev_a, ev_c = torch.cuda.Event(), torch.cuda.Event()
     stream = torch.cuda.current_stream().cuda_stream
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)             # > 126 MB L2
     tspan = float(t.max() - t.min())
@@ -199,28 +200,26 @@ def run_ours(args):
                                           d_om.data_ptr(), nf, C_WWZ, 3, 3, 0, o[0], o[1], o[2], o[3], o[4], o[5],
                                           None, nf, stream))
         if world > 1:
-            # tau-row blocks are the shards: NCCL all-gathers of the wwz outputs over NVLink on a side stream,
+            # tau-row blocks are the shards: NCCL all-gathers of the six wwz outputs over NVLink on a side stream,
             # overlapped with the second transform
             ev_a.record()
             with torch.cuda.stream(comm):
                 comm.wait_event(ev_a)
                 for i in range(6):
                     dist.all_gather_into_tensor(full6[i].view(-1), loc6[i].view(-1))
+                ev_c.record()
         _lib.check(L.wwzb200_kirchner_dev(d_t.data_ptr(), d_y.data_ptr(), n, d_tau.data_ptr(), nt_local,
                                           d_om.data_ptr(), nf, C_PSD, 3, 3, 0, loc2[0].data_ptr(), None, None, None,
                                           loc2[1].data_ptr(), None, psd.data_ptr() if world == 1 else None, nf,
                                           stream))
         if world > 1:
-            ev_b.record()
-            with torch.cuda.stream(comm):
-                comm.wait_event(ev_b)
-                for i in range(2):
-                    dist.all_gather_into_tensor(full2[i].view(-1), loc2[i].view(-1))
-                ev_c.record()
+            # wwz_psd returns psd[nf] only: each rank reduces its own rows to the partial column sums of wwa2psd,
+            # the [2, nf] parts are all-reduced and divided (utils/wavelet.py:1275-1278)
+            _lib.check(L.wwzb200_wwa2psd_parts_dev(loc2[1].data_ptr(), loc2[0].data_ptr(), nt_local, nf, tspan, n, 3,
+                                                   parts.data_ptr(), stream))
+            dist.all_reduce(parts)
+            torch.div(parts[0], parts[1], out=psd)
             torch.cuda.current_stream().wait_event(ev_c)
-            # wwa2psd reduces the gathered scalogram
-            _lib.check(L.wwzb200_wwa2psd_dev(full2[1].data_ptr(), full2[0].data_ptr(), nt_total, nf, tspan, n, 3,
-                                             psd.data_ptr(), stream))
 
     def barrier():
         if dist is not None:
@@ -302,9 +301,9 @@ def run_ours(args):
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         e2e_s = float(tmax.item())
     cabi_s = e2e_s
-    # per rank, through the public API: the inputs of both calls go up (the sharded API prepares the full tau axis),
-    # the assembled result of both calls comes back on every rank
-    h2d = 2 * 8 * (2 * n + (nt_local if world == 1 else nt_total) + nf)
+    # through the public API, rank 0: the inputs of both calls go up, the assembled result of both calls comes back
+    # (N > 1: the grid is assembled in the HBM of every GPU by the all-gather; rank 0 copies it to the host)
+    h2d = 2 * 8 * (2 * n + nt_local + nf)
     d2h = 8 * (6 * (nt_local if world == 1 else nt_total) * nf + nf)
 
     # the public Python API: what a user (or Pyleoclim through register()) calls.  Host NumPy arrays in, fresh
@@ -316,9 +315,9 @@ def run_ours(args):
             p = WV.wwz_psd(ys, t, tau=tau, freq=freq)
         else:       # the sharded public API: prepare on the full grid, tau-block per rank, NCCL all-gather / all-reduce
             from pyleoclim_util_b200 import distributed as D
-            r = D.wwz_tau_sharded(ys, t, tau=tau_all, freq=freq)
+            r = D.wwz_tau_sharded(ys, t, tau=tau_all, freq=freq, host="root")
             p = D.wwz_psd_tau_sharded(ys, t, tau=tau_all, freq=freq)
-        return r.amplitude[0, 0] + p.psd[0]
+        return (r.amplitude[0, 0] if r.amplitude is not None else 0.0) + p.psd[0]
 
     for _ in range(3):
         step_api()
@@ -475,23 +474,36 @@ def run_ours(args):
             "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "n": n, "ntau_per_gpu": nt_local, "nfreq": nf,
-                       "cells_per_step_per_gpu": cells_step_local, "partition": "tau-block per GPU + NCCL all-gather of every output "
-                       "plane into the assembled grid (side stream, overlapped with the second transform)"
+                       "cells_per_step_per_gpu": cells_step_local, "partition": "tau-block per GPU; NCCL all-gather of every wwz output "
+                       "plane into the assembled grid on every GPU (side stream, overlapped with the second transform); "
+                       "wwz_psd: all-reduce of the [2, nf] partial sums of wwa2psd"
                        if world > 1 else "single GPU", "l2": "256 MiB buffer written between timed iterations",
                        "window": "per tile of cells only the points whose weight reaches 2^-100 of a cell's largest weight are walked",
                        "kernels": "tau-recurrence kernel on rows with kappa*dtau <= 8 (all rows here), direct kernel otherwise"},
             "e2e": {"value": e2e_value, "unit": "cells/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * api_s / args.steps,
-                    "path": "pyleoclim_util_b200.wavelet.wwz + .wwz_psd (the reference's wwz / wwz_psd signatures) on host "
-                            "NumPy arrays; results land in pooled page-locked NumPy arrays",
+                    "path": ("pyleoclim_util_b200.wavelet.wwz + .wwz_psd (the reference's wwz / wwz_psd signatures) on host "
+                             "NumPy arrays; results land in pooled page-locked NumPy arrays") if world == 1 else
+                            ("pyleoclim_util_b200.distributed.wwz_tau_sharded(host='root') + .wwz_psd_tau_sharded on host "
+                             "NumPy arrays, every rank: prepare, tau block on its GPU, NCCL all-gather / all-reduce; the "
+                             "assembled [6, ntau, nf] grid is copied to page-locked host memory by rank 0, psd by every rank"),
                     "c_abi_ms_per_step": 1e3 * cabi_s / args.steps,
                     "c_abi_path": "wwzb200_kirchner + wwzb200_kirchner_psd on pre-allocated pinned host buffers"},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
             "wall_ms_per_step_incl_l2_flush": 1e3 * wall / args.steps, "extras": extras,
             "hbm_gbs_measured": peaks.get("hbm_gbs")}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_REAL_STDOUT, flush=True)
     if dist is not None:
         dist.destroy_process_group()
+
+
+def _protect_stdout():
+    """The contract is ONE JSON line on stdout: route everything else that writes to fd 1 (NCCL's version banner,
+    library chatter) to stderr and hand back a file object on the real stdout for the final line."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
 
 
 def main():
@@ -501,6 +513,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     args = ap.parse_args()
+    global _REAL_STDOUT
+    _REAL_STDOUT = _protect_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -176,6 +176,12 @@ int wwzb200_kirchner_dev(const double *d_ts, const double *d_pd_ys, int64_t nts,
 int wwzb200_wwa2psd_dev(const double *d_wwa, const double *d_Neffs, int64_t nt, int64_t nf, double tspan,
                         int64_t nts, int64_t Neff_threshold, double *d_psd, void *stream);
 
+/* wwa2psd over a block of tau rows, before the divide: d_parts[0..nf) = nansum_j(power * Neff_diff),
+ * d_parts[nf..2nf) = nansum_j(Neff_diff) (utils/wavelet.py:1275-1278).  tau-sharded runs add the parts of all
+ * blocks (an all-reduce of [2, nf]) and divide; tspan and nts are those of the whole series (:1270). */
+int wwzb200_wwa2psd_parts_dev(const double *d_wwa, const double *d_Neffs, int64_t nt, int64_t nf, double tspan,
+                              int64_t nts, int64_t Neff_threshold, double *d_parts, void *stream);
+
 int wwzb200_kirchner_shared_axis_dev(const double *d_ts, const double *d_Y, int64_t nts, int64_t S,
                                      const double *d_taus, int64_t nt, const double *d_omegas,
                                      int64_t nf, double c, int64_t Neff_threshold,

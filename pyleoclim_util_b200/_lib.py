@@ -61,6 +61,7 @@ _SIGS = {
     "wwzb200_kirchner_dev": (ctypes.c_int, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _dbl, _i64, _i64, _u32,
                                             _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "wwzb200_wwa2psd_dev": (ctypes.c_int, [_vp, _vp, _i64, _i64, _dbl, _i64, _i64, _vp, _vp]),
+    "wwzb200_wwa2psd_parts_dev": (ctypes.c_int, [_vp, _vp, _i64, _i64, _dbl, _i64, _i64, _vp, _vp]),
     "wwzb200_kirchner_shared_axis_dev": (ctypes.c_int, [_vp, _vp, _i64, _i64, _vp, _i64, _vp, _i64, _dbl, _i64,
                                                         _i64, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "wwzb200_ar1_surrogates_dev": (ctypes.c_int, [_vp, _i64, _dbl, _dbl, _dbl, _i64, _u64, _vp, _vp]),

@@ -611,6 +611,18 @@ int wwzb200_wwa2psd_dev(const double *d_wwa, const double *d_Neffs, int64_t nt, 
     return 0;
 }
 
+int wwzb200_wwa2psd_parts_dev(const double *d_wwa, const double *d_Neffs, int64_t nt, int64_t nf, double tspan,
+                              int64_t nts, int64_t Neff_threshold, double *d_parts, void *stream)
+{
+    if (nt < 0 || nf < 0 || nts < 1) return fail(WWZB200_ERR_ARG, "bad sizes");
+    if (nf == 0) return 0;
+    if (!d_parts || (nt && (!d_wwa || !d_Neffs))) return fail(WWZB200_ERR_ARG, "null pointer");
+    if (Neff_threshold < 0) return fail(WWZB200_ERR_ARG, "Neff_threshold must be >= 0");
+    CU(wwz::launch_psd_parts(d_wwa, d_Neffs, nt, nf, nf, tspan, nts, (double)Neff_threshold, d_parts,
+                             static_cast<cudaStream_t>(stream)));
+    return 0;
+}
+
 int wwzb200_kirchner_shared_axis_dev(const double *d_ts, const double *d_Y, int64_t nts, int64_t S,
                                      const double *d_taus, int64_t nt, const double *d_omegas, int64_t nf, double c,
                                      int64_t Neff_threshold, int64_t psd_Neff_threshold, uint32_t flags,

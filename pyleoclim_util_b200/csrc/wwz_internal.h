@@ -113,6 +113,10 @@ cudaError_t launch_foster_faithful(const double *d_ts, const double *d_ys, int64
 cudaError_t launch_psd(const double *d_wwa, const double *d_neffs, int64_t nt, int64_t nf, int64_t row_stride,
                        double tspan, int64_t n, double neff_thr, double *d_psd, cudaStream_t st);
 
+// partial column sums of wwa2psd over a block of tau rows: d_parts[0][k] = numerator, d_parts[1][k] = denominator
+cudaError_t launch_psd_parts(const double *d_wwa, const double *d_neffs, int64_t nt, int64_t nf, int64_t row_stride,
+                             double tspan, int64_t n, double neff_thr, double *d_parts, cudaStream_t st);
+
 // min / max of a device vector (for tspan in the device-pointer entry points) -> d_out[0..1].
 cudaError_t launch_minmax(const double *d_x, int64_t n, double *d_out, cudaStream_t st);
 cudaError_t launch_psd_devspan(const double *d_wwa, const double *d_neffs, int64_t nt, int64_t nf,

@@ -702,7 +702,7 @@ cudaError_t launch_faithful(const double *d_ts, const double *d_ys, int64_t n, c
 __global__ void __launch_bounds__(1024)
     psd_kernel(const double *__restrict__ wwa, const double *__restrict__ neffs, int64_t nt, int64_t nf,
                int64_t row_stride, double tspan, const double *__restrict__ minmax, double n_d, double thr,
-               double *__restrict__ psd)
+               double *__restrict__ psd, double *__restrict__ parts)
 {
     __shared__ double s_sp[32][33], s_se[32][33];
     const int64_t k = blockIdx.x * 32 + threadIdx.x;
@@ -729,7 +729,12 @@ __global__ void __launch_bounds__(1024)
             tp += s_sp[y][threadIdx.x];
             te += s_se[y][threadIdx.x];
         }
-        psd[k] = tp / te;
+        if (parts) {              // partial column sums of a tau block: numerator, denominator (sharded wwa2psd)
+            parts[k] = tp;
+            parts[nf + k] = te;
+        } else {
+            psd[k] = tp / te;
+        }
     }
 }
 
@@ -738,7 +743,17 @@ cudaError_t launch_psd(const double *d_wwa, const double *d_neffs, int64_t nt, i
 {
     if (nf <= 0) return cudaSuccess;
     psd_kernel<<<(unsigned)((nf + 31) / 32), dim3(32, 32), 0, st>>>(d_wwa, d_neffs, nt, nf, row_stride, tspan, nullptr,
-                                                                    (double)n, neff_thr, d_psd);
+                                                                    (double)n, neff_thr, d_psd, nullptr);
+    bump_launch_counter();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_psd_parts(const double *d_wwa, const double *d_neffs, int64_t nt, int64_t nf, int64_t row_stride,
+                             double tspan, int64_t n, double neff_thr, double *d_parts, cudaStream_t st)
+{
+    if (nf <= 0) return cudaSuccess;
+    psd_kernel<<<(unsigned)((nf + 31) / 32), dim3(32, 32), 0, st>>>(d_wwa, d_neffs, nt, nf, row_stride, tspan, nullptr,
+                                                                    (double)n, neff_thr, nullptr, d_parts);
     bump_launch_counter();
     return cudaGetLastError();
 }
@@ -749,7 +764,7 @@ cudaError_t launch_psd_devspan(const double *d_wwa, const double *d_neffs, int64
 {
     if (nf <= 0) return cudaSuccess;
     psd_kernel<<<(unsigned)((nf + 31) / 32), dim3(32, 32), 0, st>>>(d_wwa, d_neffs, nt, nf, row_stride, 0.0,
-                                                                    d_minmax, (double)n, neff_thr, d_psd);
+                                                                    d_minmax, (double)n, neff_thr, d_psd, nullptr);
     bump_launch_counter();
     return cudaGetLastError();
 }

@@ -83,7 +83,7 @@ def all_gather_rows(local, counts, group=None):
     return np.concatenate([out[r, : counts[r]] for r in range(world)], axis=0)
 
 
-def _device_blocks(pd_ys, ts_cut, tau, omega, c, Neff_threshold, flags, group, want, to_host=True):
+def _device_blocks(pd_ys, ts_cut, tau, omega, c, Neff_threshold, flags, group, want, to_host=True, gather=True):
     """NCCL fast path: this rank's tau block is transformed into a device buffer (C-ABI *_dev entry point on
     torch's current stream), the row blocks are all-gathered on the device and only the assembled
     [len(want), nt, nf] result crosses PCIe, into page-locked host memory.  `want` indexes the library's output
@@ -108,6 +108,8 @@ def _device_blocks(pd_ys, ts_cut, tau, omega, c, Neff_threshold, flags, group, w
                                                    d_om.data_ptr(), nf, float(c), int(Neff_threshold), 0, int(flags),
                                                    *ptrs, None, nf, torch.cuda.current_stream().cuda_stream))
     k = len(want)
+    if not gather:
+        return None, loc[:, : b - a]
     if len(set(counts)) == 1:
         # equal row blocks: plane i of the result is [world, hmax, nf], so every wanted output plane is gathered
         # straight into its final place (no selection copy, no re-layout)
@@ -130,10 +132,14 @@ def _device_blocks(pd_ys, ts_cut, tau, omega, c, Neff_threshold, flags, group, w
 
 
 def wwz_tau_sharded(ys, ts, tau=None, freq=None, freq_method="log", freq_kwargs=None, c=1 / (8 * np.pi ** 2),
-                    Neff_threshold=3, Neff_coi=3, standardize=True, group=None, kernel=None, flags=0):
+                    Neff_threshold=3, Neff_coi=3, standardize=True, group=None, kernel=None, flags=0, host="all"):
     """`wavelet.wwz` with the tau rows sharded over the ranks of `group`.  Every rank returns the
     full Results (amplitude, phase, coi, freq, time, Neffs, coeff, scale), like the reference's wwz
-    (utils/wavelet.py:1294-1494).  `kernel` defaults to `wavelet.kirchner_cuda`."""
+    (utils/wavelet.py:1294-1494).  `kernel` defaults to `wavelet.kirchner_cuda`.
+
+    host='all' (default): the assembled grid is copied to host memory on every rank.  host='root' (NCCL path): the
+    all-gather still assembles the grid in the HBM of every GPU, but only rank 0 -- the process that consumes the
+    result -- pays the PCIe copy of the whole grid; the other ranks get Results whose per-cell arrays are None."""
     dist = _dist()
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     kernel = _wv.kirchner_cuda if kernel is None else kernel
@@ -142,9 +148,12 @@ def wwz_tau_sharded(ys, ts, tau=None, freq=None, freq_method="log", freq_kwargs=
     pd_ys = _wv.preprocess(ys_cut, ts_cut, standardize=standardize)
     if kernel is _wv.kirchner_cuda and dist.get_backend(group) == "nccl":
         _wv.assertPositiveInt(Neff_threshold)
-        host, _ = _device_blocks(pd_ys, ts_cut, tau, _wv.make_omega(ts_cut, freq), c, Neff_threshold, flags, group,
-                                 want=(4, 5, 0, 1, 2, 3))
-        wwa, phase, Neffs, a0, a1, a2 = host
+        if host not in ("all", "root"):
+            raise ValueError("host must be 'all' or 'root'")
+        to_host = host == "all" or rank == 0
+        host_arr, _ = _device_blocks(pd_ys, ts_cut, tau, _wv.make_omega(ts_cut, freq), c, Neff_threshold, flags, group,
+                                     want=(4, 5, 0, 1, 2, 3), to_host=to_host)
+        wwa, phase, Neffs, a0, a1, a2 = host_arr if to_host else (None,) * 6
         return _wv.WwzResults(amplitude=wwa, phase=phase, coi=_wv.make_coi(tau, Neff_threshold=Neff_coi), freq=freq,
                               time=tau, Neffs=Neffs, coeff=(a0, a1, a2), scale=1 / freq)
     blocks = row_blocks(tau.size, world)
@@ -174,17 +183,20 @@ def wwz_psd_tau_sharded(ys, ts, tau=None, freq=None, freq_method="log", freq_kwa
                                                 tau=tau)
     pd_ys = _wv.preprocess(ys_cut, ts_cut, standardize=standardize)
     if kernel is _wv.kirchner_cuda and dist.get_backend(group) == "nccl":
-        # gather amplitude and Neffs on the device, reduce the gathered scalogram there (wwzb200_wwa2psd_dev)
+        # each rank reduces its own tau rows to the partial column sums of wwa2psd on the device
+        # (wwzb200_wwa2psd_parts_dev), the [2, nf] parts are all-reduced over NVLink, then divided
         from . import _lib
-        _, full = _device_blocks(pd_ys, ts_cut, tau, _wv.make_omega(ts_cut, freq), c, 3, flags, group, want=(4, 0),
-                                 to_host=False)
-        full = full.contiguous()
-        d_psd = torch.empty(freq.size, dtype=torch.float64, device=full.device)
-        _lib.check(_lib.lib().wwzb200_wwa2psd_dev(full[0].data_ptr(), full[1].data_ptr(), tau.size, freq.size,
-                                                  float(np.max(ts_cut) - np.min(ts_cut)), int(np.size(ts_cut)),
-                                                  int(Neff_threshold), d_psd.data_ptr(),
-                                                  torch.cuda.current_stream().cuda_stream))
-        return _wv.PsdResults(psd=d_psd.cpu().numpy(), freq=freq)
+        _, loc = _device_blocks(pd_ys, ts_cut, tau, _wv.make_omega(ts_cut, freq), c, 3, flags, group, want=(4, 0),
+                                to_host=False, gather=False)
+        parts = torch.zeros((2, freq.size), dtype=torch.float64, device=loc.device)
+        if loc.shape[1]:
+            wwa_loc, ne_loc = loc[4].contiguous(), loc[0].contiguous()
+            _lib.check(_lib.lib().wwzb200_wwa2psd_parts_dev(wwa_loc.data_ptr(), ne_loc.data_ptr(), loc.shape[1], freq.size,
+                                                            float(np.max(ts_cut) - np.min(ts_cut)), int(np.size(ts_cut)),
+                                                            int(Neff_threshold), parts.data_ptr(),
+                                                            torch.cuda.current_stream().cuda_stream))
+        dist.all_reduce(parts, group=group)
+        return _wv.PsdResults(psd=(parts[0] / parts[1]).cpu().numpy(), freq=freq)
     a, b = row_blocks(tau.size, world)[rank]
     kw = dict(c=c, Neff_threshold=3, standardize=False)
     if kernel is _wv.kirchner_cuda:

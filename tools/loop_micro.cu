@@ -40,7 +40,11 @@ template <int MODE, int M> __global__ void __launch_bounds__(256) k(double* out,
                     const int hi = __double2hiint(p) + ((N >> 4) << 20);
                     w = __hiloint2double(tiny ? 0 : hi, tiny ? 0 : __double2loint(p));
                 }
-                if (MODE & 4) {
+                if (MODE & 16) {       // y-shared form: products first, then three FMAs that share the operand y
+                    const double ws = w * s, wc = w * c;
+                    W[r] += w; Q[r] = fma(w, w, Q[r]); Ws[r] += ws; Wc[r] += wc;
+                    Wy[r] = fma(w, y, Wy[r]); Wys[r] = fma(ws, y, Wys[r]); Wyc[r] = fma(wc, y, Wyc[r]);
+                } else if (MODE & 4) {
                     W[r] += w; Q[r] = fma(w, w, Q[r]); Ws[r] = fma(w, s, Ws[r]); Wc[r] = fma(w, c, Wc[r]);
                     Wy[r] = fma(w, y, Wy[r]); Wys[r] = fma(w, ys, Wys[r]); Wyc[r] = fma(w, yc, Wyc[r]);
                 } else {
@@ -76,6 +80,9 @@ int main() {
         run<14, 2>("no polynomial", d_out, d_g, bps);
         run<4, 2>("accumulates only (+v,z,Nf,g)", d_out, d_g, bps);
         run<0, 2>("v,z,Nf,g + W only", d_out, d_g, bps);
+        run<15 + 16, 2>("full, y-shared accumulates", d_out, d_g, bps);
+        run<15 + 16, 4>("full, y-shared accumulates", d_out, d_g, bps);
+        run<15 + 16, 1>("full, y-shared accumulates", d_out, d_g, bps);
         run<15, 1>("full", d_out, d_g, bps);
         run<15, 4>("full", d_out, d_g, bps);
     }
