@@ -25,7 +25,7 @@ def row_blocks(n, world):
 TILE_ROWS = 16      # frequency rows of one CTA tile of the shared-axis kernel (kMmaRows, csrc/wwz_mma.cu)
 
 
-def balanced_freq_groups(ts_cut, tau, freq, c, world, cut_bits=300.0):
+def balanced_freq_groups(ts_cut, tau, freq, c, world, cut_bits=100.0):
     """Frequency rows for each rank of a frequency-sharded significance test: [index arrays].
 
     The shared-axis kernel walks, per tile of TILE_ROWS consecutive frequencies, only the points inside the
