@@ -135,8 +135,8 @@ size_t basis_budget_bytes()
 }
 
 // Number of point-axis segments: enough that (cells x segments) fills the machine for several waves
-// (1.5e6 cell-slots = 10 waves x 296 CTAs x 512 cells of the direct kernel, 3.3 waves x 1776 warp tiles x 256
-// cells of the recurrence kernel -- measured best on config 2), each segment at least 256 points.
+// (1.0e6 cell-slots; config 2 runs 2 segments: 2 and 3 tie on the c = 1/(8 pi^2) transform, 2 wins by 4% on the
+// c = 1e-3 one and leaves the epilogue one slab less to add), each segment at least 256 points.
 // It depends on the problem size only, never on the tile geometry, so every kernel variant adds
 // the same partial sums.
 int point_segments(int64_t n, int64_t ncell)
@@ -146,7 +146,7 @@ int point_segments(int64_t n, int64_t ncell)
     if (e && *e) {
         s = atoll(e);
     } else {
-        s = (1500000 + ncell - 1) / std::max<int64_t>(ncell, 1);
+        s = (1000000 + ncell - 1) / std::max<int64_t>(ncell, 1);
         s = std::min<int64_t>(s, n / 256);
     }
     return (int)std::max<int64_t>(1, std::min<int64_t>(s, 4096));
