@@ -60,6 +60,8 @@ struct Workspace {
     cudaStream_t lanes[kLanes] = {};
     cudaEvent_t lane_ev[kLanes] = {};
     cudaEvent_t fork_ev = nullptr;
+    cudaStream_t side = nullptr;          // the direct cell kernel runs here, next to the recurrence kernel
+    cudaEvent_t side_fork = nullptr, side_join = nullptr;
     std::string prefix;   // scratch namespace of the stream currently being enqueued on
     int sms = 0;
     double *h_in = nullptr;   // page-locked staging of the single-series inputs
@@ -106,6 +108,9 @@ int workspace(Workspace **out)
         CU(cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking));
         CU(cudaDeviceGetAttribute(&w.sms, cudaDevAttrMultiProcessorCount, dev));
         CU(cudaEventCreateWithFlags(&w.fork_ev, cudaEventDisableTiming));
+        CU(cudaStreamCreateWithFlags(&w.side, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&w.side_fork, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&w.side_join, cudaEventDisableTiming));
         for (int i = 0; i < kLanes; ++i) {
             CU(cudaStreamCreateWithFlags(&w.lanes[i], cudaStreamNonBlocking));
             CU(cudaEventCreateWithFlags(&w.lane_ev[i], cudaEventDisableTiming));
@@ -231,10 +236,11 @@ int transform_device(Workspace *w, const double *d_ts, const double *d_ys, int64
         double *d_sums2 = nullptr;   // Foster: sums of the second pass (y := cos)
         if (foster && (rc = wsbuf(w, "sums2", (size_t)segs * (size_t)kNumSums * (size_t)ncell, &d_sums2))) return rc;
 
-        CU(launch_freq_setup(d_omega, nf, d_tau, nt, c, allow_rec, cut_bits, d_kappa, d_dcut, d_grid, d_rec_row, st));
-        CU(launch_unsorted_check(d_ts, n, d_unsorted, st));
-        CU(launch_tau_gap(d_ts, n, d_tau, nt, d_gap, st));
-        CU(cudaMemsetAsync(d_fix_count, 0, sizeof(unsigned int), st));
+        // tspan < 0 with a psd request: the span of the time axis is taken on the device, in the same launch
+        double *d_mm = nullptr;
+        if (d_psd && tspan < 0 && (rc = wsbuf(w, "minmax", 2, &d_mm))) return rc;
+        CU(launch_setup(d_omega, nf, d_tau, nt, d_ts, n, c, allow_rec, cut_bits, d_kappa, d_dcut, d_grid, d_rec_row, d_gap,
+                        d_unsorted, d_mm, st));   // also zeroes the unsorted flag and d_fix_count (adjacent ints)
         const bool dense = (flags & WWZB200_DENSE) != 0;
         for (int64_t k0 = 0; k0 < nf; k0 += nf_batch) {
             const int64_t nb = std::min<int64_t>(nf_batch, nf - k0);
@@ -245,11 +251,23 @@ int transform_device(Workspace *w, const double *d_ts, const double *d_ys, int64
                 CU(cudaEventCreate(&ev.b));
                 CU(cudaEventRecord(ev.a, st));
             }
+            // every frequency row belongs to one flavour (decided on the device), the two kernels write disjoint
+            // cells: they run side by side, so a launch that finds no row of its own costs nothing
+            const bool fork = allow_rec && w->prefix.empty();   // (the ragged batch already runs one stream per member)
+            cudaStream_t st_direct = fork ? w->side : st;
+            if (fork) {
+                CU(cudaEventRecord(w->side_fork, st));
+                CU(cudaStreamWaitEvent(w->side, w->side_fork, 0));
+            }
             if (allow_rec)
                 CU(launch_rec(rplan, d_ty, d_basis, d_ts, n, d_tau, nt, d_kappa, d_dcut, d_gap, d_unsorted, k0, nb, nf, segs,
                               seg_len, d_rec_row, d_grid, d_sums, st));
             CU(launch_cells(plan, d_ty, d_basis, d_ts, n, d_tau, nt, d_kappa, d_dcut, d_gap, d_unsorted, k0, nb, nf, dense, segs,
-                            seg_len, allow_rec ? d_rec_row : nullptr, d_grid, d_sums, st));
+                            seg_len, allow_rec ? d_rec_row : nullptr, d_grid, d_sums, st_direct));
+            if (fork) {
+                CU(cudaEventRecord(w->side_join, w->side));
+                CU(cudaStreamWaitEvent(st, w->side_join, 0));
+            }
             if (g_profile) {
                 CU(cudaEventRecord(ev.b, st));
                 g_events.push_back(ev);
@@ -258,11 +276,19 @@ int transform_device(Workspace *w, const double *d_ts, const double *d_ys, int64
                 // second pass of the same kernels over records built with y := cos(omega t): its "y sin" and
                 // "y cos" sums are sum(w c s) and sum(w c c), the two extra entries of Foster's normal matrix
                 CU(launch_basis(d_ts, d_ys, n, plan.n_pad, d_omega + k0, nb, d_ty, d_basis, false, true, st));
+                if (fork) {
+                    CU(cudaEventRecord(w->side_fork, st));
+                    CU(cudaStreamWaitEvent(w->side, w->side_fork, 0));
+                }
                 if (allow_rec)
                     CU(launch_rec(rplan, d_ty, d_basis, d_ts, n, d_tau, nt, d_kappa, d_dcut, d_gap, d_unsorted, k0, nb, nf, segs,
                                   seg_len, d_rec_row, d_grid, d_sums2, st));
                 CU(launch_cells(plan, d_ty, d_basis, d_ts, n, d_tau, nt, d_kappa, d_dcut, d_gap, d_unsorted, k0, nb, nf, dense,
-                                segs, seg_len, allow_rec ? d_rec_row : nullptr, d_grid, d_sums2, st));
+                                segs, seg_len, allow_rec ? d_rec_row : nullptr, d_grid, d_sums2, st_direct));
+                if (fork) {
+                    CU(cudaEventRecord(w->side_join, w->side));
+                    CU(cudaStreamWaitEvent(st, w->side_join, 0));
+                }
             }
         }
         if (foster) {
@@ -284,7 +310,7 @@ int transform_device(Workspace *w, const double *d_ts, const double *d_ys, int64
         } else {
             double *d_mm;
             if ((rc = wsbuf(w, "minmax", 2, &d_mm))) return rc;
-            CU(launch_minmax(d_ts, n, d_mm, st));
+            if (flags & WWZB200_FAITHFUL) CU(launch_minmax(d_ts, n, d_mm, st));   // (otherwise filled by launch_setup)
             CU(launch_psd_devspan(d_wwa, d_neffs, nt, nf, row_stride, d_mm, n, (double)psd_thr, d_psd, st));
         }
     }
@@ -416,13 +442,12 @@ int shared_axis_device(Workspace *w, const double *d_ts, const double *d_Y, int6
     if ((rc = wsbuf(w, "rec_row", (size_t)nf, &d_rec_row))) return rc;
     // point windows of the cell tiles: same relative 2^-100 cut as the single-series path; WWZB200_DENSE walks every point
     const double cut_bits = (flags & WWZB200_DENSE) ? HUGE_VAL : (flags & WWZB200_EXACT_WINDOW) ? 1081.0 : 100.0;
-    CU(launch_freq_setup(d_omega, nf, d_tau, nt, c, false, cut_bits, d_kappa, d_dcut, d_grid, d_rec_row, st));
-    CU(launch_basis_sc(d_ts, n, plan.n_pad, d_omega, nf, d_ty, d_basis, st));
-    CU(launch_rotation(d_tau, d_omega, nt, nf, d_rot, st));
-    CU(launch_unsorted_check(d_ts, n, d_unsorted, st));
     double *d_gap;
     if ((rc = wsbuf(w, "taugap", (size_t)nt, &d_gap))) return rc;
-    CU(launch_tau_gap(d_ts, n, d_tau, nt, d_gap, st));
+    CU(launch_setup(d_omega, nf, d_tau, nt, d_ts, n, c, false, cut_bits, d_kappa, d_dcut, d_grid, d_rec_row, d_gap,
+                    d_unsorted, nullptr, st));
+    CU(launch_basis_sc(d_ts, n, plan.n_pad, d_omega, nf, d_ty, d_basis, st));
+    CU(launch_rotation(d_tau, d_omega, nt, nf, d_rot, st));
     CU(launch_standardize_retile(d_Y, n, plan.n_pad, S, NS, (flags & WWZB200_STANDARDIZE) != 0, d_mu, d_sig, d_Yt, st));
     EventPair ev{nullptr, nullptr, (double)n * (double)ncell * (double)S};
     if (g_profile) {

@@ -60,6 +60,12 @@ cudaError_t launch_freq_setup(const double *d_omega, int64_t nf, const double *d
                               bool allow_rec, double cut_bits, double *d_kappa, double *d_dcut, double *d_grid,
                               unsigned char *d_rec_row, cudaStream_t st);
 
+// One launch for the whole preamble of a transform: launch_freq_setup + launch_tau_gap + launch_unsorted_check
+// (+ launch_minmax when d_minmax != NULL) and the reset of the two ints at d_flags (unsorted flag, fix counter).
+cudaError_t launch_setup(const double *d_omega, int64_t nf, const double *d_tau, int64_t nt, const double *d_ts, int64_t n,
+                         double c, bool allow_rec, double cut_bits, double *d_kappa, double *d_dcut, double *d_grid,
+                         unsigned char *d_rec_row, double *d_gap, int *d_flags, double *d_minmax, cudaStream_t st);
+
 // gap[j] = distance from tau[j] to the nearest sample of the sorted time axis (windows relative to the largest weight)
 cudaError_t launch_tau_gap(const double *d_ts, int64_t n, const double *d_tau, int64_t nt, double *d_gap, cudaStream_t st);
 

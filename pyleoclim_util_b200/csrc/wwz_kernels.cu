@@ -131,6 +131,139 @@ cudaError_t launch_tau_gap(const double *d_ts, int64_t n, const double *d_tau, i
     return cudaGetLastError();
 }
 
+// One launch for everything a transform needs before its basis rows: per-frequency constants (with the tau-grid
+// check done by every block for itself: nt is small), the tau-to-sample gaps, the sortedness flag of the time axis,
+// the min / max of the time axis (span of wwa2psd) and the reset of the deep-underflow counter.  Blocks pick their
+// job from blockIdx.  *flags (unsorted flag, fix counter) must be zeroed by the caller (one 8-byte memset).
+struct SetupArgs {
+    const double *omega, *tau, *ts;
+    long long nf, nt, n;
+    double kscale, vcut;
+    int allow_rec;
+    double *kappa, *dcut, *grid, *gap, *minmax;   // minmax may be null
+    unsigned char *rec_row;
+    int *unsorted;
+    int nfb, ngb, nub;                            // blocks per job: frequency setup, tau gaps, sortedness
+};
+
+__global__ void __launch_bounds__(256) setup_kernel(const SetupArgs a)
+{
+    __shared__ int bad;
+    __shared__ double slo[8], shi[8];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    if (b < a.nfb) {
+        // ---- tau grid (as tau_uniform_kernel), then this block's frequency rows (as freq_setup_kernel)
+        if (tid == 0) bad = 0;
+        __syncthreads();
+        double d = 0.0;
+        if (a.nt >= 2 * kRecCells) {
+            d = (a.tau[a.nt - 1] - a.tau[0]) / (double)(a.nt - 1);
+            const double scale = fmax(fabs(a.tau[0]), fabs(a.tau[a.nt - 1]));
+            const double tol = 8.0 * (scale > 0 ? scale : 1.0) * 0x1p-52;
+            if (!(d > 0) || isinf(d)) bad = 1;
+            for (long long j = tid; j < a.nt; j += blockDim.x)
+                if (!(fabs(a.tau[j] - (a.tau[0] + (double)j * d)) <= tol)) bad = 1;
+        } else if (tid == 0) {
+            bad = 1;
+        }
+        __syncthreads();
+        const bool uniform = bad == 0;
+        if (b == 0 && tid == 0) {
+            a.grid[0] = d;
+            a.grid[1] = uniform ? 1.0 : 0.0;
+        }
+        const long long k = (long long)b * blockDim.x + tid;
+        if (k < a.nf) {
+            const double om = a.omega[k];
+            const double ka = om * a.kscale;
+            a.kappa[k] = ka;
+            a.dcut[k] = isnan(om) ? -1.0 : a.vcut / fabs(ka);
+            a.rec_row[k] = (a.allow_rec && uniform && fabs(ka) * d <= 8.0) ? 1 : 0;
+        }
+        return;
+    }
+    if (b < a.nfb + a.ngb) {
+        // ---- distance from tau to the nearest sample (as tau_gap_kernel)
+        const long long j = (long long)(b - a.nfb) * blockDim.x + tid;
+        if (j >= a.nt) return;
+        const double tj = a.tau[j];
+        long long l = 0, r = a.n;
+        while (l < r) {
+            const long long m = (l + r) >> 1;
+            if (a.ts[m] < tj) l = m + 1; else r = m;
+        }
+        double g = CUDART_INF;
+        if (l < a.n) g = fabs(a.ts[l] - tj);
+        if (l > 0) g = fmin(g, fabs(tj - a.ts[l - 1]));
+        a.gap[j] = isnan(g) ? CUDART_INF : g;
+        return;
+    }
+    if (b < a.nfb + a.ngb + a.nub) {
+        // ---- sortedness of the time axis (as unsorted_kernel)
+        const long long i = (long long)(b - a.nfb - a.ngb) * blockDim.x + tid;
+        if (i + 1 < a.n && !(a.ts[i] <= a.ts[i + 1])) *a.unsorted = 1;
+        return;
+    }
+    // ---- last block: min / max of the time axis (as minmax_kernel)
+    double lo = CUDART_INF, hi = -CUDART_INF;
+    for (long long i = tid; i < a.n; i += blockDim.x) {
+        const double v = a.ts[i];
+        lo = fmin(lo, v);
+        hi = fmax(hi, v);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if ((tid & 31) == 0) {
+        slo[tid >> 5] = lo;
+        shi[tid >> 5] = hi;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < 8; ++w) {
+            lo = fmin(lo, slo[w]);
+            hi = fmax(hi, shi[w]);
+        }
+        a.minmax[0] = lo;
+        a.minmax[1] = hi;
+    }
+}
+
+cudaError_t launch_setup(const double *d_omega, int64_t nf, const double *d_tau, int64_t nt, const double *d_ts, int64_t n,
+                         double c, bool allow_rec, double cut_bits, double *d_kappa, double *d_dcut, double *d_grid,
+                         unsigned char *d_rec_row, double *d_gap, int *d_flags, double *d_minmax, cudaStream_t st)
+{
+    cudaError_t e = cudaMemsetAsync(d_flags, 0, 2 * sizeof(int), st);   // unsorted flag + deep-underflow counter
+    if (e != cudaSuccess) return e;
+    SetupArgs a{};
+    a.omega = d_omega;
+    a.tau = d_tau;
+    a.ts = d_ts;
+    a.nf = nf;
+    a.nt = nt;
+    a.n = n;
+    a.kscale = 4.0 * std::sqrt(c * 1.4426950408889634074);  // 4*sqrt(c*log2(e))
+    a.vcut = 4.0 * std::sqrt(cut_bits);
+    a.allow_rec = allow_rec ? 1 : 0;
+    a.kappa = d_kappa;
+    a.dcut = d_dcut;
+    a.grid = d_grid;
+    a.gap = d_gap;
+    a.minmax = d_minmax;
+    a.rec_row = d_rec_row;
+    a.unsorted = d_flags;
+    a.nfb = (int)((nf + 255) / 256);
+    a.ngb = (int)((nt + 255) / 256);
+    a.nub = n >= 2 ? (int)((n + 255) / 256) : 0;
+    const int blocks = a.nfb + a.ngb + a.nub + (d_minmax ? 1 : 0);
+    if (blocks <= 0) return cudaSuccess;
+    setup_kernel<<<(unsigned)blocks, 256, 0, st>>>(a);
+    bump_launch_counter();
+    return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------------
 // Basis rows.  theta = fl(omega*t) is the argument the reference passes to sin/cos
 // (utils/wavelet.py:1002-1003); the rounding residual of the product is folded back to first
