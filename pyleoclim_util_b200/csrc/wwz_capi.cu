@@ -368,7 +368,13 @@ int host_transform(const double *ts, const double *ys, int64_t n, const double *
     rc = transform_device(w, d_ts, d_ys, n, d_tau, nt, d_om, nf, c, thr, psd_thr, flags, o_neff, o_a0, o_a1, o_a2, o_wwa, o_ph, psd ? o_psd : nullptr, nf, tspan, st);
     if (rc) return rc;
     const size_t cb = sizeof(double) * (size_t)ncell;
-    if (ncell) {
+    // six outputs laid out back to back by the caller (one [6, nt, nf] block, as the Python layer allocates them):
+    // one DMA instead of six
+    const bool one_block = ncell && Neffs && a0 == Neffs + ncell && a1 == a0 + ncell && a2 == a1 + ncell &&
+                           wwa == a2 + ncell && phase == wwa + ncell;
+    if (one_block) {
+        CU(cudaMemcpyAsync(Neffs, o_neff, 6 * cb, cudaMemcpyDeviceToHost, st));
+    } else if (ncell) {
         if (Neffs) CU(cudaMemcpyAsync(Neffs, o_neff, cb, cudaMemcpyDeviceToHost, st));
         if (a0) CU(cudaMemcpyAsync(a0, o_a0, cb, cudaMemcpyDeviceToHost, st));
         if (a1) CU(cudaMemcpyAsync(a1, o_a1, cb, cudaMemcpyDeviceToHost, st));

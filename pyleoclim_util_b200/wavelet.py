@@ -193,7 +193,7 @@ def _transform(pd_ys, ts, tau, omega, c, Neff_threshold, flags=0, psd_threshold=
     if psd_only and psd_threshold is not None:
         Neffs = a0 = a1 = a2 = wwa = phase = None
     else:
-        Neffs, a0, a1, a2, wwa, phase = (alloc((nt, nf)) for _ in range(6))
+        Neffs, a0, a1, a2, wwa, phase = alloc((6, nt, nf))      # one block, the library's output order: one DMA
     if psd_threshold is None:
         _lib.check(L.wwzb200_kirchner(_lib.ptr(ts), _lib.ptr(pd_ys), ts.size, _lib.ptr(tau), nt, _lib.ptr(omega),
                                       nf, float(c), int(Neff_threshold), int(flags), _lib.ptr(Neffs), _lib.ptr(a0),
