@@ -115,14 +115,61 @@ def freq_vector_log(ts, fmin=None, fmax=None, nf=None):
     return np.logspace(np.log2(lo), np.log2(hi), n // 10 + 1 if nf is None else nf, base=2)
 
 
+def freq_vector_lomb_scargle(ts, dt=None, nf=None, ofac=4, hifac=0.95):
+    """REDFIT-style axis (utils/wavelet.py:1689-1742): from the Nyquist frequency over ``n*ofac`` up to ``hifac``
+    times the Nyquist frequency of the median (or given) sampling interval, in steps of the lowest frequency."""
+    assert ofac >= 1 and hifac <= 1, "`ofac` should be >= 1, and `hifac` should be <= 1"
+    step = np.median(np.diff(ts)) if dt is None else dt
+    lowest = (1 / (2 * step)) / (np.size(ts) * ofac)
+    highest = hifac / (2 * step)
+    count = int((highest - lowest) / lowest + 1) if nf is None else nf
+    return np.linspace(lowest, highest, count)
+
+
+def freq_vector_welch(ts):
+    """Welch / periodogram axis (utils/wavelet.py:1744-1787): ``k * fs / n`` for the non-negative FFT bins."""
+    n = np.size(ts)
+    fs = 1 / np.median(np.diff(ts))
+    bins = n // 2 + 1 if n % 2 == 0 else (n + 1) // 2
+    return np.arange(bins) * fs / n
+
+
+def freq_vector_nfft(ts):
+    """NFFT axis (utils/wavelet.py:1789-1823): ``n//2 + 1`` points from 0 to the Nyquist frequency."""
+    fs = 1 / np.median(np.diff(ts))
+    return np.linspace(0, fs / 2, np.size(ts) // 2 + 1)
+
+
+def freq_vector_scale(ts, dj=0.25, s0=None, j1=None, mother="MORLET", param=None):
+    """Torrence-Compo scale axis turned into frequencies (utils/wavelet.py:1825-1933): scales ``s0 * 2^(j dj)``,
+    ``j = 0..j1``, divided into the Fourier factor of the mother wavelet, ascending."""
+    kind = mother.upper()
+    if kind not in ("MORLET", "DOG", "PAUL"):
+        raise ValueError('The mother wavelet should be either "MORLET","PAUL", or "DOG"')
+    step = np.diff(ts).mean()
+    smallest = 2 * step if s0 is None else s0
+    last = np.fix((np.log(len(ts) * step / smallest) / np.log(2)) / dj) if j1 is None else j1
+    if kind == "MORLET":
+        k0 = 6. if param is None else param
+        factor = 4 * np.pi / (k0 + np.sqrt(2 + k0 ** 2))
+    elif kind == "PAUL":
+        m = 4. if param is None else param
+        factor = 4 * np.pi / (2 * m + 1)
+    else:
+        m = 2. if param is None else param
+        factor = 2 * np.pi * np.sqrt(2. / (2 * m + 1))
+    scales = smallest * 2. ** (np.arange(0, last + 1) * dj)
+    return np.sort(1. / (factor * scales))
+
+
 def make_freq_vector(ts, method="log", rayleigh_bound=True, **kwargs):
-    """utils/wavelet.py:1986-2049.  Only the 'log' generator (the default of wwz / wwz_psd) is mirrored; the
-    other generators belong to estimators outside this path."""
-    if method in ("lomb_scargle", "welch", "nfft", "scale"):
-        raise NotImplementedError("freq_method=%r is not on the WWZ hot path; pass freq explicitly" % method)
-    if method != "log":
+    """utils/wavelet.py:1986-2049: the frequency axis of ``wwz`` / ``wwz_psd`` by one of the reference's five
+    generators, cut at the Rayleigh frequency ``1/span`` unless ``rayleigh_bound`` is False."""
+    makers = {"lomb_scargle": freq_vector_lomb_scargle, "welch": freq_vector_welch, "nfft": freq_vector_nfft,
+              "scale": freq_vector_scale, "log": freq_vector_log}
+    if method not in makers:
         raise ValueError("This method is not supported")
-    fr = freq_vector_log(ts, **kwargs)
+    fr = makers[method](ts, **kwargs) if method in ("lomb_scargle", "scale", "log") else makers[method](ts)
     return fr[fr >= 1 / np.ptp(ts)] if rayleigh_bound else fr
 
 

@@ -166,6 +166,23 @@ def foster():
          s_y2=k2[3][1], s_y3=k2[3][2])
 
 
+def freq_vectors():
+    """make_freq_vector with each of the reference's generators (utils/wavelet.py:1689-2049), and a wwz run on one."""
+    t, y = synth.uneven_ar1(333, 51)
+    out = {"ts": t, "ys": y}
+    out["lomb_scargle"] = W.make_freq_vector(t, method="lomb_scargle")
+    out["lomb_scargle_ofac2_hifac05"] = W.make_freq_vector(t, method="lomb_scargle", ofac=2, hifac=0.5)
+    out["welch"] = W.make_freq_vector(t, method="welch")
+    out["nfft"] = W.make_freq_vector(t, method="nfft")
+    out["scale"] = W.make_freq_vector(t, method="scale")
+    out["scale_paul_dj05"] = W.make_freq_vector(t, method="scale", mother="PAUL", dj=0.5)
+    out["scale_dog"] = W.make_freq_vector(t, method="scale", mother="DOG")
+    out["log"] = W.make_freq_vector(t, method="log")
+    out["log_nf20_unbounded"] = W.make_freq_vector(t, method="log", nf=20, rayleigh_bound=False)
+    ref = run_wwz(y, t, freq_method="scale", ntau=9)
+    save("freq_vectors", wwz_scale_amplitude=ref["amplitude"], wwz_scale_freq=ref["freq"], wwz_scale_tau=ref["tau"], **out)
+
+
 def uar1():
     """uar1_fit / uar1_sim / the likelihood (utils/tsmodel.py:612-716) with NumPy's legacy global RNG; the
     innovation matrices are stored so that a restatement can be checked draw for draw."""
@@ -209,6 +226,6 @@ def cleaning():
 
 if __name__ == "__main__":
     which = sys.argv[1:] or ["benthic", "soi", "synth_small", "edge", "c2_subsample", "c5_sample",
-                             "surrogates", "uar1", "foster", "cleaning"]
+                             "surrogates", "uar1", "foster", "freq_vectors", "cleaning"]
     for name in which:
         globals()[name]()

@@ -83,6 +83,15 @@ def test_edge_three_state_mask():
     assert np.isnan(out[2]).sum() == 13 and np.isnan(out[0]).sum() == 19
 
 
+def test_wwz_on_a_scale_based_frequency_axis():
+    """freq_method='scale' (Torrence-Compo scales, utils/wavelet.py:1825-1933) through the whole front end."""
+    g = golden("freq_vectors")
+    r = WV.wwz(g["ys"], g["ts"], freq_method="scale", ntau=9)      # ntau is accepted and unused, like in the reference
+    assert np.array_equal(r.freq, g["wwz_scale_freq"]) and np.array_equal(r.time, g["wwz_scale_tau"])
+    assert_same_nan_mask(r.amplitude, g["wwz_scale_amplitude"])
+    assert max_rel(r.amplitude, g["wwz_scale_amplitude"]) < 1e-9
+
+
 def test_cleaning_inputs():
     g = golden("cleaning")
     r = WV.wwz(g["ys"], g["ts"], tau=g["tau_in"])

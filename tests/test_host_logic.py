@@ -115,3 +115,27 @@ def test_no_gpu_means_error_not_fallback():
     from pyleoclim_util_b200 import _lib
     with pytest.raises(_lib.WwzB200Error):
         WV.wwz(y, t)
+
+
+def test_make_freq_vector_all_generators_match_the_reference():
+    """utils/wavelet.py:1689-2049: the five frequency-axis generators bit for bit against outputs of the reference
+    (tests/golden/freq_vectors.npz), the Rayleigh bound, and the errors."""
+    import os
+    from pyleoclim_util_b200 import wavelet as WV
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "freq_vectors.npz"))
+    t = g["ts"]
+    cases = {"lomb_scargle": dict(method="lomb_scargle"),
+             "lomb_scargle_ofac2_hifac05": dict(method="lomb_scargle", ofac=2, hifac=0.5),
+             "welch": dict(method="welch"), "nfft": dict(method="nfft"), "scale": dict(method="scale"),
+             "scale_paul_dj05": dict(method="scale", mother="PAUL", dj=0.5), "scale_dog": dict(method="scale", mother="DOG"),
+             "log": dict(method="log"), "log_nf20_unbounded": dict(method="log", nf=20, rayleigh_bound=False)}
+    for name, kw in cases.items():
+        assert np.array_equal(WV.make_freq_vector(t, **kw), g[name]), name
+    with pytest.raises(ValueError):
+        WV.make_freq_vector(t, method="fft")
+    with pytest.raises(ValueError):
+        WV.make_freq_vector(t, method="scale", mother="HAAR")
+    with pytest.raises(AssertionError):
+        WV.make_freq_vector(t, method="lomb_scargle", ofac=0.5)
+    ys_cut, ts_cut, freq, tau = WV.prepare_wwz(g["ys"], t, freq_method="scale", tau=g["wwz_scale_tau"])
+    assert np.array_equal(freq, g["wwz_scale_freq"])
