@@ -139,19 +139,21 @@ size_t basis_budget_bytes()
     return (size_t)2 << 30;
 }
 
-// Number of point-axis segments: enough that (cells x segments) fills the machine for several waves
-// (1.0e6 cell-slots; config 2 runs 2 segments: 2 and 3 tie on the c = 1/(8 pi^2) transform, 2 wins by 4% on the
-// c = 1e-3 one and leaves the epilogue one slab less to add), each segment at least 256 points.
-// It depends on the problem size only, never on the tile geometry, so every kernel variant adds
-// the same partial sums.
-int point_segments(int64_t n, int64_t ncell)
+// Number of point-axis segments: enough that (cells x segments) fills the machine for several waves, each segment
+// at least 256 points.  Target 1.5e6 cell-slots when only the direct kernel runs (10 waves x 296 CTAs x 512 cells:
+// measured best on config 2, dense) and 1.0e6 when the warp-tile recurrence kernel takes the rows (its tiles are
+// smaller: config 2 then runs 2 segments, which ties with 3 on the c = 1/(8 pi^2) transform, wins by 4% on the
+// c = 1e-3 one and leaves the epilogue one slab less to add).  It depends on the problem size and on the flags
+// only, never on the tile geometry, so every variant of a kernel adds the same partial sums.
+int point_segments(int64_t n, int64_t ncell, bool recurrence)
 {
     const char *e = getenv("WWZB200_POINT_SEGMENTS");
     int64_t s;
     if (e && *e) {
         s = atoll(e);
     } else {
-        s = (1000000 + ncell - 1) / std::max<int64_t>(ncell, 1);
+        const int64_t target = recurrence ? 1000000 : 1500000;
+        s = (target + ncell - 1) / std::max<int64_t>(ncell, 1);
         s = std::min<int64_t>(s, n / 256);
     }
     return (int)std::max<int64_t>(1, std::min<int64_t>(s, 4096));
@@ -202,9 +204,6 @@ int transform_device(Workspace *w, const double *d_ts, const double *d_ys, int64
             CU(launch_faithful(d_ts, d_ys, n, d_tau, d_omega, nt, nf, c, (double)thr, nullptr, nullptr, 0, d_neffs, d_a0,
                                d_a1, d_a2, d_wwa, d_phase, row_stride, w->sms, st));
     } else {
-        const int segs = point_segments(n, ncell);
-        const int64_t seg_len = (((n + segs - 1) / segs + 15) / 16) * 16;
-        CellPlan plan = plan_cells(n, nt, nf, cells_per_lane_hint(nt, nf, w->sms), seg_len);
         // rows with kappa4*dtau <= 8 on an equally spaced tau axis go to the tau-recurrence kernel; the
         // decision is taken per row on the device (freq_setup), both flavours are launched over all rows
         // and every CTA keeps only the rows that are its own
@@ -213,6 +212,9 @@ int transform_device(Workspace *w, const double *d_ts, const double *d_ys, int64
             const char *e = getenv("WWZB200_NO_RECURRENCE");
             if (e && *e && atoi(e)) allow_rec = false;
         }
+        const int segs = point_segments(n, ncell, allow_rec);
+        const int64_t seg_len = (((n + segs - 1) / segs + 15) / 16) * 16;
+        CellPlan plan = plan_cells(n, nt, nf, cells_per_lane_hint(nt, nf, w->sms), seg_len);
         RecPlan rplan{};
         if (allow_rec) {
             rplan = plan_rec(n, nt, nf, seg_len);
@@ -850,7 +852,7 @@ int wwzb200_kirchner_ragged(const double *ts, const double *pd_ys, const int64_t
         max_n = std::max(max_n, n);
         max_nf = std::max(max_nf, nf);
         max_basis = std::max(max_basis, nf * (n + wwz::kMaxPointsPerStage + 16));
-        max_sums = std::max(max_sums, (int64_t)point_segments(n, nt * nf) * wwz::kNumSums * nt * nf);
+        max_sums = std::max(max_sums, (int64_t)point_segments(n, nt * nf, false) * wwz::kNumSums * nt * nf);
     }
     std::lock_guard<std::mutex> lock(g_mu);
     Workspace *w;
