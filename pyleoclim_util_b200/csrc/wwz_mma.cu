@@ -106,6 +106,29 @@ __device__ __forceinline__ void tile_window(const MmaArgs &a, int k_base, int ro
     }
 }
 
+// The chunks of the tile's window that matter to ONE warp (8 frequency rows at one tau): its own relative window,
+// [tau - de, tau + de] with de from the widest dcut of its rows and the gap of its tau.  A warp skips the arithmetic
+// of the staged chunks outside it (high-frequency tiles: the 4-tau, 16-row window of the CTA is several times wider
+// than what one warp needs).  Returns chunk indices [lo, hi) on the whole axis; all lanes get the same values.
+__device__ __forceinline__ void warp_window(const MmaArgs &a, int kc, int jc, bool row_ok, int lane, int &lo, int &hi)
+{
+    double dc = row_ok ? a.dcut[kc] : -1.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dc = fmax(dc, __shfl_xor_sync(0xffffffffu, dc, o));
+    lo = 0;
+    hi = (int)((a.n + a.P - 1) / a.P);
+    if (dc < 0.0) {
+        hi = 0;                                   // NaN rows only
+    } else if (!*a.unsorted && dc < CUDART_INF) {
+        const double tj = a.tau[jc], gp = a.taugap[jc];
+        const double de = sqrt(fma(gp, gp, dc * dc));
+        const long long i0 = warp_bound<false>(a.ts, 0, a.n, tj - de, lane);
+        const long long i1 = warp_bound<true>(a.ts, i0, a.n, tj + de, lane);
+        lo = (int)(i0 / a.P);
+        hi = i1 > i0 ? (int)((i1 + a.P - 1) / a.P) : lo;
+    }
+}
+
 // Stored-weights mode, pass 1: the A fragments of every tile, once for all series blocks.  Same tile geometry,
 // window and lane mapping as the contraction kernel (8 warps, no staging: the operands are read straight from
 // global memory, L2 resident), plus the y-independent sums W, Q, Ws, Wc, Neff of every cell.
@@ -132,7 +155,10 @@ __global__ void __launch_bounds__(kMmaWarps * 32) wwz_tile_weights_kernel(const 
     const double2 *const brow = a.basis + (size_t)kc * (size_t)a.n_pad;
     double *const wout = a.wfrag + (size_t)blockIdx.x * (size_t)a.wf_tile_stride + (size_t)warp * (size_t)(P / 4) * 32 + lane;
     double W = 0.0, Q = 0.0, Ws = 0.0, Wc = 0.0;
+    int cw_lo, cw_hi;
+    warp_window(a, kc, jc, k < a.nf, lane, cw_lo, cw_hi);
     for (int i = 0; i < nchunks; ++i) {
+        if (c_lo + i < cw_lo || c_lo + i >= cw_hi) continue;     // outside this warp's own window: never read either
         const long long base = (long long)(c_lo + i) * P;
         double *const wo = wout + (size_t)(c_lo + i) * (size_t)P * 64;
 #pragma unroll 4
@@ -246,10 +272,18 @@ __global__ void __launch_bounds__(kMmaThreads, 1) wwz_shared_mma_kernel(const Mm
 #pragma unroll
     for (int m = 0; m < NT; ++m) Cy[m][0] = Cy[m][1] = Cs[m][0] = Cs[m][1] = Cc[m][0] = Cc[m][1] = 0.0;
 
+    int cw_lo, cw_hi;
+    warp_window(a, kc, jc, k < a.nf, lane, cw_lo, cw_hi);
     {
         int s = 0, use = 0;
         for (int i = 0; i < nchunks; ++i) {
             mbar_wait(&full[s], (uint32_t)use & 1u);
+            if (c_lo + i < cw_lo || c_lo + i >= cw_hi) {       // staged for the tile, outside this warp's own window
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[s]);
+                if (++s == kMmaStages) { s = 0; ++use; }
+                continue;
+            }
             const double2 *const st = stage_base + (size_t)s * a.stage_stride2;
             const double2 *const row = st + row_off;
             const double *const yv = reinterpret_cast<const double *>(st + a.y_off2) + r;
