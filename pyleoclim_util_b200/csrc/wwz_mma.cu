@@ -35,6 +35,9 @@
 namespace wwz {
 
 constexpr int kMmaStages = 4;
+// 2 x 4 (16 rows x 4 taus).  4 x 2 (32 rows x 2 taus: the four row groups of a tau on the four SMSPs) was measured 2%
+// faster on one GPU (config 3: 120.2 against 122.6 ms) but halves the granularity of the frequency sharding
+// (distributed.balanced_freq_groups): the slowest of 8 shares went from 17.5 to 20.1 ms.
 constexpr int kMmaWF = 2;                       // warps along the frequency axis
 constexpr int kMmaWT = 4;                       // warps along the tau axis
 constexpr int kMmaRows = 8 * kMmaWF;            // frequency rows of a CTA tile
