@@ -247,6 +247,7 @@ def run_ours(args):
     wall = time.perf_counter() - wall0
     launches = _lib.launch_count() - launches0
     cell_ms, cell_launches, cell_points = _lib.profile_read()
+    walked = _lib.profile_walked()     # (warp, point) pairs the recurrence kernel evaluated in the timed region
     _lib.profile(False)
 
     # roofline leg: the same two transforms with WWZB200_DENSE (every (cell, point) pair evaluated, nothing
@@ -441,6 +442,8 @@ def run_ours(args):
         del d5, o5
 
     clocks = sampler.stop()
+    sm_count = _lib.sm_count()
+    sm_hz = (clocks.get("sm_mhz") or 0) * 1e6
 
     # ---------------------------------------------------------------- roofline + CPU baseline
     achieved_tf = FLOP_PER_CELL_POINT * dense_points / (dense_ms * 1e-3) / 1e12 if dense_ms > 0 else None
@@ -454,7 +457,16 @@ def run_ours(args):
                 "avg_launch_ms": dense_ms / max(dense_launches, 1),
                 "timed_region": {"launches": cell_launches, "avg_launch_ms": cell_ms / max(cell_launches, 1),
                                  "algorithmic_tflops_incl_skipped_points": windowed_tf,
-                                 "kernel_share_of_step": cell_ms / dev_ms if dev_ms else None},
+                                 "kernel_share_of_step": cell_ms / dev_ms if dev_ms else None,
+                                 "kernel": "wwz_rec_kernel (tau-recurrence, point windows) + wwz_cells_kernel side by side",
+                                 "warp_points_evaluated": walked,
+                                 "fraction_of_dense_warp_points": walked / (cell_points / 8 / 32) if cell_points else None,
+                                 "executed_fp64_instr_per_warp_point": 88,
+                                 "fp64_pipe_utilisation": (walked * 88 / (cell_ms * 1e-3) / (sm_count * 2 * sm_hz))
+                                 if cell_ms > 0 and sm_hz else None,
+                                 "fp64_pipe_note": "executed FP64 instructions (88 per (warp, point) of 8 tau-adjacent cells, "
+                                 "counted in the SASS loop body) / kernel time / (2 warp instructions per clock per SM at the "
+                                 "sampled SM clock): the live counterpart of ncu's sm__inst_executed_pipe_fp64"},
                 "executed_fp64_instr_per_cell_point": 19,
                 "note": "frac is for the direct kernel (one exp2 per (cell, point)); the timed region runs the tau-recurrence "
                         "kernel, which shares one exp2 pair between 8 tau-adjacent cells (about 11 FP64 instructions per "

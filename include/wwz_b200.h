@@ -211,6 +211,10 @@ int64_t wwzb200_launch_count(void);
  * number of launches and the (cell, point) pairs they covered. */
 int wwzb200_profile(int enable);
 int wwzb200_profile_read(double *cell_kernel_ms, int64_t *cell_kernel_launches, double *cell_points);
+/* While profiling: the number of (warp, point) pairs the tau-recurrence kernel actually evaluated since
+ * wwzb200_profile(1) (point windows skip the rest).  Times the 88 FP64 instructions of its loop body per pair, this
+ * is the executed FP64 instruction count -- the live counterpart of ncu's sm__inst_executed_pipe_fp64. */
+int wwzb200_profile_walked(double *warp_points);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

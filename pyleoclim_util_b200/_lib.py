@@ -71,6 +71,7 @@ _SIGS = {
     "wwzb200_launch_count": (_i64, []),
     "wwzb200_profile": (ctypes.c_int, [ctypes.c_int]),
     "wwzb200_profile_read": (ctypes.c_int, [_dp, ctypes.POINTER(_i64), _dp]),
+    "wwzb200_profile_walked": (ctypes.c_int, [_dp]),
 }
 
 
@@ -149,6 +150,13 @@ def profile_read():
     ms, n, cp = ctypes.c_double(), _i64(), ctypes.c_double()
     check(lib().wwzb200_profile_read(ctypes.byref(ms), ctypes.byref(n), ctypes.byref(cp)))
     return ms.value, int(n.value), cp.value
+
+
+def profile_walked():
+    """(warp, point) pairs evaluated by the tau-recurrence kernel since profile(True)."""
+    v = ctypes.c_double()
+    check(lib().wwzb200_profile_walked(ctypes.byref(v)))
+    return v.value
 
 
 def _free_pinned(addr):

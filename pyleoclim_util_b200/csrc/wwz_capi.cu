@@ -215,6 +215,8 @@ int transform_device(Workspace *w, const double *d_ts, const double *d_ys, int64
         const int segs = point_segments(n, ncell, allow_rec);
         const int64_t seg_len = (((n + segs - 1) / segs + 15) / 16) * 16;
         CellPlan plan = plan_cells(n, nt, nf, cells_per_lane_hint(nt, nf, w->sms), seg_len);
+        unsigned long long *d_walked = nullptr;   // profiling: warp-points evaluated by the recurrence kernel
+        if (g_profile && (rc = wsbuf(w, "walked", 1, &d_walked))) return rc;
         RecPlan rplan{};
         if (allow_rec) {
             rplan = plan_rec(n, nt, nf, seg_len);
@@ -263,7 +265,7 @@ int transform_device(Workspace *w, const double *d_ts, const double *d_ys, int64
             }
             if (allow_rec)
                 CU(launch_rec(rplan, d_ty, d_basis, d_ts, n, d_tau, nt, d_kappa, d_dcut, d_gap, d_unsorted, k0, nb, nf, segs,
-                              seg_len, d_rec_row, d_grid, d_sums, st));
+                              seg_len, d_rec_row, d_grid, d_sums, d_walked, st));
             CU(launch_cells(plan, d_ty, d_basis, d_ts, n, d_tau, nt, d_kappa, d_dcut, d_gap, d_unsorted, k0, nb, nf, dense, segs,
                             seg_len, allow_rec ? d_rec_row : nullptr, d_grid, d_sums, st_direct));
             if (fork) {
@@ -284,7 +286,7 @@ int transform_device(Workspace *w, const double *d_ts, const double *d_ys, int64
                 }
                 if (allow_rec)
                     CU(launch_rec(rplan, d_ty, d_basis, d_ts, n, d_tau, nt, d_kappa, d_dcut, d_gap, d_unsorted, k0, nb, nf, segs,
-                                  seg_len, d_rec_row, d_grid, d_sums2, st));
+                                  seg_len, d_rec_row, d_grid, d_sums2, nullptr, st));
                 CU(launch_cells(plan, d_ty, d_basis, d_ts, n, d_tau, nt, d_kappa, d_dcut, d_gap, d_unsorted, k0, nb, nf, dense,
                                 segs, seg_len, allow_rec ? d_rec_row : nullptr, d_grid, d_sums2, st_direct));
                 if (fork) {
@@ -996,6 +998,14 @@ int wwzb200_profile(int enable)
 {
     std::lock_guard<std::mutex> lock(g_mu);
     g_profile = enable != 0;
+    if (g_profile) {   // the walked-points counter of the recurrence kernel restarts with the events
+        Workspace *w;
+        unsigned long long *d_walked;
+        int rc;
+        if ((rc = workspace(&w))) return rc;
+        if ((rc = wsbuf(w, "walked", 1, &d_walked))) return rc;
+        CU(cudaMemset(d_walked, 0, sizeof(unsigned long long)));
+    }
     for (auto &e : g_events) {
         cudaEventDestroy(e.a);
         cudaEventDestroy(e.b);
@@ -1019,6 +1029,21 @@ int wwzb200_profile_read(double *cell_kernel_ms, int64_t *cell_kernel_launches, 
     *cell_kernel_ms = ms;
     *cell_kernel_launches = (int64_t)g_events.size();
     *cell_points = cp;
+    return 0;
+}
+
+int wwzb200_profile_walked(double *warp_points)
+{
+    if (!warp_points) return fail(WWZB200_ERR_ARG, "null pointer");
+    std::lock_guard<std::mutex> lock(g_mu);
+    Workspace *w;
+    unsigned long long *d_walked, h = 0;
+    int rc;
+    if ((rc = workspace(&w))) return rc;
+    if ((rc = wsbuf(w, "walked", 1, &d_walked))) return rc;
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(&h, d_walked, sizeof h, cudaMemcpyDeviceToHost));
+    *warp_points = (double)h;
     return 0;
 }
 

@@ -49,7 +49,7 @@ cudaError_t launch_rec(const RecPlan &plan, const double2 *d_ty, const double2 *
                        const double *d_tau, int64_t nt, const double *d_kappa, const double *d_dcut,
                        const double *d_taugap, const int *d_unsorted, int64_t k0, int64_t nf_batch, int64_t nf_total, int segs,
                        int64_t seg_len, const unsigned char *d_rec_row, const double *d_grid, double *d_sums,
-                       cudaStream_t st);
+                       unsigned long long *d_walked, cudaStream_t st);
 
 // Per-frequency constants: kappa = omega*sqrt(c*log2 e), dcut = underflow distance (windowing).
 // Also decides on the device which rows the tau-recurrence kernel may take (d_rec_row) and the tau

@@ -38,6 +38,7 @@ struct RecArgs {
     const unsigned char *rec_row;
     const double *grid;
     double *sums;
+    unsigned long long *walked;   // profiling only (may be null): (lane, point) pairs actually evaluated, summed over warps
     long long n, n_pad, ncell_total, seg_len, ntiles;
     int nt, G, nf_batch, k0, nf_total, P, tg_log2, tiles_g;
     int row_stride2;     // basis row stride inside a stage, double2 units
@@ -181,6 +182,10 @@ __global__ void __launch_bounds__(kRecWarps * 32, 3) wwz_rec_kernel(const RecArg
         if (++s == kStages) { s = 0; phase ^= 1u; }
     }
 
+    if (a.walked && lane == 0 && nchunks > 0) {
+        const long long first = (long long)c_lo * P, last = min(p1 - p0, (long long)(c_lo + nchunks) * P);
+        atomicAdd(a.walked, (unsigned long long)(last - first));
+    }
     if (ok) {
         const long long kcol = (long long)a.k0 + kb;
         const double D = kap * dtau;
@@ -235,7 +240,7 @@ cudaError_t launch_rec(const RecPlan &plan, const double2 *d_ty, const double2 *
                        const double *d_tau, int64_t nt, const double *d_kappa, const double *d_dcut,
                        const double *d_taugap, const int *d_unsorted, int64_t k0, int64_t nf_batch, int64_t nf_total, int segs,
                        int64_t seg_len, const unsigned char *d_rec_row, const double *d_grid, double *d_sums,
-                       cudaStream_t st)
+                       unsigned long long *d_walked, cudaStream_t st)
 {
     if (nf_batch <= 0 || nt <= 0) return cudaSuccess;
     RecArgs a{};
@@ -250,6 +255,7 @@ cudaError_t launch_rec(const RecPlan &plan, const double2 *d_ty, const double2 *
     a.rec_row = d_rec_row;
     a.grid = d_grid;
     a.sums = d_sums;
+    a.walked = d_walked;
     a.n = n;
     a.n_pad = plan.n_pad;
     a.ncell_total = nt * nf_total;
