@@ -311,6 +311,48 @@ def test_time_origin_shift_invariance_of_amplitude():
     assert max_rel(b[0], a[0]) < 1e-9
 
 
+def test_wwa2psd_parts_of_tau_blocks_add_up_to_the_whole():
+    """wwzb200_wwa2psd_parts_dev (the tau-sharded wwz_psd): the column sums of the blocks of a tau partition, added and
+    divided, are the wwa2psd of the whole scalogram (utils/wavelet.py:1270-1278) -- NaN cells and masked cells included."""
+    torch = pytest.importorskip("torch")
+    t, y, tau, freq = _grid_case(n=1200, nt=77, nf=41)
+    r = WV.wwz(y, t, tau=tau, freq=freq, c=1e-3)
+    ref = WV.wwa2psd(r.amplitude, t, r.Neffs, freq=freq, Neff_threshold=3)
+    orc = oracle().wwa2psd(r.amplitude, t, r.Neffs, Neff_threshold=3)
+    assert max_rel(ref, orc) < 1e-13
+    dev = torch.device("cuda:0")
+    st = torch.cuda.current_stream().cuda_stream
+    L = _lib.lib()
+    total = torch.zeros((2, freq.size), dtype=torch.float64, device=dev)
+    for a, b in ((0, 30), (30, 31), (31, 77)):
+        wwa = torch.from_numpy(np.ascontiguousarray(r.amplitude[a:b])).to(dev)
+        ne = torch.from_numpy(np.ascontiguousarray(r.Neffs[a:b])).to(dev)
+        parts = torch.empty((2, freq.size), dtype=torch.float64, device=dev)
+        _lib.check(L.wwzb200_wwa2psd_parts_dev(wwa.data_ptr(), ne.data_ptr(), b - a, freq.size, float(t.max() - t.min()),
+                                               t.size, 3, parts.data_ptr(), st))
+        total += parts
+    got = (total[0] / total[1]).cpu().numpy()
+    assert np.array_equal(np.isnan(got), np.isnan(ref)) and max_rel(got, ref) < 1e-13
+
+
+def test_profile_counts_the_points_the_recurrence_kernel_walks():
+    """wwzb200_profile_walked: with point windows the recurrence kernel evaluates fewer (warp, point) pairs than the
+    dense count n * ntau/8 * nf / 32, never more, and none when the recurrence is switched off."""
+    t, y, tau, freq = synth.config_grid("C2")
+    ys = WV.standardize(y)[0]
+    om = WV.make_omega(t, freq)
+    dense = t.size * (tau.size / 8) * freq.size / 32
+    _lib.profile(True)
+    WV._transform(ys, t, tau, om, 1 / (8 * np.pi ** 2), 3)
+    walked = _lib.profile_walked()
+    _lib.profile(False)
+    assert 0.3 * dense < walked <= 1.05 * dense
+    _lib.profile(True)
+    WV._transform(ys, t, tau, om, 1 / (8 * np.pi ** 2), 3, flags=_lib.NO_RECURRENCE)
+    assert _lib.profile_walked() == 0
+    _lib.profile(False)
+
+
 # ------------------------------------------------------------------ device-pointer entry point
 def test_dev_entry_point_matches_host_entry_point():
     torch = pytest.importorskip("torch")
