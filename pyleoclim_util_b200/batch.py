@@ -146,15 +146,34 @@ def wwz_ragged(members, c=1 / (8 * np.pi ** 2), Neff_threshold=3, standardize=Tr
     members : iterable of ``(ys, ts, tau, freq)`` (already prepared with ``prepare_wwz``).
     Returns a list of ``wavelet.wwz``-style Results (plus ``.psd`` lists when requested)."""
     _wv.assertPositiveInt(Neff_threshold)
-    ys_l, ts_l, tau_l, om_l, fr_l = [], [], [], [], []
-    for ys, ts, tau, freq in members:
-        ts = _lib.f64(ts)
-        ys = _wv.preprocess(_lib.f64(ys), ts, standardize=standardize)
-        ys_l.append(_lib.f64(ys))
-        ts_l.append(ts)
-        tau_l.append(_lib.f64(tau))
-        fr_l.append(_lib.f64(freq))
-        om_l.append(_wv.make_omega(ts, fr_l[-1]))
+    members = list(members)
+    ts_l = [_lib.f64(m[1]) for m in members]
+    tau_l = [_lib.f64(m[2]) for m in members]
+    fr_l = [_lib.f64(m[3]) for m in members]
+    same_n = len(members) > 1 and len({t.size for t in ts_l}) == 1 and ts_l[0].size > 1 \
+        and all(np.ndim(m[0]) == 1 and np.size(m[0]) == ts_l[0].size for m in members)
+    if same_n:
+        # equal-length members (an age ensemble): z-scores and Nyquist frequencies of all members in one pass each,
+        # row by row the same arithmetic as wavelet.standardize / wavelet.make_omega
+        T = np.stack(ts_l)
+        Ymat = np.stack([_lib.f64(m[0]) for m in members])
+        if standardize:
+            mu, sig = Ymat.mean(axis=1), Ymat.std(axis=1)
+            if np.isnan(sig).any():
+                mu, sig = np.nanmean(Ymat, axis=1), np.nanstd(Ymat, axis=1)
+            flat = np.abs(sig) < 1e-3
+            if flat.any():
+                import warnings
+                warnings.warn("Constant or nearly constant time series not rescaled.", stacklevel=2)
+            Ymat = (Ymat - np.where(flat, 0.0, mu)[:, None]) / np.where(flat, 1.0, sig)[:, None]
+        ys_l = list(Ymat)
+        nyq = 0.5 / np.median(np.diff(T, axis=1), axis=1)
+        om_l = [2 * np.pi * np.where(f > q, np.nan, f) for f, q in zip(fr_l, nyq)]
+    else:
+        ys_l, om_l = [], []
+        for (ys, _, _, _), ts, fr in zip(members, ts_l, fr_l):
+            ys_l.append(_lib.f64(_wv.preprocess(_lib.f64(ys), ts, standardize=standardize)))
+            om_l.append(_wv.make_omega(ts, fr))
     M = len(ts_l)
     off = lambda xs: np.concatenate([[0], np.cumsum([x.size for x in xs])]).astype(np.int64)
     ts_off, tau_off, om_off = off(ts_l), off(tau_l), off(om_l)
@@ -168,11 +187,22 @@ def wwz_ragged(members, c=1 / (8 * np.pi ** 2), Neff_threshold=3, standardize=Tr
         _lib.iptr(om_off), _lib.iptr(out_off), M, float(c), int(Neff_threshold), int(psd_Neff_threshold or 0),
         int(flags), *[_lib.ptr(o) for o in outs], _lib.ptr(psd)))
     res = []
+    coi_l = None
+    if M > 1 and len({a.size for a in tau_l}) == 1 and tau_l[0].size > 1:
+        # equal-length tau axes: the cones of influence of all members at once (utils/wavelet.py:1168-1208)
+        nt0 = tau_l[0].size
+        efold = 4 * np.pi / (3 + np.sqrt(2 + 3 ** 2)) / np.sqrt(2)
+        step = np.median(np.diff(np.stack(tau_l), axis=1), axis=1)
+        idx = np.arange(nt0)
+        tent = np.minimum(idx, nt0 - 1 - idx).astype(float)
+        tent[tent == 0] = 0.00001
+        coi_l = efold * step[:, None] * tent[None, :]
     for m in range(M):
         nt, nf = tau_l[m].size, om_l[m].size
         sl = slice(int(out_off[m]), int(out_off[m + 1]))
         Neffs, a0, a1, a2, wwa, phase = (o[sl].reshape(nt, nf) for o in outs)
-        r = _wv.WwzResults(amplitude=wwa, phase=phase, coi=_wv.make_coi(tau_l[m]) if nt > 1 else None, freq=fr_l[m],
+        coi = coi_l[m] if coi_l is not None else (_wv.make_coi(tau_l[m]) if nt > 1 else None)
+        r = _wv.WwzResults(amplitude=wwa, phase=phase, coi=coi, freq=fr_l[m],
                            time=tau_l[m], Neffs=Neffs, coeff=(a0, a1, a2), scale=1 / fr_l[m])
         res.append(r)
     if psd is not None:

@@ -172,6 +172,27 @@ def test_ragged_members_match_single_calls():
         assert max_rel(p, ps) < 1e-13
 
 
+def test_ragged_equal_length_members_take_the_vectorised_host_path():
+    """Age-ensemble shape (config 4): same values and length, own time axis per member.  The host side z-scores all
+    members, takes their Nyquist frequencies and cones of influence in one pass each; results equal single calls."""
+    axes, y = synth.age_ensemble(300, 12)
+    members = []
+    for tm in axes:
+        ys_c, ts_c, fr_c, ta_c = WV.prepare_wwz(y, tm)
+        members.append((ys_c, ts_c, ta_c, fr_c))
+    res, psds = B.wwz_ragged(members, psd_Neff_threshold=3)
+    assert len(res) == 12
+    for (ys_c, ts_c, ta_c, fr_c), r, p in zip(members, res, psds):
+        one = WV.kirchner_cuda(ys_c, ts_c, fr_c, ta_c, standardize=True)
+        assert_same_nan_mask(r.amplitude, one[0])
+        assert max_rel(r.amplitude, one[0]) < 1e-12 and max_rel(r.Neffs, one[2]) < 1e-13
+        assert np.array_equal(r.coi, WV.make_coi(ta_c)) and np.array_equal(r.time, ta_c)
+        assert max_rel(p, WV.wwa2psd(one[0], ts_c, one[2], Neff_threshold=3)) < 1e-12
+    flat = [(np.full(50, 2.0), np.arange(50.0), np.linspace(0, 49, 5), np.array([0.05, 0.1]))] * 2
+    with pytest.warns(UserWarning):
+        B.wwz_ragged(flat)                                   # constant series: left unscaled, with the warning
+
+
 # ------------------------------------------------------------------ quantiles
 @pytest.mark.parametrize("S", [1, 2, 3, 10, 200, 1000, 20000])
 def test_quantiles_match_scipy_mquantiles(S):
