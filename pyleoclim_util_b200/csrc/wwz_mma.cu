@@ -13,14 +13,21 @@
 // 4 points, lane (r = lane/4, p = lane%4) evaluates the weight of (cell r, point p) -- that IS the A fragment
 // of mma.sync.m8n8k4.f64 (row = lane/4, k = lane%4), no shuffles -- and issues 3*NS/8 DMMAs against the B
 // fragments Y[p][8t + lane/4] read from the staged series tile.  W, Q, Ws, Wc are accumulated per lane and
-// reduced over the quad at the end.  18 FP64 instructions for the A side, 3*NS/8 DMMAs (16 pipe cycles
-// each): at NS = 64 the tensor instructions are 91% of the FP64-pipe cycles.
+// reduced over the quad at the end.  18 FP64 instructions for the A side, 3*NS/8 DMMAs (16 pipe cycles each); an
+// FP64 FMA-pipe instruction issued between DMMAs costs ~4.5 pipe cycles (tools/dmma_mix_micro.cu), which caps the
+// tensor pipe at ~82% with the weights evaluated in the loop -- hence the stored-weights mode below.
 //
-// A CTA = 8 compute warps = 16 frequency rows x 4 taus, + one TMA producer warp.  The tile is compact in tau
-// and frequency, so its Gaussian support is one index range of the sorted time axis: the producer finds it
-// (warp-cooperative search) and only the chunks that intersect it are staged; points below 2^-100 of the largest
-// weight of every cell of the tile are skipped exactly as in wwz_rec.cu.  Per chunk of P points: one bulk copy for (t, .), one
-// per frequency row of {sin, cos} records, one per point for the [P][NS] series tile (rows skewed by 32 B); 4-stage ring, full/empty mbarriers.
+// A CTA = 8 compute warps = 16 frequency rows x 4 taus, + one TMA producer warp.  The tile is compact in tau and
+// frequency, so its Gaussian support is one index range of the sorted time axis: the producer finds it (warp-
+// cooperative search) and only the chunks that intersect it are staged; points below 2^-100 of the largest weight
+// of every cell of the tile are skipped exactly as in wwz_rec.cu, and inside the tile's window every warp skips the
+// chunks outside its own (warp_window).  Per chunk of P points: one bulk copy for (t, .), one per frequency row of
+// {sin, cos} records, one per point for the [P][NS] series tile (rows skewed by 32 B: conflict-free B fragments),
+// one for the stored A fragments; 4-stage ring, full/empty mbarriers.
+//
+// Stored weights (PRE).  The weights do not depend on the series block: wwz_tile_weights_kernel evaluates the A
+// fragments of every tile once, in fragment order, with the y-independent sums of every cell, and the contraction
+// kernel streams them through the ring -- 2 DMULs per 24 DMMAs remain, the tensor pipe runs at 90%.
 //
 // Grid: x = cell tiles (low frequencies, i.e. the long windows, first), y = series blocks: CTAs that run
 // together share the series block (streamed from HBM once) and differ in the basis rows (L2 resident).
