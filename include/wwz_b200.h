@@ -195,6 +195,22 @@ int wwzb200_ar1_surrogates_dev(const double *d_ts, int64_t nts, double tau_est, 
 int wwzb200_uar1_surrogates_dev(const double *d_ts, int64_t nts, double tau, double sigma_2, double mu,
                                 int64_t S, uint64_t seed, double *d_Y, void *stream);
 
+/* ---- building blocks of the surrogate-sharded significance test (one rank = one block of surrogates) ----
+ * wwzb200_surrogates_block_dev: rows [first_series, first_series + S) of the surrogate batch that
+ * wwzb200_ar1_surrogates / wwzb200_uar1_surrogates (flags & WWZB200_UAR1) would generate with the same seed.
+ * wwzb200_series_pad: the padded series count S_pad the batch kernels use for S series.
+ * wwzb200_shared_axis_cells_dev: entry (3) with the amplitudes left cell-major, d_amp_cells[nt*nf][S_pad]
+ * (what the per-cell quantiles read); the caller exchanges cell blocks between ranks (all-to-all) and calls
+ * wwzb200_quantiles_cells_dev: quantiles of X[ncell][stride] over the first S entries of every row -> q[nq][ncell]. */
+int wwzb200_surrogates_block_dev(const double *d_ts, int64_t nts, double tau, double sigma, double mu, int64_t S,
+                                 int64_t first_series, uint64_t seed, uint32_t flags, double *d_Y, void *stream);
+int wwzb200_series_pad(int64_t S, int64_t *S_pad);
+int wwzb200_shared_axis_cells_dev(const double *d_ts, const double *d_Y, int64_t nts, int64_t S, const double *d_taus,
+                                  int64_t nt, const double *d_omegas, int64_t nf, double c, int64_t Neff_threshold,
+                                  uint32_t flags, double *d_Neffs, double *d_amp_cells, void *stream);
+int wwzb200_quantiles_cells_dev(const double *d_Xcells, int64_t S, int64_t stride, int64_t ncell,
+                                const double *d_probs, int64_t nq, double *d_q, void *stream);
+
 int wwzb200_quantiles_dev(const double *d_X, int64_t S, int64_t ncell, const double *d_probs,
                           int64_t nq, double *d_q, void *stream);
 

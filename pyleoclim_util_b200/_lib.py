@@ -66,6 +66,11 @@ _SIGS = {
                                                         _i64, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "wwzb200_ar1_surrogates_dev": (ctypes.c_int, [_vp, _i64, _dbl, _dbl, _dbl, _i64, _u64, _vp, _vp]),
     "wwzb200_uar1_surrogates_dev": (ctypes.c_int, [_vp, _i64, _dbl, _dbl, _dbl, _i64, _u64, _vp, _vp]),
+    "wwzb200_surrogates_block_dev": (ctypes.c_int, [_vp, _i64, _dbl, _dbl, _dbl, _i64, _i64, _u64, _u32, _vp, _vp]),
+    "wwzb200_series_pad": (ctypes.c_int, [_i64, ctypes.POINTER(_i64)]),
+    "wwzb200_shared_axis_cells_dev": (ctypes.c_int, [_vp, _vp, _i64, _i64, _vp, _i64, _vp, _i64, _dbl, _i64, _u32,
+                                                     _vp, _vp, _vp]),
+    "wwzb200_quantiles_cells_dev": (ctypes.c_int, [_vp, _i64, _i64, _i64, _vp, _i64, _vp, _vp]),
     "wwzb200_quantiles_dev": (ctypes.c_int, [_vp, _i64, _i64, _vp, _i64, _vp, _vp]),
     "wwzb200_measure_fp64_peak": (ctypes.c_int, [_dp, _dp]),
     "wwzb200_launch_count": (_i64, []),

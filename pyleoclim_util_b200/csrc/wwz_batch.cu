@@ -97,14 +97,14 @@ __global__ void ar1_coeff_kernel(const double *__restrict__ ts, int64_t n, doubl
 // q_0 = 1 (uar1_sim: y[0] = z_0, :704-705); stored value is y + mu (core/surrogateseries.py:139, :156).
 // Step i consumes z0 of Philox pair i/2 when i is even and z1 when i is odd.
 __global__ void __launch_bounds__(256)
-    ar1_normals_kernel(int64_t n, int64_t S, uint64_t seed, double *__restrict__ Y)
+    ar1_normals_kernel(int64_t n, int64_t S, uint64_t first_series, uint64_t seed, double *__restrict__ Y)
 {
     const int64_t npair = (n + 1) / 2;
     const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (idx >= S * npair) return;
     const int64_t s = idx / npair, pr = idx - s * npair;
     double z0, z1;
-    normal_pair((uint64_t)pr, (uint64_t)s, seed, z0, z1);
+    normal_pair((uint64_t)pr, first_series + (uint64_t)s, seed, z0, z1);   // the stream of a series is keyed by its global index
     double *row = Y + s * n + 2 * pr;
     row[0] = z0;
     if (2 * pr + 1 < n) row[1] = z1;
@@ -155,12 +155,12 @@ __global__ void __launch_bounds__(128)
 }
 
 cudaError_t launch_ar1(const double *d_ts, int64_t n, double tau, double sigma, double mu, int64_t S, uint64_t seed,
-                       bool uar1, double *d_rho, double *d_q, double *d_Y, cudaStream_t st)
+                       bool uar1, double *d_rho, double *d_q, double *d_Y, cudaStream_t st, uint64_t first_series)
 {
     if (n <= 0 || S <= 0) return cudaSuccess;
     ar1_coeff_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_ts, n, tau, sigma, uar1 ? 1 : 0, d_rho, d_q);
     const int64_t npair = (n + 1) / 2;
-    ar1_normals_kernel<<<(unsigned)((S * npair + 255) / 256), 256, 0, st>>>(n, S, seed, d_Y);
+    ar1_normals_kernel<<<(unsigned)((S * npair + 255) / 256), 256, 0, st>>>(n, S, first_series, seed, d_Y);
     const int64_t per_block = 4 * kRecurSeries;
     ar1_recur_kernel<<<(unsigned)((S + per_block - 1) / per_block), 128, 0, st>>>(d_rho, d_q, n, S, mu, d_Y);
     bump_launch_counter(3);

@@ -401,7 +401,7 @@ int shared_axis_device(Workspace *w, const double *d_ts, const double *d_Y, int6
                        int64_t nt, const double *d_omega, int64_t nf, double c, int64_t thr, int64_t psd_thr,
                        uint32_t flags, double *d_neffs, double *d_wwa, double *d_phase, double *d_a0, double *d_a1,
                        double *d_a2, double *d_psd, double tspan, double **amp_cells_out, int64_t *S_pad_out,
-                       cudaStream_t st)
+                       cudaStream_t st, double *d_amp_cells_ext = nullptr)
 {
     using namespace wwz;
     const int64_t ncell = nt * nf;
@@ -432,7 +432,10 @@ int shared_axis_device(Workspace *w, const double *d_ts, const double *d_Y, int6
     if ((rc = wsbuf(w, "sig", (size_t)S_pad, &d_sig))) return rc;
     if ((rc = wsbuf(w, "Yt", (size_t)S_pad * (size_t)plan.n_pad, &d_Yt))) return rc;
     if ((rc = wsbuf(w, "wq", (size_t)2 * ncell, &d_wq))) return rc;
-    if ((rc = wsbuf(w, "amp_t", (size_t)ncell * (size_t)S_pad, &d_amp_t))) return rc;
+    if (d_amp_cells_ext)
+        d_amp_t = d_amp_cells_ext;       // the caller keeps the cell-major amplitudes [ncell][S_pad]
+    else if ((rc = wsbuf(w, "amp_t", (size_t)ncell * (size_t)S_pad, &d_amp_t)))
+        return rc;
     if (d_phase && (rc = wsbuf(w, "ph_t", (size_t)ncell * (size_t)S_pad, &d_ph_t))) return rc;
     if (d_a0 && (rc = wsbuf(w, "a0_t", (size_t)ncell * (size_t)S_pad, &d_a0_t))) return rc;
     if (d_a1 && (rc = wsbuf(w, "a1_t", (size_t)ncell * (size_t)S_pad, &d_a1_t))) return rc;
@@ -727,7 +730,7 @@ int wwzb200_kirchner_shared_axis(const double *ts, const double *Y, int64_t nts,
 }
 
 static int surrogates_dev(const double *d_ts, int64_t nts, double tau_est, double sigma, double mu, int64_t S,
-                          uint64_t seed, bool uar1, double *d_Y, void *stream)
+                          uint64_t seed, bool uar1, double *d_Y, void *stream, uint64_t first_series = 0)
 {
     if (nts < 1 || S < 0) return fail(WWZB200_ERR_ARG, "bad sizes");
     if (!d_ts || (S && !d_Y)) return fail(WWZB200_ERR_ARG, "null pointer");
@@ -740,7 +743,7 @@ static int surrogates_dev(const double *d_ts, int64_t nts, double tau_est, doubl
     double *d_rq;
     if ((rc = wsbuf(w, "ar1_rq", (size_t)2 * nts, &d_rq))) return rc;
     CU(wwz::launch_ar1(d_ts, nts, tau_est, sigma, mu, S, seed, uar1, d_rq, d_rq + nts, d_Y,
-                       static_cast<cudaStream_t>(stream)));
+                       static_cast<cudaStream_t>(stream), first_series));
     return 0;
 }
 
@@ -787,6 +790,51 @@ int wwzb200_uar1_surrogates(const double *ts, int64_t nts, double tau, double si
                             uint64_t seed, double *Y)
 {
     return surrogates_host(ts, nts, tau, sigma_2, mu, S, seed, true, Y);
+}
+
+int wwzb200_surrogates_block_dev(const double *d_ts, int64_t nts, double tau, double sigma, double mu, int64_t S,
+                                 int64_t first_series, uint64_t seed, uint32_t flags, double *d_Y, void *stream)
+{
+    if (first_series < 0) return fail(WWZB200_ERR_ARG, "first_series must be >= 0");
+    return surrogates_dev(d_ts, nts, tau, sigma, mu, S, seed, (flags & WWZB200_UAR1) != 0, d_Y, stream,
+                          (uint64_t)first_series);
+}
+
+int wwzb200_series_pad(int64_t S, int64_t *S_pad)
+{
+    if (S < 0 || !S_pad) return fail(WWZB200_ERR_ARG, "bad arguments");
+    const int64_t NS = wwz::shared_series_block(S);
+    *S_pad = ((S + NS - 1) / NS) * NS;
+    return 0;
+}
+
+int wwzb200_shared_axis_cells_dev(const double *d_ts, const double *d_Y, int64_t nts, int64_t S, const double *d_taus,
+                                  int64_t nt, const double *d_omegas, int64_t nf, double c, int64_t Neff_threshold,
+                                  uint32_t flags, double *d_Neffs, double *d_amp_cells, void *stream)
+{
+    int rc = check_grid_args(d_ts, d_Y, nts, d_taus, nt, d_omegas, nf, c, Neff_threshold);
+    if (rc) return rc;
+    if (S < 0 || (S && nt * nf && !d_amp_cells)) return fail(WWZB200_ERR_ARG, "bad batch arguments");
+    std::lock_guard<std::mutex> lock(g_mu);
+    Workspace *w;
+    if ((rc = workspace(&w))) return rc;
+    return shared_axis_device(w, d_ts, d_Y, nts, S, d_taus, nt, d_omegas, nf, c, Neff_threshold, 0, flags, d_Neffs,
+                              nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0.0, nullptr, nullptr,
+                              static_cast<cudaStream_t>(stream), d_amp_cells);
+}
+
+int wwzb200_quantiles_cells_dev(const double *d_Xcells, int64_t S, int64_t stride, int64_t ncell, const double *d_probs,
+                                int64_t nq, double *d_q, void *stream)
+{
+    if (S < 1 || ncell < 0 || nq < 0 || stride < S) return fail(WWZB200_ERR_ARG, "bad sizes");
+    if (ncell == 0 || nq == 0) return 0;
+    if (!d_Xcells || !d_probs || !d_q) return fail(WWZB200_ERR_ARG, "null pointer");
+    if (S > ((int64_t)1 << 24)) return fail(WWZB200_ERR_ARG, "S too large for the quantile kernel");
+    std::lock_guard<std::mutex> lock(g_mu);
+    Workspace *w;
+    int rc;
+    if ((rc = workspace(&w))) return rc;
+    return quantiles_device(w, d_Xcells, S, stride, ncell, d_probs, nq, d_q, static_cast<cudaStream_t>(stream));
 }
 
 int wwzb200_quantiles_dev(const double *d_X, int64_t S, int64_t ncell, const double *d_probs, int64_t nq, double *d_q,

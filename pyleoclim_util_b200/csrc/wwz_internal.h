@@ -141,8 +141,11 @@ SharedPlan plan_shared(int64_t n, int64_t nt, int64_t nf, int64_t S);
 
 // AR(1) surrogates Y[S][n] (row-major); d_rho, d_q are n-element scratch.  uar1: uar1_sim semantics
 // (y_0 = z_0, sigma = innovation variance sigma_2) instead of ar1_model's.
+// first_series: global index of row 0 (the Philox stream of a series is keyed by its global index, so a block of
+// surrogates generated on its own equals the same rows of the whole batch).
 cudaError_t launch_ar1(const double *d_ts, int64_t n, double tau, double sigma, double mu, int64_t S, uint64_t seed,
-                       bool uar1, double *d_rho, double *d_q, double *d_Y, cudaStream_t st);
+                       bool uar1, double *d_rho, double *d_q, double *d_Y, cudaStream_t st, uint64_t first_series = 0);
+int shared_series_block(int64_t S);
 // per-series mean/std (identity when !standardize) and the tiled copy Yt[S_pad/NS][n_pad][NS]
 cudaError_t launch_standardize_retile(const double *d_Y, int64_t n, int64_t n_pad, int64_t S, int series_block,
                                       bool standardize, double *d_mu, double *d_sig, double *d_Yt, cudaStream_t st);

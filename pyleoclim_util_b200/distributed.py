@@ -221,7 +221,9 @@ def wwz_psd_tau_sharded(ys, ts, tau=None, freq=None, freq_method="log", freq_kwa
 
 def wwz_signif_sharded(ys, ts, tau=None, freq=None, number=200, qs=(0.95,), seed=0, c=1 / (8 * np.pi ** 2),
                        Neff_threshold=3, freq_method="log", freq_kwargs=None, group=None, signif=None, axis="auto"):
-    """Scalogram significance levels with the (tau, f) grid sharded over the ranks: each rank runs the fused
+    """Scalogram significance levels sharded over the ranks.  axis='surrogates' (the default under NCCL): every rank
+    transforms its block of the surrogates on the whole grid, an all-to-all regroups the amplitudes by cell block and
+    the quantiles are taken there (`_signif_by_surrogates`).  Grid sharding: each rank runs the fused
     device pipeline (`batch.signif_prepared`) for all `number` surrogates on its block of tau rows
     (axis='tau') or on its share of the frequency columns (axis='freq': groups of 16 consecutive frequencies dealt
     to the ranks by modelled cost, `balanced_freq_groups`; 'auto' takes the longer axis -- the reference's default
@@ -234,10 +236,18 @@ def wwz_signif_sharded(ys, ts, tau=None, freq=None, number=200, qs=(0.95,), seed
     signif = batch.signif_prepared if signif is None else signif
     ys_cut, ts_cut, freq, tau = _wv.prepare_wwz(ys, ts, freq=freq, freq_method=freq_method, freq_kwargs=freq_kwargs,
                                                 tau=tau)
-    if axis == "auto":
-        axis = "freq" if freq.size >= tau.size else "tau"
     probs = np.atleast_1d(np.asarray(qs, dtype=float))
     nq = probs.size
+    if axis == "auto":
+        # NCCL: shard the surrogates (balanced by construction; the all-to-all of the amplitudes rides NVLink);
+        # otherwise (CPU tests, custom `signif`) shard the longer grid axis
+        if signif is batch.signif_prepared and dist.get_backend(group) == "nccl" and number >= world:
+            axis = "surrogates"
+        else:
+            axis = "freq" if freq.size >= tau.size else "tau"
+    if axis == "surrogates":
+        q, Neffs = _signif_by_surrogates(ys_cut, ts_cut, tau, freq, number, probs, seed, c, Neff_threshold, group)
+        return batch.SignifResults(qs=probs, amplitude_qs=q, psd_qs=None, Neffs=Neffs, freq=freq, time=tau)
     if axis == "tau":
         blocks = row_blocks(tau.size, world)
         a, b = blocks[rank]
@@ -249,7 +259,7 @@ def wwz_signif_sharded(ys, ts, tau=None, freq=None, number=200, qs=(0.95,), seed
         a, b = blocks[rank]
         tau_loc, freq_loc = tau, freq[rows[rank]]
     else:
-        raise ValueError("axis must be 'tau', 'freq' or 'auto'")
+        raise ValueError("axis must be 'surrogates', 'tau', 'freq' or 'auto'")
     counts = [y - x for x, y in blocks]
     if b > a:
         q_wwa, _, Neffs = signif(ys_cut, ts_cut, tau_loc, freq_loc, number=number, probs=probs, seed=seed, c=c,
@@ -266,6 +276,79 @@ def wwz_signif_sharded(ys, ts, tau=None, freq=None, number=200, qs=(0.95,), seed
     full = np.moveaxis(full, 0, 1 if axis == "tau" else 2)                   # back to [nq+1, nt, nf]
     return batch.SignifResults(qs=probs, amplitude_qs=np.ascontiguousarray(full[:nq]), psd_qs=None,
                                Neffs=np.ascontiguousarray(full[nq]), freq=freq, time=tau)
+
+
+def _signif_by_surrogates(ys_cut, ts_cut, tau, freq, number, probs, seed, c, Neff_threshold, group, method="ar1sim"):
+    """Surrogates sharded over the ranks (NCCL): rank r generates rows [s0_r, s1_r) of the surrogate batch (the Philox
+    stream of a series is keyed by its global index: same surrogates as the single-GPU test), transforms them as one
+    shared-axis batch on the whole (tau, f) grid -- perfectly balanced, whatever the point windows -- and keeps the
+    amplitudes cell-major in HBM; one all-to-all over NVLink hands every rank ALL surrogates of its block of cells,
+    the per-cell quantiles run there, and the [nq, cells/world] tiles are all-gathered.  Returns (q [nq, nt, nf],
+    Neffs [nt, nf]) as NumPy arrays, equal on every rank and to the single-GPU result."""
+    import ctypes
+    import torch
+    from . import _lib, batch
+    dist = _dist()
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    st = torch.cuda.current_stream().cuda_stream
+    L = _lib.lib()
+    ys_cut = np.asarray(ys_cut, dtype=float)
+    mu = float(np.mean(ys_cut))
+    flags = _lib.STANDARDIZE
+    if method == "ar1sim":
+        sig, tau_est = float(np.std(ys_cut)), float(batch.tau_estimation(ys_cut, ts_cut))
+    elif method == "uar1":
+        tau_est, sig = (float(v) for v in batch.uar1_fit(ys_cut, ts_cut))
+        flags |= _lib.UAR1
+    else:
+        raise ValueError("surrogate method must be 'ar1sim' or 'uar1'")
+    omega = _wv.make_omega(ts_cut, freq)
+    n, nt, nf, nq = ts_cut.size, tau.size, freq.size, probs.size
+    ncell = nt * nf
+    sblocks = row_blocks(number, world)
+    s0, s1 = sblocks[rank]
+    S_loc = s1 - s0
+    S_max = max(b - a for a, b in sblocks)
+    pad = ctypes.c_int64()
+    _lib.check(L.wwzb200_series_pad(max(S_max, 1), ctypes.byref(pad)))
+    S_pad = int(pad.value)                                   # same row stride on every rank (the all-to-all is regular)
+    up = lambda x: torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64)).to(dev, non_blocking=True)
+    d_ts, d_tau, d_om, d_probs = up(ts_cut), up(tau), up(omega), up(probs)
+    cells_per = (ncell + world - 1) // world
+    d_amp = torch.zeros((cells_per * world, S_pad), dtype=torch.float64, device=dev)   # cell-major, cells padded to world
+    d_ne = torch.empty((nt, nf), dtype=torch.float64, device=dev)
+    if S_loc > 0:
+        own = ctypes.c_int64()
+        _lib.check(L.wwzb200_series_pad(S_loc, ctypes.byref(own)))
+        d_Y = torch.empty((S_loc, n), dtype=torch.float64, device=dev)
+        _lib.check(L.wwzb200_surrogates_block_dev(d_ts.data_ptr(), n, tau_est, sig, mu, S_loc, s0,
+                                                  int(seed) & 0xFFFFFFFFFFFFFFFF, flags & _lib.UAR1, d_Y.data_ptr(), st))
+        if int(own.value) == S_pad:
+            tgt = d_amp
+        else:                                               # a short last block pads to fewer columns: its own buffer
+            tgt = torch.empty((ncell, int(own.value)), dtype=torch.float64, device=dev)
+        _lib.check(L.wwzb200_shared_axis_cells_dev(d_ts.data_ptr(), d_Y.data_ptr(), n, S_loc, d_tau.data_ptr(), nt,
+                                                   d_om.data_ptr(), nf, float(c), int(Neff_threshold), flags,
+                                                   d_ne.data_ptr(), tgt.data_ptr(), st))
+        if tgt is not d_amp:
+            d_amp[:ncell, :S_loc] = tgt[:, :S_loc]
+    # every rank gets all surrogates of its block of cells
+    recv = torch.empty((world, cells_per, S_pad), dtype=torch.float64, device=dev)
+    dist.all_to_all_single(recv.view(-1), d_amp.view(-1), group=group)
+    X = torch.cat([recv[r, :, : sblocks[r][1] - sblocks[r][0]] for r in range(world)], dim=1).contiguous()  # [cells_per, number]
+    d_q = torch.empty((nq, cells_per), dtype=torch.float64, device=dev)
+    _lib.check(L.wwzb200_quantiles_cells_dev(X.data_ptr(), number, number, cells_per, d_probs.data_ptr(), nq,
+                                             d_q.data_ptr(), st))
+    qall = torch.empty((world, nq, cells_per), dtype=torch.float64, device=dev)
+    dist.all_gather_into_tensor(qall.view(-1), d_q.view(-1), group=group)
+    q = qall.permute(1, 0, 2).reshape(nq, world * cells_per)[:, :ncell].reshape(nq, nt, nf)
+    if S_loc == 0:                                          # (more ranks than surrogates) Neffs from a rank that has some
+        src = torch.zeros((nt, nf), dtype=torch.float64, device=dev)
+        d_ne = src
+    ne = d_ne.clone()
+    dist.broadcast(ne, src=0, group=group)
+    return q.cpu().numpy(), ne.cpu().numpy()
 
 
 def wwz_signif_tau_sharded(ys, ts, **kw):
