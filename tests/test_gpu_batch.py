@@ -255,6 +255,50 @@ def test_wwz_signif_equals_the_unfused_pipeline():
     assert max_rel(sg.psd_qs, pref) < 1e-10
 
 
+def test_surrogate_blocks_reassemble_the_fused_test():
+    """The building blocks of the surrogate-sharded test (distributed._signif_by_surrogates) on one GPU: two blocks of
+    surrogates generated with their global offsets equal the rows of the whole batch bit for bit; their cell-major
+    amplitudes side by side, reduced by wwzb200_quantiles_cells_dev, give the levels of the fused single-GPU test."""
+    import ctypes
+    torch = pytest.importorskip("torch")
+    dev = torch.device("cuda:0")
+    st = torch.cuda.current_stream().cuda_stream
+    L = _lib.lib()
+    t, y = synth.uneven_ar1(420, 3)
+    number, seed, qs = 150, 9, np.array([0.5, 0.95])
+    sg = B.wwz_signif(y, t, number=number, qs=qs, seed=seed)
+    ys_cut, ts_cut, freq, tau = WV.prepare_wwz(y, t)
+    tau_est, sig, mu = B.tau_estimation(ys_cut, ts_cut), np.std(ys_cut), np.mean(ys_cut)
+    whole = B.ar1_surrogates(ts_cut, tau_est, sigma=sig, mu=mu, number=number, seed=seed)
+    up = lambda x: torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64)).to(dev)
+    d_ts, d_tau, d_om, d_p = up(ts_cut), up(tau), up(WV.make_omega(ts_cut, freq)), up(qs)
+    n, nt, nf = ts_cut.size, tau.size, freq.size
+    ncell = nt * nf
+    parts, ne = [], None
+    for s0, s1 in ((0, 90), (90, 150)):
+        S = s1 - s0
+        d_Y = torch.empty((S, n), dtype=torch.float64, device=dev)
+        _lib.check(L.wwzb200_surrogates_block_dev(d_ts.data_ptr(), n, float(tau_est), float(sig), float(mu), S, s0, seed, 0,
+                                                  d_Y.data_ptr(), st))
+        assert np.array_equal(d_Y.cpu().numpy(), whole[s0:s1])
+        pad = ctypes.c_int64()
+        _lib.check(L.wwzb200_series_pad(S, ctypes.byref(pad)))
+        assert pad.value % 16 == 0 and pad.value >= S
+        d_amp = torch.empty((ncell, pad.value), dtype=torch.float64, device=dev)
+        d_ne = torch.empty((nt, nf), dtype=torch.float64, device=dev)
+        _lib.check(L.wwzb200_shared_axis_cells_dev(d_ts.data_ptr(), d_Y.data_ptr(), n, S, d_tau.data_ptr(), nt,
+                                                   d_om.data_ptr(), nf, 1 / (8 * np.pi ** 2), 3, _lib.STANDARDIZE,
+                                                   d_ne.data_ptr(), d_amp.data_ptr(), st))
+        parts.append(d_amp[:, :S])
+        ne = d_ne
+    X = torch.cat(parts, dim=1).contiguous()
+    d_q = torch.empty((2, ncell), dtype=torch.float64, device=dev)
+    _lib.check(L.wwzb200_quantiles_cells_dev(X.data_ptr(), number, number, ncell, d_p.data_ptr(), 2, d_q.data_ptr(), st))
+    q = d_q.cpu().numpy().reshape(2, nt, nf)
+    assert_same_nan_mask(q, sg.amplitude_qs)
+    assert max_rel(q, sg.amplitude_qs) < 1e-12 and max_rel(ne.cpu().numpy(), sg.Neffs) < 1e-13
+
+
 def test_config3_size_significance_test():
     """Config 3 at full size: 10,000 AR(1) surrogates of an n=5,000 series on the default 50 x 501 grid, fused on
     the device.  Size-independent properties: quantiles ordered, mask equal to the target's, reproducible for a
