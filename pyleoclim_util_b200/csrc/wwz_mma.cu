@@ -17,7 +17,7 @@
 // FP64 FMA-pipe instruction issued between DMMAs costs ~4.5 pipe cycles (tools/dmma_mix_micro.cu), which caps the
 // tensor pipe at ~82% with the weights evaluated in the loop -- hence the stored-weights mode below.
 //
-// A CTA = 8 compute warps = 16 frequency rows x 4 taus, + one TMA producer warp.  The tile is compact in tau and
+// A CTA = 8 compute warps = 32 frequency rows x 2 taus, + one TMA producer warp.  The tile is compact in tau and
 // frequency, so its Gaussian support is one index range of the sorted time axis: the producer finds it (warp-
 // cooperative search) and only the chunks that intersect it are staged; points below 2^-100 of the largest weight
 // of every cell of the tile are skipped exactly as in wwz_rec.cu, and inside the tile's window every warp skips the
@@ -42,15 +42,17 @@
 namespace wwz {
 
 constexpr int kMmaStages = 4;
-// 2 x 4 (16 rows x 4 taus).  4 x 2 (32 rows x 2 taus: the four row groups of a tau on the four SMSPs) was measured 2%
-// faster on one GPU (config 3: 120.2 against 122.6 ms) but halves the granularity of the frequency sharding
-// (distributed.balanced_freq_groups): the slowest of 8 shares went from 17.5 to 20.1 ms.
-constexpr int kMmaWF = 2;                       // warps along the frequency axis
-constexpr int kMmaWT = 4;                       // warps along the tau axis
+// 4 x 2: 32 frequency rows x 2 taus.  Warp w = wf + 4*wt sits on SMSP wf, so the four row groups of one tau cover the
+// four SMSPs: a tau whose window is disjoint from its neighbour's (high frequencies) still keeps the whole SM busy
+// (2 x 4 left two SMSPs idle there: config 3 122.6 -> 120.2 ms), and nt = 50 needs no padding.  The price is a coarser
+// unit for frequency-sharded runs (distributed.balanced_freq_groups deals 32-row groups); the default multi-GPU
+// significance test shards surrogates and always sees the whole grid.
+constexpr int kMmaWF = 4;                       // warps along the frequency axis
+constexpr int kMmaWT = 2;                       // warps along the tau axis
 constexpr int kMmaRows = 8 * kMmaWF;            // frequency rows of a CTA tile
 constexpr int kMmaWarps = kMmaWF * kMmaWT;      // compute warps
 constexpr int kMmaThreads = (kMmaWarps + 1) * 32;
-static_assert(kMmaWarps == 8, "tile geometry");
+static_assert(kMmaWarps == 8 && kMmaRows <= 32, "tile geometry");
 
 struct MmaArgs {
     const double2 *ty;      // [n_pad] (t, .)
@@ -118,7 +120,7 @@ __device__ __forceinline__ void tile_window(const MmaArgs &a, int k_base, int ro
 
 // The chunks of the tile's window that matter to ONE warp (8 frequency rows at one tau): its own relative window,
 // [tau - de, tau + de] with de from the widest dcut of its rows and the gap of its tau.  A warp skips the arithmetic
-// of the staged chunks outside it (high-frequency tiles: the 4-tau, 16-row window of the CTA is several times wider
+// of the staged chunks outside it (high-frequency tiles: the 2-tau, 32-row window of the CTA is several times wider
 // than what one warp needs).  Returns chunk indices [lo, hi) on the whole axis; all lanes get the same values.
 __device__ __forceinline__ void warp_window(const MmaArgs &a, int kc, int jc, bool row_ok, int lane, int &lo, int &hi)
 {
@@ -247,15 +249,16 @@ __global__ void __launch_bounds__(kMmaThreads, 1) wwz_shared_mma_kernel(const Mm
             const size_t start = (size_t)(c_lo + i) * P;
             if (lane == 0) mbar_arrive_expect_tx(&full[s], bytes);
             __syncwarp();
+            if (lane < rows) {
+                const size_t row = (size_t)(k_base + lane);
+                tma_load_1d(st + P + (size_t)lane * a.row_stride2, a.basis + row * (size_t)a.n_pad + start,
+                            (uint32_t)P * 16u, &full[s]);
+            }
             if (lane == 0) {
                 tma_load_1d(st, a.ty + start, (uint32_t)P * 16u, &full[s]);
             } else if (PRE && lane == 1) {
                 tma_load_1d(st + a.w_off2, a.wfrag + (size_t)blockIdx.x * (size_t)a.wf_tile_stride + start * 64,
                             (uint32_t)P * 512u, &full[s]);
-            } else if (lane - 2 < rows && lane >= 2) {
-                const size_t row = (size_t)(k_base + lane - 2);
-                tma_load_1d(st + P + (size_t)(lane - 2) * a.row_stride2, a.basis + row * (size_t)a.n_pad + start,
-                            (uint32_t)P * 16u, &full[s]);
             }
             // series tile: one copy per point, rows skewed by 32 B in shared memory (conflict-free B fragments)
             const double *const ysrc = a.Yt + ((size_t)sb * a.n_pad + start) * NS;

@@ -22,7 +22,7 @@ def row_blocks(n, world):
     return out
 
 
-TILE_ROWS = 16      # frequency rows of one CTA tile of the shared-axis kernel (kMmaRows, csrc/wwz_mma.cu)
+TILE_ROWS = 32      # frequency rows of one CTA tile of the shared-axis kernel (kMmaRows, csrc/wwz_mma.cu)
 
 
 def balanced_freq_groups(ts_cut, tau, freq, c, world, cut_bits=100.0):
@@ -225,7 +225,7 @@ def wwz_signif_sharded(ys, ts, tau=None, freq=None, number=200, qs=(0.95,), seed
     transforms its block of the surrogates on the whole grid, an all-to-all regroups the amplitudes by cell block and
     the quantiles are taken there (`_signif_by_surrogates`).  Grid sharding: each rank runs the fused
     device pipeline (`batch.signif_prepared`) for all `number` surrogates on its block of tau rows
-    (axis='tau') or on its share of the frequency columns (axis='freq': groups of 16 consecutive frequencies dealt
+    (axis='tau') or on its share of the frequency columns (axis='freq': groups of 32 consecutive frequencies dealt
     to the ranks by modelled cost, `balanced_freq_groups`; 'auto' takes the longer axis -- the reference's default
     grid is 50 tau x n/10 frequencies).  The same seed gives every rank the same
     surrogates, so the per-cell quantiles are exchange-free; only the quantile tiles are gathered.
