@@ -653,13 +653,9 @@ cudaError_t launch_quantiles(const double *d_X, int64_t S, int64_t stride, int64
         // few probabilities: radix select
         const size_t kb = (size_t)S * 8;
         if (kb <= 200 * 1024) {
-            static size_t configured_sel = 0;
-            if (kb > configured_sel) {
-                cudaError_t e = cudaFuncSetAttribute(quantile_select_kernel<true>,
-                                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kb);
-                if (e != cudaSuccess) return e;
-                configured_sel = kb;
-            }
+            static SmemOptIn done_sel;
+            cudaError_t e = ensure_dynamic_smem(quantile_select_kernel<true>, (int)kb, done_sel);
+            if (e != cudaSuccess) return e;
             const int64_t grid = std::min<int64_t>(ncell, (int64_t)sms * 16);
             quantile_select_kernel<true><<<(unsigned)grid, 512, kb, st>>>(d_X, S, stride, ncell, d_probs, (int)nq, d_q);
         } else {
@@ -673,12 +669,9 @@ cudaError_t launch_quantiles(const double *d_X, int64_t S, int64_t stride, int64
     while (npow2 < S) npow2 <<= 1;
     const size_t smem = (size_t)npow2 * 8;
     if (smem <= 200 * 1024) {
-        static size_t configured = 0;
-        if (smem > configured) {
-            cudaError_t e = cudaFuncSetAttribute(quantile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return e;
-            configured = smem;
-        }
+        static SmemOptIn done;
+        cudaError_t e = ensure_dynamic_smem(quantile_kernel, (int)smem, done);
+        if (e != cudaSuccess) return e;
         const int64_t grid = std::min<int64_t>(ncell, (int64_t)sms * 8);
         quantile_kernel<<<(unsigned)grid, 1024, smem, st>>>(d_X, S, stride, ncell, d_probs, (int)nq, npow2, d_q, nullptr);
     } else {

@@ -178,6 +178,25 @@ cudaError_t launch_quantiles(const double *d_X, int64_t S, int64_t stride, int64
 // FP64 FMA peak microbenchmark.
 cudaError_t run_fp64_peak(double *tflops, double *ms);
 
+// Opt-in dynamic shared memory is a per-device attribute of a kernel: remember, per device, the largest size set.
+constexpr int kMaxDevices = 64;
+struct SmemOptIn {
+    int bytes[kMaxDevices];
+    SmemOptIn() { for (int i = 0; i < kMaxDevices; ++i) bytes[i] = -1; }
+};
+template <typename Kernel>
+inline cudaError_t ensure_dynamic_smem(Kernel kernel, int bytes, SmemOptIn &done)
+{
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const bool tracked = dev >= 0 && dev < kMaxDevices;
+    if (tracked && bytes <= done.bytes[dev]) return cudaSuccess;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess && tracked) done.bytes[dev] = bytes;
+    return e;
+}
+
 int64_t launch_counter();
 void bump_launch_counter(int64_t k = 1);
 

@@ -638,13 +638,9 @@ template <int M, bool REC, int CW>
 static cudaError_t launch_cells_m(const CellPlan &plan, const CellArgs &args, int64_t tiles, int segs,
                                   cudaStream_t st)
 {
-    static int configured_smem = -1;
-    if (plan.smem_bytes > configured_smem) {
-        cudaError_t e = cudaFuncSetAttribute(wwz_cells_kernel<M, REC, CW>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem_bytes);
-        if (e != cudaSuccess) return e;
-        configured_smem = plan.smem_bytes;
-    }
+    static SmemOptIn done;
+    cudaError_t e = ensure_dynamic_smem(wwz_cells_kernel<M, REC, CW>, plan.smem_bytes, done);
+    if (e != cudaSuccess) return e;
     wwz_cells_kernel<M, REC, CW><<<dim3((unsigned)tiles, (unsigned)segs), (CW + 1) * 32, plan.smem_bytes, st>>>(args);
     bump_launch_counter();
     return cudaGetLastError();

@@ -443,12 +443,9 @@ SharedPlan plan_shared(int64_t n, int64_t nt, int64_t nf, int64_t S)
 template <int NS, bool PRE>
 static cudaError_t launch_mma(const MmaArgs &a, dim3 grid, int smem, cudaStream_t st)
 {
-    static int configured = -1;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(wwz_shared_mma_kernel<NS, PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return e;
-        configured = smem;
-    }
+    static SmemOptIn done;
+    cudaError_t e = ensure_dynamic_smem(wwz_shared_mma_kernel<NS, PRE>, smem, done);
+    if (e != cudaSuccess) return e;
     wwz_shared_mma_kernel<NS, PRE><<<grid, kMmaThreads, smem, st>>>(a);
     return cudaGetLastError();
 }

@@ -274,12 +274,9 @@ cudaError_t launch_rec(const RecPlan &plan, const double2 *d_ty, const double2 *
     a.row_stride2 = (int)(plan.row_stride / 16);
     a.stage_stride2 = plan.stage_bytes / 16;
     a.warp_stride = plan.warp_bytes;
-    static int configured_smem = -1;
-    if (plan.smem_bytes > configured_smem) {
-        cudaError_t e = cudaFuncSetAttribute(wwz_rec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem_bytes);
-        if (e != cudaSuccess) return e;
-        configured_smem = plan.smem_bytes;
-    }
+    static SmemOptIn done;
+    cudaError_t e = ensure_dynamic_smem(wwz_rec_kernel, plan.smem_bytes, done);
+    if (e != cudaSuccess) return e;
     const int64_t ctas = (a.ntiles + kRecWarps - 1) / kRecWarps;
     wwz_rec_kernel<<<dim3((unsigned)ctas, (unsigned)segs), kRecWarps * 32, plan.smem_bytes, st>>>(a);
     bump_launch_counter();
