@@ -139,3 +139,24 @@ def test_make_freq_vector_all_generators_match_the_reference():
         WV.make_freq_vector(t, method="lomb_scargle", ofac=0.5)
     ys_cut, ts_cut, freq, tau = WV.prepare_wwz(g["ys"], t, freq_method="scale", tau=g["wwz_scale_tau"])
     assert np.array_equal(freq, g["wwz_scale_freq"])
+
+
+def test_len_bd_ghost_padding_documented_behaviour():
+    """len_bd (utils/wavelet.py:2172-2189): the reference's own branch cannot run in this environment (np.lib.pad is gone
+    from NumPy 2, and it hands np.linspace a float count), so there is no reference output to pin: this checks the
+    behaviour its source and docstring describe -- len_bd ghost samples per side at the median spacing, odd reflection
+    of the values, tau extended by len_bd*dt//dtau steps per side, series cut to the new tau span."""
+    t = np.arange(0.0, 100.0, 1.0) + 0.25 * np.sin(np.arange(100))       # uneven, median spacing ~ 1
+    y = np.linspace(-1.0, 2.0, 100) ** 2
+    tau = np.linspace(t[0], t[-1], 34)
+    with pytest.warns(UserWarning):
+        ys_cut, ts_cut, freq, tau_out = WV.prepare_wwz(y, t, tau=tau, len_bd=6)
+    dt, dtau = np.median(np.diff(t)), np.median(np.diff(tau))
+    k = int(6 * dt // dtau)
+    assert tau_out.size == tau.size + 2 * k and np.allclose(np.diff(tau_out), dtau)
+    assert np.array_equal(tau_out[k:k + tau.size], tau)
+    inside = (ts_cut >= tau_out.min()) & (ts_cut <= tau_out.max())
+    assert inside.all() and ts_cut.size >= t.size and np.all(np.diff(ts_cut) > 0)
+    assert np.array_equal(ts_cut[np.isin(ts_cut, t)], t)
+    left = ys_cut[ts_cut < t[0]]
+    assert left.size and np.allclose(left, (2 * y[0] - y[1:7][::-1])[-left.size:])      # odd reflection about the first sample
