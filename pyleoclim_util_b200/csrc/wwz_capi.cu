@@ -62,6 +62,9 @@ struct Workspace {
     cudaEvent_t fork_ev = nullptr;
     cudaStream_t side = nullptr;          // the direct cell kernel runs here, next to the recurrence kernel
     cudaEvent_t side_fork = nullptr, side_join = nullptr;
+    cudaEvent_t busy_ev = nullptr;        // end of the last piece of work that used this scratch set (any stream)
+    cudaStream_t busy_stream = nullptr;
+    bool busy = false;
     std::string prefix;   // scratch namespace of the stream currently being enqueued on
     int sms = 0;
     double *h_in = nullptr;   // page-locked staging of the single-series inputs
@@ -111,6 +114,7 @@ int workspace(Workspace **out)
         CU(cudaStreamCreateWithFlags(&w.side, cudaStreamNonBlocking));
         CU(cudaEventCreateWithFlags(&w.side_fork, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&w.side_join, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&w.busy_ev, cudaEventDisableTiming));
         for (int i = 0; i < kLanes; ++i) {
             CU(cudaStreamCreateWithFlags(&w.lanes[i], cudaStreamNonBlocking));
             CU(cudaEventCreateWithFlags(&w.lane_ev[i], cudaEventDisableTiming));
@@ -119,6 +123,33 @@ int workspace(Workspace **out)
     *out = &w;
     return 0;
 }
+
+// The scratch set of a device is shared by every entry point, whatever stream the caller passes: work enqueued on
+// `st` first waits for the last work that used the scratch (if that was enqueued on another stream), and leaves its
+// own end marker behind.  Calls on one stream keep their stream order for free; calls on different streams are
+// serialised on the device instead of racing on kappa / basis / sums / ... (include/wwz_b200.h, "Streams").
+int scratch_begin(Workspace *w, cudaStream_t st)
+{
+    if (w->busy && w->busy_stream != st) CU(cudaStreamWaitEvent(st, w->busy_ev, 0));
+    return 0;
+}
+
+int scratch_end(Workspace *w, cudaStream_t st)
+{
+    CU(cudaEventRecord(w->busy_ev, st));
+    w->busy_stream = st;
+    w->busy = true;
+    return 0;
+}
+
+// begin() on entry, end marker on every way out (also the error returns)
+struct ScratchScope {
+    Workspace *w;
+    cudaStream_t st;
+    ScratchScope(Workspace *w_, cudaStream_t st_) : w(w_), st(st_) {}
+    int begin() { return scratch_begin(w, st); }
+    ~ScratchScope() { scratch_end(w, st); }
+};
 
 template <typename T>
 int wsbuf(Workspace *w, const char *name, size_t count, T **out)
@@ -139,21 +170,28 @@ size_t basis_budget_bytes()
     return (size_t)2 << 30;
 }
 
-// Number of point-axis segments: enough that (cells x segments) fills the machine for several waves, each segment
-// at least 256 points.  Target 1.5e6 cell-slots when only the direct kernel runs (10 waves x 296 CTAs x 512 cells:
-// measured best on config 2, dense) and 1.0e6 when the warp-tile recurrence kernel takes the rows (its tiles are
-// smaller: config 2 then runs 2 segments, which ties with 3 on the c = 1/(8 pi^2) transform, wins by 4% on the
-// c = 1e-3 one and leaves the epilogue one slab less to add).  It depends on the problem size and on the flags
-// only, never on the tile geometry, so every variant of a kernel adds the same partial sums.
-int point_segments(int64_t n, int64_t ncell, bool recurrence)
+// Number of point-axis segments.  CTA-wide direct kernel: enough that (cells x segments) fills the machine for several
+// waves -- 1.5e6 cell-slots (10 waves x 296 CTAs x 512 cells: measured best on config 2, dense).  Warp-tile kernels
+// (persistent, work items = (warp tile, segment) pulled from a queue, longest first): the largest items are the
+// low-frequency tiles that walk their whole segment, and the launch ends with its last item, so there should be a few
+// dozen items per resident warp (measured: a 256-tau x 2047-f slab of config 5 takes 17.4 ms per launch with 2
+// segments and 12.8 with 16) -- but every segment costs a slab of partial sums that the epilogue reads back, so a
+// segment is at least 1000 points on large grids (config 2: 2 segments; 3 cost 7% on its c = 1e-3 transform), 256 on small ones.  The count depends on
+// the problem size and on the flags only, never on the tile geometry, so every variant of a kernel adds the same
+// partial sums.
+int point_segments(int64_t n, int64_t nt, int64_t nf, bool recurrence)
 {
+    const int64_t ncell = nt * nf;
     const char *e = getenv("WWZB200_POINT_SEGMENTS");
     int64_t s;
     if (e && *e) {
         s = atoll(e);
+    } else if (recurrence) {
+        const int64_t tiles = ((nt + 63) / 64) * ((std::min<int64_t>(nf, 65535) + 3) / 4);   // 64 taus x 4 rows per warp tile
+        s = (65536 + tiles - 1) / std::max<int64_t>(tiles, 1);
+        s = std::min<int64_t>(s, n / (ncell >= 100000 ? 1000 : 256));   // (small grids: the slabs cost nothing)
     } else {
-        const int64_t target = recurrence ? 1000000 : 1500000;
-        s = (target + ncell - 1) / std::max<int64_t>(ncell, 1);
+        s = (1500000 + ncell - 1) / std::max<int64_t>(ncell, 1);
         s = std::min<int64_t>(s, n / 256);
     }
     return (int)std::max<int64_t>(1, std::min<int64_t>(s, 4096));
@@ -186,7 +224,7 @@ int transform_device(Workspace *w, const double *d_ts, const double *d_ys, int64
     int rc;
     if ((rc = wsbuf(w, "kappa", (size_t)nf, &d_kappa))) return rc;
     if ((rc = wsbuf(w, "dcut", (size_t)nf, &d_dcut))) return rc;
-    if ((rc = wsbuf(w, "flags", 4, &d_unsorted))) return rc;
+    if ((rc = wsbuf(w, "flags", wwz::kFlagInts, &d_unsorted))) return rc;
     d_fix_count = reinterpret_cast<unsigned int *>(d_unsorted + 1);
     if ((rc = wsbuf(w, "fix_list", (size_t)ncell, &d_fix_list))) return rc;
 
@@ -212,16 +250,27 @@ int transform_device(Workspace *w, const double *d_ts, const double *d_ys, int64
             const char *e = getenv("WWZB200_NO_RECURRENCE");
             if (e && *e && atoi(e)) allow_rec = false;
         }
-        const int segs = point_segments(n, ncell, allow_rec);
+        const bool dense = (flags & WWZB200_DENSE) != 0;
+        // small tau grids (the reference default is 50 taus): every row goes to a warp-tile kernel with tau-compact
+        // tiles -- the recurrence flavour where it applies, the direct flavour elsewhere -- because a tile of the
+        // CTA-wide kernel would span the whole tau axis and its point window the whole series
+        bool tile_direct = !dense && nt <= kSmallTauGrid;
+        {
+            const char *e = getenv("WWZB200_NO_TILE_DIRECT");
+            if (e && *e && atoi(e)) tile_direct = false;
+        }
+        const int segs = point_segments(n, nt, nf, allow_rec);   // (not on tile_direct: windowed == dense bit for bit)
         const int64_t seg_len = (((n + segs - 1) / segs + 15) / 16) * 16;
         CellPlan plan = plan_cells(n, nt, nf, cells_per_lane_hint(nt, nf, w->sms), seg_len);
         unsigned long long *d_walked = nullptr;   // profiling: warp-points evaluated by the recurrence kernel
         if (g_profile && (rc = wsbuf(w, "walked", 1, &d_walked))) return rc;
-        RecPlan rplan{};
-        if (allow_rec) {
-            rplan = plan_rec(n, nt, nf, seg_len);
-            const int64_t np = std::max(plan.n_pad, rplan.n_pad);   // one row stride for both kernels
-            plan.n_pad = rplan.n_pad = np;
+        RecPlan rplan{}, dplan{};
+        if (allow_rec) rplan = plan_rec(n, nt, nf, seg_len, kRecCells);
+        if (tile_direct) dplan = plan_rec(n, nt, nf, seg_len, kTileDirectCells);
+        {   // one row stride of the basis scratch for all kernels of the transform
+            int64_t np = tile_direct ? dplan.n_pad : plan.n_pad;
+            if (allow_rec) np = std::max(np, rplan.n_pad);
+            plan.n_pad = rplan.n_pad = dplan.n_pad = np;
         }
         const double cut_bits = (flags & WWZB200_EXACT_WINDOW) ? 1081.0 : 100.0;
         double *d_grid;
@@ -245,7 +294,7 @@ int transform_device(Workspace *w, const double *d_ts, const double *d_ys, int64
         if (d_psd && tspan < 0 && (rc = wsbuf(w, "minmax", 2, &d_mm))) return rc;
         CU(launch_setup(d_omega, nf, d_tau, nt, d_ts, n, c, allow_rec, cut_bits, d_kappa, d_dcut, d_grid, d_rec_row, d_gap,
                         d_unsorted, d_mm, st));   // also zeroes the unsorted flag and d_fix_count (adjacent ints)
-        const bool dense = (flags & WWZB200_DENSE) != 0;
+        unsigned int *d_queue = reinterpret_cast<unsigned int *>(d_unsorted) + 2;   // zeroed by launch_setup
         for (int64_t k0 = 0; k0 < nf; k0 += nf_batch) {
             const int64_t nb = std::min<int64_t>(nf_batch, nf - k0);
             CU(launch_basis(d_ts, d_ys, n, plan.n_pad, d_omega + k0, nb, d_ty, d_basis, k0 == 0, false, st));
@@ -265,9 +314,13 @@ int transform_device(Workspace *w, const double *d_ts, const double *d_ys, int64
             }
             if (allow_rec)
                 CU(launch_rec(rplan, d_ty, d_basis, d_ts, n, d_tau, nt, d_kappa, d_dcut, d_gap, d_unsorted, k0, nb, nf, segs,
-                              seg_len, d_rec_row, d_grid, d_sums, d_walked, st));
-            CU(launch_cells(plan, d_ty, d_basis, d_ts, n, d_tau, nt, d_kappa, d_dcut, d_gap, d_unsorted, k0, nb, nf, dense, segs,
-                            seg_len, allow_rec ? d_rec_row : nullptr, d_grid, d_sums, st_direct));
+                              seg_len, d_rec_row, d_grid, d_sums, d_queue, d_walked, w->sms, st));
+            if (tile_direct)
+                CU(launch_rec(dplan, d_ty, d_basis, d_ts, n, d_tau, nt, d_kappa, d_dcut, d_gap, d_unsorted, k0, nb, nf, segs,
+                              seg_len, allow_rec ? d_rec_row : nullptr, d_grid, d_sums, d_queue + 2, nullptr, w->sms, st_direct));
+            else
+                CU(launch_cells(plan, d_ty, d_basis, d_ts, n, d_tau, nt, d_kappa, d_dcut, d_gap, d_unsorted, k0, nb, nf, dense, segs,
+                                seg_len, allow_rec ? d_rec_row : nullptr, d_grid, d_sums, st_direct));
             if (fork) {
                 CU(cudaEventRecord(w->side_join, w->side));
                 CU(cudaStreamWaitEvent(st, w->side_join, 0));
@@ -286,9 +339,14 @@ int transform_device(Workspace *w, const double *d_ts, const double *d_ys, int64
                 }
                 if (allow_rec)
                     CU(launch_rec(rplan, d_ty, d_basis, d_ts, n, d_tau, nt, d_kappa, d_dcut, d_gap, d_unsorted, k0, nb, nf, segs,
-                                  seg_len, d_rec_row, d_grid, d_sums2, nullptr, st));
-                CU(launch_cells(plan, d_ty, d_basis, d_ts, n, d_tau, nt, d_kappa, d_dcut, d_gap, d_unsorted, k0, nb, nf, dense,
-                                segs, seg_len, allow_rec ? d_rec_row : nullptr, d_grid, d_sums2, st_direct));
+                                  seg_len, d_rec_row, d_grid, d_sums2, d_queue, nullptr, w->sms, st));
+                if (tile_direct)
+                    CU(launch_rec(dplan, d_ty, d_basis, d_ts, n, d_tau, nt, d_kappa, d_dcut, d_gap, d_unsorted, k0, nb, nf,
+                                  segs, seg_len, allow_rec ? d_rec_row : nullptr, d_grid, d_sums2, d_queue + 2, nullptr, w->sms,
+                                  st_direct));
+                else
+                    CU(launch_cells(plan, d_ty, d_basis, d_ts, n, d_tau, nt, d_kappa, d_dcut, d_gap, d_unsorted, k0, nb, nf, dense,
+                                    segs, seg_len, allow_rec ? d_rec_row : nullptr, d_grid, d_sums2, st_direct));
                 if (fork) {
                     CU(cudaEventRecord(w->side_join, w->side));
                     CU(cudaStreamWaitEvent(st, w->side_join, 0));
@@ -342,6 +400,8 @@ int host_transform(const double *ts, const double *ys, int64_t n, const double *
     Workspace *w;
     if ((rc = workspace(&w))) return rc;
     cudaStream_t st = w->stream;
+    ScratchScope scope(w, st);
+    if ((rc = scope.begin())) return rc;
     const int64_t ncell = nt * nf;
     double *d_in, *d_out;
     const size_t in_count = (size_t)(2 * n + nt + nf);
@@ -422,7 +482,7 @@ int shared_axis_device(Workspace *w, const double *d_ts, const double *d_Y, int6
     double2 *d_ty, *d_basis, *d_rot;
     unsigned int *d_fix;
     int *d_unsorted;
-    if ((rc = wsbuf(w, "flags", 4, &d_unsorted))) return rc;
+    if ((rc = wsbuf(w, "flags", wwz::kFlagInts, &d_unsorted))) return rc;
     if ((rc = wsbuf(w, "kappa", (size_t)nf, &d_kappa))) return rc;
     if ((rc = wsbuf(w, "dcut", (size_t)nf, &d_dcut))) return rc;
     if ((rc = wsbuf(w, "ty", (size_t)plan.n_pad, &d_ty))) return rc;
@@ -607,8 +667,10 @@ int wwzb200_wwa2psd(const double *wwa, const double *Neffs, int64_t nt, int64_t 
     if ((rc = workspace(&w))) return rc;
     const int64_t ncell = nt * nf;
     double *d;
-    if ((rc = wsbuf(w, "out", (size_t)(6 * ncell + nf), &d))) return rc;
     cudaStream_t st = w->stream;
+    ScratchScope scope(w, st);
+    if ((rc = scope.begin())) return rc;
+    if ((rc = wsbuf(w, "out", (size_t)(6 * ncell + nf), &d))) return rc;
     if (ncell) {
         CU(cudaMemcpyAsync(d, wwa, sizeof(double) * ncell, cudaMemcpyHostToDevice, st));
         CU(cudaMemcpyAsync(d + ncell, Neffs, sizeof(double) * ncell, cudaMemcpyHostToDevice, st));
@@ -633,6 +695,8 @@ int wwzb200_kirchner_dev(const double *d_ts, const double *d_pd_ys, int64_t nts,
     std::lock_guard<std::mutex> lock(g_mu);
     Workspace *w;
     if ((rc = workspace(&w))) return rc;
+    ScratchScope scope(w, static_cast<cudaStream_t>(stream));
+    if ((rc = scope.begin())) return rc;
     return transform_device(w, d_ts, d_pd_ys, nts, d_taus, nt, d_omegas, nf, c, Neff_threshold, psd_Neff_threshold,
                             flags, d_Neffs, d_a0, d_a1, d_a2, d_wwa, d_phase, d_psd, out_row_stride, -1.0,
                             static_cast<cudaStream_t>(stream));
@@ -674,6 +738,8 @@ int wwzb200_kirchner_shared_axis_dev(const double *d_ts, const double *d_Y, int6
     Workspace *w;
     if ((rc = workspace(&w))) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    ScratchScope scope(w, st);
+    if ((rc = scope.begin())) return rc;
     double tspan = 0;
     if (d_psd) {   // span of the (device) time axis, needed by wwa2psd
         double *d_mm, mm[2];
@@ -699,6 +765,8 @@ int wwzb200_kirchner_shared_axis(const double *ts, const double *Y, int64_t nts,
     Workspace *w;
     if ((rc = workspace(&w))) return rc;
     cudaStream_t st = w->stream;
+    ScratchScope scope(w, st);
+    if ((rc = scope.begin())) return rc;
     const int64_t ncell = nt * nf;
     double *d_in, *d_Y, *d_ne, *d_psd = nullptr;
     if ((rc = wsbuf(w, "in", (size_t)(2 * nts + nt + nf), &d_in))) return rc;
@@ -729,42 +797,61 @@ int wwzb200_kirchner_shared_axis(const double *ts, const double *Y, int64_t nts,
     return 0;
 }
 
-static int surrogates_dev(const double *d_ts, int64_t nts, double tau_est, double sigma, double mu, int64_t S,
-                          uint64_t seed, bool uar1, double *d_Y, void *stream, uint64_t first_series = 0)
+// (caller holds g_mu and has opened a ScratchScope on the stream)
+static int surrogates_nolock(Workspace *w, const double *d_ts, int64_t nts, double tau_est, double sigma, double mu,
+                             int64_t S, uint64_t seed, bool uar1, double *d_Y, cudaStream_t st, uint64_t first_series)
 {
-    if (nts < 1 || S < 0) return fail(WWZB200_ERR_ARG, "bad sizes");
-    if (!d_ts || (S && !d_Y)) return fail(WWZB200_ERR_ARG, "null pointer");
-    if (!(tau_est > 0)) return fail(WWZB200_ERR_ARG, "tau must be positive");
-    if (uar1 && !(sigma >= 0)) return fail(WWZB200_ERR_ARG, "sigma_2 must be non-negative");
-    std::lock_guard<std::mutex> lock(g_mu);
-    Workspace *w;
-    int rc;
-    if ((rc = workspace(&w))) return rc;
     double *d_rq;
+    int rc;
     if ((rc = wsbuf(w, "ar1_rq", (size_t)2 * nts, &d_rq))) return rc;
-    CU(wwz::launch_ar1(d_ts, nts, tau_est, sigma, mu, S, seed, uar1, d_rq, d_rq + nts, d_Y,
-                       static_cast<cudaStream_t>(stream), first_series));
+    CU(wwz::launch_ar1(d_ts, nts, tau_est, sigma, mu, S, seed, uar1, d_rq, d_rq + nts, d_Y, st, first_series));
     return 0;
 }
 
-static int surrogates_host(const double *ts, int64_t nts, double tau_est, double sigma, double mu, int64_t S,
-                           uint64_t seed, bool uar1, double *Y)
+static int check_surrogate_args(const void *ts, int64_t nts, double tau_est, double sigma, int64_t S, bool uar1,
+                                const void *Y)
 {
     if (nts < 1 || S < 0) return fail(WWZB200_ERR_ARG, "bad sizes");
     if (!ts || (S && !Y)) return fail(WWZB200_ERR_ARG, "null pointer");
+    if (!(tau_est > 0)) return fail(WWZB200_ERR_ARG, "tau must be positive");
+    if (uar1 && !(sigma >= 0)) return fail(WWZB200_ERR_ARG, "sigma_2 must be non-negative");
+    return 0;
+}
+
+static int surrogates_dev(const double *d_ts, int64_t nts, double tau_est, double sigma, double mu, int64_t S,
+                          uint64_t seed, bool uar1, double *d_Y, void *stream, uint64_t first_series = 0)
+{
+    int rc = check_surrogate_args(d_ts, nts, tau_est, sigma, S, uar1, d_Y);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lock(g_mu);
     Workspace *w;
-    int rc;
+    if ((rc = workspace(&w))) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    ScratchScope scope(w, st);
+    if ((rc = scope.begin())) return rc;
+    return surrogates_nolock(w, d_ts, nts, tau_est, sigma, mu, S, seed, uar1, d_Y, st, first_series);
+}
+
+// Host buffers in and out.  The lock is held from the first workspace request to the final synchronisation: the
+// named buffers ("in", "Y") belong to this call until its results have left the device.
+static int surrogates_host(const double *ts, int64_t nts, double tau_est, double sigma, double mu, int64_t S,
+                           uint64_t seed, bool uar1, double *Y)
+{
+    int rc = check_surrogate_args(ts, nts, tau_est, sigma, S, uar1, Y);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lock(g_mu);
+    Workspace *w;
     double *d_ts, *d_Y;
-    {
-        std::lock_guard<std::mutex> lock(g_mu);
-        if ((rc = workspace(&w))) return rc;
-        if ((rc = wsbuf(w, "in", (size_t)nts, &d_ts))) return rc;
-        if ((rc = wsbuf(w, "Y", (size_t)S * (size_t)nts, &d_Y))) return rc;
-        CU(cudaMemcpyAsync(d_ts, ts, sizeof(double) * nts, cudaMemcpyHostToDevice, w->stream));
-    }
-    if ((rc = surrogates_dev(d_ts, nts, tau_est, sigma, mu, S, seed, uar1, d_Y, w->stream))) return rc;
-    if (S) CU(cudaMemcpyAsync(Y, d_Y, sizeof(double) * (size_t)S * (size_t)nts, cudaMemcpyDeviceToHost, w->stream));
-    CU(cudaStreamSynchronize(w->stream));
+    if ((rc = workspace(&w))) return rc;
+    cudaStream_t st = w->stream;
+    ScratchScope scope(w, st);
+    if ((rc = scope.begin())) return rc;
+    if ((rc = wsbuf(w, "in", (size_t)nts, &d_ts))) return rc;
+    if ((rc = wsbuf(w, "Y", (size_t)S * (size_t)nts, &d_Y))) return rc;
+    CU(cudaMemcpyAsync(d_ts, ts, sizeof(double) * nts, cudaMemcpyHostToDevice, st));
+    if ((rc = surrogates_nolock(w, d_ts, nts, tau_est, sigma, mu, S, seed, uar1, d_Y, st, 0))) return rc;
+    if (S) CU(cudaMemcpyAsync(Y, d_Y, sizeof(double) * (size_t)S * (size_t)nts, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
     return 0;
 }
 
@@ -818,63 +905,81 @@ int wwzb200_shared_axis_cells_dev(const double *d_ts, const double *d_Y, int64_t
     std::lock_guard<std::mutex> lock(g_mu);
     Workspace *w;
     if ((rc = workspace(&w))) return rc;
+    ScratchScope scope(w, static_cast<cudaStream_t>(stream));
+    if ((rc = scope.begin())) return rc;
     return shared_axis_device(w, d_ts, d_Y, nts, S, d_taus, nt, d_omegas, nf, c, Neff_threshold, 0, flags, d_Neffs,
                               nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0.0, nullptr, nullptr,
                               static_cast<cudaStream_t>(stream), d_amp_cells);
 }
 
-int wwzb200_quantiles_cells_dev(const double *d_Xcells, int64_t S, int64_t stride, int64_t ncell, const double *d_probs,
-                                int64_t nq, double *d_q, void *stream)
-{
-    if (S < 1 || ncell < 0 || nq < 0 || stride < S) return fail(WWZB200_ERR_ARG, "bad sizes");
-    if (ncell == 0 || nq == 0) return 0;
-    if (!d_Xcells || !d_probs || !d_q) return fail(WWZB200_ERR_ARG, "null pointer");
-    if (S > ((int64_t)1 << 24)) return fail(WWZB200_ERR_ARG, "S too large for the quantile kernel");
-    std::lock_guard<std::mutex> lock(g_mu);
-    Workspace *w;
-    int rc;
-    if ((rc = workspace(&w))) return rc;
-    return quantiles_device(w, d_Xcells, S, stride, ncell, d_probs, nq, d_q, static_cast<cudaStream_t>(stream));
-}
-
-int wwzb200_quantiles_dev(const double *d_X, int64_t S, int64_t ncell, const double *d_probs, int64_t nq, double *d_q,
-                          void *stream)
+static int check_quantile_args(const void *X, int64_t S, int64_t ncell, const void *probs, int64_t nq, const void *q)
 {
     if (S < 1 || ncell < 0 || nq < 0) return fail(WWZB200_ERR_ARG, "bad sizes");
     if (ncell == 0 || nq == 0) return 0;
-    if (!d_X || !d_probs || !d_q) return fail(WWZB200_ERR_ARG, "null pointer");
+    if (!X || !probs || !q) return fail(WWZB200_ERR_ARG, "null pointer");
     if (S > ((int64_t)1 << 24)) return fail(WWZB200_ERR_ARG, "S too large for the quantile kernel");
+    return 0;
+}
+
+int wwzb200_quantiles_cells_dev(const double *d_Xcells, int64_t S, int64_t stride, int64_t ncell, const double *d_probs,
+                                int64_t nq, double *d_q, void *stream)
+{
+    if (stride < S) return fail(WWZB200_ERR_ARG, "bad sizes");
+    int rc = check_quantile_args(d_Xcells, S, ncell, d_probs, nq, d_q);
+    if (rc || ncell == 0 || nq == 0) return rc;
     std::lock_guard<std::mutex> lock(g_mu);
     Workspace *w;
-    int rc;
     if ((rc = workspace(&w))) return rc;
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    ScratchScope scope(w, static_cast<cudaStream_t>(stream));
+    if ((rc = scope.begin())) return rc;
+    return quantiles_device(w, d_Xcells, S, stride, ncell, d_probs, nq, d_q, static_cast<cudaStream_t>(stream));
+}
+
+// series-major [S][ncell] input (caller holds g_mu and a ScratchScope on the stream)
+static int quantiles_series_major_nolock(Workspace *w, const double *d_X, int64_t S, int64_t ncell, const double *d_probs,
+                                         int64_t nq, double *d_q, cudaStream_t st)
+{
     double *d_Xc;
+    int rc;
     if ((rc = wsbuf(w, "q_cells", (size_t)S * (size_t)ncell, &d_Xc))) return rc;
     CU(wwz::launch_transpose(d_X, S, ncell, ncell, d_Xc, S, st));   // [S][ncell] -> [ncell][S]
     return quantiles_device(w, d_Xc, S, S, ncell, d_probs, nq, d_q, st);
 }
 
+int wwzb200_quantiles_dev(const double *d_X, int64_t S, int64_t ncell, const double *d_probs, int64_t nq, double *d_q,
+                          void *stream)
+{
+    int rc = check_quantile_args(d_X, S, ncell, d_probs, nq, d_q);
+    if (rc || ncell == 0 || nq == 0) return rc;
+    std::lock_guard<std::mutex> lock(g_mu);
+    Workspace *w;
+    if ((rc = workspace(&w))) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    ScratchScope scope(w, st);
+    if ((rc = scope.begin())) return rc;
+    return quantiles_series_major_nolock(w, d_X, S, ncell, d_probs, nq, d_q, st);
+}
+
+// Host buffers in and out: the lock is held until the quantiles have left the device (see surrogates_host).
 int wwzb200_quantiles(const double *X, int64_t S, int64_t ncell, const double *probs, int64_t nq, double *q)
 {
-    if (S < 1 || ncell < 0 || nq < 0) return fail(WWZB200_ERR_ARG, "bad sizes");
-    if (ncell == 0 || nq == 0) return 0;
-    if (!X || !probs || !q) return fail(WWZB200_ERR_ARG, "null pointer");
+    int rc = check_quantile_args(X, S, ncell, probs, nq, q);
+    if (rc || ncell == 0 || nq == 0) return rc;
+    std::lock_guard<std::mutex> lock(g_mu);
     Workspace *w;
-    int rc;
     double *d_X, *d_p, *d_q;
-    {
-        std::lock_guard<std::mutex> lock(g_mu);
-        if ((rc = workspace(&w))) return rc;
-        if ((rc = wsbuf(w, "q_in", (size_t)S * (size_t)ncell, &d_X))) return rc;
-        if ((rc = wsbuf(w, "q_out", (size_t)nq * (size_t)ncell + (size_t)nq, &d_q))) return rc;
-        d_p = d_q + (size_t)nq * (size_t)ncell;
-        CU(cudaMemcpyAsync(d_X, X, sizeof(double) * (size_t)S * (size_t)ncell, cudaMemcpyHostToDevice, w->stream));
-        CU(cudaMemcpyAsync(d_p, probs, sizeof(double) * nq, cudaMemcpyHostToDevice, w->stream));
-    }
-    if ((rc = wwzb200_quantiles_dev(d_X, S, ncell, d_p, nq, d_q, w->stream))) return rc;
-    CU(cudaMemcpyAsync(q, d_q, sizeof(double) * (size_t)nq * (size_t)ncell, cudaMemcpyDeviceToHost, w->stream));
-    CU(cudaStreamSynchronize(w->stream));
+    if ((rc = workspace(&w))) return rc;
+    cudaStream_t st = w->stream;
+    ScratchScope scope(w, st);
+    if ((rc = scope.begin())) return rc;
+    if ((rc = wsbuf(w, "q_in", (size_t)S * (size_t)ncell, &d_X))) return rc;
+    if ((rc = wsbuf(w, "q_out", (size_t)nq * (size_t)ncell + (size_t)nq, &d_q))) return rc;
+    d_p = d_q + (size_t)nq * (size_t)ncell;
+    CU(cudaMemcpyAsync(d_X, X, sizeof(double) * (size_t)S * (size_t)ncell, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_p, probs, sizeof(double) * nq, cudaMemcpyHostToDevice, st));
+    if ((rc = quantiles_series_major_nolock(w, d_X, S, ncell, d_p, nq, d_q, st))) return rc;
+    CU(cudaMemcpyAsync(q, d_q, sizeof(double) * (size_t)nq * (size_t)ncell, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
     return 0;
 }
 
@@ -893,7 +998,7 @@ int wwzb200_kirchner_ragged(const double *ts, const double *pd_ys, const int64_t
         return fail(WWZB200_ERR_ARG, "null pointer");
     if (Neff_threshold < 1) return fail(WWZB200_ERR_ARG, "Neff_threshold must be a positive integer");
     if (!(c > 0) || !std::isfinite(c)) return fail(WWZB200_ERR_ARG, "decay constant c must be positive and finite");
-    int64_t max_cells = 0, max_n = 0, max_nf = 0, max_basis = 0, max_sums = 0;
+    int64_t max_cells = 0, max_n = 0, max_nf = 0, max_nt = 0, max_basis = 0, max_sums = 0;
     for (int64_t m = 0; m < M; ++m) {
         const int64_t n = ts_off[m + 1] - ts_off[m], nt = tau_off[m + 1] - tau_off[m], nf = om_off[m + 1] - om_off[m];
         if (n < 1 || nt < 0 || nf < 0 || out_off[m + 1] - out_off[m] != nt * nf)
@@ -901,14 +1006,17 @@ int wwzb200_kirchner_ragged(const double *ts, const double *pd_ys, const int64_t
         max_cells = std::max(max_cells, nt * nf);
         max_n = std::max(max_n, n);
         max_nf = std::max(max_nf, nf);
+        max_nt = std::max(max_nt, nt);
         max_basis = std::max(max_basis, nf * (n + wwz::kMaxPointsPerStage + 16));
-        max_sums = std::max(max_sums, (int64_t)point_segments(n, nt * nf, false) * wwz::kNumSums * nt * nf);
+        max_sums = std::max(max_sums, (int64_t)std::max(point_segments(n, nt, nf, false), point_segments(n, nt, nf, true)) * wwz::kNumSums * nt * nf);
     }
     std::lock_guard<std::mutex> lock(g_mu);
     Workspace *w;
     int rc;
     if ((rc = workspace(&w))) return rc;
     cudaStream_t st = w->stream;
+    ScratchScope scope(w, st);
+    if ((rc = scope.begin())) return rc;
     const int64_t NT = ts_off[M] - ts_off[0], NTAU = tau_off[M] - tau_off[0], NOM = om_off[M] - om_off[0];
     const int64_t NOUT = out_off[M] - out_off[0];
     double *d_in, *d_out;
@@ -923,7 +1031,8 @@ int wwzb200_kirchner_ragged(const double *ts, const double *pd_ys, const int64_t
     for (int i = 0; i < 6; ++i) o[i] = d_out + (size_t)i * NOUT;
     double *o_psd = d_out + (size_t)6 * NOUT;
     // Members are independent: they are enqueued round-robin on kLanes streams, each with its own scratch
-    // set (pre-sized for the largest member so that nothing is re-allocated while work is in flight).
+    // set, pre-sized for the largest member (every buffer transform_device asks for, with upper bounds for the
+    // padded lengths) so that nothing is re-allocated -- cudaFree synchronises the device -- while work is in flight.
     const int nl = (int)std::min<int64_t>(kLanes, M);
     for (int l = 0; l < nl; ++l) {
         double *dd;
@@ -933,7 +1042,7 @@ int wwzb200_kirchner_ragged(const double *ts, const double *pd_ys, const int64_t
         w->prefix = "lane" + std::to_string(l) + "_";
         if ((rc = wsbuf(w, "kappa", (size_t)max_nf, &dd))) break;
         if ((rc = wsbuf(w, "dcut", (size_t)max_nf, &dd))) break;
-        if ((rc = wsbuf(w, "flags", 4, &di))) break;
+        if ((rc = wsbuf(w, "flags", wwz::kFlagInts, &di))) break;
         if ((rc = wsbuf(w, "grid", 2, &dd))) break;
         { unsigned char *dc; if ((rc = wsbuf(w, "rec_row", (size_t)max_nf, &dc))) break; }
         if ((rc = wsbuf(w, "ty", (size_t)(max_n + wwz::kMaxPointsPerStage + 16), &d2))) break;
@@ -942,6 +1051,13 @@ int wwzb200_kirchner_ragged(const double *ts, const double *pd_ys, const int64_t
         if ((rc = wsbuf(w, "sums", (size_t)max_sums, &dd))) break;
         if ((rc = wsbuf(w, "fix_list", (size_t)max_cells + 1, &du))) break;
         if (psd && (rc = wsbuf(w, "psd_wwa", (size_t)max_cells, &dd))) break;
+        if ((rc = wsbuf(w, "taugap", (size_t)std::max<int64_t>(max_nt, 1), &dd))) break;
+        if ((rc = wsbuf(w, "minmax", 2, &dd))) break;
+        if ((flags & WWZB200_FOSTER) && (rc = wsbuf(w, "sums2", (size_t)max_sums, &dd))) break;
+        if (g_profile) {
+            unsigned long long *dw;
+            if ((rc = wsbuf(w, "walked", 1, &dw))) break;
+        }
     }
     w->prefix.clear();
     if (rc) return rc;
@@ -993,6 +1109,8 @@ int wwzb200_ar1_signif(const double *ts, int64_t nts, double tau_est, double sig
     Workspace *w;
     if ((rc = workspace(&w))) return rc;
     cudaStream_t st = w->stream;
+    ScratchScope scope(w, st);
+    if ((rc = scope.begin())) return rc;
     const int64_t ncell = nt * nf;
     double *d_in, *d_Y, *d_rq, *d_ne, *d_q, *d_psd = nullptr, *d_psd_t = nullptr;
     if ((rc = wsbuf(w, "in", (size_t)(2 * nts + nt + nf + nq), &d_in))) return rc;

@@ -13,8 +13,11 @@ constexpr int kStages = 3;
 constexpr int kNumSums = 7;  // W, Q, Ws, Wc, Wy, Wys, Wyc
 constexpr int kStageBudget = 32 * 1024;
 constexpr int kMaxPointsPerStage = 512;
-constexpr int kRecCells = 8;     // tau-adjacent cells per lane in the tau-recurrence kernel
-constexpr int kRecConsumerWarps = 8;    // consumer warps of its CTA (11 warps, 384 threads, measured slower)
+constexpr int kRecCells = 8;     // tau-adjacent cells per lane in the tau-recurrence flavour of the warp-tile kernel
+constexpr int kTileDirectCells = 2;     // ... in its direct flavour (small tau grids)
+constexpr int kSmallTauGrid = 64;       // at most this many taus: tau-compact warp tiles for every row
+constexpr int kFlagInts = 8;     // per-transform device ints: [0] unsorted flag, [1] deep-underflow counter,
+                                 // [2..3] work queue of the recurrence launch, [4..5] of the direct warp-tile launch
 constexpr int kMaxWarps = 16;
 
 // Geometry of one launch of the cell kernel, derived on the host by plan_cells().
@@ -33,41 +36,37 @@ struct CellPlan {
 
 CellPlan plan_cells(int64_t n, int64_t nt, int64_t nf, int cells_per_lane_hint, int64_t seg_len);
 
-// Geometry of the warp-tile tau-recurrence kernel (wwz_rec.cu), derived on the host by plan_rec().
+// Geometry of the warp-tile kernels (wwz_rec.cu), derived on the host by plan_rec().
 struct RecPlan {
-    int groups;           // G = ceil(nt / 8) tau-groups per frequency row
+    int cells_per_lane;   // kRecCells = tau-recurrence flavour, kTileDirectCells = direct flavour
+    int groups;           // G = ceil(nt / cells_per_lane) tau-groups per frequency row
     int tg_log2;          // a warp tile is 2^tg_log2 tau-groups x (32 >> tg_log2) frequency rows
     int points;           // P: points per stage of a warp's ring
     int64_t n_pad;
-    int64_t row_stride;   // smem basis row stride in bytes ((P+1)*32)
+    int64_t row_stride;   // smem basis row stride in bytes (P*32 + 16)
     int stage_bytes;      // bytes of one stage
     int warp_bytes;       // shared memory per warp (ring + mbarriers)
+    int warps, nreg;      // CTA shape: warps per CTA, register budget per thread
     int smem_bytes;       // dynamic shared memory of the CTA
 };
-RecPlan plan_rec(int64_t n, int64_t nt, int64_t nf, int64_t seg_len);
+RecPlan plan_rec(int64_t n, int64_t nt, int64_t nf, int64_t seg_len, int cells_per_lane = kRecCells);
+// d_queue: two zeroed ints (work queue; left zeroed by the launch).  d_rec_row: rows marked 1 belong to the recurrence
+// flavour, rows marked 0 to the direct flavour (null: the launch takes every row).
 cudaError_t launch_rec(const RecPlan &plan, const double2 *d_ty, const double2 *d_basis, const double *d_ts, int64_t n,
                        const double *d_tau, int64_t nt, const double *d_kappa, const double *d_dcut,
                        const double *d_taugap, const int *d_unsorted, int64_t k0, int64_t nf_batch, int64_t nf_total, int segs,
                        int64_t seg_len, const unsigned char *d_rec_row, const double *d_grid, double *d_sums,
-                       unsigned long long *d_walked, cudaStream_t st);
+                       unsigned int *d_queue, unsigned long long *d_walked, int sms, cudaStream_t st);
 
-// Per-frequency constants: kappa = omega*sqrt(c*log2 e), dcut = underflow distance (windowing).
-// Also decides on the device which rows the tau-recurrence kernel may take (d_rec_row) and the tau
-// spacing (d_grid[0]); allow_rec = false marks every row for the direct kernel.
-// cut_bits: weights below 2^-cut_bits of a cell's largest weight are outside the point window of a tile
-// (1081 = exactly zero weights only).
-cudaError_t launch_freq_setup(const double *d_omega, int64_t nf, const double *d_tau, int64_t nt, double c,
-                              bool allow_rec, double cut_bits, double *d_kappa, double *d_dcut, double *d_grid,
-                              unsigned char *d_rec_row, cudaStream_t st);
-
-// One launch for the whole preamble of a transform: launch_freq_setup + launch_tau_gap + launch_unsorted_check
-// (+ launch_minmax when d_minmax != NULL) and the reset of the two ints at d_flags (unsorted flag, fix counter).
+// Per-frequency constants kappa4 = 4*omega*sqrt(c*log2 e) and dcut = distance beyond which a weight is below
+// 2^-cut_bits (1081 = exactly zero weights only; windowing); which rows the tau-recurrence flavour may take
+// (d_rec_row; allow_rec = false marks every row for the direct flavour) and the tau spacing (d_grid[0]), decided on
+// the device; gap[j] = distance from tau[j] to the nearest sample of the sorted time axis; the sortedness flag; the
+// min / max of the time axis when d_minmax != NULL; and the reset of the kFlagInts ints at d_flags.
+// One launch (+ one memset) for the whole preamble of a transform.
 cudaError_t launch_setup(const double *d_omega, int64_t nf, const double *d_tau, int64_t nt, const double *d_ts, int64_t n,
                          double c, bool allow_rec, double cut_bits, double *d_kappa, double *d_dcut, double *d_grid,
                          unsigned char *d_rec_row, double *d_gap, int *d_flags, double *d_minmax, cudaStream_t st);
-
-// gap[j] = distance from tau[j] to the nearest sample of the sorted time axis (windows relative to the largest weight)
-cudaError_t launch_tau_gap(const double *d_ts, int64_t n, const double *d_tau, int64_t nt, double *d_gap, cudaStream_t st);
 
 // (t, y) interleaved + per-frequency basis rows (sin, cos, y sin, y cos), zero padded to n_pad.
 // cos_as_y: records (sin, cos, cos*sin, cos*cos) -- the second pass of Foster's method (wwz_foster.cu).
@@ -83,9 +82,6 @@ cudaError_t launch_cells(const CellPlan &plan, const double2 *d_ty, const double
                          const double *d_dcut, const double *d_taugap, const int *d_unsorted, int64_t k0, int64_t nf_batch,
                          int64_t nf_total, bool dense, int segs, int64_t seg_len, const unsigned char *d_rec_row,
                          const double *d_grid, double *d_sums, cudaStream_t st);
-
-// *d_flag = 1 if d_x is not ascending (the windowed path needs a sorted time axis).
-cudaError_t launch_unsorted_check(const double *d_x, int64_t n, int *d_flag, cudaStream_t st);
 
 // Per-cell epilogue: Neff, mask, a0, a1, a2, amplitude, phase from the seven sums.
 cudaError_t launch_finalize(const double *d_sums, const double *d_tau, const double *d_omega, int64_t nt,

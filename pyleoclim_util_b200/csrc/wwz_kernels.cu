@@ -13,7 +13,7 @@
 //   W = sum w, Q = sum w^2, Ws = sum w s, Wc = sum w c, Wy = sum w y, Wys = sum w y s, Wyc = sum w y c.
 //
 // Kernels
-//   freq_setup_kernel   per-frequency constants
+//   setup_kernel        per-frequency constants, tau-grid check, tau-to-sample gaps, sortedness, time span
 //   basis_kernel        sincos(omega_k * t_i) once per (frequency, point) -> packed basis rows
 //   wwz_cells_kernel    the hot kernel: TMA-staged points, one lane per M tau-adjacent cells,
 //                       FP64 accumulation on the CUDA cores, no cross-lane reduction
@@ -39,102 +39,30 @@ void bump_launch_counter(int64_t k) { g_launches.fetch_add(k); }
 // ------------------------------------------------------------------------------------------------
 // Per-frequency constants.
 //   kappa4 = 4*omega*sqrt(c*log2(e))         so that  exp(-c*omega^2*d^2) = 2^(-(kappa4*d)^2/16)
-//   dcut   = 4*sqrt(cut_bits)/|kappa4|       |d| > dcut  =>  weight < 2^-cut_bits (default 300; 1081 with
+//   dcut   = 4*sqrt(cut_bits)/|kappa4|       |d| > dcut  =>  weight < 2^-cut_bits (default 100; 1081 with
 //                                            WWZB200_EXACT_WINDOW: exactly 0.0 in the direct kernel);
 //                                            used only to window the point range of a tile
 // omega = NaN (frequency above Nyquist, utils/wavelet.py:1229-1232): kappa = NaN is kept; NaN then
 // flows through every sum of the column and the epilogue yields NaN Neff / coefficients, exactly
 // what NaN arithmetic gives in the reference.  dcut = -1 marks the row as "no window constraint".
 // ------------------------------------------------------------------------------------------------
-// tau-recurrence applicability (wwz_cells_kernel<8, true, .>), decided on the device so that no
+// tau-recurrence applicability (wwz_tile_kernel<8, true>, wwz_rec.cu), decided on the device so that no
 // entry point has to synchronise: tau must be equally spaced (to 8 ulp) with at least 16 points, and
 // a frequency row qualifies while D = kappa4*dtau <= 8.  The recurrence runs from the first of the
 // lane's 8 cells, so a weight is dropped (w_0 flushed at |a| > 127.8) only when every one of the 8
 // cells sees it below 2^(-(127.8 - 7*8)^2/16) = 2^-322 -- far below the 2^-200 threshold under
 // which the epilogue hands a cell to the faithful kernel.
 // grid[0] = dtau, grid[1] = 1.0 if tau is equally spaced else 0.0.
-__global__ void tau_uniform_kernel(const double *__restrict__ tau, int64_t nt, double *__restrict__ grid)
-{
-    __shared__ int bad;
-    if (threadIdx.x == 0) bad = 0;
-    __syncthreads();
-    double d = 0.0;
-    if (nt >= 2 * kRecCells) {
-        d = (tau[nt - 1] - tau[0]) / (double)(nt - 1);
-        const double scale = fmax(fabs(tau[0]), fabs(tau[nt - 1]));
-        const double tol = 8.0 * (scale > 0 ? scale : 1.0) * 0x1p-52;
-        if (!(d > 0) || isinf(d)) bad = 1;
-        for (int64_t j = threadIdx.x; j < nt; j += blockDim.x)
-            if (!(fabs(tau[j] - (tau[0] + (double)j * d)) <= tol)) bad = 1;
-    } else if (threadIdx.x == 0) {
-        bad = 1;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        grid[0] = d;
-        grid[1] = bad ? 0.0 : 1.0;
-    }
-}
-
-__global__ void freq_setup_kernel(const double *__restrict__ omega, int64_t nf, double kscale, double vcut,
-                                  const double *__restrict__ grid, int allow_rec, double *__restrict__ kappa,
-                                  double *__restrict__ dcut, unsigned char *__restrict__ rec_row)
-{
-    int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (k >= nf) return;
-    const double om = omega[k];
-    const double ka = om * kscale;
-    kappa[k] = ka;
-    dcut[k] = isnan(om) ? -1.0 : vcut / fabs(ka);  // |kappa4*d| > vcut => weight < 2^-cut_bits; +inf for omega == 0
-    rec_row[k] = (allow_rec && grid[1] != 0.0 && fabs(ka) * grid[0] <= 8.0) ? 1 : 0;   // NaN omega -> 0
-}
-
-cudaError_t launch_freq_setup(const double *d_omega, int64_t nf, const double *d_tau, int64_t nt, double c,
-                              bool allow_rec, double cut_bits, double *d_kappa, double *d_dcut, double *d_grid,
-                              unsigned char *d_rec_row, cudaStream_t st)
-{
-    if (nf <= 0) return cudaSuccess;
-    const double kscale = 4.0 * std::sqrt(c * 1.4426950408889634074);  // 4*sqrt(c*log2(e))
-    tau_uniform_kernel<<<1, 256, 0, st>>>(d_tau, nt, d_grid);
-    freq_setup_kernel<<<(unsigned)((nf + 127) / 128), 128, 0, st>>>(d_omega, nf, kscale, 4.0 * std::sqrt(cut_bits), d_grid, allow_rec ? 1 : 0,
-                                                                    d_kappa, d_dcut, d_rec_row);
-    bump_launch_counter(2);
-    return cudaGetLastError();
-}
-
+//
 // Distance from every tau to the nearest sample of the (sorted) time axis.  The point window of a tile is measured
 // relative to the largest weight of its cells: a cell whose nearest sample is gap away has a largest weight of
 // 2^-(kappa4*gap)^2/16, so points beyond sqrt(dcut^2 + gap^2) weigh less than 2^-cut_bits of it -- inside a hiatus the
 // window widens by itself and no cell ever loses a weight that matters relative to its own sums.
-__global__ void tau_gap_kernel(const double *__restrict__ ts, int64_t n, const double *__restrict__ tau, int64_t nt,
-                               double *__restrict__ gap)
-{
-    const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (j >= nt) return;
-    const double tj = tau[j];
-    int64_t l = 0, r = n;   // first index with ts >= tj
-    while (l < r) {
-        const int64_t m = (l + r) >> 1;
-        if (ts[m] < tj) l = m + 1; else r = m;
-    }
-    double g = CUDART_INF;
-    if (l < n) g = fabs(ts[l] - tj);
-    if (l > 0) g = fmin(g, fabs(tj - ts[l - 1]));
-    gap[j] = isnan(g) ? CUDART_INF : g;
-}
-
-cudaError_t launch_tau_gap(const double *d_ts, int64_t n, const double *d_tau, int64_t nt, double *d_gap, cudaStream_t st)
-{
-    if (nt <= 0) return cudaSuccess;
-    tau_gap_kernel<<<(unsigned)((nt + 127) / 128), 128, 0, st>>>(d_ts, n, d_tau, nt, d_gap);
-    bump_launch_counter();
-    return cudaGetLastError();
-}
-
+//
 // One launch for everything a transform needs before its basis rows: per-frequency constants (with the tau-grid
 // check done by every block for itself: nt is small), the tau-to-sample gaps, the sortedness flag of the time axis,
-// the min / max of the time axis (span of wwa2psd) and the reset of the deep-underflow counter.  Blocks pick their
-// job from blockIdx.  *flags (unsorted flag, fix counter) must be zeroed by the caller (one 8-byte memset).
+// the min / max of the time axis (span of wwa2psd).  Blocks pick their job from blockIdx.  The kFlagInts ints at
+// *flags (unsorted flag, deep-underflow counter, work queues of the warp-tile kernels) are zeroed by launch_setup.
 struct SetupArgs {
     const double *omega, *tau, *ts;
     long long nf, nt, n;
@@ -152,7 +80,7 @@ __global__ void __launch_bounds__(256) setup_kernel(const SetupArgs a)
     __shared__ double slo[8], shi[8];
     const int b = blockIdx.x, tid = threadIdx.x;
     if (b < a.nfb) {
-        // ---- tau grid (as tau_uniform_kernel), then this block's frequency rows (as freq_setup_kernel)
+        // ---- tau grid, then this block's frequency rows
         if (tid == 0) bad = 0;
         __syncthreads();
         double d = 0.0;
@@ -183,7 +111,7 @@ __global__ void __launch_bounds__(256) setup_kernel(const SetupArgs a)
         return;
     }
     if (b < a.nfb + a.ngb) {
-        // ---- distance from tau to the nearest sample (as tau_gap_kernel)
+        // ---- distance from tau to the nearest sample
         const long long j = (long long)(b - a.nfb) * blockDim.x + tid;
         if (j >= a.nt) return;
         const double tj = a.tau[j];
@@ -199,12 +127,12 @@ __global__ void __launch_bounds__(256) setup_kernel(const SetupArgs a)
         return;
     }
     if (b < a.nfb + a.ngb + a.nub) {
-        // ---- sortedness of the time axis (as unsorted_kernel)
+        // ---- sortedness of the time axis
         const long long i = (long long)(b - a.nfb - a.ngb) * blockDim.x + tid;
         if (i + 1 < a.n && !(a.ts[i] <= a.ts[i + 1])) *a.unsorted = 1;
         return;
     }
-    // ---- last block: min / max of the time axis (as minmax_kernel)
+    // ---- last block: min / max of the time axis
     double lo = CUDART_INF, hi = -CUDART_INF;
     for (long long i = tid; i < a.n; i += blockDim.x) {
         const double v = a.ts[i];
@@ -235,7 +163,7 @@ cudaError_t launch_setup(const double *d_omega, int64_t nf, const double *d_tau,
                          double c, bool allow_rec, double cut_bits, double *d_kappa, double *d_dcut, double *d_grid,
                          unsigned char *d_rec_row, double *d_gap, int *d_flags, double *d_minmax, cudaStream_t st)
 {
-    cudaError_t e = cudaMemsetAsync(d_flags, 0, 2 * sizeof(int), st);   // unsorted flag + deep-underflow counter
+    cudaError_t e = cudaMemsetAsync(d_flags, 0, kFlagInts * sizeof(int), st);   // flag, counter, work queues
     if (e != cudaSuccess) return e;
     SetupArgs a{};
     a.omega = d_omega;
@@ -345,7 +273,7 @@ struct CellArgs {
     const double *tau;
     const double *kappa;
     const double *dcut;
-    const double *taugap; // distance from each tau to the nearest sample (tau_gap_kernel)
+    const double *taugap; // distance from each tau to the nearest sample (setup_kernel)
     const int *unsorted;  // device flag: 1 if ts is not ascending (forces the dense path)
     const unsigned char *rec_row;   // per frequency row: 1 = handled by the recurrence kernel (null: all direct)
     const double *grid;             // [0] = dtau of the equally spaced tau axis
@@ -357,15 +285,10 @@ struct CellArgs {
     int dense;
 };
 
-// REC = true: tau-recurrence flavour.  The lane's M tau-adjacent cells share one exp2 for the first
-// cell and one for the neighbour ratio per point (gauss_weight_ratio); the sums are accumulated with
-// the unscaled weights w_0*rho^m and multiplied by the per-cell constant h_m (h_m^2 for Q) when
-// they are stored.  Only for equally spaced tau and rows with kappa4*dtau <= 8 (host decides).
-// CW = consumer warps per CTA (the CTA has CW + 1 warps): 8 everywhere (the direct kernels then fit
-// 2 CTAs/SM at <= 113 registers; the recurrence kernel needs 168 registers, 1 CTA/SM -- 11 consumer
-// warps were measured slower on config 2 because the wider tile touches more frequency rows).
-template <int M, bool REC, int CW>
-__global__ void __launch_bounds__((CW + 1) * 32, REC ? 1 : 2) wwz_cells_kernel(const CellArgs a)
+// CW = consumer warps per CTA (the CTA has CW + 1 warps): 8; the kernel then fits 2 CTAs/SM at <= 113 registers.
+// Rows marked in rec_row belong to the tau-recurrence flavour of the warp-tile kernel (wwz_rec.cu) and are skipped.
+template <int M, int CW>
+__global__ void __launch_bounds__((CW + 1) * 32, 2) wwz_cells_kernel(const CellArgs a)
 {
     constexpr int kConsumerWarps = CW;                 // shadows the namespace-level default
     constexpr int kConsumerThreads = CW * 32;
@@ -412,7 +335,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, REC ? 1 : 2) wwz_cells_kernel(c
         k_loc = k - k_first;
         g = (int)(q - (long long)k * a.G);
         // each frequency row belongs to exactly one kernel flavour
-        if (a.rec_row) slot_ok = (a.rec_row[a.k0 + k] != 0) == REC;
+        if (a.rec_row) slot_ok = a.rec_row[a.k0 + k] == 0;
     }
     if (!__syncthreads_or(slot_ok ? 1 : 0)) return;   // nothing in this tile is ours
     double kap = 0.0;
@@ -522,40 +445,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, REC ? 1 : 2) wwz_cells_kernel(c
             const double2 *const st = stage_base + (size_t)s * a.stage_stride2;
             const double2 *const row = st + row_off;
             const int cnt = (int)min((long long)P, p1 - p0 - (long long)c * P);
-            if constexpr (REC) {
-                const double step16 = 2.0 * kap * a.grid[0];
-#pragma unroll 2
-                for (int p = 0; p < cnt; ++p) {
-                    const double2 t_y = st[p];
-                    const double2 sc = row[2 * p];
-                    const double2 ysc = row[2 * p + 1];
-                    double w0, rho;
-                    gauss_weight_ratio(kap * (t_y.x - tau_r[0]), step16, tbl, w0, rho);
-                    // w_m = w_0 * rho^m through a product tree (depth 3 instead of a chain of 7 multiplies)
-                    double wv[M];
-                    static_assert(M == 8, "the power tree below is written for 8 cells per lane");
-                    const double rho2 = rho * rho, rho4 = rho2 * rho2;
-                    wv[0] = w0;
-                    wv[1] = w0 * rho;
-                    wv[2] = w0 * rho2;
-                    wv[3] = wv[1] * rho2;
-                    wv[4] = w0 * rho4;
-                    wv[5] = wv[1] * rho4;
-                    wv[6] = wv[2] * rho4;
-                    wv[7] = wv[3] * rho4;
-#pragma unroll
-                    for (int r = 0; r < M; ++r) {
-                        const double w = wv[r];
-                        W[r] += w;
-                        Q[r] = fma(w, w, Q[r]);
-                        Ws[r] = fma(w, sc.x, Ws[r]);
-                        Wc[r] = fma(w, sc.y, Wc[r]);
-                        Wy[r] = fma(w, t_y.y, Wy[r]);
-                        Wys[r] = fma(w, ysc.x, Wys[r]);
-                        Wyc[r] = fma(w, ysc.y, Wyc[r]);
-                    }
-                }
-            } else {
+            {
 #pragma unroll 2
                 for (int p = 0; p < cnt; ++p) {
                     const double2 t_y = st[p];
@@ -583,22 +473,19 @@ __global__ void __launch_bounds__((CW + 1) * 32, REC ? 1 : 2) wwz_cells_kernel(c
 
     if (slot_ok) {
         const long long kcol = (long long)a.k0 + k_first + k_loc;
-        const double D = REC ? kap * a.grid[0] : 0.0;
 #pragma unroll
         for (int r = 0; r < M; ++r) {
             const int j = g * M + r;
             if (j < a.nt) {
                 const size_t nc = (size_t)a.ncell_total;
                 const size_t cell = (size_t)blockIdx.y * (size_t)kNumSums * nc + (size_t)j * (size_t)a.nf_total + (size_t)kcol;
-                // REC: undo the per-cell scale h_r = 2^(-(r D)^2/16) that was factored out of the weights
-                const double h = REC ? exp2(-(double)(r * r) * D * D * 0.0625) : 1.0;
-                a.sums[0 * nc + cell] = W[r] * h;
-                a.sums[1 * nc + cell] = Q[r] * h * h;
-                a.sums[2 * nc + cell] = Ws[r] * h;
-                a.sums[3 * nc + cell] = Wc[r] * h;
-                a.sums[4 * nc + cell] = Wy[r] * h;
-                a.sums[5 * nc + cell] = Wys[r] * h;
-                a.sums[6 * nc + cell] = Wyc[r] * h;
+                a.sums[0 * nc + cell] = W[r];
+                a.sums[1 * nc + cell] = Q[r];
+                a.sums[2 * nc + cell] = Ws[r];
+                a.sums[3 * nc + cell] = Wc[r];
+                a.sums[4 * nc + cell] = Wy[r];
+                a.sums[5 * nc + cell] = Wys[r];
+                a.sums[6 * nc + cell] = Wyc[r];
             }
         }
     }
@@ -608,11 +495,11 @@ CellPlan plan_cells(int64_t n, int64_t nt, int64_t nf, int cells_per_lane_hint, 
 {
     CellPlan p{};
     int M = cells_per_lane_hint;
-    if (M != 1 && M != 2 && M != 4 && M != kRecCells) M = 2;
-    if (nt < M && M != kRecCells) M = 1;
+    if (M != 1 && M != 2 && M != 4) M = 2;
+    if (nt < M) M = 1;
     p.cells_per_lane = M;
     p.groups = (int)((nt + M - 1) / M);
-    p.consumer_warps = (M == kRecCells) ? kRecConsumerWarps : kConsumerWarps;
+    p.consumer_warps = kConsumerWarps;
     const int64_t cthreads = (int64_t)p.consumer_warps * 32;
     int64_t ft = (cthreads + p.groups - 1) / p.groups + 1;
     if (ft > nf) ft = nf;
@@ -634,14 +521,14 @@ CellPlan plan_cells(int64_t n, int64_t nt, int64_t nf, int cells_per_lane_hint, 
     return p;
 }
 
-template <int M, bool REC, int CW>
+template <int M, int CW>
 static cudaError_t launch_cells_m(const CellPlan &plan, const CellArgs &args, int64_t tiles, int segs,
                                   cudaStream_t st)
 {
     static SmemOptIn done;
-    cudaError_t e = ensure_dynamic_smem(wwz_cells_kernel<M, REC, CW>, plan.smem_bytes, done);
+    cudaError_t e = ensure_dynamic_smem(wwz_cells_kernel<M, CW>, plan.smem_bytes, done);
     if (e != cudaSuccess) return e;
-    wwz_cells_kernel<M, REC, CW><<<dim3((unsigned)tiles, (unsigned)segs), (CW + 1) * 32, plan.smem_bytes, st>>>(args);
+    wwz_cells_kernel<M, CW><<<dim3((unsigned)tiles, (unsigned)segs), (CW + 1) * 32, plan.smem_bytes, st>>>(args);
     bump_launch_counter();
     return cudaGetLastError();
 }
@@ -681,10 +568,9 @@ cudaError_t launch_cells(const CellPlan &plan, const double2 *d_ty, const double
     const int64_t cthreads = (int64_t)plan.consumer_warps * 32;
     const int64_t tiles = (a.nslots + cthreads - 1) / cthreads;
     switch (plan.cells_per_lane) {
-        case 1: return launch_cells_m<1, false, kConsumerWarps>(plan, a, tiles, segs, st);
-        case 4: return launch_cells_m<4, false, kConsumerWarps>(plan, a, tiles, segs, st);
-        case kRecCells: return launch_cells_m<kRecCells, true, kRecConsumerWarps>(plan, a, tiles, segs, st);
-        default: return launch_cells_m<2, false, kConsumerWarps>(plan, a, tiles, segs, st);
+        case 1: return launch_cells_m<1, kConsumerWarps>(plan, a, tiles, segs, st);
+        case 4: return launch_cells_m<4, kConsumerWarps>(plan, a, tiles, segs, st);
+        default: return launch_cells_m<2, kConsumerWarps>(plan, a, tiles, segs, st);
     }
 }
 
@@ -927,22 +813,6 @@ __global__ void minmax_kernel(const double *__restrict__ x, int64_t n, double *_
         out[0] = lo;
         out[1] = hi;
     }
-}
-
-// 1 if x is not ascending (ties allowed), else 0.  *flag must be zeroed by the caller.
-__global__ void unsorted_kernel(const double *__restrict__ x, int64_t n, int *__restrict__ flag)
-{
-    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i + 1 < n && !(x[i] <= x[i + 1])) *flag = 1;
-}
-
-cudaError_t launch_unsorted_check(const double *d_x, int64_t n, int *d_flag, cudaStream_t st)
-{
-    cudaError_t e = cudaMemsetAsync(d_flag, 0, sizeof(int), st);
-    if (e != cudaSuccess || n < 2) return e;
-    unsorted_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_x, n, d_flag);
-    bump_launch_counter();
-    return cudaGetLastError();
 }
 
 cudaError_t launch_minmax(const double *d_x, int64_t n, double *d_out, cudaStream_t st)
