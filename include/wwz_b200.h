@@ -24,6 +24,14 @@
  * Host-pointer entry points copy host<->device internally (pinned staging, one stream).
  * The *_dev entry points take device pointers and a cudaStream_t (passed as void*); they
  * enqueue work and return without synchronising.
+ *
+ * Threads and streams.  Every entry point may be called from any host thread: one process-wide lock is held from
+ * the first workspace request of a call to its last enqueue (host-pointer entry points: to the final
+ * synchronisation).  All calls on one device share one grow-only scratch set; a call whose stream differs from the
+ * stream of the previous call first waits (cudaStreamWaitEvent) for the end of that call's work, so calls on
+ * different streams are ordered on the device instead of racing on the scratch -- results are always those of the
+ * serial order of the calls, and concurrency between two library calls on one device is not available.  Growing a
+ * scratch buffer frees the old one (cudaFree synchronises the device).
  */
 #ifndef WWZ_B200_H
 #define WWZ_B200_H
@@ -61,6 +69,9 @@ extern "C" {
                                    {1, cos w(t-tau), sin w(t-tau)} with the 3x3 pseudo-inverse solve of the           \
                                    reference's method='Foster' (wwz_basic, utils/wavelet.py:341-374) instead of        \
                                    Kirchner's centred covariances; a0,a1,a2 then hold ywave_1,2,3 (:372-374) */
+#define WWZB200_FREQ_HZ 128u    /* wwzb200_kirchner_members(_dev): the `omegas` argument holds FREQUENCIES; make_omega   \
+                                   (utils/wavelet.py:1210-1234: NaN above 0.5/median(diff(ts)), omega = 2 pi f) is        \
+                                   applied per member on the device; needs nts <= 16385 */
 #define WWZB200_FAITHFUL 4u     /* validation mode: evaluate every cell with the reference's own    \
                                    two-pass expressions (utils/wavelet.py:988-1032), one warp per   \
                                    cell; ~10x slower, agrees with kirchner_numba to ~1e-12 */
@@ -130,6 +141,22 @@ int wwzb200_kirchner_ragged(const double *ts, const double *pd_ys, const int64_t
                             double *Neffs, double *a0, double *a1, double *a2, double *wwa,
                             double *phase, double *psd);
 
+/* (4b) Batched transform of M members of EQUAL shape: the age ensemble of core/ensembleseries.py:47-175 (one value
+ * vector on M time axes; default grids of equal size), which the reference hands member by member to a process pool
+ * (core/multipleseries.py:1520-1532).  ts [M][nts]; pd_ys [M][ys_stride] or, with ys_stride = 0, one [nts] vector
+ * shared by all members; taus [M][nt]; omegas [M][nf] (frequencies with WWZB200_FREQ_HZ).  WWZB200_STANDARDIZE
+ * z-scores every member on the device.  Every kernel of the transform is launched once for all members of a group;
+ * the host variant moves finished groups over PCIe while the next group is computed.  Outputs [M][nt][nf] each
+ * (Neffs required, the others optional), psd [M][nf] optional (wwa2psd per member, time span taken on the device),
+ * mu_sig [M][2] optional: the mean and standard deviation applied by WWZB200_STANDARDIZE ((0, 1): member left as it is,
+ * the case the reference warns about, utils/tsutils.py:1146-1149).
+ * WWZB200_FOSTER / WWZB200_FAITHFUL are refused here (use the ragged entry point). */
+int wwzb200_kirchner_members(const double *ts, const double *pd_ys, int64_t ys_stride, int64_t M, int64_t nts,
+                             const double *taus, int64_t nt, const double *omegas, int64_t nf, double c,
+                             int64_t Neff_threshold, int64_t psd_Neff_threshold, uint32_t flags, double *Neffs,
+                             double *a0, double *a1, double *a2, double *wwa, double *phase, double *psd,
+                             double *mu_sig);
+
 /* (5) AR(1) surrogates on an uneven time axis: S realisations of ar1_model
  * (utils/tsmodel.py:59-69) as driven by ar1_sim (:159-165) and SurrogateSeries.from_series
  * (core/surrogateseries.py:137-139):  y[0]=0; rho_i=exp(-(t_i-t_{i-1})/tau_est);
@@ -167,6 +194,13 @@ int wwzb200_ar1_signif(const double *ts, int64_t nts, double tau_est, double sig
                        const double *probs, int64_t nq, double *Neffs, double *q_wwa, double *q_psd);
 
 /* ---- device-pointer entry points (inputs/outputs resident in HBM; async on `stream`) ---- */
+/* (4b) on device-resident members: same layouts as wwzb200_kirchner_members, all M members in one group. */
+int wwzb200_kirchner_members_dev(const double *d_ts, const double *d_pd_ys, int64_t ys_stride, int64_t M, int64_t nts,
+                                 const double *d_taus, int64_t nt, const double *d_omegas, int64_t nf, double c,
+                                 int64_t Neff_threshold, int64_t psd_Neff_threshold, uint32_t flags, double *d_Neffs,
+                                 double *d_a0, double *d_a1, double *d_a2, double *d_wwa, double *d_phase, double *d_psd,
+                                 double *d_mu_sig, void *stream);
+
 int wwzb200_kirchner_dev(const double *d_ts, const double *d_pd_ys, int64_t nts, const double *d_taus,
                          int64_t nt, const double *d_omegas, int64_t nf, double c,
                          int64_t Neff_threshold, int64_t psd_Neff_threshold, uint32_t flags,

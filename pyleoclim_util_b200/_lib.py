@@ -18,6 +18,7 @@ NO_RECURRENCE = 8
 EXACT_WINDOW = 16
 UAR1 = 32
 FOSTER = 64
+FREQ_HZ = 128
 
 _dp = ctypes.POINTER(ctypes.c_double)
 _ip = ctypes.POINTER(ctypes.c_int64)
@@ -53,6 +54,10 @@ _SIGS = {
                                                     _u32, _dp, _dp, _dp, _dp, _dp, _dp, _dp]),
     "wwzb200_kirchner_ragged": (ctypes.c_int, [_dp, _dp, _ip, _dp, _ip, _dp, _ip, _ip, _i64, _dbl, _i64, _i64,
                                                _u32, _dp, _dp, _dp, _dp, _dp, _dp, _dp]),
+    "wwzb200_kirchner_members": (ctypes.c_int, [_dp, _dp, _i64, _i64, _i64, _dp, _i64, _dp, _i64, _dbl, _i64, _i64, _u32,
+                                                _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp]),
+    "wwzb200_kirchner_members_dev": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i64, _vp, _i64, _vp, _i64, _dbl, _i64, _i64,
+                                                    _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "wwzb200_ar1_surrogates": (ctypes.c_int, [_dp, _i64, _dbl, _dbl, _dbl, _i64, _u64, _dp]),
     "wwzb200_uar1_surrogates": (ctypes.c_int, [_dp, _i64, _dbl, _dbl, _dbl, _i64, _u64, _dp]),
     "wwzb200_quantiles": (ctypes.c_int, [_dp, _i64, _i64, _dp, _i64, _dp]),

@@ -10,7 +10,7 @@ from . import _lib
 from . import wavelet as _wv
 
 __all__ = ["tau_estimation", "ar1_surrogates", "ar1_sim", "n_ll_unevenly_spaced_ar1", "uar1_fit", "uar1_surrogates",
-           "uar1_sim", "wwz_shared_axis", "wwz_ragged", "quantiles",
+           "uar1_sim", "wwz_shared_axis", "wwz_ragged", "wwz_members", "quantiles",
            "wwz_signif", "signif_prepared", "SharedAxisResults", "SignifResults"]
 
 SharedAxisResults = collections.namedtuple(
@@ -138,6 +138,69 @@ def wwz_shared_axis(Y, ts, tau, freq, c=1 / (8 * np.pi ** 2), Neff_threshold=3, 
                              psd=psd, freq=freq, time=tau, coi=coi, scale=1 / freq)
 
 
+def _cois(tau):
+    """make_coi (utils/wavelet.py:1168-1208) of every row of tau [M, nt] at once."""
+    nt0 = tau.shape[1]
+    efold = 4 * np.pi / (3 + np.sqrt(2 + 3 ** 2)) / np.sqrt(2)
+    step = np.median(np.diff(tau, axis=1), axis=1)
+    idx = np.arange(nt0)
+    tent = np.minimum(idx, nt0 - 1 - idx).astype(float)
+    tent[tent == 0] = 0.00001
+    return efold * step[:, None] * tent[None, :]
+
+
+def wwz_members(T, Y, tau, freq, c=1 / (8 * np.pi ** 2), Neff_threshold=3, standardize=True, psd_Neff_threshold=None,
+                flags=0):
+    """M members of EQUAL shape -- an age ensemble (core/ensembleseries.py:47-175), which the reference transforms
+    member by member in a process pool (core/multipleseries.py:1520-1532) -- through ONE C call
+    (``wwzb200_kirchner_members``): z-score, Nyquist clipping of the frequencies (make_omega), setup, basis rows,
+    cell kernels, epilogue and wwa2psd each run once for all members of a group on the device, and finished groups
+    cross PCIe under the next group's kernels.
+
+    T [M, n] time axes (prepared: sorted, no NaN); Y [M, n] values, or [n] when all members share them; tau [M, nt];
+    freq [M, nf].  Returns a list of ``wavelet.wwz``-style Results whose arrays are views of one page-locked block
+    (plus the list of psd vectors when ``psd_Neff_threshold`` is given)."""
+    _wv.assertPositiveInt(Neff_threshold)
+    T, tau, freq, Y = _lib.f64(T), _lib.f64(tau), _lib.f64(freq), _lib.f64(Y)
+    if T.ndim != 2 or tau.ndim != 2 or freq.ndim != 2 or not (T.shape[0] == tau.shape[0] == freq.shape[0]):
+        raise ValueError("T, tau and freq must be [M, n], [M, nt], [M, nf]")
+    M, n = T.shape
+    nt, nf = tau.shape[1], freq.shape[1]
+    if Y.ndim == 1:
+        if Y.size != n:
+            raise ValueError("shared values must have the length of a time axis")
+        ys_stride = 0
+    elif Y.shape == (M, n):
+        ys_stride = n
+    else:
+        raise ValueError("Y must be [n] or [M, n]")
+    fl = int(flags) | (_lib.STANDARDIZE if standardize else 0)
+    if n - 1 <= 16384 and n >= 2:
+        fl |= _lib.FREQ_HZ                      # make_omega on the device
+        om = freq
+    else:
+        nyq = 0.5 / np.median(np.diff(T, axis=1), axis=1)
+        om = _lib.f64(2 * np.pi * np.where(freq > nyq[:, None], np.nan, freq))
+    out = _lib.output_empty((6, M, nt, nf))
+    psd = np.empty((M, nf)) if psd_Neff_threshold is not None else None
+    stats = np.empty((M, 2)) if standardize else None
+    _lib.check(_lib.lib().wwzb200_kirchner_members(
+        _lib.ptr(T), _lib.ptr(Y), ys_stride, M, n, _lib.ptr(tau), nt, _lib.ptr(om), nf, float(c), int(Neff_threshold),
+        int(psd_Neff_threshold or 0), fl, _lib.ptr(out[0]), _lib.ptr(out[1]), _lib.ptr(out[2]), _lib.ptr(out[3]),
+        _lib.ptr(out[4]), _lib.ptr(out[5]), _lib.ptr(psd), _lib.ptr(stats)))
+    if stats is not None and ((stats[:, 0] == 0) & (stats[:, 1] == 1)).any():
+        import warnings
+        warnings.warn("Constant or nearly constant time series not rescaled.", stacklevel=2)
+    coi = _cois(tau) if nt > 1 else [None] * M
+    scale = 1 / freq
+    Ne, a0, a1, a2, wwa, ph = out
+    res = [_wv.WwzResults(amplitude=wwa[m], phase=ph[m], coi=coi[m], freq=freq[m], time=tau[m], Neffs=Ne[m],
+                          coeff=(a0[m], a1[m], a2[m]), scale=scale[m]) for m in range(M)]
+    if psd is not None:
+        return res, list(psd)
+    return res
+
+
 def wwz_ragged(members, c=1 / (8 * np.pi ** 2), Neff_threshold=3, standardize=True, psd_Neff_threshold=None,
                flags=0):
     """Transform M series with their own time axes and grids (age ensembles:
@@ -150,6 +213,32 @@ def wwz_ragged(members, c=1 / (8 * np.pi ** 2), Neff_threshold=3, standardize=Tr
     ts_l = [_lib.f64(m[1]) for m in members]
     tau_l = [_lib.f64(m[2]) for m in members]
     fr_l = [_lib.f64(m[3]) for m in members]
+    nfs = [f.size for f in fr_l]
+    if len(members) > 1 and not (int(flags) & (_lib.FOSTER | _lib.FAITHFUL)) and ts_l[0].size > 1 \
+            and len({t.size for t in ts_l}) == 1 and len({a.size for a in tau_l}) == 1 and tau_l[0].size \
+            and min(nfs) > 0 and max(nfs) - min(nfs) <= max(2, max(nfs) // 8) \
+            and all(np.ndim(m[0]) == 1 and np.size(m[0]) == ts_l[0].size for m in members):
+        # equally shaped members (an age ensemble on its default grids: same n, same ntau, frequency axes that differ by
+        # a point or two): one C call, every kernel launched once per group.  Shorter frequency axes are padded with NaN
+        # (a NaN frequency gives a NaN column, like a frequency above Nyquist) and the padding is sliced off again.
+        nf = max(nfs)
+        F = np.full((len(members), nf), np.nan)
+        for m, f in enumerate(fr_l):
+            F[m, : f.size] = f
+        out = wwz_members(np.stack(ts_l), np.stack([_lib.f64(m[0]) for m in members]), np.stack(tau_l), F, c=c,
+                          Neff_threshold=Neff_threshold, standardize=standardize,
+                          psd_Neff_threshold=psd_Neff_threshold, flags=flags)
+        res, psds = out if psd_Neff_threshold is not None else (out, None)
+        if min(nfs) != nf:
+            for m, k in enumerate(nfs):
+                if k != nf:
+                    r = res[m]
+                    res[m] = _wv.WwzResults(amplitude=r.amplitude[:, :k], phase=r.phase[:, :k], coi=r.coi, freq=fr_l[m],
+                                            time=r.time, Neffs=r.Neffs[:, :k], coeff=tuple(x[:, :k] for x in r.coeff),
+                                            scale=1 / fr_l[m])
+                    if psds is not None:
+                        psds[m] = psds[m][:k]
+        return (res, psds) if psds is not None else res
     same_n = len(members) > 1 and len({t.size for t in ts_l}) == 1 and ts_l[0].size > 1 \
         and all(np.ndim(m[0]) == 1 and np.size(m[0]) == ts_l[0].size for m in members)
     if same_n:

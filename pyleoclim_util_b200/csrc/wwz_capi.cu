@@ -62,6 +62,8 @@ struct Workspace {
     cudaEvent_t fork_ev = nullptr;
     cudaStream_t side = nullptr;          // the direct cell kernel runs here, next to the recurrence kernel
     cudaEvent_t side_fork = nullptr, side_join = nullptr;
+    cudaStream_t copy = nullptr;          // device-to-host copies of finished member groups, under the next group's kernels
+    cudaEvent_t group_ev[2] = {};
     cudaEvent_t busy_ev = nullptr;        // end of the last piece of work that used this scratch set (any stream)
     cudaStream_t busy_stream = nullptr;
     bool busy = false;
@@ -115,6 +117,9 @@ int workspace(Workspace **out)
         CU(cudaEventCreateWithFlags(&w.side_fork, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&w.side_join, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&w.busy_ev, cudaEventDisableTiming));
+        CU(cudaStreamCreateWithFlags(&w.copy, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&w.group_ev[0], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&w.group_ev[1], cudaEventDisableTiming));
         for (int i = 0; i < kLanes; ++i) {
             CU(cudaStreamCreateWithFlags(&w.lanes[i], cudaStreamNonBlocking));
             CU(cudaEventCreateWithFlags(&w.lane_ev[i], cudaEventDisableTiming));
@@ -179,7 +184,7 @@ size_t basis_budget_bytes()
 // segment is at least 1000 points on large grids (config 2: 2 segments; 3 cost 7% on its c = 1e-3 transform), 256 on small ones.  The count depends on
 // the problem size and on the flags only, never on the tile geometry, so every variant of a kernel adds the same
 // partial sums.
-int point_segments(int64_t n, int64_t nt, int64_t nf, bool recurrence)
+int point_segments(int64_t n, int64_t nt, int64_t nf, bool recurrence, int64_t members = 1)
 {
     const int64_t ncell = nt * nf;
     const char *e = getenv("WWZB200_POINT_SEGMENTS");
@@ -187,7 +192,7 @@ int point_segments(int64_t n, int64_t nt, int64_t nf, bool recurrence)
     if (e && *e) {
         s = atoll(e);
     } else if (recurrence) {
-        const int64_t tiles = ((nt + 63) / 64) * ((std::min<int64_t>(nf, 65535) + 3) / 4);   // 64 taus x 4 rows per warp tile
+        const int64_t tiles = ((nt + 63) / 64) * ((std::min<int64_t>(nf, 65535) + 3) / 4) * members;   // 64 taus x 4 rows per warp tile
         s = (65536 + tiles - 1) / std::max<int64_t>(tiles, 1);
         s = std::min<int64_t>(s, n / (ncell >= 100000 ? 1000 : 256));   // (small grids: the slabs cost nothing)
     } else {
@@ -545,6 +550,110 @@ int shared_axis_device(Workspace *w, const double *d_ts, const double *d_Y, int6
     if (d_psd) CU(launch_psd_batch(d_amp_t, d_ne, nt, nf, S, S_pad, tspan, n, (double)psd_thr, d_psd, st));
     if (amp_cells_out) *amp_cells_out = d_amp_t;
     if (S_pad_out) *S_pad_out = S_pad;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// M members of equal shape in one set of launches (age ensembles: core/ensembleseries.py:47-175 feeding
+// core/multipleseries.py:1520-1532): per-member Nyquist frequency and z-score, setup, basis rows, the warp-tile
+// kernels over (member, tile, segment) work items -- recurrence flavour where it applies, direct flavour elsewhere --
+// epilogue, deep-underflow fix-up and wwa2psd, each as ONE launch for all members.  Inputs by member strides
+// (0 = shared), outputs [M][nt][nf] (psd [M][nf]).
+// ---------------------------------------------------------------------------------------------
+int members_device(Workspace *w, const double *d_ts, int64_t m_ts, const double *d_ys, int64_t m_ys, int64_t M, int64_t n,
+                   const double *d_tau, int64_t m_tau, int64_t nt, const double *d_om, int64_t m_om, int64_t nf, double c,
+                   int64_t thr, int64_t psd_thr, uint32_t flags, double *d_neffs, double *d_a0, double *d_a1, double *d_a2,
+                   double *d_wwa, double *d_phase, double *d_psd, double *d_stats, cudaStream_t st)
+{
+    using namespace wwz;
+    const int64_t ncell = nt * nf;
+    if (ncell == 0 || M == 0) return 0;
+    if (ncell * M >= ((int64_t)1 << 32)) return fail(WWZB200_ERR_ARG, "M*nt*nf = %lld exceeds 2^32 cells", (long long)(ncell * M));
+    if (flags & (WWZB200_FOSTER | WWZB200_FAITHFUL))
+        return fail(WWZB200_ERR_ARG, "WWZB200_FOSTER / WWZB200_FAITHFUL are not available for member batches; use the ragged entry point");
+    if (M > 65535 || nf > 65535) return fail(WWZB200_ERR_ARG, "at most 65535 members and frequencies per member batch");
+    const bool freq_hz = (flags & WWZB200_FREQ_HZ) != 0, zs = (flags & WWZB200_STANDARDIZE) != 0;
+    if (freq_hz && n - 1 > kNyquistMaxPoints)
+        return fail(WWZB200_ERR_ARG, "WWZB200_FREQ_HZ needs nts <= %d (pass omega instead)", kNyquistMaxPoints + 1);
+    int rc;
+    double *d_kappa, *d_dcut, *d_grid, *d_gap, *d_mm, *d_sums, *d_fnyq = nullptr, *d_ysz = nullptr, *d_omega = nullptr;
+    unsigned char *d_rec_row;
+    int *d_flags;
+    unsigned int *d_fix_list;
+    double2 *d_ty, *d_basis;
+    bool allow_rec = !(flags & (WWZB200_DENSE | WWZB200_NO_RECURRENCE)) && nt >= 2 * kRecCells;
+    {
+        const char *e = getenv("WWZB200_NO_RECURRENCE");
+        if (e && *e && atoi(e)) allow_rec = false;
+    }
+    const int segs = point_segments(n, nt, nf, true, M);
+    const int64_t seg_len = (((n + segs - 1) / segs + 15) / 16) * 16;
+    RecPlan rplan{}, dplan = plan_rec(n, nt, nf, seg_len, kTileDirectCells);
+    if (allow_rec) {
+        rplan = plan_rec(n, nt, nf, seg_len, kRecCells);
+        rplan.n_pad = dplan.n_pad = std::max(rplan.n_pad, dplan.n_pad);
+    }
+    const int64_t n_pad = dplan.n_pad;
+    if ((rc = wsbuf(w, "kappa", (size_t)(M * nf), &d_kappa))) return rc;
+    if ((rc = wsbuf(w, "dcut", (size_t)(M * nf), &d_dcut))) return rc;
+    if ((rc = wsbuf(w, "rec_row", (size_t)(M * nf), &d_rec_row))) return rc;
+    if ((rc = wsbuf(w, "grid", (size_t)(2 * M), &d_grid))) return rc;
+    if ((rc = wsbuf(w, "taugap", (size_t)(M * nt), &d_gap))) return rc;
+    if ((rc = wsbuf(w, "flags", (size_t)(M * kFlagInts), &d_flags))) return rc;
+    if ((rc = wsbuf(w, "minmax", (size_t)(2 * M), &d_mm))) return rc;
+    if ((rc = wsbuf(w, "fix_list", (size_t)(M * ncell) + 1, &d_fix_list))) return rc;
+    if ((rc = wsbuf(w, "ty", (size_t)(M * n_pad), &d_ty))) return rc;
+    if ((rc = wsbuf(w, "basis", (size_t)M * (size_t)nf * (size_t)n_pad * 2, &d_basis))) return rc;
+    if ((rc = wsbuf(w, "sums", (size_t)M * (size_t)segs * kNumSums * (size_t)ncell, &d_sums))) return rc;
+    if (freq_hz) {
+        if ((rc = wsbuf(w, "mb_fnyq", (size_t)M, &d_fnyq))) return rc;
+        if ((rc = wsbuf(w, "mb_omega", (size_t)(M * nf), &d_omega))) return rc;
+    }
+    if (zs && (rc = wsbuf(w, "mb_ysz", (size_t)(M * n), &d_ysz))) return rc;
+    if (d_psd && !d_wwa && (rc = wsbuf(w, "psd_wwa", (size_t)(M * ncell), &d_wwa))) return rc;
+    unsigned int *d_fix_count = reinterpret_cast<unsigned int *>(d_flags) + 1;   // of member 0: one list for the batch
+    unsigned int *d_queue = reinterpret_cast<unsigned int *>(d_flags) + 2;
+
+    if (freq_hz || zs) CU(launch_member_prep(d_ts, m_ts, n, d_ys, m_ys, M, zs, d_fnyq, d_ysz, zs ? d_stats : nullptr, st));
+    const double *ys_use = zs ? d_ysz : d_ys;
+    const int64_t m_ys_use = zs ? n : m_ys;
+    const double cut_bits = (flags & WWZB200_DENSE) ? HUGE_VAL : (flags & WWZB200_EXACT_WINDOW) ? 1081.0 : 100.0;
+    CU(launch_setup_members(d_om, m_om, nf, d_tau, m_tau, nt, d_ts, m_ts, n, M, c, allow_rec, cut_bits, d_kappa, d_dcut, d_grid,
+                            d_rec_row, d_gap, d_flags, d_psd ? d_mm : nullptr, d_fnyq, d_omega, st));
+    const double *om_use = freq_hz ? d_omega : d_om;
+    const int64_t m_om_use = freq_hz ? nf : m_om;
+    CU(launch_basis_members(d_ts, m_ts, ys_use, m_ys_use, n, n_pad, om_use, m_om_use, nf, M, d_ty, d_basis, st));
+    EventPair ev{nullptr, nullptr, (double)n * (double)ncell * (double)M};
+    if (g_profile) {
+        CU(cudaEventCreate(&ev.a));
+        CU(cudaEventCreate(&ev.b));
+        CU(cudaEventRecord(ev.a, st));
+    }
+    // the two flavours write disjoint cells: side by side, as in transform_device
+    const bool fork = allow_rec;
+    cudaStream_t st_direct = fork ? w->side : st;
+    if (fork) {
+        CU(cudaEventRecord(w->side_fork, st));
+        CU(cudaStreamWaitEvent(w->side, w->side_fork, 0));
+        CU(launch_rec(rplan, d_ty, d_basis, d_ts, n, d_tau, nt, d_kappa, d_dcut, d_gap, d_flags, 0, nf, nf, segs, seg_len,
+                      d_rec_row, d_grid, d_sums, d_queue, nullptr, w->sms, st, M, m_ts, m_tau));
+    }
+    CU(launch_rec(dplan, d_ty, d_basis, d_ts, n, d_tau, nt, d_kappa, d_dcut, d_gap, d_flags, 0, nf, nf, segs, seg_len,
+                  allow_rec ? d_rec_row : nullptr, d_grid, d_sums, d_queue + 2, nullptr, w->sms, st_direct, M, m_ts, m_tau));
+    if (fork) {
+        CU(cudaEventRecord(w->side_join, w->side));
+        CU(cudaStreamWaitEvent(st, w->side_join, 0));
+    }
+    if (g_profile) {
+        CU(cudaEventRecord(ev.b, st));
+        g_events.push_back(ev);
+    }
+    CU(launch_finalize_members(d_sums, d_tau, m_tau, om_use, m_om_use, nt, nf, M, (double)thr, d_neffs, d_a0, d_a1, d_a2,
+                               d_wwa, d_phase, nf, d_fix_count, d_fix_list, (unsigned int)(M * ncell), segs, st));
+    CU(launch_faithful_members(d_ts, m_ts, ys_use, m_ys_use, n, d_tau, m_tau, om_use, m_om_use, nt, nf, M, c, (double)thr,
+                               d_fix_count, d_fix_list, (unsigned int)(M * ncell), d_neffs, d_a0, d_a1, d_a2, d_wwa,
+                               d_phase, nf, w->sms, st));
+    if (d_psd) CU(launch_psd_devspan(d_wwa, d_neffs, nt, nf, nf, d_mm, n, (double)psd_thr, d_psd, st, M));
     return 0;
 }
 
@@ -980,6 +1089,99 @@ int wwzb200_quantiles(const double *X, int64_t S, int64_t ncell, const double *p
     if ((rc = quantiles_series_major_nolock(w, d_X, S, ncell, d_p, nq, d_q, st))) return rc;
     CU(cudaMemcpyAsync(q, d_q, sizeof(double) * (size_t)nq * (size_t)ncell, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    return 0;
+}
+
+static int check_member_args(const void *ts, const void *ys, int64_t ys_stride, int64_t M, int64_t nts, const void *taus,
+                             int64_t nt, const void *oms, int64_t nf, double c, int64_t thr, const void *Neffs)
+{
+    if (M < 0 || nts < 1 || nt < 0 || nf < 0) return fail(WWZB200_ERR_ARG, "sizes must satisfy M>=0, nts>=1, nt>=0, nf>=0");
+    if (ys_stride != 0 && ys_stride < nts) return fail(WWZB200_ERR_ARG, "ys_stride must be 0 (shared values) or >= nts");
+    if (M && (!ts || !ys || (nt && !taus) || (nf && !oms))) return fail(WWZB200_ERR_ARG, "null input pointer");
+    if (thr < 1) return fail(WWZB200_ERR_ARG, "Neff_threshold must be a positive integer (utils/wavelet.py:971)");
+    if (!(c > 0) || !std::isfinite(c)) return fail(WWZB200_ERR_ARG, "decay constant c must be positive and finite");
+    if (M * nt * nf && !Neffs) return fail(WWZB200_ERR_ARG, "Neffs output is required");
+    return 0;
+}
+
+int wwzb200_kirchner_members_dev(const double *d_ts, const double *d_ys, int64_t ys_stride, int64_t M, int64_t nts,
+                                 const double *d_taus, int64_t nt, const double *d_omegas, int64_t nf, double c,
+                                 int64_t Neff_threshold, int64_t psd_Neff_threshold, uint32_t flags, double *d_Neffs,
+                                 double *d_a0, double *d_a1, double *d_a2, double *d_wwa, double *d_phase, double *d_psd,
+                                 double *d_mu_sig, void *stream)
+{
+    int rc = check_member_args(d_ts, d_ys, ys_stride, M, nts, d_taus, nt, d_omegas, nf, c, Neff_threshold, d_Neffs);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lock(g_mu);
+    Workspace *w;
+    if ((rc = workspace(&w))) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    ScratchScope scope(w, st);
+    if ((rc = scope.begin())) return rc;
+    return members_device(w, d_ts, nts, d_ys, ys_stride, M, nts, d_taus, nt, nt, d_omegas, nf, nf, c, Neff_threshold,
+                          psd_Neff_threshold, flags, d_Neffs, d_a0, d_a1, d_a2, d_wwa, d_phase, d_psd, d_mu_sig, st);
+}
+
+// Host buffers.  The inputs go up once; the members are transformed in groups (scratch bounded by the basis budget,
+// at least four groups when there are enough members) and the outputs of a finished group cross PCIe on a copy
+// stream while the next group is computed.
+int wwzb200_kirchner_members(const double *ts, const double *ys, int64_t ys_stride, int64_t M, int64_t nts,
+                             const double *taus, int64_t nt, const double *omegas, int64_t nf, double c,
+                             int64_t Neff_threshold, int64_t psd_Neff_threshold, uint32_t flags, double *Neffs,
+                             double *a0, double *a1, double *a2, double *wwa, double *phase, double *psd, double *mu_sig)
+{
+    int rc = check_member_args(ts, ys, ys_stride, M, nts, taus, nt, omegas, nf, c, Neff_threshold, Neffs);
+    if (rc) return rc;
+    if (M == 0) return 0;
+    std::lock_guard<std::mutex> lock(g_mu);
+    Workspace *w;
+    if ((rc = workspace(&w))) return rc;
+    cudaStream_t st = w->stream;
+    ScratchScope scope(w, st);
+    if ((rc = scope.begin())) return rc;
+    const int64_t ncell = nt * nf;
+    const int64_t ny = ys_stride ? M * ys_stride : nts;
+    double *d_in, *d_out;
+    if ((rc = wsbuf(w, "mb_in", (size_t)(M * nts + ny + M * nt + M * nf), &d_in))) return rc;
+    if ((rc = wsbuf(w, "mb_out", (size_t)(6 * M * ncell + M * nf + 2 * M), &d_out))) return rc;
+    double *d_ts = d_in, *d_ys = d_ts + M * nts, *d_tau = d_ys + ny, *d_om = d_tau + M * nt;
+    CU(cudaMemcpyAsync(d_ts, ts, sizeof(double) * M * nts, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_ys, ys, sizeof(double) * ny, cudaMemcpyHostToDevice, st));
+    if (nt) CU(cudaMemcpyAsync(d_tau, taus, sizeof(double) * M * nt, cudaMemcpyHostToDevice, st));
+    if (nf) CU(cudaMemcpyAsync(d_om, omegas, sizeof(double) * M * nf, cudaMemcpyHostToDevice, st));
+    double *o[6], *h[6] = {Neffs, a0, a1, a2, wwa, phase};
+    for (int i = 0; i < 6; ++i) o[i] = d_out + (size_t)i * M * ncell;
+    double *o_psd = d_out + (size_t)6 * M * ncell, *o_stats = o_psd + M * nf;
+    // group size: the basis rows of a group fit the basis budget; at least four groups once there are 64 members
+    const size_t per_member = (size_t)nf * (size_t)(nts + 64) * 32;
+    int64_t gsize = (int64_t)std::max<size_t>(1, basis_budget_bytes() / std::max<size_t>(per_member, 1));
+    if (M >= 64) gsize = std::min<int64_t>(gsize, (M + 3) / 4);
+    gsize = std::max<int64_t>(1, std::min<int64_t>(gsize, M));
+    // the copy stream must not start before earlier work on it has finished reading mb_out (stream order), nor read a
+    // group before its kernels are done (event)
+    int slot = 0;
+    for (int64_t m0 = 0; m0 < M; m0 += gsize, slot ^= 1) {
+        const int64_t mg = std::min<int64_t>(gsize, M - m0);
+        rc = members_device(w, d_ts + m0 * nts, nts, d_ys + m0 * ys_stride, ys_stride, mg, nts, d_tau + m0 * nt, nt, nt,
+                            d_om + m0 * nf, nf, nf, c, Neff_threshold, psd_Neff_threshold, flags, o[0] + m0 * ncell,
+                            o[1] + m0 * ncell, o[2] + m0 * ncell, o[3] + m0 * ncell, o[4] + m0 * ncell, o[5] + m0 * ncell,
+                            psd ? o_psd + m0 * nf : nullptr, mu_sig ? o_stats + 2 * m0 : nullptr, st);
+        if (rc) break;
+        CU(cudaEventRecord(w->group_ev[slot], st));
+        CU(cudaStreamWaitEvent(w->copy, w->group_ev[slot], 0));
+        for (int i = 0; i < 6; ++i)
+            if (h[i] && ncell)
+                CU(cudaMemcpyAsync(h[i] + m0 * ncell, o[i] + m0 * ncell, sizeof(double) * mg * ncell, cudaMemcpyDeviceToHost,
+                                   w->copy));
+        if (psd && nf)
+            CU(cudaMemcpyAsync(psd + m0 * nf, o_psd + m0 * nf, sizeof(double) * mg * nf, cudaMemcpyDeviceToHost, w->copy));
+    }
+    if (!rc && mu_sig && (flags & WWZB200_STANDARDIZE))
+        cudaMemcpyAsync(mu_sig, o_stats, sizeof(double) * 2 * M, cudaMemcpyDeviceToHost, st);
+    cudaError_t e1 = cudaStreamSynchronize(w->copy), e2 = cudaStreamSynchronize(st);
+    if (rc) return rc;
+    CU(e1);
+    CU(e2);
     return 0;
 }
 

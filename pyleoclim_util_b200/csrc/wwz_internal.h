@@ -56,7 +56,8 @@ cudaError_t launch_rec(const RecPlan &plan, const double2 *d_ty, const double2 *
                        const double *d_tau, int64_t nt, const double *d_kappa, const double *d_dcut,
                        const double *d_taugap, const int *d_unsorted, int64_t k0, int64_t nf_batch, int64_t nf_total, int segs,
                        int64_t seg_len, const unsigned char *d_rec_row, const double *d_grid, double *d_sums,
-                       unsigned int *d_queue, unsigned long long *d_walked, int sms, cudaStream_t st);
+                       unsigned int *d_queue, unsigned long long *d_walked, int sms, cudaStream_t st, int64_t members = 1,
+                       int64_t m_ts = 0, int64_t m_tau = 0);
 
 // Per-frequency constants kappa4 = 4*omega*sqrt(c*log2 e) and dcut = distance beyond which a weight is below
 // 2^-cut_bits (1081 = exactly zero weights only; windowing); which rows the tau-recurrence flavour may take
@@ -67,6 +68,36 @@ cudaError_t launch_rec(const RecPlan &plan, const double2 *d_ty, const double2 *
 cudaError_t launch_setup(const double *d_omega, int64_t nf, const double *d_tau, int64_t nt, const double *d_ts, int64_t n,
                          double c, bool allow_rec, double cut_bits, double *d_kappa, double *d_dcut, double *d_grid,
                          unsigned char *d_rec_row, double *d_gap, int *d_flags, double *d_minmax, cudaStream_t st);
+
+// ---- batches of equally shaped members (ensembles).  m_* = element stride between consecutive members of an input
+// (0 = one vector shared by all members); scratch and outputs are laid out [member][...].
+constexpr int kNyquistMaxPoints = 16384;   // member_prep sorts the sampling steps of a member in shared memory
+// setup of every member; with d_omega_out != NULL, d_omega holds FREQUENCIES and make_omega (utils/wavelet.py:1210-1234)
+// is applied here with the per-member Nyquist frequencies d_fnyq
+cudaError_t launch_setup_members(const double *d_omega, int64_t m_omega, int64_t nf, const double *d_tau, int64_t m_tau,
+                                 int64_t nt, const double *d_ts, int64_t m_ts, int64_t n, int64_t members, double c,
+                                 bool allow_rec, double cut_bits, double *d_kappa, double *d_dcut, double *d_grid,
+                                 unsigned char *d_rec_row, double *d_gap, int *d_flags, double *d_minmax,
+                                 const double *d_fnyq, double *d_omega_out, cudaStream_t st);
+// d_fnyq (nullable): 0.5 / median(diff(ts)) per member; d_ysz (nullable): [member][n] values, z-scored when asked;
+// d_stats (nullable): [member][2] the mean and standard deviation applied ((0, 1) for a nearly constant member)
+cudaError_t launch_member_prep(const double *d_ts, int64_t m_ts, int64_t n, const double *d_ys, int64_t m_ys,
+                               int64_t members, bool standardize, double *d_fnyq, double *d_ysz, double *d_stats,
+                               cudaStream_t st);
+cudaError_t launch_basis_members(const double *d_ts, int64_t m_ts, const double *d_ys, int64_t m_ys, int64_t n,
+                                 int64_t n_pad, const double *d_omega, int64_t m_omega, int64_t nf, int64_t members,
+                                 double2 *d_ty, double2 *d_basis, cudaStream_t st);
+cudaError_t launch_finalize_members(const double *d_sums, const double *d_tau, int64_t m_tau, const double *d_omega,
+                                    int64_t m_omega, int64_t nt, int64_t nf, int64_t members, double neff_thr,
+                                    double *d_neffs, double *d_a0, double *d_a1, double *d_a2, double *d_wwa,
+                                    double *d_phase, int64_t out_row_stride, unsigned int *d_fix_count,
+                                    unsigned int *d_fix_list, unsigned int fix_cap, int segs, cudaStream_t st);
+cudaError_t launch_faithful_members(const double *d_ts, int64_t m_ts, const double *d_ys, int64_t m_ys, int64_t n,
+                                    const double *d_tau, int64_t m_tau, const double *d_omega, int64_t m_omega, int64_t nt,
+                                    int64_t nf, int64_t members, double c, double neff_thr,
+                                    const unsigned int *d_fix_count, const unsigned int *d_fix_list, unsigned int fix_cap,
+                                    double *d_neffs, double *d_a0, double *d_a1, double *d_a2, double *d_wwa,
+                                    double *d_phase, int64_t out_row_stride, int sms, cudaStream_t st);
 
 // (t, y) interleaved + per-frequency basis rows (sin, cos, y sin, y cos), zero padded to n_pad.
 // cos_as_y: records (sin, cos, cos*sin, cos*cos) -- the second pass of Foster's method (wwz_foster.cu).
@@ -123,7 +154,7 @@ cudaError_t launch_psd_parts(const double *d_wwa, const double *d_neffs, int64_t
 cudaError_t launch_minmax(const double *d_x, int64_t n, double *d_out, cudaStream_t st);
 cudaError_t launch_psd_devspan(const double *d_wwa, const double *d_neffs, int64_t nt, int64_t nf,
                                int64_t row_stride, const double *d_minmax, int64_t n, double neff_thr,
-                               double *d_psd, cudaStream_t st);
+                               double *d_psd, cudaStream_t st, int64_t members = 1);
 
 // ---- batched paths (wwz_batch.cu) -------------------------------------------------------------
 struct SharedPlan {

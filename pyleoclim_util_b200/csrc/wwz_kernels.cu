@@ -72,13 +72,34 @@ struct SetupArgs {
     unsigned char *rec_row;
     int *unsorted;
     int nfb, ngb, nub;                            // blocks per job: frequency setup, tau gaps, sortedness
+    // members of a batch (blockIdx.y): element strides of the inputs (0 = shared); the outputs are [member][...]
+    long long m_omega, m_tau, m_ts;
+    const double *fnyq;                           // per member; with omega_out: `omega` holds frequencies (make_omega here)
+    double *omega_out;                            // [member][nf]
 };
 
-__global__ void __launch_bounds__(256) setup_kernel(const SetupArgs a)
+__global__ void __launch_bounds__(256) setup_kernel(SetupArgs a)
 {
     __shared__ int bad;
     __shared__ double slo[8], shi[8];
     const int b = blockIdx.x, tid = threadIdx.x;
+    {
+        const long long m = blockIdx.y;
+        a.omega += m * a.m_omega;
+        a.tau += m * a.m_tau;
+        a.ts += m * a.m_ts;
+        a.kappa += m * a.nf;
+        a.dcut += m * a.nf;
+        a.rec_row += m * a.nf;
+        a.grid += m * 2;
+        a.gap += m * a.nt;
+        a.unsorted += m * kFlagInts;
+        if (a.minmax) a.minmax += m * 2;
+        if (a.omega_out) {
+            a.omega_out += m * a.nf;
+            a.fnyq += m;
+        }
+    }
     if (b < a.nfb) {
         // ---- tau grid, then this block's frequency rows
         if (tid == 0) bad = 0;
@@ -102,7 +123,13 @@ __global__ void __launch_bounds__(256) setup_kernel(const SetupArgs a)
         }
         const long long k = (long long)b * blockDim.x + tid;
         if (k < a.nf) {
-            const double om = a.omega[k];
+            double om = a.omega[k];
+            if (a.omega_out) {
+                // make_omega (utils/wavelet.py:1229-1232): frequencies above the Nyquist frequency become NaN, omega = 2 pi f
+                const double f = om;
+                om = (f > *a.fnyq) ? CUDART_NAN : 2.0 * 3.141592653589793 * f;
+                a.omega_out[k] = om;
+            }
             const double ka = om * a.kscale;
             a.kappa[k] = ka;
             a.dcut[k] = isnan(om) ? -1.0 : a.vcut / fabs(ka);
@@ -159,11 +186,13 @@ __global__ void __launch_bounds__(256) setup_kernel(const SetupArgs a)
     }
 }
 
-cudaError_t launch_setup(const double *d_omega, int64_t nf, const double *d_tau, int64_t nt, const double *d_ts, int64_t n,
-                         double c, bool allow_rec, double cut_bits, double *d_kappa, double *d_dcut, double *d_grid,
-                         unsigned char *d_rec_row, double *d_gap, int *d_flags, double *d_minmax, cudaStream_t st)
+cudaError_t launch_setup_members(const double *d_omega, int64_t m_omega, int64_t nf, const double *d_tau, int64_t m_tau,
+                                 int64_t nt, const double *d_ts, int64_t m_ts, int64_t n, int64_t members, double c,
+                                 bool allow_rec, double cut_bits, double *d_kappa, double *d_dcut, double *d_grid,
+                                 unsigned char *d_rec_row, double *d_gap, int *d_flags, double *d_minmax,
+                                 const double *d_fnyq, double *d_omega_out, cudaStream_t st)
 {
-    cudaError_t e = cudaMemsetAsync(d_flags, 0, kFlagInts * sizeof(int), st);   // flag, counter, work queues
+    cudaError_t e = cudaMemsetAsync(d_flags, 0, (size_t)members * kFlagInts * sizeof(int), st);   // flag, counter, work queues
     if (e != cudaSuccess) return e;
     SetupArgs a{};
     a.omega = d_omega;
@@ -185,9 +214,119 @@ cudaError_t launch_setup(const double *d_omega, int64_t nf, const double *d_tau,
     a.nfb = (int)((nf + 255) / 256);
     a.ngb = (int)((nt + 255) / 256);
     a.nub = n >= 2 ? (int)((n + 255) / 256) : 0;
+    a.m_omega = m_omega;
+    a.m_tau = m_tau;
+    a.m_ts = m_ts;
+    a.fnyq = d_fnyq;
+    a.omega_out = d_omega_out;
     const int blocks = a.nfb + a.ngb + a.nub + (d_minmax ? 1 : 0);
-    if (blocks <= 0) return cudaSuccess;
-    setup_kernel<<<(unsigned)blocks, 256, 0, st>>>(a);
+    if (blocks <= 0 || members <= 0) return cudaSuccess;
+    if (members > 65535) return cudaErrorInvalidValue;
+    setup_kernel<<<dim3((unsigned)blocks, (unsigned)members), 256, 0, st>>>(a);
+    bump_launch_counter();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_setup(const double *d_omega, int64_t nf, const double *d_tau, int64_t nt, const double *d_ts, int64_t n,
+                         double c, bool allow_rec, double cut_bits, double *d_kappa, double *d_dcut, double *d_grid,
+                         unsigned char *d_rec_row, double *d_gap, int *d_flags, double *d_minmax, cudaStream_t st)
+{
+    return launch_setup_members(d_omega, 0, nf, d_tau, 0, nt, d_ts, 0, n, 1, c, allow_rec, cut_bits, d_kappa, d_dcut, d_grid,
+                                d_rec_row, d_gap, d_flags, d_minmax, nullptr, nullptr, st);
+}
+
+// Nyquist frequency of every member, 0.5 / median(diff(ts)) (utils/wavelet.py:1229), and the member's z-scored values
+// (utils/tsutils.py:1134-1154: mean and population standard deviation; a series with |std| < 1e-3 is left as it is).
+// One CTA per member; the n-1 sampling steps are sorted in shared memory (bitonic), n - 1 <= kNyquistMaxPoints.
+__global__ void __launch_bounds__(1024) member_prep_kernel(const double *__restrict__ ts, long long m_ts, long long n,
+                                                           const double *__restrict__ ys, long long m_ys, int standardize,
+                                                           int npow2, double *__restrict__ fnyq, double *__restrict__ ysz,
+                                                           double *__restrict__ stats)
+{
+    extern __shared__ double sh[];      // [npow2] when the Nyquist frequency is wanted
+    __shared__ double red[32];
+    const long long m = blockIdx.x;
+    const int tid = threadIdx.x, nth = blockDim.x;
+    if (fnyq) {
+        const double *t = ts + m * m_ts;
+        for (int i = tid; i < npow2; i += nth) sh[i] = (i < n - 1) ? t[i + 1] - t[i] : CUDART_INF;
+        __syncthreads();
+        for (int k = 2; k <= npow2; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int i = tid; i < npow2; i += nth) {
+                    const int l = i ^ j;
+                    if (l > i) {
+                        const double x = sh[i], y = sh[l];
+                        const bool up = (i & k) == 0;
+                        if ((x > y) == up) {
+                            sh[i] = y;
+                            sh[l] = x;
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        if (tid == 0) {
+            const long long cnt = n - 1;
+            // np.median: the middle element, or the mean of the two middle elements
+            const double med = (cnt & 1) ? sh[cnt >> 1] : (sh[(cnt >> 1) - 1] + sh[cnt >> 1]) * 0.5;
+            fnyq[m] = 0.5 / med;
+        }
+    }
+    if (ysz) {
+        const double *y = ys + m * m_ys;
+        double *z = ysz + m * n;
+        double mu = 0.0, sig = 1.0;
+        if (standardize) {
+            auto block_sum = [&](double v) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                __syncthreads();
+                if ((tid & 31) == 0) red[tid >> 5] = v;
+                __syncthreads();
+                double tot = 0.0;
+                for (int w = 0; w < (nth >> 5); ++w) tot += red[w];
+                return tot;
+            };
+            double acc = 0.0;
+            for (long long i = tid; i < n; i += nth) acc += y[i];
+            const double mean = block_sum(acc) / (double)n;
+            double v = 0.0;
+            for (long long i = tid; i < n; i += nth) {
+                const double d = y[i] - mean;
+                v += d * d;
+            }
+            const double sd = sqrt(block_sum(v) / (double)n);
+            if (!(fabs(sd) < 1e-3)) {
+                mu = mean;
+                sig = sd;
+            }
+        }
+        for (long long i = tid; i < n; i += nth) z[i] = (y[i] - mu) / sig;
+        if (stats && tid == 0) {      // the shift and scale actually applied ((0, 1): left as it is)
+            stats[2 * m] = mu;
+            stats[2 * m + 1] = sig;
+        }
+    }
+}
+
+cudaError_t launch_member_prep(const double *d_ts, int64_t m_ts, int64_t n, const double *d_ys, int64_t m_ys,
+                               int64_t members, bool standardize, double *d_fnyq, double *d_ysz, double *d_stats,
+                               cudaStream_t st)
+{
+    if (members <= 0) return cudaSuccess;
+    int npow2 = 2;
+    while (npow2 < n - 1) npow2 <<= 1;
+    size_t smem = 0;
+    if (d_fnyq) {
+        if (n - 1 > kNyquistMaxPoints || n < 2) return cudaErrorInvalidValue;
+        smem = (size_t)npow2 * sizeof(double);
+        static SmemOptIn done;
+        cudaError_t e = ensure_dynamic_smem(member_prep_kernel, (int)smem, done);
+        if (e != cudaSuccess) return e;
+    }
+    member_prep_kernel<<<(unsigned)members, 1024, smem, st>>>(d_ts, m_ts, n, d_ys, m_ys, standardize ? 1 : 0, npow2, d_fnyq, d_ysz, d_stats);
     bump_launch_counter();
     return cudaGetLastError();
 }
@@ -200,11 +339,20 @@ cudaError_t launch_setup(const double *d_omega, int64_t nf, const double *d_tau,
 // ------------------------------------------------------------------------------------------------
 __global__ void basis_kernel(const double *__restrict__ ts, const double *__restrict__ ys, int64_t n,
                              int64_t n_pad, const double *__restrict__ omega, double2 *__restrict__ ty,
-                             double2 *__restrict__ basis, int write_ty, int cos_as_y)
+                             double2 *__restrict__ basis, int write_ty, int cos_as_y, int64_t m_ts, int64_t m_ys,
+                             int64_t m_omega)
 {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n_pad) return;
     const int64_t k = blockIdx.y;
+    {   // member of a batch: inputs by their strides, ty [member][n_pad], basis [member][rows][n_pad]
+        const int64_t m = blockIdx.z;
+        ts += m * m_ts;
+        ys += m * m_ys;
+        omega += m * m_omega;
+        ty += m * n_pad;
+        basis += (size_t)m * (size_t)gridDim.y * (size_t)n_pad * 2;
+    }
     const double om = omega[k];
     double t = 0.0, y = 0.0, s = 0.0, c = 0.0;
     if (i < n) {
@@ -234,7 +382,19 @@ cudaError_t launch_basis(const double *d_ts, const double *d_ys, int64_t n, int6
     if (nf_batch <= 0 || n_pad <= 0) return cudaSuccess;
     dim3 grid((unsigned)((n_pad + 255) / 256), (unsigned)nf_batch);
     basis_kernel<<<grid, 256, 0, st>>>(d_ts, d_ys, n, n_pad, d_omega, d_ty, d_basis, write_ty ? 1 : 0,
-                                      cos_as_y ? 1 : 0);
+                                      cos_as_y ? 1 : 0, 0, 0, 0);
+    bump_launch_counter();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_basis_members(const double *d_ts, int64_t m_ts, const double *d_ys, int64_t m_ys, int64_t n,
+                                 int64_t n_pad, const double *d_omega, int64_t m_omega, int64_t nf, int64_t members,
+                                 double2 *d_ty, double2 *d_basis, cudaStream_t st)
+{
+    if (nf <= 0 || n_pad <= 0 || members <= 0) return cudaSuccess;
+    if (nf > 65535 || members > 65535) return cudaErrorInvalidValue;
+    dim3 grid((unsigned)((n_pad + 255) / 256), (unsigned)nf, (unsigned)members);
+    basis_kernel<<<grid, 256, 0, st>>>(d_ts, d_ys, n, n_pad, d_omega, d_ty, d_basis, 1, 0, m_ts, m_ys, m_omega);
     bump_launch_counter();
     return cudaGetLastError();
 }
@@ -602,11 +762,27 @@ __global__ void finalize_kernel(const double *__restrict__ sums, const double *_
                                 double *__restrict__ neffs, double *__restrict__ a0o, double *__restrict__ a1o,
                                 double *__restrict__ a2o, double *__restrict__ wwa, double *__restrict__ phase,
                                 int64_t row_stride, unsigned int *__restrict__ fix_count,
-                                unsigned int *__restrict__ fix_list, unsigned int fix_cap, int segs)
+                                unsigned int *__restrict__ fix_list, unsigned int fix_cap, int segs, int64_t members,
+                                int64_t m_tau, int64_t m_omega)
 {
-    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int64_t nc = nt * nf;
-    if (idx >= nc) return;
+    if (idx >= nc * members) return;
+    const int64_t gidx = idx;                    // index over all members (what the fix-up list records)
+    const int64_t mem = idx / nc;
+    idx -= mem * nc;
+    {   // member of a batch: sums [member][segs][7][nc], outputs [member][nt][row_stride]
+        sums += (size_t)mem * (size_t)segs * kNumSums * (size_t)nc;
+        tau += mem * m_tau;
+        omega += mem * m_omega;
+        const int64_t oo = mem * nt * row_stride;
+        neffs += oo;
+        if (a0o) a0o += oo;
+        if (a1o) a1o += oo;
+        if (a2o) a2o += oo;
+        if (wwa) wwa += oo;
+        if (phase) phase += oo;
+    }
     const int64_t j = idx / nf, k = idx - j * nf;
     // add the point-segment slabs in order
     double acc[kNumSums];
@@ -620,7 +796,7 @@ __global__ void finalize_kernel(const double *__restrict__ sums, const double *_
     const double W = acc[0], Q = acc[1];
     if (fix_list && (W < 0x1p-200 || Q < 0x1p-400)) {
         const unsigned int slot = atomicAdd(fix_count, 1u);
-        if (slot < fix_cap) fix_list[slot] = (unsigned int)idx;
+        if (slot < fix_cap) fix_list[slot] = (unsigned int)gidx;
     }
     const double neff = W * W / Q;
     double a0 = CUDART_NAN, a1 = CUDART_NAN, a2 = CUDART_NAN;
@@ -656,23 +832,44 @@ __global__ void __launch_bounds__(128)
                           const unsigned int *__restrict__ fix_list, unsigned int fix_cap,
                           double *__restrict__ neffs, double *__restrict__ a0o, double *__restrict__ a1o,
                           double *__restrict__ a2o, double *__restrict__ wwa, double *__restrict__ phase,
-                          int64_t row_stride)
+                          int64_t row_stride, int64_t members, int64_t m_ts, int64_t m_ys, int64_t m_tau, int64_t m_omega)
 {
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    int64_t total = nt * nf;
+    const int64_t nc = nt * nf;
+    int64_t total = nc * members;
     if (fix_list) {
         const unsigned int cnt = *fix_count;
         total = cnt < fix_cap ? cnt : fix_cap;
     }
     for (int64_t item = warp0; item < total; item += nwarps) {
-        const int64_t idx = fix_list ? (int64_t)fix_list[item] : item;
+        int64_t idx = fix_list ? (int64_t)fix_list[item] : item;
+        const int64_t mem = idx / nc;
+        idx -= mem * nc;
         const int64_t j = idx / nf, k = idx - j * nf;
         double neff, a0, a1, a2;
-        faithful_cell_warp(ts, ys, 1, n, tau[j], omega[k], c, thr, lane, neff, a0, a1, a2);
-        if (lane == 0) store_cell(j * row_stride + k, neff, a0, a1, a2, neffs, a0o, a1o, a2o, wwa, phase);
+        faithful_cell_warp(ts + mem * m_ts, ys + mem * m_ys, 1, n, tau[mem * m_tau + j], omega[mem * m_omega + k], c, thr, lane,
+                           neff, a0, a1, a2);
+        if (lane == 0)
+            store_cell(mem * nt * row_stride + j * row_stride + k, neff, a0, a1, a2, neffs, a0o, a1o, a2o, wwa, phase);
     }
+}
+
+cudaError_t launch_finalize_members(const double *d_sums, const double *d_tau, int64_t m_tau, const double *d_omega,
+                                    int64_t m_omega, int64_t nt, int64_t nf, int64_t members, double neff_thr,
+                                    double *d_neffs, double *d_a0, double *d_a1, double *d_a2, double *d_wwa,
+                                    double *d_phase, int64_t out_row_stride, unsigned int *d_fix_count,
+                                    unsigned int *d_fix_list, unsigned int fix_cap, int segs, cudaStream_t st)
+{
+    const int64_t nc = nt * nf * members;
+    if (nc <= 0) return cudaSuccess;
+    finalize_kernel<<<(unsigned)((nc + 255) / 256), 256, 0, st>>>(d_sums, d_tau, d_omega, nt, nf, neff_thr, d_neffs,
+                                                                  d_a0, d_a1, d_a2, d_wwa, d_phase, out_row_stride,
+                                                                  d_fix_count, d_fix_list, fix_cap, segs, members, m_tau,
+                                                                  m_omega);
+    bump_launch_counter();
+    return cudaGetLastError();
 }
 
 cudaError_t launch_finalize(const double *d_sums, const double *d_tau, const double *d_omega, int64_t nt,
@@ -681,11 +878,25 @@ cudaError_t launch_finalize(const double *d_sums, const double *d_tau, const dou
                             unsigned int *d_fix_count, unsigned int *d_fix_list, unsigned int fix_cap, int segs,
                             cudaStream_t st)
 {
-    const int64_t nc = nt * nf;
-    if (nc <= 0) return cudaSuccess;
-    finalize_kernel<<<(unsigned)((nc + 255) / 256), 256, 0, st>>>(d_sums, d_tau, d_omega, nt, nf, neff_thr, d_neffs,
-                                                                  d_a0, d_a1, d_a2, d_wwa, d_phase, out_row_stride,
-                                                                  d_fix_count, d_fix_list, fix_cap, segs);
+    return launch_finalize_members(d_sums, d_tau, 0, d_omega, 0, nt, nf, 1, neff_thr, d_neffs, d_a0, d_a1, d_a2, d_wwa,
+                                   d_phase, out_row_stride, d_fix_count, d_fix_list, fix_cap, segs, st);
+}
+
+cudaError_t launch_faithful_members(const double *d_ts, int64_t m_ts, const double *d_ys, int64_t m_ys, int64_t n,
+                                    const double *d_tau, int64_t m_tau, const double *d_omega, int64_t m_omega, int64_t nt,
+                                    int64_t nf, int64_t members, double c, double neff_thr,
+                                    const unsigned int *d_fix_count, const unsigned int *d_fix_list, unsigned int fix_cap,
+                                    double *d_neffs, double *d_a0, double *d_a1, double *d_a2, double *d_wwa,
+                                    double *d_phase, int64_t out_row_stride, int sms, cudaStream_t st)
+{
+    if (nt * nf * members <= 0) return cudaSuccess;
+    int64_t blocks = (int64_t)sms * 8;
+    if (!d_fix_list) blocks = std::min<int64_t>(blocks * 2, (nt * nf * members + 3) / 4);
+    if (blocks < 1) blocks = 1;
+    faithful_cells_kernel<<<(unsigned)blocks, 128, 0, st>>>(d_ts, d_ys, n, d_tau, d_omega, nt, nf, c, neff_thr,
+                                                            d_fix_count, d_fix_list, fix_cap, d_neffs, d_a0, d_a1,
+                                                            d_a2, d_wwa, d_phase, out_row_stride, members, m_ts, m_ys,
+                                                            m_tau, m_omega);
     bump_launch_counter();
     return cudaGetLastError();
 }
@@ -696,15 +907,8 @@ cudaError_t launch_faithful(const double *d_ts, const double *d_ys, int64_t n, c
                             double *d_neffs, double *d_a0, double *d_a1, double *d_a2, double *d_wwa,
                             double *d_phase, int64_t out_row_stride, int sms, cudaStream_t st)
 {
-    if (nt * nf <= 0) return cudaSuccess;
-    int64_t blocks = (int64_t)sms * 8;
-    if (!d_fix_list) blocks = std::min<int64_t>(blocks * 2, (nt * nf + 3) / 4);
-    if (blocks < 1) blocks = 1;
-    faithful_cells_kernel<<<(unsigned)blocks, 128, 0, st>>>(d_ts, d_ys, n, d_tau, d_omega, nt, nf, c, neff_thr,
-                                                            d_fix_count, d_fix_list, fix_cap, d_neffs, d_a0, d_a1,
-                                                            d_a2, d_wwa, d_phase, out_row_stride);
-    bump_launch_counter();
-    return cudaGetLastError();
+    return launch_faithful_members(d_ts, 0, d_ys, 0, n, d_tau, 0, d_omega, 0, nt, nf, 1, c, neff_thr, d_fix_count, d_fix_list,
+                                   fix_cap, d_neffs, d_a0, d_a1, d_a2, d_wwa, d_phase, out_row_stride, sms, st);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -724,6 +928,13 @@ __global__ void __launch_bounds__(kPsdCols * kPsdRows)
 {
     __shared__ double s_sp[kPsdRows][kPsdCols + 1], s_se[kPsdRows][kPsdCols + 1];
     const int64_t k = blockIdx.x * kPsdCols + threadIdx.x;
+    {   // member of a batch (blockIdx.y): scalograms [member][nt][row_stride], psd [member][nf], minmax [member][2]
+        const int64_t m = blockIdx.y;
+        wwa += m * nt * row_stride;
+        neffs += m * nt * row_stride;
+        if (psd) psd += m * nf;
+        if (minmax) minmax += 2 * m;
+    }
     if (minmax) tspan = minmax[1] - minmax[0];
     double sp = 0.0, se = 0.0;
     if (k < nf) {
@@ -778,11 +989,12 @@ cudaError_t launch_psd_parts(const double *d_wwa, const double *d_neffs, int64_t
 
 cudaError_t launch_psd_devspan(const double *d_wwa, const double *d_neffs, int64_t nt, int64_t nf,
                                int64_t row_stride, const double *d_minmax, int64_t n, double neff_thr,
-                               double *d_psd, cudaStream_t st)
+                               double *d_psd, cudaStream_t st, int64_t members)
 {
-    if (nf <= 0) return cudaSuccess;
-    psd_kernel<<<(unsigned)((nf + kPsdCols - 1) / kPsdCols), dim3(kPsdCols, kPsdRows), 0, st>>>(d_wwa, d_neffs, nt, nf, row_stride, 0.0,
-                                                                    d_minmax, (double)n, neff_thr, d_psd, nullptr);
+    if (nf <= 0 || members <= 0) return cudaSuccess;
+    if (members > 65535) return cudaErrorInvalidValue;
+    psd_kernel<<<dim3((unsigned)((nf + kPsdCols - 1) / kPsdCols), (unsigned)members), dim3(kPsdCols, kPsdRows), 0, st>>>(
+        d_wwa, d_neffs, nt, nf, row_stride, 0.0, d_minmax, (double)n, neff_thr, d_psd, nullptr);
     bump_launch_counter();
     return cudaGetLastError();
 }

@@ -55,6 +55,8 @@ struct RecArgs {
     unsigned int *queue;          // [0] next work item, [1] warps that have left (self-resetting)
     unsigned long long *walked;   // profiling only (may be null): (lane, point) pairs actually evaluated, summed over warps
     long long n, n_pad, ncell_total, seg_len, ntiles, nitems;
+    long long m_ts, m_tau;        // members of a batch: element strides of ts and tau (scratch is [member][...])
+    int members;
     int nt, G, nf_batch, k0, nf_total, P, tg_log2, tiles_g, segs;
     int row_stride2;     // basis row stride inside a stage, double2 units (odd multiple of 16 B: conflict-free rows)
     int stage_stride2;   // stage stride, double2 units
@@ -90,8 +92,6 @@ __global__ void __maxnreg__(NREG) wwz_tile_kernel(const RecArgs a)
 
     const int TG = 1 << a.tg_log2, TR = 32 >> a.tg_log2;
     const int r_loc = lane >> a.tg_log2;
-    const double dtau = REC ? a.grid[0] : 0.0;
-    const bool sorted = !*a.unsorted;
     unsigned long long walked = 0;
 
     for (;;) {
@@ -99,15 +99,30 @@ __global__ void __maxnreg__(NREG) wwz_tile_kernel(const RecArgs a)
         if (lane == 0) item = atomicAdd(&a.queue[0], 1u);
         item = __shfl_sync(0xffffffffu, item, 0);
         if ((long long)item >= a.nitems) break;
-        // items are numbered tile-major (low frequencies = long windows first), point segment fastest
-        const long long tile = item / (unsigned)a.segs;
-        const int seg = (int)(item - (unsigned)(tile * a.segs));
+        // items are numbered tile-major (low frequencies = long windows first), then member, point segment fastest
+        const unsigned int per_tile = (unsigned)a.segs * (unsigned)a.members;
+        const long long tile = item / per_tile;
+        const unsigned int rem = item - (unsigned)tile * per_tile;
+        const int mem = (int)(rem / (unsigned)a.segs);
+        const int seg = (int)(rem - (unsigned)mem * (unsigned)a.segs);
         const int kt = (int)(tile / a.tiles_g), gt = (int)(tile - (long long)kt * a.tiles_g);
+        // this member's inputs and scratch
+        const double2 *const m_ty = a.ty + (size_t)mem * (size_t)a.n_pad;
+        const double2 *const m_basis = a.basis + (size_t)mem * (size_t)a.nf_batch * (size_t)a.n_pad * 2;
+        const double *const m_tsp = a.ts + (long long)mem * a.m_ts;
+        const double *const m_taup = a.tau + (long long)mem * a.m_tau;
+        const double *const m_kappa = a.kappa + (size_t)mem * a.nf_total;
+        const double *const m_dcut = a.dcut + (size_t)mem * a.nf_total;
+        const double *const m_gap = a.taugap + (size_t)mem * a.nt;
+        const unsigned char *const m_rec = a.rec_row ? a.rec_row + (size_t)mem * a.nf_total : nullptr;
+        double *const m_sums = a.sums + (size_t)mem * (size_t)a.segs * kNumSums * (size_t)a.ncell_total;
+        const double dtau = REC ? a.grid[2 * mem] : 0.0;
+        const bool sorted = !a.unsorted[mem * kFlagInts];
         const int g = gt * TG + (lane & (TG - 1));
         const int kb = kt * TR + r_loc;                       // row inside the frequency batch
         const int rows = min(TR, a.nf_batch - kt * TR);       // rows of this tile that exist
         bool ok = g < a.G && kb < a.nf_batch;
-        if (ok && a.rec_row) ok = (a.rec_row[a.k0 + kb] != 0) == REC;
+        if (ok && m_rec) ok = (m_rec[a.k0 + kb] != 0) == REC;
         if (!__any_sync(0xffffffffu, ok)) continue;           // every row of the tile belongs to the other flavour
 
         const long long p0 = (long long)seg * a.seg_len;
@@ -120,15 +135,15 @@ __global__ void __maxnreg__(NREG) wwz_tile_kernel(const RecArgs a)
         for (int r = 0; r < M; ++r) tau_r[r] = 0.0;
         double wlo = CUDART_INF, whi = -CUDART_INF;
         if (ok) {
-            kap = a.kappa[a.k0 + kb];
-            const double dc = a.dcut[a.k0 + kb];
+            kap = m_kappa[a.k0 + kb];
+            const double dc = m_dcut[a.k0 + kb];
             double gmax = 0.0;                                   // widest sample gap seen by the lane's cells
             double tmin = CUDART_INF, tmax = -CUDART_INF;        // (the tau axis may come in any order)
 #pragma unroll
             for (int r = 0; r < M; ++r) {
                 const int j = min(g * M + r, a.nt - 1);
-                tau_r[r] = a.tau[j];
-                gmax = fmax(gmax, a.taugap[j]);
+                tau_r[r] = m_taup[j];
+                gmax = fmax(gmax, m_gap[j]);
                 tmin = fmin(tmin, tau_r[r]);
                 tmax = fmax(tmax, tau_r[r]);
             }
@@ -148,8 +163,8 @@ __global__ void __maxnreg__(NREG) wwz_tile_kernel(const RecArgs a)
         }
         long long i0 = p0, i1 = p1;
         if (sorted) {
-            i0 = warp_bound<false>(a.ts, p0, p1, wlo, lane);
-            i1 = warp_bound<true>(a.ts, i0, p1, whi, lane);
+            i0 = warp_bound<false>(m_tsp, p0, p1, wlo, lane);
+            i1 = warp_bound<true>(m_tsp, i0, p1, whi, lane);
         }
         const int c_lo = (int)((i0 - p0) / P);
         const int nchunks = (i1 > i0) ? (int)((i1 - p0 + P - 1) / P) - c_lo : 0;
@@ -162,12 +177,12 @@ __global__ void __maxnreg__(NREG) wwz_tile_kernel(const RecArgs a)
             const size_t start = (size_t)p0 + (size_t)c * P;
             if (lane == 0) {
                 mbar_arrive_expect_tx(&full[sg], bytes);
-                tma_load_1d(st, a.ty + start, (uint32_t)P * 16u, &full[sg]);
+                tma_load_1d(st, m_ty + start, (uint32_t)P * 16u, &full[sg]);
             }
             __syncwarp();
             if (lane < rows) {
                 const size_t row = (size_t)(kt * TR + lane);
-                tma_load_1d(st + P + (size_t)lane * a.row_stride2, a.basis + (row * (size_t)a.n_pad + start) * 2,
+                tma_load_1d(st + P + (size_t)lane * a.row_stride2, m_basis + (row * (size_t)a.n_pad + start) * 2,
                             (uint32_t)P * 32u, &full[sg]);
             }
         };
@@ -284,13 +299,13 @@ __global__ void __maxnreg__(NREG) wwz_tile_kernel(const RecArgs a)
                     const size_t cell = (size_t)seg * (size_t)kNumSums * nc + (size_t)j * (size_t)a.nf_total + (size_t)kcol;
                     // REC: undo the per-cell scale h_r = 2^(-(r D)^2/16) that was factored out of the weights
                     const double h = REC ? exp2(-(double)(r * r) * D * D * 0.0625) : 1.0;
-                    a.sums[0 * nc + cell] = W[r] * h;
-                    a.sums[1 * nc + cell] = Q[r] * h * h;
-                    a.sums[2 * nc + cell] = Ws[r] * h;
-                    a.sums[3 * nc + cell] = Wc[r] * h;
-                    a.sums[4 * nc + cell] = Wy[r] * h;
-                    a.sums[5 * nc + cell] = Wys[r] * h;
-                    a.sums[6 * nc + cell] = Wyc[r] * h;
+                    m_sums[0 * nc + cell] = W[r] * h;
+                    m_sums[1 * nc + cell] = Q[r] * h * h;
+                    m_sums[2 * nc + cell] = Ws[r] * h;
+                    m_sums[3 * nc + cell] = Wc[r] * h;
+                    m_sums[4 * nc + cell] = Wy[r] * h;
+                    m_sums[5 * nc + cell] = Wys[r] * h;
+                    m_sums[6 * nc + cell] = Wyc[r] * h;
                 }
             }
         }
@@ -387,9 +402,10 @@ cudaError_t launch_rec(const RecPlan &plan, const double2 *d_ty, const double2 *
                        const double *d_tau, int64_t nt, const double *d_kappa, const double *d_dcut,
                        const double *d_taugap, const int *d_unsorted, int64_t k0, int64_t nf_batch, int64_t nf_total, int segs,
                        int64_t seg_len, const unsigned char *d_rec_row, const double *d_grid, double *d_sums,
-                       unsigned int *d_queue, unsigned long long *d_walked, int sms, cudaStream_t st)
+                       unsigned int *d_queue, unsigned long long *d_walked, int sms, cudaStream_t st, int64_t members,
+                       int64_t m_ts, int64_t m_tau)
 {
-    if (nf_batch <= 0 || nt <= 0) return cudaSuccess;
+    if (nf_batch <= 0 || nt <= 0 || members <= 0) return cudaSuccess;
     RecArgs a{};
     a.ty = d_ty;
     a.basis = d_basis;
@@ -420,7 +436,10 @@ cudaError_t launch_rec(const RecPlan &plan, const double2 *d_ty, const double2 *
     a.tiles_g = (plan.groups + TG - 1) / TG;
     const int64_t tiles_k = (nf_batch + TR - 1) / TR;
     a.ntiles = (int64_t)a.tiles_g * tiles_k;
-    a.nitems = a.ntiles * segs;
+    a.members = (int)members;
+    a.m_ts = m_ts;
+    a.m_tau = m_tau;
+    a.nitems = a.ntiles * segs * members;
     if (a.nitems >= ((int64_t)1 << 32)) return cudaErrorInvalidValue;
     a.row_stride2 = (int)(plan.row_stride / 16);
     a.stage_stride2 = plan.stage_bytes / 16;

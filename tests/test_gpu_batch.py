@@ -193,6 +193,69 @@ def test_ragged_equal_length_members_take_the_vectorised_host_path():
         B.wwz_ragged(flat)                                   # constant series: left unscaled, with the warning
 
 
+def test_config4_size_ensemble_against_the_oracle():
+    """BASELINE.json configs[3] at its size: 1,000 age-ensemble members of n = 1,500 on their default 50 x 151 grids
+    through the member-batch entry point (core/ensembleseries.py:169-173 -> core/multipleseries.py:1520-1532).
+    32 sampled members against the ORACLE (two-pass Kirchner, host z-score, host make_omega) at the parity bar, and the
+    three-state Neff mask and Neff values of EVERY member against single calls of the single-series path."""
+    O = oracle()
+    axes, y = synth.age_ensemble(1500, 1000)
+    members = []
+    for tm in axes:
+        ys_c, ts_c, fr_c, ta_c = WV.prepare_wwz(y, tm)
+        members.append((ys_c, ts_c, ta_c, fr_c))
+    res, psds = B.wwz_ragged(members, psd_Neff_threshold=3)
+    assert len(res) == 1000 and res[0].amplitude.shape == (50, members[0][3].size)
+    worst = 0.0
+    for m in range(0, 1000, 32)[:32]:
+        ys_c, ts_c, ta_c, fr_c = members[m]
+        o = O.kirchner(ys_c, ts_c, fr_c, ta_c, standardize=True)
+        r = res[m]
+        got = dict(amplitude=r.amplitude, phase=r.phase, Neffs=r.Neffs, a0=r.coeff[0], a1=r.coeff[1], a2=r.coeff[2])
+        assert_scalogram_parity(got, as_dict(*o), what="member %d vs oracle" % m)
+        worst = max(worst, max_rel(r.amplitude, o[0]))
+        po = O.wwa2psd(o[0], ts_c, o[2], Neff_threshold=3)
+        assert max_rel(psds[m], po) < 1e-9
+        assert np.array_equal(r.coi, WV.make_coi(ta_c))
+    print("config-4 ensemble: worst amplitude error of 32 sampled members vs the oracle %.2e" % worst)
+    for m, (ys_c, ts_c, ta_c, fr_c) in enumerate(members):
+        one = WV.kirchner_cuda(ys_c, ts_c, fr_c, ta_c, standardize=True)
+        assert_same_nan_mask(res[m].Neffs, one[2], "member %d Neffs" % m)
+        assert_same_nan_mask(res[m].amplitude, one[0], "member %d amplitude" % m)
+        assert max_rel(res[m].Neffs, one[2]) < 1e-12
+        assert max_rel(res[m].amplitude, one[0]) < 1e-11
+
+
+def test_member_batch_shared_values_strides_and_flags():
+    """wwz_members: one value vector shared by all members (ys_stride = 0) equals per-member copies bit for bit; the
+    dense flag, explicit omega (no device make_omega) and a frequency above every member's Nyquist agree with single
+    calls; groups (forced by a small basis budget) change nothing."""
+    axes, y = synth.age_ensemble(400, 9)
+    T = np.stack(axes)
+    tau = np.stack([np.linspace(t.min(), t.max(), 23) for t in axes])
+    freq = np.stack([np.append(synth.freq_log(t, 30), 3.0) for t in axes])          # last column above Nyquist
+    a = B.wwz_members(T, y, tau, freq)
+    b = B.wwz_members(T, np.tile(y, (9, 1)), tau, freq)
+    for ra, rb in zip(a, b):
+        assert np.array_equal(ra.amplitude.view(np.uint64), rb.amplitude.view(np.uint64))
+    old = os.environ.get("WWZB200_BASIS_BYTES")
+    os.environ["WWZB200_BASIS_BYTES"] = str(3 << 20)          # a few members per group
+    try:
+        g = B.wwz_members(T, y, tau, freq)
+    finally:
+        if old is None:
+            os.environ.pop("WWZB200_BASIS_BYTES")
+        else:
+            os.environ["WWZB200_BASIS_BYTES"] = old
+    d = B.wwz_members(T, y, tau, freq, flags=_lib.DENSE)
+    for m in range(9):
+        one = WV.kirchner_cuda(y, T[m], freq[m], tau[m], standardize=True)
+        for r in (a[m], g[m], d[m]):
+            assert_scalogram_parity(dict(amplitude=r.amplitude, phase=r.phase, Neffs=r.Neffs, a0=r.coeff[0],
+                                         a1=r.coeff[1], a2=r.coeff[2]), as_dict(*one), amp_rtol=1e-11, phase_atol=1e-11)
+        assert np.isnan(a[m].amplitude[:, -1]).all() and np.isnan(a[m].Neffs[:, -1]).all()
+
+
 # ------------------------------------------------------------------ quantiles
 @pytest.mark.parametrize("S", [1, 2, 3, 10, 200, 1000, 20000])
 def test_quantiles_match_scipy_mquantiles(S):
