@@ -72,6 +72,9 @@ extern "C" {
 #define WWZB200_FREQ_HZ 128u    /* wwzb200_kirchner_members(_dev): the `omegas` argument holds FREQUENCIES; make_omega   \
                                    (utils/wavelet.py:1210-1234: NaN above 0.5/median(diff(ts)), omega = 2 pi f) is        \
                                    applied per member on the device; needs nts <= 16385 */
+#define WWZB200_PREPARED 256u   /* wwzb200_shared_axis_cells_dev: the scratch already holds the y-independent pass of     \
+                                   this batch (wwzb200_shared_axis_prepare_dev with the same arguments reported            \
+                                   *prepared = 1 and no other transform ran on the device since) */
 #define WWZB200_FAITHFUL 4u     /* validation mode: evaluate every cell with the reference's own    \
                                    two-pass expressions (utils/wavelet.py:988-1032), one warp per   \
                                    cell; ~10x slower, agrees with kirchner_numba to ~1e-12 */
@@ -93,6 +96,14 @@ int wwzb200_free_pinned(void *ptr);
  * dst is page-locked (wwzb200_alloc_pinned).  For callers that keep results in HBM (the *_dev entry
  * points) and bring an assembled result to the host once. */
 int wwzb200_copy_to_host(void *dst, const void *d_src, size_t bytes, void *stream);
+/* The same without the synchronisation, and the synchronisation on its own: several blocks of a sharded result are
+ * queued back to back and awaited once. */
+int wwzb200_copy_to_host_async(void *dst, const void *d_src, size_t bytes, void *stream);
+int wwzb200_stream_synchronize(void *stream);
+/* Page-lock (and release) host memory the caller owns -- e.g. a POSIX shared-memory segment that the ranks of one box
+ * map, so that every GPU copies its block of a sharded result over its own PCIe link into the consumer's buffer. */
+int wwzb200_host_register(void *ptr, size_t bytes);
+int wwzb200_host_unregister(void *ptr);
 
 /* (1) Single-series Kirchner transform.  Replaces f2py_wwz.wwa (f2py_wwz.f90:13-44) and the cell
  * loop of kirchner_numba (utils/wavelet.py:985-1042), plus wwa/phase (:1044-1045).
@@ -245,6 +256,19 @@ int wwzb200_shared_axis_cells_dev(const double *d_ts, const double *d_Y, int64_t
 int wwzb200_quantiles_cells_dev(const double *d_Xcells, int64_t S, int64_t stride, int64_t ncell,
                                 const double *d_probs, int64_t nq, double *d_q, void *stream);
 
+/* The part of wwzb200_shared_axis_cells_dev that does not depend on the series -- setup, basis rows, rotations, the
+ * stored weight fragments and Neffs (utils/wavelet.py:988-1019 depend on ts, tau, omega only) -- enqueued on its own, so
+ * that a caller can run it under host work that the series depend on (the tau_estimation fit of the surrogates,
+ * utils/tsmodel.py:243-275).  S = series the batch will hold.  *prepared = 1 if the following cells call may pass
+ * WWZB200_PREPARED (the batch is large enough for stored weights), 0 if it has to run in full.  d_Neffs optional. */
+int wwzb200_shared_axis_prepare_dev(const double *d_ts, int64_t nts, int64_t S, const double *d_taus, int64_t nt,
+                                    const double *d_omegas, int64_t nf, double c, int64_t Neff_threshold, uint32_t flags,
+                                    double *d_Neffs, int *prepared, void *stream);
+/* wwzb200_quantiles_cells_dev on rows that are cut into segments: value i of row `cell` lies at
+ * X[(i / seg_len) * seg_stride + cell * stride + i % seg_len] -- the receive buffer [rank][cell][stride] of an
+ * all-to-all in which every rank contributed seg_len surrogates (the last one possibly fewer). */
+int wwzb200_quantiles_segments_dev(const double *d_X, int64_t S, int64_t seg_len, int64_t seg_stride, int64_t stride,
+                                   int64_t ncell, const double *d_probs, int64_t nq, double *d_q, void *stream);
 int wwzb200_quantiles_dev(const double *d_X, int64_t S, int64_t ncell, const double *d_probs,
                           int64_t nq, double *d_q, void *stream);
 

@@ -19,6 +19,7 @@ EXACT_WINDOW = 16
 UAR1 = 32
 FOSTER = 64
 FREQ_HZ = 128
+PREPARED = 256
 
 _dp = ctypes.POINTER(ctypes.c_double)
 _ip = ctypes.POINTER(ctypes.c_int64)
@@ -45,6 +46,10 @@ _SIGS = {
     "wwzb200_alloc_pinned": (ctypes.c_int, [ctypes.c_size_t, ctypes.POINTER(_vp)]),
     "wwzb200_free_pinned": (ctypes.c_int, [_vp]),
     "wwzb200_copy_to_host": (ctypes.c_int, [_vp, _vp, ctypes.c_size_t, _vp]),
+    "wwzb200_copy_to_host_async": (ctypes.c_int, [_vp, _vp, ctypes.c_size_t, _vp]),
+    "wwzb200_stream_synchronize": (ctypes.c_int, [_vp]),
+    "wwzb200_host_register": (ctypes.c_int, [_vp, ctypes.c_size_t]),
+    "wwzb200_host_unregister": (ctypes.c_int, [_vp]),
     "wwzb200_kirchner": (ctypes.c_int, [_dp, _dp, _i64, _dp, _i64, _dp, _i64, _dbl, _i64, _u32,
                                         _dp, _dp, _dp, _dp, _dp, _dp]),
     "wwzb200_kirchner_psd": (ctypes.c_int, [_dp, _dp, _i64, _dp, _i64, _dp, _i64, _dbl, _i64, _i64, _u32,
@@ -77,6 +82,9 @@ _SIGS = {
                                                      _vp, _vp, _vp]),
     "wwzb200_quantiles_cells_dev": (ctypes.c_int, [_vp, _i64, _i64, _i64, _vp, _i64, _vp, _vp]),
     "wwzb200_quantiles_dev": (ctypes.c_int, [_vp, _i64, _i64, _vp, _i64, _vp, _vp]),
+    "wwzb200_shared_axis_prepare_dev": (ctypes.c_int, [_vp, _i64, _i64, _vp, _i64, _vp, _i64, _dbl, _i64, _u32, _vp,
+                                                       ctypes.POINTER(ctypes.c_int), _vp]),
+    "wwzb200_quantiles_segments_dev": (ctypes.c_int, [_vp, _i64, _i64, _i64, _i64, _i64, _vp, _i64, _vp, _vp]),
     "wwzb200_measure_fp64_peak": (ctypes.c_int, [_dp, _dp]),
     "wwzb200_launch_count": (_i64, []),
     "wwzb200_profile": (ctypes.c_int, [ctypes.c_int]),

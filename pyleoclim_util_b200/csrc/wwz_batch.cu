@@ -467,15 +467,25 @@ __device__ __forceinline__ double key_value(unsigned long long k)
     return __longlong_as_double((long long)b);
 }
 
+// Row `cell` of the sample matrix: contiguous (seg_len == 0: X[cell*stride + i]) or cut into segments of seg_len
+// values that lie seg_stride apart (the receive buffer of an all-to-all: segment r of every row comes from rank r).
+__device__ __forceinline__ int64_t segmented_index(int64_t cell, int64_t i, int64_t stride, int64_t seg_len, int64_t seg_stride)
+{
+    if (seg_len == 0) return cell * stride + i;
+    const int64_t r = i / seg_len;
+    return r * seg_stride + cell * stride + (i - r * seg_len);
+}
+
 __global__ void __launch_bounds__(1024)
     quantile_kernel(const double *__restrict__ X, int64_t S, int64_t stride, int64_t ncell, const double *__restrict__ probs,
-                    int nq, int npow2, double *__restrict__ q, unsigned long long *__restrict__ gscratch)
+                    int nq, int npow2, double *__restrict__ q, unsigned long long *__restrict__ gscratch, int64_t seg_len,
+                    int64_t seg_stride)
 {
     extern __shared__ unsigned long long keys_sh[];
     for (int64_t cell = blockIdx.x; cell < ncell; cell += gridDim.x) {
         unsigned long long *keys = gscratch ? gscratch + (size_t)blockIdx.x * npow2 : keys_sh;
         for (int i = threadIdx.x; i < npow2; i += blockDim.x)
-            keys[i] = (i < S) ? sort_key(X[cell * stride + i]) : 0xFFFFFFFFFFFFFFFFull;
+            keys[i] = (i < S) ? sort_key(X[segmented_index(cell, i, stride, seg_len, seg_stride)]) : 0xFFFFFFFFFFFFFFFFull;
         __syncthreads();
         for (int size = 2; size <= npow2; size <<= 1) {
             for (int str = size >> 1; str > 0; str >>= 1) {
@@ -525,7 +535,8 @@ __global__ void __launch_bounds__(1024)
 template <bool SMEM_KEYS>
 __global__ void __launch_bounds__(512)
     quantile_select_kernel(const double *__restrict__ X, int64_t S, int64_t stride, int64_t ncell,
-                           const double *__restrict__ probs, int nq, double *__restrict__ q)
+                           const double *__restrict__ probs, int nq, double *__restrict__ q, int64_t seg_len,
+                           int64_t seg_stride)
 {
     extern __shared__ unsigned long long keys_sh[];
     __shared__ unsigned int hist[256];
@@ -536,12 +547,13 @@ __global__ void __launch_bounds__(512)
     const int tid = threadIdx.x, lane = tid & 31;
     const int N = (int)S;
     for (int64_t cell = blockIdx.x; cell < ncell; cell += gridDim.x) {
-        const double *const xc = X + cell * stride;
         if (SMEM_KEYS) {
-            for (int i = tid; i < N; i += blockDim.x) keys_sh[i] = sort_key(xc[i]);
+            for (int i = tid; i < N; i += blockDim.x) keys_sh[i] = sort_key(X[segmented_index(cell, i, stride, seg_len, seg_stride)]);
         }
         __syncthreads();
-        auto key_at = [&](int i) -> unsigned long long { return SMEM_KEYS ? keys_sh[i] : sort_key(xc[i]); };
+        auto key_at = [&](int i) -> unsigned long long {
+            return SMEM_KEYS ? keys_sh[i] : sort_key(X[segmented_index(cell, i, stride, seg_len, seg_stride)]);
+        };
         for (int iq = 0; iq < nq; ++iq) {
             // every operation rounded separately, in scipy's order (see quantile_kernel)
             const double p = probs[iq];
@@ -646,7 +658,7 @@ __global__ void __launch_bounds__(512)
 
 cudaError_t launch_quantiles(const double *d_X, int64_t S, int64_t stride, int64_t ncell, const double *d_probs,
                              int64_t nq, double *d_q, unsigned long long *d_scratch, int64_t scratch_ctas, int sms,
-                             cudaStream_t st)
+                             cudaStream_t st, int64_t seg_len, int64_t seg_stride)
 {
     if (ncell <= 0 || nq <= 0 || S <= 0) return cudaSuccess;
     if (nq <= 16 && S >= 64 && S < ((int64_t)1 << 31)) {
@@ -657,10 +669,10 @@ cudaError_t launch_quantiles(const double *d_X, int64_t S, int64_t stride, int64
             cudaError_t e = ensure_dynamic_smem(quantile_select_kernel<true>, (int)kb, done_sel);
             if (e != cudaSuccess) return e;
             const int64_t grid = std::min<int64_t>(ncell, (int64_t)sms * 16);
-            quantile_select_kernel<true><<<(unsigned)grid, 512, kb, st>>>(d_X, S, stride, ncell, d_probs, (int)nq, d_q);
+            quantile_select_kernel<true><<<(unsigned)grid, 512, kb, st>>>(d_X, S, stride, ncell, d_probs, (int)nq, d_q, seg_len, seg_stride);
         } else {
             const int64_t grid = std::min<int64_t>(ncell, (int64_t)sms * 4);
-            quantile_select_kernel<false><<<(unsigned)grid, 512, 0, st>>>(d_X, S, stride, ncell, d_probs, (int)nq, d_q);
+            quantile_select_kernel<false><<<(unsigned)grid, 512, 0, st>>>(d_X, S, stride, ncell, d_probs, (int)nq, d_q, seg_len, seg_stride);
         }
         bump_launch_counter();
         return cudaGetLastError();
@@ -673,11 +685,11 @@ cudaError_t launch_quantiles(const double *d_X, int64_t S, int64_t stride, int64
         cudaError_t e = ensure_dynamic_smem(quantile_kernel, (int)smem, done);
         if (e != cudaSuccess) return e;
         const int64_t grid = std::min<int64_t>(ncell, (int64_t)sms * 8);
-        quantile_kernel<<<(unsigned)grid, 1024, smem, st>>>(d_X, S, stride, ncell, d_probs, (int)nq, npow2, d_q, nullptr);
+        quantile_kernel<<<(unsigned)grid, 1024, smem, st>>>(d_X, S, stride, ncell, d_probs, (int)nq, npow2, d_q, nullptr, seg_len, seg_stride);
     } else {
         if (!d_scratch || scratch_ctas < 1) return cudaErrorInvalidValue;
         const int64_t grid = std::min<int64_t>(ncell, scratch_ctas);
-        quantile_kernel<<<(unsigned)grid, 1024, 0, st>>>(d_X, S, stride, ncell, d_probs, (int)nq, npow2, d_q, d_scratch);
+        quantile_kernel<<<(unsigned)grid, 1024, 0, st>>>(d_X, S, stride, ncell, d_probs, (int)nq, npow2, d_q, d_scratch, seg_len, seg_stride);
     }
     bump_launch_counter();
     return cudaGetLastError();

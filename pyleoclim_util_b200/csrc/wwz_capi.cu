@@ -67,6 +67,15 @@ struct Workspace {
     cudaEvent_t busy_ev = nullptr;        // end of the last piece of work that used this scratch set (any stream)
     cudaStream_t busy_stream = nullptr;
     bool busy = false;
+    // the y-independent pass of a shared-axis batch that wwzb200_shared_axis_prepare_dev left in the scratch
+    struct Prepared {
+        bool valid = false;
+        const void *ts = nullptr, *tau = nullptr, *omega = nullptr;
+        int64_t n = 0, nt = 0, nf = 0, S_pad = 0;
+        double c = 0;
+        int64_t thr = 0;
+        uint32_t flags = 0;
+    } prepared;
     std::string prefix;   // scratch namespace of the stream currently being enqueued on
     int sms = 0;
     double *h_in = nullptr;   // page-locked staging of the single-series inputs
@@ -222,6 +231,7 @@ int transform_device(Workspace *w, const double *d_ts, const double *d_ys, int64
     const int64_t ncell = nt * nf;
     if (ncell == 0) return 0;
     if (ncell >= ((int64_t)1 << 32)) return fail(WWZB200_ERR_ARG, "nt*nf = %lld exceeds 2^32 cells", (long long)ncell);
+    w->prepared.valid = false;   // (this call reuses the scratch a prepared shared-axis batch would rely on)
 
     double *d_kappa, *d_dcut, *d_sums;
     int *d_unsorted;
@@ -466,8 +476,10 @@ int shared_axis_device(Workspace *w, const double *d_ts, const double *d_Y, int6
                        int64_t nt, const double *d_omega, int64_t nf, double c, int64_t thr, int64_t psd_thr,
                        uint32_t flags, double *d_neffs, double *d_wwa, double *d_phase, double *d_a0, double *d_a1,
                        double *d_a2, double *d_psd, double tspan, double **amp_cells_out, int64_t *S_pad_out,
-                       cudaStream_t st, double *d_amp_cells_ext = nullptr)
+                       cudaStream_t st, double *d_amp_cells_ext = nullptr, int phase = 3)
 {
+    // phase 1: only what does not depend on the series (setup, basis rows, rotations, stored weights + Neffs);
+    // phase 2: the rest, on a scratch that a phase-1 call with the same arguments has prepared; 3: everything
     using namespace wwz;
     const int64_t ncell = nt * nf;
     if (ncell == 0 || S == 0) return 0;
@@ -499,6 +511,8 @@ int shared_axis_device(Workspace *w, const double *d_ts, const double *d_Y, int6
     if ((rc = wsbuf(w, "wq", (size_t)2 * ncell, &d_wq))) return rc;
     if (d_amp_cells_ext)
         d_amp_t = d_amp_cells_ext;       // the caller keeps the cell-major amplitudes [ncell][S_pad]
+    else if (phase == 1)
+        d_amp_t = nullptr;
     else if ((rc = wsbuf(w, "amp_t", (size_t)ncell * (size_t)S_pad, &d_amp_t)))
         return rc;
     if (d_phase && (rc = wsbuf(w, "ph_t", (size_t)ncell * (size_t)S_pad, &d_ph_t))) return rc;
@@ -522,10 +536,40 @@ int shared_axis_device(Workspace *w, const double *d_ts, const double *d_Y, int6
     const double cut_bits = (flags & WWZB200_DENSE) ? HUGE_VAL : (flags & WWZB200_EXACT_WINDOW) ? 1081.0 : 100.0;
     double *d_gap;
     if ((rc = wsbuf(w, "taugap", (size_t)nt, &d_gap))) return rc;
-    CU(launch_setup(d_omega, nf, d_tau, nt, d_ts, n, c, false, cut_bits, d_kappa, d_dcut, d_grid, d_rec_row, d_gap,
-                    d_unsorted, nullptr, st));
-    CU(launch_basis_sc(d_ts, n, plan.n_pad, d_omega, nf, d_ty, d_basis, st));
-    CU(launch_rotation(d_tau, d_omega, nt, nf, d_rot, st));
+    Workspace::Prepared key;
+    key.valid = true;
+    key.ts = d_ts;
+    key.tau = d_tau;
+    key.omega = d_omega;
+    key.n = n;
+    key.nt = nt;
+    key.nf = nf;
+    key.S_pad = S_pad;
+    key.c = c;
+    key.thr = thr;
+    key.flags = flags & (WWZB200_DENSE | WWZB200_EXACT_WINDOW);
+    if (phase == 2) {
+        const Workspace::Prepared &p = w->prepared;
+        if (!(p.valid && p.ts == key.ts && p.tau == key.tau && p.omega == key.omega && p.n == n && p.nt == nt && p.nf == nf &&
+              p.S_pad == S_pad && p.c == c && p.thr == thr && p.flags == key.flags && plan.stored_weights))
+            return fail(WWZB200_ERR_ARG, "WWZB200_PREPARED: the scratch does not hold the y-independent pass of this batch "
+                                         "(call wwzb200_shared_axis_prepare_dev with the same arguments first)");
+    }
+    w->prepared.valid = false;
+    if (phase & 1) {
+        CU(launch_setup(d_omega, nf, d_tau, nt, d_ts, n, c, false, cut_bits, d_kappa, d_dcut, d_grid, d_rec_row, d_gap,
+                        d_unsorted, nullptr, st));
+        CU(launch_basis_sc(d_ts, n, plan.n_pad, d_omega, nf, d_ty, d_basis, st));
+        CU(launch_rotation(d_tau, d_omega, nt, nf, d_rot, st));
+    }
+    if (phase == 1) {
+        if (plan.stored_weights) {
+            CU(launch_shared(plan, d_ty, d_basis, d_Yt, d_ts, n, S_pad, d_tau, nt, d_kappa, d_dcut, d_gap, d_unsorted, nf, d_rot,
+                             (double)thr, d_wfrag, d_cellsums, d_ne, d_wq, d_amp_t, d_ph_t, d_a0_t, d_a1_t, d_a2_t, st, 1));
+            w->prepared = key;
+        }
+        return 0;
+    }
     CU(launch_standardize_retile(d_Y, n, plan.n_pad, S, NS, (flags & WWZB200_STANDARDIZE) != 0, d_mu, d_sig, d_Yt, st));
     EventPair ev{nullptr, nullptr, (double)n * (double)ncell * (double)S};
     if (g_profile) {
@@ -534,7 +578,7 @@ int shared_axis_device(Workspace *w, const double *d_ts, const double *d_Y, int6
         CU(cudaEventRecord(ev.a, st));
     }
     CU(launch_shared(plan, d_ty, d_basis, d_Yt, d_ts, n, S_pad, d_tau, nt, d_kappa, d_dcut, d_gap, d_unsorted, nf, d_rot,
-                     (double)thr, d_wfrag, d_cellsums, d_ne, d_wq, d_amp_t, d_ph_t, d_a0_t, d_a1_t, d_a2_t, st));
+                     (double)thr, d_wfrag, d_cellsums, d_ne, d_wq, d_amp_t, d_ph_t, d_a0_t, d_a1_t, d_a2_t, st, phase));
     if (g_profile) {
         CU(cudaEventRecord(ev.b, st));
         g_events.push_back(ev);
@@ -571,6 +615,7 @@ int members_device(Workspace *w, const double *d_ts, int64_t m_ts, const double 
     if (ncell * M >= ((int64_t)1 << 32)) return fail(WWZB200_ERR_ARG, "M*nt*nf = %lld exceeds 2^32 cells", (long long)(ncell * M));
     if (flags & (WWZB200_FOSTER | WWZB200_FAITHFUL))
         return fail(WWZB200_ERR_ARG, "WWZB200_FOSTER / WWZB200_FAITHFUL are not available for member batches; use the ragged entry point");
+    w->prepared.valid = false;
     if (M > 65535 || nf > 65535) return fail(WWZB200_ERR_ARG, "at most 65535 members and frequencies per member batch");
     const bool freq_hz = (flags & WWZB200_FREQ_HZ) != 0, zs = (flags & WWZB200_STANDARDIZE) != 0;
     if (freq_hz && n - 1 > kNyquistMaxPoints)
@@ -658,7 +703,8 @@ int members_device(Workspace *w, const double *d_ts, int64_t m_ts, const double 
 }
 
 int quantiles_device(Workspace *w, const double *d_Xcells, int64_t S, int64_t stride, int64_t ncell,
-                     const double *d_probs, int64_t nq, double *d_q, cudaStream_t st)
+                     const double *d_probs, int64_t nq, double *d_q, cudaStream_t st, int64_t seg_len = 0,
+                     int64_t seg_stride = 0)
 {
     int npow2 = 2;
     while (npow2 < S) npow2 <<= 1;
@@ -669,7 +715,7 @@ int quantiles_device(Workspace *w, const double *d_Xcells, int64_t S, int64_t st
         int rc = wsbuf(w, "qscratch", (size_t)ctas * (size_t)npow2, &d_scr);
         if (rc) return rc;
     }
-    CU(wwz::launch_quantiles(d_Xcells, S, stride, ncell, d_probs, nq, d_q, d_scr, ctas, w->sms, st));
+    CU(wwz::launch_quantiles(d_Xcells, S, stride, ncell, d_probs, nq, d_q, d_scr, ctas, w->sms, st, seg_len, seg_stride));
     return 0;
 }
 
@@ -742,6 +788,33 @@ int wwzb200_copy_to_host(void *dst, const void *d_src, size_t bytes, void *strea
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     CU(cudaMemcpyAsync(dst, d_src, bytes, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int wwzb200_copy_to_host_async(void *dst, const void *d_src, size_t bytes, void *stream)
+{
+    if (bytes == 0) return 0;
+    if (!dst || !d_src) return fail(WWZB200_ERR_ARG, "null pointer");
+    CU(cudaMemcpyAsync(dst, d_src, bytes, cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream)));
+    return 0;
+}
+
+int wwzb200_stream_synchronize(void *stream)
+{
+    CU(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+    return 0;
+}
+
+int wwzb200_host_register(void *ptr, size_t bytes)
+{
+    if (!ptr || !bytes) return fail(WWZB200_ERR_ARG, "null pointer");
+    CU(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
+    return 0;
+}
+
+int wwzb200_host_unregister(void *ptr)
+{
+    if (ptr) CU(cudaHostUnregister(ptr));
     return 0;
 }
 
@@ -988,6 +1061,15 @@ int wwzb200_uar1_surrogates(const double *ts, int64_t nts, double tau, double si
     return surrogates_host(ts, nts, tau, sigma_2, mu, S, seed, true, Y);
 }
 
+static int check_quantile_args(const void *X, int64_t S, int64_t ncell, const void *probs, int64_t nq, const void *q)
+{
+    if (S < 1 || ncell < 0 || nq < 0) return fail(WWZB200_ERR_ARG, "bad sizes");
+    if (ncell == 0 || nq == 0) return 0;
+    if (!X || !probs || !q) return fail(WWZB200_ERR_ARG, "null pointer");
+    if (S > ((int64_t)1 << 24)) return fail(WWZB200_ERR_ARG, "S too large for the quantile kernel");
+    return 0;
+}
+
 int wwzb200_surrogates_block_dev(const double *d_ts, int64_t nts, double tau, double sigma, double mu, int64_t S,
                                  int64_t first_series, uint64_t seed, uint32_t flags, double *d_Y, void *stream)
 {
@@ -1016,19 +1098,48 @@ int wwzb200_shared_axis_cells_dev(const double *d_ts, const double *d_Y, int64_t
     if ((rc = workspace(&w))) return rc;
     ScratchScope scope(w, static_cast<cudaStream_t>(stream));
     if ((rc = scope.begin())) return rc;
-    return shared_axis_device(w, d_ts, d_Y, nts, S, d_taus, nt, d_omegas, nf, c, Neff_threshold, 0, flags, d_Neffs,
-                              nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0.0, nullptr, nullptr,
-                              static_cast<cudaStream_t>(stream), d_amp_cells);
+    return shared_axis_device(w, d_ts, d_Y, nts, S, d_taus, nt, d_omegas, nf, c, Neff_threshold, 0,
+                              flags & ~WWZB200_PREPARED, d_Neffs, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0.0,
+                              nullptr, nullptr, static_cast<cudaStream_t>(stream), d_amp_cells,
+                              (flags & WWZB200_PREPARED) ? 2 : 3);
 }
 
-static int check_quantile_args(const void *X, int64_t S, int64_t ncell, const void *probs, int64_t nq, const void *q)
+int wwzb200_shared_axis_prepare_dev(const double *d_ts, int64_t nts, int64_t S, const double *d_taus, int64_t nt,
+                                    const double *d_omegas, int64_t nf, double c, int64_t Neff_threshold, uint32_t flags,
+                                    double *d_Neffs, int *prepared, void *stream)
 {
-    if (S < 1 || ncell < 0 || nq < 0) return fail(WWZB200_ERR_ARG, "bad sizes");
-    if (ncell == 0 || nq == 0) return 0;
-    if (!X || !probs || !q) return fail(WWZB200_ERR_ARG, "null pointer");
-    if (S > ((int64_t)1 << 24)) return fail(WWZB200_ERR_ARG, "S too large for the quantile kernel");
+    int rc = check_grid_args(d_ts, d_ts, nts, d_taus, nt, d_omegas, nf, c, Neff_threshold);
+    if (rc) return rc;
+    if (S < 0 || !prepared) return fail(WWZB200_ERR_ARG, "bad batch arguments");
+    *prepared = 0;
+    std::lock_guard<std::mutex> lock(g_mu);
+    Workspace *w;
+    if ((rc = workspace(&w))) return rc;
+    ScratchScope scope(w, static_cast<cudaStream_t>(stream));
+    if ((rc = scope.begin())) return rc;
+    rc = shared_axis_device(w, d_ts, nullptr, nts, S, d_taus, nt, d_omegas, nf, c, Neff_threshold, 0,
+                            flags & ~WWZB200_PREPARED, d_Neffs, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0.0,
+                            nullptr, nullptr, static_cast<cudaStream_t>(stream), nullptr, 1);
+    if (rc) return rc;
+    *prepared = w->prepared.valid ? 1 : 0;
     return 0;
 }
+
+int wwzb200_quantiles_segments_dev(const double *d_X, int64_t S, int64_t seg_len, int64_t seg_stride, int64_t stride,
+                                   int64_t ncell, const double *d_probs, int64_t nq, double *d_q, void *stream)
+{
+    if (seg_len < 1 || stride < seg_len || seg_stride < 0) return fail(WWZB200_ERR_ARG, "bad segment layout");
+    int rc = check_quantile_args(d_X, S, ncell, d_probs, nq, d_q);
+    if (rc || ncell == 0 || nq == 0) return rc;
+    std::lock_guard<std::mutex> lock(g_mu);
+    Workspace *w;
+    if ((rc = workspace(&w))) return rc;
+    ScratchScope scope(w, static_cast<cudaStream_t>(stream));
+    if ((rc = scope.begin())) return rc;
+    return quantiles_device(w, d_X, S, stride, ncell, d_probs, nq, d_q, static_cast<cudaStream_t>(stream), seg_len,
+                            seg_stride);
+}
+
 
 int wwzb200_quantiles_cells_dev(const double *d_Xcells, int64_t S, int64_t stride, int64_t ncell, const double *d_probs,
                                 int64_t nq, double *d_q, void *stream)

@@ -187,7 +187,7 @@ cudaError_t launch_shared(const SharedPlan &plan, const double2 *d_ty, const dou
                           const double *d_kappa, const double *d_dcut, const double *d_taugap, const int *d_unsorted,
                           int64_t nf, const double2 *d_rot, double thr, double *d_wfrag, double *d_cellsums, double *d_neffs,
                           double *d_wq, double *d_amp, double *d_phase, double *d_a0, double *d_a1, double *d_a2,
-                          cudaStream_t st);
+                          cudaStream_t st, int phase = 3);   // phase: 1 = y-independent pass (stored weights), 2 = contraction
 // deep-underflow cells of a shared-axis batch (flagged from W, Q), recomputed faithfully for every series
 cudaError_t launch_shared_fixup(const double *d_ts, const double *d_Yt, int64_t n, int64_t n_pad, int64_t S,
                                 int64_t S_pad, int series_block, const double *d_tau, const double *d_omega, int64_t nt,
@@ -200,7 +200,7 @@ cudaError_t launch_psd_batch(const double *d_amp, const double *d_neffs, int64_t
                              int64_t S_pad, double tspan, int64_t n, double thr, double *d_psd, cudaStream_t st);
 cudaError_t launch_quantiles(const double *d_X, int64_t S, int64_t stride, int64_t ncell, const double *d_probs,
                              int64_t nq, double *d_q, unsigned long long *d_scratch, int64_t scratch_ctas, int sms,
-                             cudaStream_t st);
+                             cudaStream_t st, int64_t seg_len = 0, int64_t seg_stride = 0);
 
 // FP64 FMA peak microbenchmark.
 cudaError_t run_fp64_peak(double *tflops, double *ms);

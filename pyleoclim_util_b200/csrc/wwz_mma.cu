@@ -455,7 +455,7 @@ cudaError_t launch_shared(const SharedPlan &plan, const double2 *d_ty, const dou
                           const double *d_kappa, const double *d_dcut, const double *d_taugap, const int *d_unsorted,
                           int64_t nf, const double2 *d_rot, double thr, double *d_wfrag, double *d_cellsums, double *d_neffs,
                           double *d_wq, double *d_amp, double *d_phase, double *d_a0, double *d_a1, double *d_a2,
-                          cudaStream_t st)
+                          cudaStream_t st, int phase)
 {
     const int64_t ncell = nt * nf;
     if (ncell <= 0 || S_pad <= 0) return cudaSuccess;
@@ -499,11 +499,15 @@ cudaError_t launch_shared(const SharedPlan &plan, const double2 *d_ty, const dou
     cudaError_t e;
     if (plan.stored_weights) {
         if (!d_wfrag || !d_cellsums) return cudaErrorInvalidValue;
-        wwz_tile_weights_kernel<<<grid.x, kMmaWarps * 32, 0, st>>>(a);
-        bump_launch_counter();
-        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        if (phase & 1) {     // the y-independent pass: weights in fragment order, W, Q, Ws, Wc, Neff of every cell
+            wwz_tile_weights_kernel<<<grid.x, kMmaWarps * 32, 0, st>>>(a);
+            bump_launch_counter();
+            if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        }
+        if (!(phase & 2)) return cudaSuccess;
         e = NS == 64 ? launch_mma<64, true>(a, grid, plan.smem_bytes, st) : launch_mma<16, true>(a, grid, plan.smem_bytes, st);
     } else {
+        if (!(phase & 2)) return cudaSuccess;
         e = NS == 64 ? launch_mma<64, false>(a, grid, plan.smem_bytes, st) : launch_mma<16, false>(a, grid, plan.smem_bytes, st);
     }
     bump_launch_counter();

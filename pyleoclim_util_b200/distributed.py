@@ -83,7 +83,95 @@ def all_gather_rows(local, counts, group=None):
     return np.concatenate([out[r, : counts[r]] for r in range(world)], axis=0)
 
 
-def _device_blocks(pd_ys, ts_cut, tau, omega, c, Neff_threshold, flags, group, want, to_host=True, gather=True):
+class _SharedHostSegments:
+    """Page-locked POSIX shared-memory segments mapped by every rank of the box (host='root' results).
+
+    Rank 0 -- the consumer -- owns the free list: a result array handed to the caller is a view of a segment, and the
+    segment returns to the free list when the array (and every view of it) has been collected, like the page-locked
+    pool of `_lib`.  Every rank maps each segment once and page-locks its own mapping (`wwzb200_host_register`), so
+    that its GPU copies its block of rows over its own PCIe link straight into the consumer's buffer."""
+
+    def __init__(self):
+        self.segs = []          # [dict(shm, nbytes, addr, free)]
+        self.same_host = {}     # group -> bool
+
+    def on_one_host(self, group):
+        key = id(group)
+        if key not in self.same_host:
+            import socket
+            dist = _dist()
+            names = [None] * dist.get_world_size(group)
+            dist.all_gather_object(names, socket.gethostname(), group=group)
+            self.same_host[key] = len(set(names)) == 1
+        return self.same_host[key]
+
+    def acquire(self, nbytes, group):
+        """Collective: every rank returns its mapping (a dict) of the same segment, of at least nbytes."""
+        import atexit
+        import ctypes
+        import torch
+        from multiprocessing import shared_memory, resource_tracker
+        from . import _lib
+        dist = _dist()
+        rank = dist.get_rank(group)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        pick = torch.full((1,), -1, dtype=torch.int64, device=dev)
+        if rank == 0:
+            for i, sg in enumerate(self.segs):
+                if sg["free"] and sg["nbytes"] >= nbytes:
+                    pick[0] = i
+                    break
+        dist.broadcast(pick, src=0, group=group)
+        idx = int(pick.item())
+        if idx < 0:
+            size = max(int(nbytes), 1 << 20)
+            size = (size + (1 << 21) - 1) & ~((1 << 21) - 1)
+            name = [None]
+            shm = None
+            if rank == 0:
+                shm = shared_memory.SharedMemory(create=True, size=size)
+                name[0] = shm.name
+            dist.broadcast_object_list(name, src=0, group=group)
+            if rank != 0:
+                shm = shared_memory.SharedMemory(name=name[0])
+                try:                     # the creator unlinks; an attaching process must not (Python < 3.13 tracks both)
+                    resource_tracker.unregister(shm._name, "shared_memory")
+                except Exception:
+                    pass
+            addr = ctypes.addressof(ctypes.c_char.from_buffer(shm.buf))
+            _lib.check(_lib.lib().wwzb200_host_register(addr, size))
+            sg = dict(shm=shm, nbytes=size, addr=addr, free=True)
+            self.segs.append(sg)
+            idx = len(self.segs) - 1
+            if rank == 0:
+                atexit.register(self._unlink, shm)
+            dist.barrier(group=group)    # every rank has mapped the segment before anybody copies into it
+        sg = self.segs[idx]
+        sg["free"] = False
+        return sg
+
+    @staticmethod
+    def _unlink(shm):
+        try:
+            shm.unlink()
+        except Exception:
+            pass
+
+    def view(self, sg, shape):
+        """float64 array over the segment; the segment is free again once the array has been collected."""
+        import weakref
+        count = int(np.prod(shape, dtype=np.int64))
+        arr = np.frombuffer(sg["shm"].buf, dtype=np.float64, count=count).reshape(shape)
+        holder = arr.base if arr.base is not None else arr
+        weakref.finalize(holder, sg.__setitem__, "free", True)
+        return arr
+
+
+_shared_segments = _SharedHostSegments()
+
+
+def _device_blocks(pd_ys, ts_cut, tau, omega, c, Neff_threshold, flags, group, want, to_host=True, gather=True,
+                   root_only=False):
     """NCCL fast path: this rank's tau block is transformed into a device buffer (C-ABI *_dev entry point on
     torch's current stream), the row blocks are all-gathered on the device and only the assembled
     [len(want), nt, nf] result crosses PCIe, into page-locked host memory.  `want` indexes the library's output
@@ -110,6 +198,22 @@ def _device_blocks(pd_ys, ts_cut, tau, omega, c, Neff_threshold, flags, group, w
     k = len(want)
     if not gather:
         return None, loc[:, : b - a]
+    if root_only and _shared_segments.on_one_host(group):
+        # host='root': the consumer is rank 0.  No all-gather: every rank copies its own row block of every wanted
+        # plane over its own PCIe link into one page-locked shared-memory buffer that rank 0 then reads in place.
+        L = _lib.lib()
+        st = torch.cuda.current_stream().cuda_stream
+        sg = _shared_segments.acquire(k * nt * nf * 8, group)
+        if b > a:
+            for i, w_i in enumerate(want):
+                _lib.check(L.wwzb200_copy_to_host_async(sg["addr"] + (i * nt + a) * nf * 8, loc[w_i].data_ptr(),
+                                                        (b - a) * nf * 8, st))
+        _lib.check(L.wwzb200_stream_synchronize(st))
+        dist.barrier(group=group)                       # every block has landed
+        if rank == 0:
+            return _shared_segments.view(sg, (k, nt, nf)), None
+        sg["free"] = True
+        return None, None
     if len(set(counts)) == 1:
         # equal row blocks: plane i of the result is [world, hmax, nf], so every wanted output plane is gathered
         # straight into its final place (no selection copy, no re-layout)
@@ -137,9 +241,11 @@ def wwz_tau_sharded(ys, ts, tau=None, freq=None, freq_method="log", freq_kwargs=
     full Results (amplitude, phase, coi, freq, time, Neffs, coeff, scale), like the reference's wwz
     (utils/wavelet.py:1294-1494).  `kernel` defaults to `wavelet.kirchner_cuda`.
 
-    host='all' (default): the assembled grid is copied to host memory on every rank.  host='root' (NCCL path): the
-    all-gather still assembles the grid in the HBM of every GPU, but only rank 0 -- the process that consumes the
-    result -- pays the PCIe copy of the whole grid; the other ranks get Results whose per-cell arrays are None."""
+    host='all' (default): the all-gather assembles the grid in the HBM of every GPU and every rank copies it to its
+    host memory.  host='root' (NCCL path, ranks on one box): rank 0 is the consumer; there is no all-gather -- every
+    rank copies its own tau block over its own PCIe link into one page-locked shared-memory buffer (8 links in
+    parallel instead of one carrying the whole grid) which rank 0 returns in place; the other ranks get Results whose
+    per-cell arrays are None."""
     dist = _dist()
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     kernel = _wv.kirchner_cuda if kernel is None else kernel
@@ -152,8 +258,8 @@ def wwz_tau_sharded(ys, ts, tau=None, freq=None, freq_method="log", freq_kwargs=
             raise ValueError("host must be 'all' or 'root'")
         to_host = host == "all" or rank == 0
         host_arr, _ = _device_blocks(pd_ys, ts_cut, tau, _wv.make_omega(ts_cut, freq), c, Neff_threshold, flags, group,
-                                     want=(4, 5, 0, 1, 2, 3), to_host=to_host)
-        wwa, phase, Neffs, a0, a1, a2 = host_arr if to_host else (None,) * 6
+                                     want=(4, 5, 0, 1, 2, 3), to_host=to_host, root_only=host == "root")
+        wwa, phase, Neffs, a0, a1, a2 = host_arr if host_arr is not None else (None,) * 6
         return _wv.WwzResults(amplitude=wwa, phase=phase, coi=_wv.make_coi(tau, Neff_threshold=Neff_coi), freq=freq,
                               time=tau, Neffs=Neffs, coeff=(a0, a1, a2), scale=1 / freq)
     blocks = row_blocks(tau.size, world)
@@ -278,13 +384,23 @@ def wwz_signif_sharded(ys, ts, tau=None, freq=None, number=200, qs=(0.95,), seed
                                Neffs=np.ascontiguousarray(full[nq]), freq=freq, time=tau)
 
 
+def surrogate_blocks(number, world):
+    """Partition of the surrogates over the ranks: blocks of ceil(number / world), the last ranks take what is left
+    (so that every block but the last has the same length: the all-to-all receive buffer is then a row of equal
+    segments, which `wwzb200_quantiles_segments_dev` reads in place)."""
+    per = -(-int(number) // int(world))
+    return per, [(min(r * per, number), min((r + 1) * per, number)) for r in range(world)]
+
+
 def _signif_by_surrogates(ys_cut, ts_cut, tau, freq, number, probs, seed, c, Neff_threshold, group, method="ar1sim"):
     """Surrogates sharded over the ranks (NCCL): rank r generates rows [s0_r, s1_r) of the surrogate batch (the Philox
     stream of a series is keyed by its global index: same surrogates as the single-GPU test), transforms them as one
     shared-axis batch on the whole (tau, f) grid -- perfectly balanced, whatever the point windows -- and keeps the
     amplitudes cell-major in HBM; one all-to-all over NVLink hands every rank ALL surrogates of its block of cells,
-    the per-cell quantiles run there, and the [nq, cells/world] tiles are all-gathered.  Returns (q [nq, nt, nf],
-    Neffs [nt, nf]) as NumPy arrays, equal on every rank and to the single-GPU result."""
+    the per-cell quantiles are taken straight from the receive buffer, and the [nq, cells/world] tiles are
+    all-gathered.  The part of the transform that does not depend on the surrogates (setup, basis rows, stored weights,
+    Neffs) is enqueued first and runs under the host-side AR(1) fit.  Returns (q [nq, nt, nf], Neffs [nt, nf]) as
+    NumPy arrays, equal on every rank and to the single-GPU result."""
     import ctypes
     import torch
     from . import _lib, batch
@@ -294,30 +410,39 @@ def _signif_by_surrogates(ys_cut, ts_cut, tau, freq, number, probs, seed, c, Nef
     st = torch.cuda.current_stream().cuda_stream
     L = _lib.lib()
     ys_cut = np.asarray(ys_cut, dtype=float)
-    mu = float(np.mean(ys_cut))
     flags = _lib.STANDARDIZE
-    if method == "ar1sim":
-        sig, tau_est = float(np.std(ys_cut)), float(batch.tau_estimation(ys_cut, ts_cut))
-    elif method == "uar1":
-        tau_est, sig = (float(v) for v in batch.uar1_fit(ys_cut, ts_cut))
+    if method == "uar1":
         flags |= _lib.UAR1
-    else:
+    elif method != "ar1sim":
         raise ValueError("surrogate method must be 'ar1sim' or 'uar1'")
     omega = _wv.make_omega(ts_cut, freq)
     n, nt, nf, nq = ts_cut.size, tau.size, freq.size, probs.size
     ncell = nt * nf
-    sblocks = row_blocks(number, world)
+    per, sblocks = surrogate_blocks(number, world)
     s0, s1 = sblocks[rank]
     S_loc = s1 - s0
-    S_max = max(b - a for a, b in sblocks)
     pad = ctypes.c_int64()
-    _lib.check(L.wwzb200_series_pad(max(S_max, 1), ctypes.byref(pad)))
+    _lib.check(L.wwzb200_series_pad(max(per, 1), ctypes.byref(pad)))
     S_pad = int(pad.value)                                   # same row stride on every rank (the all-to-all is regular)
-    up = lambda x: torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64)).to(dev, non_blocking=True)
-    d_ts, d_tau, d_om, d_probs = up(ts_cut), up(tau), up(omega), up(probs)
+    # one upload for the four small inputs
+    packed = np.concatenate([np.asarray(x, dtype=np.float64).ravel() for x in (ts_cut, tau, omega, probs)])
+    d_in = torch.from_numpy(packed).to(dev, non_blocking=True)
+    d_ts, d_tau, d_om, d_probs = d_in[:n], d_in[n:n + nt], d_in[n + nt:n + nt + nf], d_in[n + nt + nf:]
     cells_per = (ncell + world - 1) // world
-    d_amp = torch.zeros((cells_per * world, S_pad), dtype=torch.float64, device=dev)   # cell-major, cells padded to world
     d_ne = torch.empty((nt, nf), dtype=torch.float64, device=dev)
+    prepared = ctypes.c_int(0)
+    if S_loc > 0:
+        # y-independent pass first: it runs on the device while the host fits the AR(1) model below
+        _lib.check(L.wwzb200_shared_axis_prepare_dev(d_ts.data_ptr(), n, S_loc, d_tau.data_ptr(), nt, d_om.data_ptr(), nf,
+                                                     float(c), int(Neff_threshold), flags, d_ne.data_ptr(),
+                                                     ctypes.byref(prepared), st))
+    mu = float(np.mean(ys_cut))
+    if method == "ar1sim":
+        sig, tau_est = float(np.std(ys_cut)), float(batch.tau_estimation(ys_cut, ts_cut))
+    else:
+        tau_est, sig = (float(v) for v in batch.uar1_fit(ys_cut, ts_cut))
+    # cell-major amplitudes, cells padded to a multiple of world (padding rows are never read back)
+    d_amp = torch.empty((cells_per * world, S_pad), dtype=torch.float64, device=dev)
     if S_loc > 0:
         own = ctypes.c_int64()
         _lib.check(L.wwzb200_series_pad(S_loc, ctypes.byref(own)))
@@ -328,27 +453,27 @@ def _signif_by_surrogates(ys_cut, ts_cut, tau, freq, number, probs, seed, c, Nef
             tgt = d_amp
         else:                                               # a short last block pads to fewer columns: its own buffer
             tgt = torch.empty((ncell, int(own.value)), dtype=torch.float64, device=dev)
+        fl = flags | (_lib.PREPARED if prepared.value else 0)
         _lib.check(L.wwzb200_shared_axis_cells_dev(d_ts.data_ptr(), d_Y.data_ptr(), n, S_loc, d_tau.data_ptr(), nt,
-                                                   d_om.data_ptr(), nf, float(c), int(Neff_threshold), flags,
+                                                   d_om.data_ptr(), nf, float(c), int(Neff_threshold), fl,
                                                    d_ne.data_ptr(), tgt.data_ptr(), st))
         if tgt is not d_amp:
             d_amp[:ncell, :S_loc] = tgt[:, :S_loc]
-    # every rank gets all surrogates of its block of cells
+    # every rank gets all surrogates of its block of cells: recv[r] = rank r's surrogates of my cells
     recv = torch.empty((world, cells_per, S_pad), dtype=torch.float64, device=dev)
     dist.all_to_all_single(recv.view(-1), d_amp.view(-1), group=group)
-    X = torch.cat([recv[r, :, : sblocks[r][1] - sblocks[r][0]] for r in range(world)], dim=1).contiguous()  # [cells_per, number]
     d_q = torch.empty((nq, cells_per), dtype=torch.float64, device=dev)
-    _lib.check(L.wwzb200_quantiles_cells_dev(X.data_ptr(), number, number, cells_per, d_probs.data_ptr(), nq,
-                                             d_q.data_ptr(), st))
+    _lib.check(L.wwzb200_quantiles_segments_dev(recv.data_ptr(), number, per, cells_per * S_pad, S_pad, cells_per,
+                                                d_probs.data_ptr(), nq, d_q.data_ptr(), st))
     qall = torch.empty((world, nq, cells_per), dtype=torch.float64, device=dev)
     dist.all_gather_into_tensor(qall.view(-1), d_q.view(-1), group=group)
     q = qall.permute(1, 0, 2).reshape(nq, world * cells_per)[:, :ncell].reshape(nq, nt, nf)
-    if S_loc == 0:                                          # (more ranks than surrogates) Neffs from a rank that has some
-        src = torch.zeros((nt, nf), dtype=torch.float64, device=dev)
-        d_ne = src
-    ne = d_ne.clone()
-    dist.broadcast(ne, src=0, group=group)
-    return q.cpu().numpy(), ne.cpu().numpy()
+    if number < world:                                      # some ranks hold no surrogate: Neffs from rank 0
+        if S_loc == 0:
+            d_ne.zero_()
+        dist.broadcast(d_ne, src=0, group=group)
+    out = torch.cat([q.reshape(-1), d_ne.reshape(-1)]).cpu().numpy()      # one device-to-host copy
+    return out[:nq * ncell].reshape(nq, nt, nf), out[nq * ncell:].reshape(nt, nf)
 
 
 def wwz_signif_tau_sharded(ys, ts, **kw):

@@ -19,7 +19,20 @@ import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("WWZ_REFERENCE_ROOT", "/root/reference")
+def _find_root():
+    """$WWZ_REFERENCE_ROOT, else the read-only reference tree of the build container, else the (git-ignored) offline
+    install `pip install --no-deps --target baseline/_ref /root/reference`, which travels to the GPU box."""
+    env = os.environ.get("WWZ_REFERENCE_ROOT")
+    if env:
+        return env
+    repo = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    for cand in ("/root/reference", os.path.join(repo, "baseline", "_ref")):
+        if os.path.isdir(os.path.join(cand, "pyleoclim")):
+            return cand
+    return "/root/reference"
+
+
+REF_ROOT = _find_root()
 REF_PKG = os.path.join(REF_ROOT, "pyleoclim")
 
 

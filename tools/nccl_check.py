@@ -15,6 +15,8 @@ s = D.wwz_signif_tau_sharded(y, t, tau=tau, freq=freq, number=64, qs=[0.9, 0.95]
 sf = D.wwz_signif_sharded(y, t, tau=tau, freq=freq, number=64, qs=[0.9, 0.95], seed=3, axis="freq")
 ss = D.wwz_signif_sharded(y, t, tau=tau, freq=freq, number=333, qs=[0.5, 0.95], seed=4)          # by surrogates (NCCL default)
 ss1 = B.wwz_signif(y, t, tau=tau, freq=freq, number=333, qs=[0.5, 0.95], seed=4)
+rr = D.wwz_tau_sharded(y, t, tau=tau, freq=freq, host="root")       # rank 0: blocks DMA'd into one shared pinned buffer
+rr2 = D.wwz_tau_sharded(y, t, tau=tau, freq=freq, host="root")      # a second result while the first is alive
 r1 = WV.wwz(y, t, tau=tau, freq=freq); p1 = WV.wwz_psd(y, t, tau=tau, freq=freq)
 s1 = B.wwz_signif(y, t, tau=tau, freq=freq, number=64, qs=[0.9, 0.95], seed=3)
 # (a tau block and the full grid use different point segmentations: equal to rounding, not bit for bit)
@@ -27,6 +29,10 @@ checks = {
     "wwz phase": np.allclose(r.phase, r1.phase, rtol=0, atol=1e-12, equal_nan=True),
     "wwz a0": np.allclose(r.coeff[0], r1.coeff[0], rtol=0, atol=1e-13, equal_nan=True),
     "psd": np.allclose(p.psd, p1.psd, rtol=1e-12),
+    "wwz host=root": (rr.amplitude is None) if dist.get_rank() else
+                     (np.array_equal(rr.amplitude, r.amplitude, equal_nan=True) and np.array_equal(rr.Neffs, r.Neffs, equal_nan=True)
+                      and np.array_equal(rr2.phase, r.phase, equal_nan=True) and rr2.amplitude is not rr.amplitude
+                      and not np.shares_memory(rr2.amplitude, rr.amplitude)),
     "signif tau-sharded": np.allclose(s.amplitude_qs, s1.amplitude_qs, rtol=1e-11, equal_nan=True),
     "signif freq-sharded": np.allclose(sf.amplitude_qs, s1.amplitude_qs, rtol=1e-11, equal_nan=True),
     # same surrogates (Philox streams keyed by the global series index), same per-series arithmetic
