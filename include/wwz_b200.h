@@ -256,6 +256,24 @@ int wwzb200_shared_axis_cells_dev(const double *d_ts, const double *d_Y, int64_t
 int wwzb200_quantiles_cells_dev(const double *d_Xcells, int64_t S, int64_t stride, int64_t ncell,
                                 const double *d_probs, int64_t nq, double *d_q, void *stream);
 
+/* wwzb200_shared_axis_cells_dev with the exchange of the surrogate-sharded significance test fused into the kernel:
+ * the (tau, f) cells are dealt in blocks of cells_per to n_peers GPUs of the box (cell block i belongs to peer i), and
+ * the contraction kernel stores every amplitude straight into the owner's buffer peer_bufs[i] over NVLink (peer memory
+ * mapped through CUDA IPC, wwzb200_ipc_*): row = cell inside the block, row stride dst_stride doubles, this batch's
+ * series at columns col0 .. col0 + S (padding columns up to the padded series count are written too and must lie
+ * inside the row).  No staging buffer, no separate all-to-all: the transfer overlaps the contraction tile by tile.  The
+ * caller orders "all peers have finished writing" before it reads its own buffer (any collective on the stream). */
+int wwzb200_shared_axis_cells_scatter_dev(const double *d_ts, const double *d_Y, int64_t nts, int64_t S,
+                                          const double *d_taus, int64_t nt, const double *d_omegas, int64_t nf, double c,
+                                          int64_t Neff_threshold, uint32_t flags, double *d_Neffs, void *const *peer_bufs,
+                                          int64_t n_peers, int64_t cells_per, int64_t dst_stride, int64_t col0,
+                                          void *stream);
+/* Device memory the other ranks of the box can map: allocate + export a 64-byte handle; map a peer's handle; unmap;
+ * free.  (cudaIpcGetMemHandle / cudaIpcOpenMemHandle: one process per GPU, all on one node.) */
+int wwzb200_ipc_alloc(size_t bytes, void **d_ptr, unsigned char *handle64);
+int wwzb200_ipc_open(const unsigned char *handle64, void **d_ptr);
+int wwzb200_ipc_close(void *d_ptr);
+int wwzb200_ipc_free(void *d_ptr);
 /* The part of wwzb200_shared_axis_cells_dev that does not depend on the series -- setup, basis rows, rotations, the
  * stored weight fragments and Neffs (utils/wavelet.py:988-1019 depend on ts, tau, omega only) -- enqueued on its own, so
  * that a caller can run it under host work that the series depend on (the tau_estimation fit of the surrogates,

@@ -84,6 +84,12 @@ _SIGS = {
     "wwzb200_quantiles_dev": (ctypes.c_int, [_vp, _i64, _i64, _vp, _i64, _vp, _vp]),
     "wwzb200_shared_axis_prepare_dev": (ctypes.c_int, [_vp, _i64, _i64, _vp, _i64, _vp, _i64, _dbl, _i64, _u32, _vp,
                                                        ctypes.POINTER(ctypes.c_int), _vp]),
+    "wwzb200_shared_axis_cells_scatter_dev": (ctypes.c_int, [_vp, _vp, _i64, _i64, _vp, _i64, _vp, _i64, _dbl, _i64, _u32,
+                                                             _vp, ctypes.POINTER(_vp), _i64, _i64, _i64, _i64, _vp]),
+    "wwzb200_ipc_alloc": (ctypes.c_int, [ctypes.c_size_t, ctypes.POINTER(_vp), ctypes.c_char_p]),
+    "wwzb200_ipc_open": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(_vp)]),
+    "wwzb200_ipc_close": (ctypes.c_int, [_vp]),
+    "wwzb200_ipc_free": (ctypes.c_int, [_vp]),
     "wwzb200_quantiles_segments_dev": (ctypes.c_int, [_vp, _i64, _i64, _i64, _i64, _i64, _vp, _i64, _vp, _vp]),
     "wwzb200_measure_fp64_peak": (ctypes.c_int, [_dp, _dp]),
     "wwzb200_launch_count": (_i64, []),

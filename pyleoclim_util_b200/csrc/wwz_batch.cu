@@ -14,6 +14,7 @@
 #include <math_constants.h>
 
 #include <algorithm>
+#include <cstring>
 #include <cmath>
 
 #include "wwz_device.cuh"
@@ -322,7 +323,7 @@ __global__ void __launch_bounds__(128)
                           int64_t nf, double c, double thr, const unsigned int *__restrict__ count,
                           const unsigned int *__restrict__ list, double *__restrict__ neffs, double *__restrict__ amp,
                           double *__restrict__ phase, double *__restrict__ a0o, double *__restrict__ a1o,
-                          double *__restrict__ a2o)
+                          double *__restrict__ a2o, const AmpScatterDev sc)
 {
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
@@ -337,7 +338,7 @@ __global__ void __launch_bounds__(128)
         if (lane == 0) {
             const size_t o = (size_t)cell * (size_t)S_pad + (size_t)s;
             if (s == 0) neffs[cell] = neff;
-            amp[o] = sqrt(a1 * a1 + a2 * a2);
+            amp_row(sc, amp, (size_t)cell, S_pad)[s] = sqrt(a1 * a1 + a2 * a2);
             if (phase) phase[o] = atan2(a2, a1);
             if (a0o) a0o[o] = a0;
             if (a1o) a1o[o] = a1;
@@ -350,16 +351,19 @@ cudaError_t launch_shared_fixup(const double *d_ts, const double *d_Yt, int64_t 
                                 int64_t S_pad, int series_block, const double *d_tau, const double *d_omega, int64_t nt, int64_t nf,
                                 double c, double thr, const double *d_wq, unsigned int *d_fix_count,
                                 unsigned int *d_fix_list, double *d_neffs, double *d_amp, double *d_phase,
-                                double *d_a0, double *d_a1, double *d_a2, int sms, cudaStream_t st)
+                                double *d_a0, double *d_a1, double *d_a2, int sms, cudaStream_t st,
+                                const AmpScatter *scatter)
 {
     const int64_t ncell = nt * nf;
     if (ncell <= 0 || S <= 0) return cudaSuccess;
+    AmpScatterDev sc{};
+    if (scatter) memcpy(&sc, scatter, sizeof sc);
     cudaError_t e = cudaMemsetAsync(d_fix_count, 0, sizeof(unsigned int), st);
     if (e != cudaSuccess) return e;
     flag_cells_kernel<<<(unsigned)((ncell + 255) / 256), 256, 0, st>>>(d_wq, ncell, d_fix_count, d_fix_list);
     faithful_batch_kernel<<<(unsigned)(sms * 8), 128, 0, st>>>(d_ts, d_Yt, n, n_pad, S, S_pad, series_block, d_tau, d_omega,
                                                                             nf, c, thr, d_fix_count, d_fix_list, d_neffs,
-                                                                            d_amp, d_phase, d_a0, d_a1, d_a2);
+                                                                            d_amp, d_phase, d_a0, d_a1, d_a2, sc);
     bump_launch_counter(2);
     return cudaGetLastError();
 }

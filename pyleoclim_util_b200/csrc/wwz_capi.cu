@@ -476,7 +476,8 @@ int shared_axis_device(Workspace *w, const double *d_ts, const double *d_Y, int6
                        int64_t nt, const double *d_omega, int64_t nf, double c, int64_t thr, int64_t psd_thr,
                        uint32_t flags, double *d_neffs, double *d_wwa, double *d_phase, double *d_a0, double *d_a1,
                        double *d_a2, double *d_psd, double tspan, double **amp_cells_out, int64_t *S_pad_out,
-                       cudaStream_t st, double *d_amp_cells_ext = nullptr, int phase = 3)
+                       cudaStream_t st, double *d_amp_cells_ext = nullptr, int phase = 3,
+                       const wwz::AmpScatter *scatter = nullptr)
 {
     // phase 1: only what does not depend on the series (setup, basis rows, rotations, stored weights + Neffs);
     // phase 2: the rest, on a scratch that a phase-1 call with the same arguments has prepared; 3: everything
@@ -491,6 +492,8 @@ int shared_axis_device(Workspace *w, const double *d_ts, const double *d_Y, int6
     const int NS = plan.series_block;
     const int64_t S_pad = ((S + NS - 1) / NS) * NS;
     if (S_pad / NS > 65535) return fail(WWZB200_ERR_ARG, "more than 65535*%d series in one batch", NS);
+    if (nf > 65535) return fail(WWZB200_ERR_ARG, "the shared-axis batch takes at most 65535 frequencies (one grid row of its "
+                                                 "basis and psd kernels per frequency); split the frequency axis");
     if ((size_t)nf * (size_t)plan.n_pad * 16 > ((size_t)16 << 30))
         return fail(WWZB200_ERR_NOMEM, "basis rows of the shared-axis batch exceed 16 GiB");
     int rc;
@@ -511,8 +514,8 @@ int shared_axis_device(Workspace *w, const double *d_ts, const double *d_Y, int6
     if ((rc = wsbuf(w, "wq", (size_t)2 * ncell, &d_wq))) return rc;
     if (d_amp_cells_ext)
         d_amp_t = d_amp_cells_ext;       // the caller keeps the cell-major amplitudes [ncell][S_pad]
-    else if (phase == 1)
-        d_amp_t = nullptr;
+    else if (phase == 1 || scatter)
+        d_amp_t = nullptr;               // (scatter: the amplitudes go to the owners of the cell blocks)
     else if ((rc = wsbuf(w, "amp_t", (size_t)ncell * (size_t)S_pad, &d_amp_t)))
         return rc;
     if (d_phase && (rc = wsbuf(w, "ph_t", (size_t)ncell * (size_t)S_pad, &d_ph_t))) return rc;
@@ -578,13 +581,13 @@ int shared_axis_device(Workspace *w, const double *d_ts, const double *d_Y, int6
         CU(cudaEventRecord(ev.a, st));
     }
     CU(launch_shared(plan, d_ty, d_basis, d_Yt, d_ts, n, S_pad, d_tau, nt, d_kappa, d_dcut, d_gap, d_unsorted, nf, d_rot,
-                     (double)thr, d_wfrag, d_cellsums, d_ne, d_wq, d_amp_t, d_ph_t, d_a0_t, d_a1_t, d_a2_t, st, phase));
+                     (double)thr, d_wfrag, d_cellsums, d_ne, d_wq, d_amp_t, d_ph_t, d_a0_t, d_a1_t, d_a2_t, st, phase, scatter));
     if (g_profile) {
         CU(cudaEventRecord(ev.b, st));
         g_events.push_back(ev);
     }
     CU(launch_shared_fixup(d_ts, d_Yt, n, plan.n_pad, S, S_pad, NS, d_tau, d_omega, nt, nf, c, (double)thr, d_wq, d_fix,
-                           d_fix + 1, d_ne, d_amp_t, d_ph_t, d_a0_t, d_a1_t, d_a2_t, w->sms, st));
+                           d_fix + 1, d_ne, d_amp_t, d_ph_t, d_a0_t, d_a1_t, d_a2_t, w->sms, st, scatter));
     // cell-major [ncell][S_pad] -> series-major [S][ncell]
     if (d_wwa) CU(launch_transpose(d_amp_t, ncell, S, S_pad, d_wwa, ncell, st));
     if (d_phase) CU(launch_transpose(d_ph_t, ncell, S, S_pad, d_phase, ncell, st));
@@ -1102,6 +1105,77 @@ int wwzb200_shared_axis_cells_dev(const double *d_ts, const double *d_Y, int64_t
                               flags & ~WWZB200_PREPARED, d_Neffs, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0.0,
                               nullptr, nullptr, static_cast<cudaStream_t>(stream), d_amp_cells,
                               (flags & WWZB200_PREPARED) ? 2 : 3);
+}
+
+int wwzb200_shared_axis_cells_scatter_dev(const double *d_ts, const double *d_Y, int64_t nts, int64_t S,
+                                          const double *d_taus, int64_t nt, const double *d_omegas, int64_t nf, double c,
+                                          int64_t Neff_threshold, uint32_t flags, double *d_Neffs, void *const *peer_bufs,
+                                          int64_t n_peers, int64_t cells_per, int64_t dst_stride, int64_t col0,
+                                          void *stream)
+{
+    int rc = check_grid_args(d_ts, d_Y, nts, d_taus, nt, d_omegas, nf, c, Neff_threshold);
+    if (rc) return rc;
+    int64_t S_pad = 0;
+    if (S < 1 || (rc = wwzb200_series_pad(S, &S_pad))) return fail(WWZB200_ERR_ARG, "bad batch arguments");
+    if (!peer_bufs || n_peers < 1 || n_peers > wwz::kMaxPeers || cells_per < 1 || cells_per * n_peers < nt * nf ||
+        col0 < 0 || dst_stride < col0 + S_pad)
+        return fail(WWZB200_ERR_ARG, "bad scatter layout (peers <= %d, cells_per * peers >= nt * nf, dst_stride >= col0 + "
+                                     "padded series count)", wwz::kMaxPeers);
+    wwz::AmpScatter sc{};
+    for (int64_t i = 0; i < n_peers; ++i) {
+        if (!peer_bufs[i]) return fail(WWZB200_ERR_ARG, "null peer buffer");
+        sc.peer[i] = static_cast<double *>(peer_bufs[i]);
+    }
+    sc.cells_per = cells_per;
+    sc.dst_stride = dst_stride;
+    sc.col0 = col0;
+    std::lock_guard<std::mutex> lock(g_mu);
+    Workspace *w;
+    if ((rc = workspace(&w))) return rc;
+    ScratchScope scope(w, static_cast<cudaStream_t>(stream));
+    if ((rc = scope.begin())) return rc;
+    return shared_axis_device(w, d_ts, d_Y, nts, S, d_taus, nt, d_omegas, nf, c, Neff_threshold, 0,
+                              flags & ~WWZB200_PREPARED, d_Neffs, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0.0,
+                              nullptr, nullptr, static_cast<cudaStream_t>(stream), nullptr,
+                              (flags & WWZB200_PREPARED) ? 2 : 3, &sc);
+}
+
+// Device buffers that the other ranks of the box can map (CUDA IPC): cudaMalloc'ed here, exported as a 64-byte handle.
+int wwzb200_ipc_alloc(size_t bytes, void **d_ptr, unsigned char *handle64)
+{
+    if (!d_ptr || !handle64 || !bytes) return fail(WWZB200_ERR_ARG, "bad arguments");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    CU(cudaMalloc(d_ptr, bytes));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, *d_ptr);
+    if (e != cudaSuccess) {
+        cudaFree(*d_ptr);
+        *d_ptr = nullptr;
+        return fail(WWZB200_ERR_CUDA, "cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e));
+    }
+    memcpy(handle64, &h, 64);
+    return 0;
+}
+
+int wwzb200_ipc_open(const unsigned char *handle64, void **d_ptr)
+{
+    if (!d_ptr || !handle64) return fail(WWZB200_ERR_ARG, "bad arguments");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    CU(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+
+int wwzb200_ipc_close(void *d_ptr)
+{
+    if (d_ptr) CU(cudaIpcCloseMemHandle(d_ptr));
+    return 0;
+}
+
+int wwzb200_ipc_free(void *d_ptr)
+{
+    if (d_ptr) CU(cudaFree(d_ptr));
+    return 0;
 }
 
 int wwzb200_shared_axis_prepare_dev(const double *d_ts, int64_t nts, int64_t S, const double *d_taus, int64_t nt,

@@ -156,7 +156,7 @@ __device__ __forceinline__ double gauss_weight_estrin(double v, const double *__
 // rho costs a second exp2 per (lane, point) but then every further cell of the lane costs one DMUL
 // instead of an exp2.  When w_0 is flushed (|a| > 127.8) rho is forced to 0 as well, so that the
 // products stay 0 instead of 0*inf; with D <= 8 and M <= 8 every weight dropped that way is below
-// 2^-320 (see rec_rows_prefix in wwz_capi.cu).
+// 2^-320 (the row classification in setup_kernel, wwz_kernels.cu).
 __device__ __forceinline__ void gauss_weight_ratio(double a, double step16, const double *__restrict__ tbl,
                                                    double &w0, double &rho)
 {
@@ -190,6 +190,18 @@ __device__ __forceinline__ void gauss_weight_ratio(double a, double step16, cons
 __device__ __forceinline__ void load_exp2_table(double *tbl, int tid)
 {
     if (tid < 16) tbl[tid] = c_exp2_table[tid];
+}
+
+// Row of cell `cell` in the cell-major amplitude output of a shared-axis batch (AmpScatter, wwz_internal.h).
+struct AmpScatterDev {
+    double *peer[16];
+    long long cells_per, dst_stride, col0;
+};
+__device__ __forceinline__ double *amp_row(const AmpScatterDev &sc, double *amp, size_t cell, long long S_pad)
+{
+    if (sc.cells_per == 0) return amp + cell * (size_t)S_pad;
+    const size_t owner = cell / (size_t)sc.cells_per;
+    return sc.peer[owner] + (cell - owner * (size_t)sc.cells_per) * (size_t)sc.dst_stride + sc.col0;
 }
 
 // ----------------------------------------------------------------------------------------------

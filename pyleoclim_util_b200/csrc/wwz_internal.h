@@ -157,6 +157,17 @@ cudaError_t launch_psd_devspan(const double *d_wwa, const double *d_neffs, int64
                                double *d_psd, cudaStream_t st, int64_t members = 1);
 
 // ---- batched paths (wwz_batch.cu) -------------------------------------------------------------
+// Where the cell-major amplitudes of a shared-axis batch go.  cells_per == 0: one local buffer [ncell][S_pad].
+// Otherwise the cells are dealt in blocks of cells_per to up to kMaxPeers destinations -- buffers in the HBM of the
+// GPUs of this box, mapped through CUDA IPC -- and the contraction kernel stores every amplitude straight into the
+// owner's buffer over NVLink: row = cell inside the owner's block, row stride dst_stride, this batch's series at
+// columns col0 ...  (the exchange of the surrogate-sharded significance test, fused into the kernel's epilogue).
+constexpr int kMaxPeers = 16;
+struct AmpScatter {
+    double *peer[kMaxPeers];
+    long long cells_per, dst_stride, col0;
+};
+
 struct SharedPlan {
     int series_block;     // NS: series per CTA tile of the shared-time-axis kernel (64, or 16 for small batches)
     int points, stage_bytes, smem_bytes;
@@ -187,13 +198,15 @@ cudaError_t launch_shared(const SharedPlan &plan, const double2 *d_ty, const dou
                           const double *d_kappa, const double *d_dcut, const double *d_taugap, const int *d_unsorted,
                           int64_t nf, const double2 *d_rot, double thr, double *d_wfrag, double *d_cellsums, double *d_neffs,
                           double *d_wq, double *d_amp, double *d_phase, double *d_a0, double *d_a1, double *d_a2,
-                          cudaStream_t st, int phase = 3);   // phase: 1 = y-independent pass (stored weights), 2 = contraction
+                          cudaStream_t st, int phase = 3,    // phase: 1 = y-independent pass (stored weights), 2 = contraction
+                          const AmpScatter *scatter = nullptr);
 // deep-underflow cells of a shared-axis batch (flagged from W, Q), recomputed faithfully for every series
 cudaError_t launch_shared_fixup(const double *d_ts, const double *d_Yt, int64_t n, int64_t n_pad, int64_t S,
                                 int64_t S_pad, int series_block, const double *d_tau, const double *d_omega, int64_t nt,
                                 int64_t nf, double c, double thr, const double *d_wq, unsigned int *d_fix_count,
                                 unsigned int *d_fix_list, double *d_neffs, double *d_amp, double *d_phase,
-                                double *d_a0, double *d_a1, double *d_a2, int sms, cudaStream_t st);
+                                double *d_a0, double *d_a1, double *d_a2, int sms, cudaStream_t st,
+                                const AmpScatter *scatter = nullptr);
 cudaError_t launch_transpose(const double *d_in, int64_t rows, int64_t cols, int64_t in_stride, double *d_out,
                              int64_t out_stride, cudaStream_t st);
 cudaError_t launch_psd_batch(const double *d_amp, const double *d_neffs, int64_t nt, int64_t nf, int64_t S,

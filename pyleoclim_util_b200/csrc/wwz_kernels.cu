@@ -916,8 +916,8 @@ cudaError_t launch_faithful(const double *d_ts, const double *d_ys, int64_t n, c
 //   power = wwa**2 * 0.5 * (max(ts)-min(ts))/size(ts) * Neffs ;  d = max(Neffs - thr, 0)
 //   psd = nansum(power*d, axis=0) / nansum(d, axis=0).
 // ------------------------------------------------------------------------------------------------
-// One CTA = 32 frequency columns x 32 row lanes: lane y of a column adds rows y, y+32, ... in order,
-// the 32 partial sums of a column are then added in lane order (fixed, deterministic association).
+// One CTA = kPsdCols (8) frequency columns x kPsdRows (128) row threads: thread y of a column adds rows y, y+128, ...
+// in order, the 128 partial sums of a column are then added in thread order (fixed, deterministic association).
 constexpr int kPsdCols = 8;      // frequency columns per CTA: nf/8 CTAs instead of nf/32, four times the SMs
 constexpr int kPsdRows = 128;    // row threads per column
 

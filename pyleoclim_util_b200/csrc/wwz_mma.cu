@@ -34,6 +34,7 @@
 #include <math_constants.h>
 
 #include <algorithm>
+#include <cstring>
 #include <cstdlib>
 
 #include "wwz_device.cuh"
@@ -77,6 +78,7 @@ struct MmaArgs {
     int nt, nf, P, tiles_t;
     int row_stride2, stage_stride2, y_off2, w_off2;   // double2 units
     double thr;
+    AmpScatterDev sc;       // destination of the amplitudes (cells_per == 0: the local buffer `amp`)
 };
 
 __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b)
@@ -364,6 +366,8 @@ __global__ void __launch_bounds__(kMmaThreads, 1) wwz_shared_mma_kernel(const Mm
     const double2 rt = a.rot[cell];
     // C fragment: row = lane/4 (the cell), columns 2*(lane%4) + {0, 1} of n-tile m
     const size_t o = cell * (size_t)a.S_pad + (size_t)sb * NS + (size_t)(2 * p);
+    // the amplitudes may go to the owner of the cell's block over NVLink (peer memory), see AmpScatter
+    double *const arow = amp_row(a.sc, a.amp, cell, a.S_pad) + (size_t)sb * NS + (size_t)(2 * p);
 #pragma unroll
     for (int m = 0; m < NT; ++m) {
         double amp2[2], ph2[2], c02[2], c12[2], c22[2];
@@ -385,7 +389,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) wwz_shared_mma_kernel(const Mm
             c22[e] = c2;
         }
         const size_t oo = o + (size_t)(8 * m);
-        *reinterpret_cast<double2 *>(a.amp + oo) = make_double2(amp2[0], amp2[1]);
+        *reinterpret_cast<double2 *>(arow + (size_t)(8 * m)) = make_double2(amp2[0], amp2[1]);
         if (a.phase) *reinterpret_cast<double2 *>(a.phase + oo) = make_double2(ph2[0], ph2[1]);
         if (a.a0) *reinterpret_cast<double2 *>(a.a0 + oo) = make_double2(c02[0], c02[1]);
         if (a.a1) *reinterpret_cast<double2 *>(a.a1 + oo) = make_double2(c12[0], c12[1]);
@@ -455,7 +459,7 @@ cudaError_t launch_shared(const SharedPlan &plan, const double2 *d_ty, const dou
                           const double *d_kappa, const double *d_dcut, const double *d_taugap, const int *d_unsorted,
                           int64_t nf, const double2 *d_rot, double thr, double *d_wfrag, double *d_cellsums, double *d_neffs,
                           double *d_wq, double *d_amp, double *d_phase, double *d_a0, double *d_a1, double *d_a2,
-                          cudaStream_t st, int phase)
+                          cudaStream_t st, int phase, const AmpScatter *scatter)
 {
     const int64_t ncell = nt * nf;
     if (ncell <= 0 || S_pad <= 0) return cudaSuccess;
@@ -493,6 +497,8 @@ cudaError_t launch_shared(const SharedPlan &plan, const double2 *d_ty, const dou
     a.y_off2 = (int)(plan.y_off / 16);
     a.w_off2 = (int)(plan.w_off / 16);
     a.thr = thr;
+    static_assert(sizeof(AmpScatter) == sizeof(AmpScatterDev), "host and device views of the scatter map");
+    if (scatter) memcpy(&a.sc, scatter, sizeof a.sc);
     const int NS = plan.series_block;
     const int64_t tiles_k = (nf + kMmaRows - 1) / kMmaRows;
     const dim3 grid((unsigned)(tiles_k * a.tiles_t), (unsigned)(S_pad / NS));

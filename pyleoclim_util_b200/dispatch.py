@@ -35,6 +35,12 @@ FOSTER_METHOD = "Foster_cuda"          # the reference's method='Foster' (wwz_ba
 CUDA_METHODS = (CUDA_METHOD, FOSTER_METHOD)
 
 
+def _fresh_seed():
+    """An unseeded significance test draws fresh surrogates on every call, like the reference's use of NumPy's
+    global stream (utils/tsmodel.py:66): one 64-bit seed from the OS entropy pool per call."""
+    return int(np.random.SeedSequence().entropy & 0xFFFFFFFFFFFFFFFF)
+
+
 # ----------------------------------------------------------------------------------- kernel level
 def _make_kernel(mod, foster=False):
     pre = getattr(mod, "preprocess", None)
@@ -266,7 +272,7 @@ def _patch_core(pyleo, wavemod):
         ts, args = self.timeseries, self.wave_args
         ys_cut, ts_cut, freq, tau = _surrogate_grid(ts, args)
         sg = batch.wwz_signif(ys_cut, ts_cut, tau=tau, freq=freq, number=number, qs=qs,
-                              seed=0 if seed is None else seed, c=args.get("c", 1 / (8 * np.pi ** 2)),
+                              seed=_fresh_seed() if seed is None else seed, c=args.get("c", 1 / (8 * np.pi ** 2)),
                               Neff_threshold=args.get("Neff_threshold", 3), method=method)
         new = self.copy()
         coi = wavemod.make_coi(tau, Neff_threshold=args.get("Neff_coi", 3))
@@ -293,7 +299,7 @@ def _patch_core(pyleo, wavemod):
         freq = np.asarray(args["freq"], dtype=float)
         ys_cut, ts_cut, freq, tau = wavemod.prepare_wwz(ts.value, ts.time, freq=freq)   # utils/spectral.py:882
         sg = batch.wwz_signif(ys_cut, ts_cut, tau=tau, freq=freq, number=number, qs=qs,
-                              seed=0 if seed is None else seed, c=args.get("c", 1e-3), Neff_threshold=3, psd=True,
+                              seed=_fresh_seed() if seed is None else seed, c=args.get("c", 1e-3), Neff_threshold=3, psd=True,
                               psd_Neff_threshold=args.get("Neff_threshold", 3), method=method)
         new = self.copy()
         lw = [0.5, 1.5, 0.5] if len(qs) == 3 else [1.0] * len(qs)

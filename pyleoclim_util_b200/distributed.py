@@ -83,17 +83,38 @@ def all_gather_rows(local, counts, group=None):
     return np.concatenate([out[r, : counts[r]] for r in range(world)], axis=0)
 
 
+def _shm_class():
+    from multiprocessing import shared_memory
+
+    class _Shm(shared_memory.SharedMemory):
+        """A mapping that lives as long as the process: result arrays and the page-lock keep pointers into it, so
+        it is never closed by the garbage collector (the kernel unmaps it at exit; the creator unlinks the name)."""
+
+        def __del__(self):
+            pass
+
+    return _Shm
+
+
 class _SharedHostSegments:
     """Page-locked POSIX shared-memory segments mapped by every rank of the box (host='root' results).
 
     Rank 0 -- the consumer -- owns the free list: a result array handed to the caller is a view of a segment, and the
     segment returns to the free list when the array (and every view of it) has been collected, like the page-locked
     pool of `_lib`.  Every rank maps each segment once and page-locks its own mapping (`wwzb200_host_register`), so
-    that its GPU copies its block of rows over its own PCIe link straight into the consumer's buffer."""
+    that its GPU copies its block of rows over its own PCIe link straight into the consumer's buffer.
+
+    The ranks agree on the segment of a call, and rank 0 learns that every block has landed, through a small control
+    segment (a mailbox of int64 words in shared memory): no collective and no device synchronisation beyond each
+    rank's own stream.  Only the creation of a new segment (first call, or a larger result) is a collective."""
+
+    CTRL_WORDS = 512            # [0] sequence number of the published pick, [1] picked segment, [8 + r] rank r's done flag
 
     def __init__(self):
         self.segs = []          # [dict(shm, nbytes, addr, free)]
         self.same_host = {}     # group -> bool
+        self.ctrl = None        # int64 view of the control segment
+        self.seq = 0
 
     def on_one_host(self, group):
         key = id(group)
@@ -102,53 +123,81 @@ class _SharedHostSegments:
             dist = _dist()
             names = [None] * dist.get_world_size(group)
             dist.all_gather_object(names, socket.gethostname(), group=group)
-            self.same_host[key] = len(set(names)) == 1
+            self.same_host[key] = len(set(names)) == 1 and dist.get_world_size(group) <= self.CTRL_WORDS - 8
         return self.same_host[key]
 
-    def acquire(self, nbytes, group):
-        """Collective: every rank returns its mapping (a dict) of the same segment, of at least nbytes."""
+    def _create(self, size, group, register=True):
+        """Collective: a new segment of `size` bytes mapped (and page-locked) by every rank."""
         import atexit
         import ctypes
-        import torch
-        from multiprocessing import shared_memory, resource_tracker
+        from multiprocessing import resource_tracker
         from . import _lib
         dist = _dist()
         rank = dist.get_rank(group)
-        dev = torch.device("cuda", torch.cuda.current_device())
-        pick = torch.full((1,), -1, dtype=torch.int64, device=dev)
+        Shm = _shm_class()
+        name = [None]
+        shm = None
         if rank == 0:
+            shm = Shm(create=True, size=size)
+            name[0] = shm.name
+            atexit.register(self._unlink, shm)
+        dist.broadcast_object_list(name, src=0, group=group)
+        if rank != 0:
+            shm = Shm(name=name[0])
+            try:                     # the creator unlinks; an attaching process must not (Python < 3.13 tracks both)
+                resource_tracker.unregister(shm._name, "shared_memory")
+            except Exception:
+                pass
+        addr = ctypes.addressof(ctypes.c_char.from_buffer(shm.buf))
+        if register:
+            _lib.check(_lib.lib().wwzb200_host_register(addr, size))
+        dist.barrier(group=group)    # every rank has mapped the segment before anybody uses it
+        return dict(shm=shm, nbytes=size, addr=addr, free=True)
+
+    def acquire(self, nbytes, group):
+        """Every rank returns its mapping (a dict) of the same segment, of at least nbytes.  Called by all ranks in
+        the same order."""
+        dist = _dist()
+        rank = dist.get_rank(group)
+        if self.ctrl is None:
+            c = self._create(self.CTRL_WORDS * 8, group, register=False)
+            self.ctrl_seg = c
+            self.ctrl = np.ndarray((self.CTRL_WORDS,), dtype=np.int64, buffer=c["shm"].buf)
+            if rank == 0:
+                self.ctrl[:] = 0
+            dist.barrier(group=group)
+        self.seq += 1
+        ctrl = self.ctrl
+        if rank == 0:
+            idx = -1
             for i, sg in enumerate(self.segs):
                 if sg["free"] and sg["nbytes"] >= nbytes:
-                    pick[0] = i
+                    idx = i
                     break
-        dist.broadcast(pick, src=0, group=group)
-        idx = int(pick.item())
+            ctrl[1] = idx
+            ctrl[0] = self.seq                       # publish
+        else:
+            while ctrl[0] != self.seq:
+                pass
+            idx = int(ctrl[1])
         if idx < 0:
             size = max(int(nbytes), 1 << 20)
             size = (size + (1 << 21) - 1) & ~((1 << 21) - 1)
-            name = [None]
-            shm = None
-            if rank == 0:
-                shm = shared_memory.SharedMemory(create=True, size=size)
-                name[0] = shm.name
-            dist.broadcast_object_list(name, src=0, group=group)
-            if rank != 0:
-                shm = shared_memory.SharedMemory(name=name[0])
-                try:                     # the creator unlinks; an attaching process must not (Python < 3.13 tracks both)
-                    resource_tracker.unregister(shm._name, "shared_memory")
-                except Exception:
-                    pass
-            addr = ctypes.addressof(ctypes.c_char.from_buffer(shm.buf))
-            _lib.check(_lib.lib().wwzb200_host_register(addr, size))
-            sg = dict(shm=shm, nbytes=size, addr=addr, free=True)
-            self.segs.append(sg)
+            self.segs.append(self._create(size, group))
             idx = len(self.segs) - 1
-            if rank == 0:
-                atexit.register(self._unlink, shm)
-            dist.barrier(group=group)    # every rank has mapped the segment before anybody copies into it
         sg = self.segs[idx]
         sg["free"] = False
         return sg
+
+    def landed(self, group):
+        """This rank's copies into the segment of the current call are complete; rank 0 waits for every rank."""
+        dist = _dist()
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        self.ctrl[8 + rank] = self.seq
+        if rank == 0:
+            flags = self.ctrl[8:8 + world]
+            while not (flags == self.seq).all():
+                pass
 
     @staticmethod
     def _unlink(shm):
@@ -209,7 +258,7 @@ def _device_blocks(pd_ys, ts_cut, tau, omega, c, Neff_threshold, flags, group, w
                 _lib.check(L.wwzb200_copy_to_host_async(sg["addr"] + (i * nt + a) * nf * 8, loc[w_i].data_ptr(),
                                                         (b - a) * nf * 8, st))
         _lib.check(L.wwzb200_stream_synchronize(st))
-        dist.barrier(group=group)                       # every block has landed
+        _shared_segments.landed(group)                  # rank 0 waits until every block has landed (shared-memory flags)
         if rank == 0:
             return _shared_segments.view(sg, (k, nt, nf)), None
         sg["free"] = True
@@ -384,6 +433,59 @@ def wwz_signif_sharded(ys, ts, tau=None, freq=None, number=200, qs=(0.95,), seed
                                Neffs=np.ascontiguousarray(full[nq]), freq=freq, time=tau)
 
 
+class _PeerBuffers:
+    """One device buffer per rank that every other rank of the box has mapped (CUDA IPC through the C ABI's
+    wwzb200_ipc_*): the destination of the fused exchange of the surrogate-sharded significance test.  Grown
+    collectively; reused across calls (a call ends with a collective that follows the last read of the buffer on
+    every rank's stream, so the next call's peers cannot overwrite data still in use)."""
+
+    def __init__(self):
+        self.entries = {}       # id(group) -> dict(nbytes, own, peers (ctypes array of void*))
+
+    def get(self, nbytes, group):
+        import ctypes
+        import torch
+        from . import _lib
+        dist = _dist()
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        key = id(group)
+        ent = self.entries.get(key)
+        if ent is not None and ent["nbytes"] >= nbytes:
+            return ent
+        L = _lib.lib()
+        dev = torch.device("cuda", torch.cuda.current_device())
+        torch.cuda.synchronize()
+        if ent is not None:                          # grow: unmap the peers, then (after everybody did) free
+            for r in range(world):
+                if r != rank:
+                    _lib.check(L.wwzb200_ipc_close(ent["peers"][r]))
+            dist.barrier(group=group)
+            _lib.check(L.wwzb200_ipc_free(ent["own"]))
+        size = (int(nbytes) + (1 << 21) - 1) & ~((1 << 21) - 1)
+        own = ctypes.c_void_p()
+        handle = ctypes.create_string_buffer(64)
+        _lib.check(L.wwzb200_ipc_alloc(size, ctypes.byref(own), handle))
+        mine = torch.tensor(list(handle.raw), dtype=torch.uint8, device=dev)
+        allh = torch.empty((world, 64), dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(allh.view(-1), mine, group=group)
+        allh = allh.cpu().numpy()
+        peers = (ctypes.c_void_p * world)()
+        for r in range(world):
+            if r == rank:
+                peers[r] = own.value
+            else:
+                p = ctypes.c_void_p()
+                _lib.check(L.wwzb200_ipc_open(allh[r].tobytes(), ctypes.byref(p)))
+                peers[r] = p.value
+        dist.barrier(group=group)
+        ent = dict(nbytes=size, own=own.value, peers=peers)
+        self.entries[key] = ent
+        return ent
+
+
+_peer_buffers = _PeerBuffers()
+
+
 def surrogate_blocks(number, world):
     """Partition of the surrogates over the ranks: blocks of ceil(number / world), the last ranks take what is left
     (so that every block but the last has the same length: the all-to-all receive buffer is then a row of equal
@@ -396,9 +498,10 @@ def _signif_by_surrogates(ys_cut, ts_cut, tau, freq, number, probs, seed, c, Nef
     """Surrogates sharded over the ranks (NCCL): rank r generates rows [s0_r, s1_r) of the surrogate batch (the Philox
     stream of a series is keyed by its global index: same surrogates as the single-GPU test), transforms them as one
     shared-axis batch on the whole (tau, f) grid -- perfectly balanced, whatever the point windows -- and keeps the
-    amplitudes cell-major in HBM; one all-to-all over NVLink hands every rank ALL surrogates of its block of cells,
-    the per-cell quantiles are taken straight from the receive buffer, and the [nq, cells/world] tiles are
-    all-gathered.  The part of the transform that does not depend on the surrogates (setup, basis rows, stored weights,
+    amplitudes of a cell with the rank that owns the cell's block: the contraction kernel stores them straight into
+    that rank's HBM over NVLink (fused exchange, `wwzb200_shared_axis_cells_scatter_dev`; on several hosts, or with
+    WWZB200_NO_PEER_SCATTER, a staged all-to-all instead), the per-cell quantiles are taken in place, and the
+    [nq, cells/world] tiles are all-gathered.  The part of the transform that does not depend on the surrogates (setup, basis rows, stored weights,
     Neffs) is enqueued first and runs under the host-side AR(1) fit.  Returns (q [nq, nt, nf], Neffs [nt, nf]) as
     NumPy arrays, equal on every rank and to the single-GPU result."""
     import ctypes
@@ -441,30 +544,52 @@ def _signif_by_surrogates(ys_cut, ts_cut, tau, freq, number, probs, seed, c, Nef
         sig, tau_est = float(np.std(ys_cut)), float(batch.tau_estimation(ys_cut, ts_cut))
     else:
         tau_est, sig = (float(v) for v in batch.uar1_fit(ys_cut, ts_cut))
-    # cell-major amplitudes, cells padded to a multiple of world (padding rows are never read back)
-    d_amp = torch.empty((cells_per * world, S_pad), dtype=torch.float64, device=dev)
-    if S_loc > 0:
-        own = ctypes.c_int64()
-        _lib.check(L.wwzb200_series_pad(S_loc, ctypes.byref(own)))
-        d_Y = torch.empty((S_loc, n), dtype=torch.float64, device=dev)
-        _lib.check(L.wwzb200_surrogates_block_dev(d_ts.data_ptr(), n, tau_est, sig, mu, S_loc, s0,
-                                                  int(seed) & 0xFFFFFFFFFFFFFFFF, flags & _lib.UAR1, d_Y.data_ptr(), st))
-        if int(own.value) == S_pad:
-            tgt = d_amp
-        else:                                               # a short last block pads to fewer columns: its own buffer
-            tgt = torch.empty((ncell, int(own.value)), dtype=torch.float64, device=dev)
-        fl = flags | (_lib.PREPARED if prepared.value else 0)
-        _lib.check(L.wwzb200_shared_axis_cells_dev(d_ts.data_ptr(), d_Y.data_ptr(), n, S_loc, d_tau.data_ptr(), nt,
-                                                   d_om.data_ptr(), nf, float(c), int(Neff_threshold), fl,
-                                                   d_ne.data_ptr(), tgt.data_ptr(), st))
-        if tgt is not d_amp:
-            d_amp[:ncell, :S_loc] = tgt[:, :S_loc]
-    # every rank gets all surrogates of its block of cells: recv[r] = rank r's surrogates of my cells
-    recv = torch.empty((world, cells_per, S_pad), dtype=torch.float64, device=dev)
-    dist.all_to_all_single(recv.view(-1), d_amp.view(-1), group=group)
+    import os
+    fused = world <= 16 and not os.environ.get("WWZB200_NO_PEER_SCATTER") and _shared_segments.on_one_host(group)
     d_q = torch.empty((nq, cells_per), dtype=torch.float64, device=dev)
-    _lib.check(L.wwzb200_quantiles_segments_dev(recv.data_ptr(), number, per, cells_per * S_pad, S_pad, cells_per,
-                                                d_probs.data_ptr(), nq, d_q.data_ptr(), st))
+    if fused:
+        # FUSED EXCHANGE: every rank owns a block of cells_per cells and a buffer [cells_per][world][S_pad] that all
+        # ranks have mapped; the contraction kernel stores each amplitude straight into the owner's buffer over NVLink
+        # (peer memory), column slot `rank` -- the transfer rides under the contraction, tile by tile.  No staging
+        # buffer and no all-to-all.
+        ent = _peer_buffers.get(cells_per * world * S_pad * 8, group)
+        if S_loc > 0:
+            d_Y = torch.empty((S_loc, n), dtype=torch.float64, device=dev)
+            _lib.check(L.wwzb200_surrogates_block_dev(d_ts.data_ptr(), n, tau_est, sig, mu, S_loc, s0,
+                                                      int(seed) & 0xFFFFFFFFFFFFFFFF, flags & _lib.UAR1, d_Y.data_ptr(), st))
+            fl = flags | (_lib.PREPARED if prepared.value else 0)
+            _lib.check(L.wwzb200_shared_axis_cells_scatter_dev(
+                d_ts.data_ptr(), d_Y.data_ptr(), n, S_loc, d_tau.data_ptr(), nt, d_om.data_ptr(), nf, float(c),
+                int(Neff_threshold), fl, d_ne.data_ptr(), ent["peers"], world, cells_per, world * S_pad, rank * S_pad, st))
+        # "every peer has finished writing into my buffer": a collective in stream order behind the kernels
+        token = torch.zeros(1, dtype=torch.float64, device=dev)
+        dist.all_reduce(token, group=group)
+        _lib.check(L.wwzb200_quantiles_segments_dev(ent["own"], number, per, S_pad, world * S_pad, cells_per,
+                                                    d_probs.data_ptr(), nq, d_q.data_ptr(), st))
+    else:
+        # cell-major amplitudes, cells padded to a multiple of world (padding rows are never read back)
+        d_amp = torch.empty((cells_per * world, S_pad), dtype=torch.float64, device=dev)
+        if S_loc > 0:
+            own = ctypes.c_int64()
+            _lib.check(L.wwzb200_series_pad(S_loc, ctypes.byref(own)))
+            d_Y = torch.empty((S_loc, n), dtype=torch.float64, device=dev)
+            _lib.check(L.wwzb200_surrogates_block_dev(d_ts.data_ptr(), n, tau_est, sig, mu, S_loc, s0,
+                                                      int(seed) & 0xFFFFFFFFFFFFFFFF, flags & _lib.UAR1, d_Y.data_ptr(), st))
+            if int(own.value) == S_pad:
+                tgt = d_amp
+            else:                                           # a short last block pads to fewer columns: its own buffer
+                tgt = torch.empty((ncell, int(own.value)), dtype=torch.float64, device=dev)
+            fl = flags | (_lib.PREPARED if prepared.value else 0)
+            _lib.check(L.wwzb200_shared_axis_cells_dev(d_ts.data_ptr(), d_Y.data_ptr(), n, S_loc, d_tau.data_ptr(), nt,
+                                                       d_om.data_ptr(), nf, float(c), int(Neff_threshold), fl,
+                                                       d_ne.data_ptr(), tgt.data_ptr(), st))
+            if tgt is not d_amp:
+                d_amp[:ncell, :S_loc] = tgt[:, :S_loc]
+        # every rank gets all surrogates of its block of cells: recv[r] = rank r's surrogates of my cells
+        recv = torch.empty((world, cells_per, S_pad), dtype=torch.float64, device=dev)
+        dist.all_to_all_single(recv.view(-1), d_amp.view(-1), group=group)
+        _lib.check(L.wwzb200_quantiles_segments_dev(recv.data_ptr(), number, per, cells_per * S_pad, S_pad, cells_per,
+                                                    d_probs.data_ptr(), nq, d_q.data_ptr(), st))
     qall = torch.empty((world, nq, cells_per), dtype=torch.float64, device=dev)
     dist.all_gather_into_tensor(qall.view(-1), d_q.view(-1), group=group)
     q = qall.permute(1, 0, 2).reshape(nq, world * cells_per)[:, :ncell].reshape(nq, nt, nf)

@@ -362,6 +362,31 @@ def test_surrogate_blocks_reassemble_the_fused_test():
     assert max_rel(q, sg.amplitude_qs) < 1e-12 and max_rel(ne.cpu().numpy(), sg.Neffs) < 1e-13
 
 
+def test_config3_full_grid_surrogates_against_the_oracle():
+    """Surrogates of config 3 (n = 5,000, default 50 x 501 grid) through the path the 10,000-surrogate test takes --
+    64-series tiles, stored weight fragments, DMMA contraction -- checked DIRECTLY against the oracle on the full grid:
+    320 surrogates are transformed in one batch (5 series blocks: the stored-weights mode), 8 of them, from every
+    block and both ends of a block, are compared cell for cell (25,050 cells each)."""
+    O = oracle()
+    t, y, tau, freq = synth.config_grid("C3")
+    ys_cut, ts_cut, freq_c, tau_c = WV.prepare_wwz(y, t, tau=tau, freq=freq)
+    Y = B.ar1_surrogates(ts_cut, B.tau_estimation(ys_cut, ts_cut), sigma=np.std(ys_cut), mu=np.mean(ys_cut),
+                         number=320, seed=5)
+    r = B.wwz_shared_axis(Y, ts_cut, tau_c, freq_c, outputs=("amplitude", "phase"))
+    worst = 0.0
+    for s in (0, 63, 64, 130, 191, 200, 256, 319):
+        o = O.kirchner(Y[s], ts_cut, freq_c, tau_c, standardize=True)
+        assert_same_nan_mask(r.amplitude[s], o[0], "surrogate %d" % s)
+        assert max_rel(r.Neffs, o[2]) < 1e-12
+        e = max_rel(r.amplitude[s], o[0])
+        worst = max(worst, e)
+        assert e < 1e-9, "surrogate %d amplitude" % s
+        d = np.abs(r.phase[s] - o[1])
+        m = ~np.isnan(d)
+        assert np.max(np.minimum(d[m], 2 * np.pi - d[m])) < 1e-9
+    print("config 3, 8 full-grid surrogates (stored-weights DMMA path) vs the oracle: worst amplitude error %.2e" % worst)
+
+
 def test_config3_size_significance_test():
     """Config 3 at full size: 10,000 AR(1) surrogates of an n=5,000 series on the default 50 x 501 grid, fused on
     the device.  Size-independent properties: quantiles ordered, mask equal to the target's, reproducible for a

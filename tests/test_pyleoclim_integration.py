@@ -63,7 +63,7 @@ def cuda_standins(monkeypatch, pyleo):
                psd=False, psd_c=None, psd_Neff_threshold=3, **kw):
         calls["signif"] += 1
         calls["signif_method"] = kw.get("method", "ar1sim")
-        rng = np.random.RandomState(seed)
+        rng = np.random.RandomState(seed % (2 ** 32))
         tau_est = O.tau_estimation(ys, ts)
         Y = np.stack([O.ar1_model(ts, tau_est, output_sigma=np.std(ys), rng=rng) + np.mean(ys) for _ in range(number)])
         r = shared(Y, ts, tau, freq, c=c, Neff_threshold=Neff_threshold, psd_Neff_threshold=psd_Neff_threshold if psd else None)
