@@ -276,6 +276,9 @@ def run_ours(args):
     dev = torch.device("cuda", torch.cuda.current_device())
     _lib.set_device(dev.index)
     L = _lib.lib()
+    from pyleoclim_util_b200 import distributed as _D
+    # (N > 1 only: at N = 1 the CPU baseline of this process uses all host cores)
+    numa_cpus = _D.bind_to_gpu_numa_node(dev.index) if world > 1 else None   # before the first page-locked allocation
 
     t, ys, tau_all, freq, omega = workload(world)
     n, nf = t.size, freq.size
@@ -729,6 +732,8 @@ def run_ours(args):
                              "PCIe link into one page-locked shared-memory buffer that rank 0 returns; psd all-reduced"),
                     "c_abi_ms_per_step": 1e3 * cabi_s / args.steps,
                     "c_abi_path": "wwzb200_kirchner + wwzb200_kirchner_psd on pre-allocated pinned host buffers"},
+            "host_binding": ("rank pinned to the %d CPUs next to its GPU (sysfs local_cpulist)" % len(numa_cpus)) if numa_cpus
+                            else "no CPU binding",
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
             "signif_test": signif, "config5": c5, "ensemble": ensemble, "parity": parity,
             "wall_ms_per_step_incl_l2_flush": 1e3 * wall / args.steps, "extras": extras,

@@ -83,6 +83,37 @@ def all_gather_rows(local, counts, group=None):
     return np.concatenate([out[r, : counts[r]] for r in range(world)], axis=0)
 
 
+def bind_to_gpu_numa_node(device_index=None):
+    """Pin this process to the CPUs next to its GPU (the PCI device's `local_cpulist` in sysfs), so that page-locked
+    result buffers are allocated on -- and the GPU's DMA writes go to -- the memory of the GPU's own socket.  torchrun
+    does not bind its workers; with eight ranks moving results to the host at once the difference is the aggregate
+    host-side bandwidth.  Returns the CPU set, or None when the topology cannot be read (or WWZB200_NO_NUMA_BIND)."""
+    import os
+    if os.environ.get("WWZB200_NO_NUMA_BIND"):
+        return None
+    try:
+        import torch
+        i = torch.cuda.current_device() if device_index is None else int(device_index)
+        pr = torch.cuda.get_device_properties(i)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/local_cpulist" % bdf) as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return None
+
+
 def _shm_class():
     from multiprocessing import shared_memory
 
@@ -150,6 +181,12 @@ class _SharedHostSegments:
                 pass
         addr = ctypes.addressof(ctypes.c_char.from_buffer(shm.buf))
         if register:
+            # first touch: every rank faults in its share of the pages from the CPUs next to its GPU, so the segment is
+            # spread over the sockets of the box instead of sitting on the node of whoever page-locks it first
+            world = dist.get_world_size(group)
+            lo, hi = rank * size // world, (rank + 1) * size // world
+            ctypes.memset(addr + lo, 0, hi - lo)
+            dist.barrier(group=group)
             _lib.check(_lib.lib().wwzb200_host_register(addr, size))
         dist.barrier(group=group)    # every rank has mapped the segment before anybody uses it
         return dict(shm=shm, nbytes=size, addr=addr, free=True)
@@ -160,6 +197,7 @@ class _SharedHostSegments:
         dist = _dist()
         rank = dist.get_rank(group)
         if self.ctrl is None:
+            bind_to_gpu_numa_node()
             c = self._create(self.CTRL_WORDS * 8, group, register=False)
             self.ctrl_seg = c
             self.ctrl = np.ndarray((self.CTRL_WORDS,), dtype=np.int64, buffer=c["shm"].buf)

@@ -471,6 +471,6 @@ def test_config5_stratified_cells_against_the_oracle():
     low = ref["amplitude"] <= np.nanpercentile(ref["amplitude"], 2)
     low_err = max_rel(np.where(low, got["amplitude"], np.nan), np.where(low, ref["amplitude"], np.nan))
     print("config 5, %d stratified cells vs the oracle: amplitude %.2e rel (lowest-amplitude 2%%: %.2e), phase %.2e rad, "
-          "%d masked" % (ref["amplitude"].size, amp_err, low_err, int((~m).sum())))
+          "%d masked" % (ref["amplitude"].size, amp_err, low_err, ph_err, int((~m).sum())))
     assert low_err < 1e-9
 
