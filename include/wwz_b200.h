@@ -204,6 +204,18 @@ int wwzb200_ar1_signif(const double *ts, int64_t nts, double tau_est, double sig
                        double c, int64_t Neff_threshold, int64_t psd_Neff_threshold, uint32_t flags,
                        const double *probs, int64_t nq, double *Neffs, double *q_wwa, double *q_psd);
 
+/* (7) Wavelet transform coherency of S pairs of WWZ coefficient sets on one (tau, f) grid -- utils/wavelet.py:2240-2364
+ * (wtc) and :2201-2238 (xwt), what wwz_coherence (:1667-1672) computes for one pair and Coherence.signif_test
+ * (core/coherences.py:748-963) for every surrogate pair.  a1, a2: coefficients of the first series, b1, b2 of the
+ * second, each [S][nt][nf] (coeff = a1 - i a2, :1664-1665); freq [nf] (scale = 1/freq); dt_tau = median(diff(tau));
+ * smooth_factor as the reference's (0.25); boxcar = int(round(0.6 / dj * 2)) with dj = log2(scale[0]/scale[-1]) / nf
+ * (:2346-2349, >= 1).  Outputs [S][nt][nf]: xw_coherence (required), xw_phase and xw_amplitude (optional).  The
+ * Gaussian smoothing in time is evaluated as the circular convolution over npad = 2^ceil(log2 nt) points that the
+ * reference's FFT / multiply / inverse FFT computes; NaN cells propagate as they do there. */
+int wwzb200_wtc(const double *a1, const double *a2, const double *b1, const double *b2, int64_t S, int64_t nt, int64_t nf,
+                const double *freq, double dt_tau, double smooth_factor, int64_t boxcar, double *xw_coherence,
+                double *xw_phase, double *xw_amplitude);
+
 /* ---- device-pointer entry points (inputs/outputs resident in HBM; async on `stream`) ---- */
 /* (4b) on device-resident members: same layouts as wwzb200_kirchner_members, all M members in one group. */
 int wwzb200_kirchner_members_dev(const double *d_ts, const double *d_pd_ys, int64_t ys_stride, int64_t M, int64_t nts,
@@ -211,6 +223,10 @@ int wwzb200_kirchner_members_dev(const double *d_ts, const double *d_pd_ys, int6
                                  int64_t Neff_threshold, int64_t psd_Neff_threshold, uint32_t flags, double *d_Neffs,
                                  double *d_a0, double *d_a1, double *d_a2, double *d_wwa, double *d_phase, double *d_psd,
                                  double *d_mu_sig, void *stream);
+
+int wwzb200_wtc_dev(const double *d_a1, const double *d_a2, const double *d_b1, const double *d_b2, int64_t S, int64_t nt,
+                    int64_t nf, const double *d_freq, double dt_tau, double smooth_factor, int64_t boxcar,
+                    double *d_xw_coherence, double *d_xw_phase, double *d_xw_amplitude, void *stream);
 
 int wwzb200_kirchner_dev(const double *d_ts, const double *d_pd_ys, int64_t nts, const double *d_taus,
                          int64_t nt, const double *d_omegas, int64_t nf, double c,

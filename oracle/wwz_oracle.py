@@ -429,3 +429,70 @@ def philox_normals(seed, series, n):
     z0, z1 = rad * np.cos(2 * np.pi * u2), rad * np.sin(2 * np.pi * u2)
     i = np.arange(n)
     return np.where(i % 2 == 0, z0[i // 2], z1[i // 2])
+
+
+# ------------------------------------------------------------------------------------------------
+# wavelet coherence
+# ------------------------------------------------------------------------------------------------
+def xwt(coeff1, coeff2):
+    """utils/wavelet.py:2201-2238: cross wavelet transform, its amplitude and phase."""
+    prod = coeff1 * np.conj(coeff2)                                                       # :2229
+    return prod, np.sqrt(prod.real ** 2 + prod.imag ** 2), np.arctan2(prod.imag, prod.real)   # :2230-2231
+
+
+def boxcar_length(scales):
+    """Length of the scale-smoothing window of wtc: dj = log2(scales[0] / scales[-1]) / N (utils/wavelet.py:2346-2349),
+    window int(round(0.6 / dj * 2)) (:2331-2332)."""
+    dj = np.log2(scales[0] / scales[-1]) / np.size(scales)
+    return int(np.round(0.6 / dj * 2))
+
+
+def _smooth(coeff, snorm, length, smooth_factor):
+    """The `smoothing` closure of wtc (utils/wavelet.py:2288-2338): Gaussian in time through an FFT of the
+    zero-padded rows, then a normalised boxcar over the scales."""
+    from scipy import fft, signal
+    rows = coeff.transpose()                                                              # :2313 [scale, time]
+    n = rows.shape[1]
+    npad = int(2 ** np.ceil(np.log2(n)))                                                  # :2310
+    k2 = (2 * np.pi * fft.fftfreq(npad)) ** 2                                             # :2317-2318
+    gauss = np.exp(-smooth_factor * (snorm[:, np.newaxis] ** 2) * k2)                     # :2323
+    sm = fft.ifft(gauss * fft.fft(rows, axis=1, n=npad), axis=1, n=npad)[:, :n]           # :2324-2327
+    if np.isreal(rows).all():                                                             # :2328-2329
+        sm = sm.real
+    win = np.zeros(length)                                                                # rect(), :2265-2286
+    win[0] = win[-1] = 0.5
+    win[1:-1] = 1
+    win /= win.sum()
+    return signal.convolve2d(sm, win[:, np.newaxis], "same").transpose()                  # :2334-2336
+
+
+def wtc(coeff1, coeff2, scales, tau, smooth_factor=0.25):
+    """utils/wavelet.py:2240-2364: wavelet transform coherency and its phase."""
+    cross = coeff1 * np.conj(coeff2)                                                      # :2340
+    p1, p2 = np.abs(coeff1) ** 2, np.abs(coeff2) ** 2                                     # :2341-2342
+    snorm = scales / np.median(np.diff(tau))                                              # :2344-2345
+    length = boxcar_length(scales)
+    s12 = _smooth(cross / scales, snorm, length, smooth_factor)                           # :2350
+    s1 = _smooth(p1 / scales, snorm, length, smooth_factor)                               # :2351
+    s2 = _smooth(p2 / scales, snorm, length, smooth_factor)                               # :2352
+    coherence = np.abs(s12) ** 2 / (s1 * s2)                                              # :2355
+    return coherence, np.angle(s12 / (np.sqrt(s1) * np.sqrt(s2)))                         # :2356-2357
+
+
+def wwz_coherence(y1, t1, y2, t2, smooth_factor=0.25, tau=None, freq=None, c=1 / (8 * np.pi ** 2), Neff_threshold=3,
+                  standardize=True):
+    """utils/wavelet.py:1660-1687 for the truncated series and the common grid that :1621-1658 arrive at (that part is
+    the caller's business here): two transforms through wwz -- whose own prepare_wwz may repair tau per series --,
+    coeff = a1 - i a2 (:1664-1665), then wtc, xwt and coi on the COMMON tau."""
+    r1 = wwz(y1, t1, tau=tau, freq=freq, c=c, Neff_threshold=Neff_threshold, standardize=standardize)
+    r2 = wwz(y2, t2, tau=tau, freq=freq, c=c, Neff_threshold=Neff_threshold, standardize=standardize)
+    c1 = r1.coeff[1] - r1.coeff[2] * 1j
+    c2 = r2.coeff[1] - r2.coeff[2] * 1j
+    freq = np.asarray(freq, dtype=float)
+    tau = np.asarray(tau, dtype=float)
+    coh, ph = wtc(c1, c2, 1 / freq, tau, smooth_factor=smooth_factor)                     # :1669-1670
+    prod, amp, _ = xwt(c1, c2)
+    Res = collections.namedtuple("CoherenceResults", ["xw_coherence", "xw_amplitude", "xw_phase", "xwt", "freq", "time",
+                                                      "coi", "scale"])
+    return Res(xw_coherence=coh, xw_amplitude=amp, xw_phase=ph, xwt=prod, freq=freq, time=tau,
+               coi=make_coi(tau, Neff_threshold=Neff_threshold), scale=1 / freq)

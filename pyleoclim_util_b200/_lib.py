@@ -90,6 +90,8 @@ _SIGS = {
     "wwzb200_ipc_open": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(_vp)]),
     "wwzb200_ipc_close": (ctypes.c_int, [_vp]),
     "wwzb200_ipc_free": (ctypes.c_int, [_vp]),
+    "wwzb200_wtc": (ctypes.c_int, [_dp, _dp, _dp, _dp, _i64, _i64, _i64, _dp, _dbl, _dbl, _i64, _dp, _dp, _dp]),
+    "wwzb200_wtc_dev": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _dbl, _dbl, _i64, _vp, _vp, _vp, _vp]),
     "wwzb200_quantiles_segments_dev": (ctypes.c_int, [_vp, _i64, _i64, _i64, _i64, _i64, _vp, _i64, _vp, _vp]),
     "wwzb200_measure_fp64_peak": (ctypes.c_int, [_dp, _dp]),
     "wwzb200_launch_count": (_i64, []),

@@ -11,7 +11,8 @@ from . import wavelet as _wv
 
 __all__ = ["tau_estimation", "ar1_surrogates", "ar1_sim", "n_ll_unevenly_spaced_ar1", "uar1_fit", "uar1_surrogates",
            "uar1_sim", "wwz_shared_axis", "wwz_ragged", "wwz_members", "quantiles",
-           "wwz_signif", "signif_prepared", "SharedAxisResults", "SignifResults"]
+           "wwz_signif", "signif_prepared", "coherence_signif", "SharedAxisResults", "SignifResults",
+           "CoherenceSignifResults"]
 
 SharedAxisResults = collections.namedtuple(
     "SharedAxisResults", ["amplitude", "Neffs", "phase", "coeff", "psd", "freq", "time", "coi", "scale"])
@@ -364,3 +365,76 @@ def signif_prepared(ys_cut, ts_cut, tau, freq, number, probs, seed=0, c=1 / (8 *
         _lib.ptr(tau), nt, _lib.ptr(omega), nf, float(c), int(Neff_threshold), int(psd_Neff_threshold), int(flags),
         _lib.ptr(probs), probs.size, _lib.ptr(Neffs), _lib.ptr(q_wwa), _lib.ptr(q_psd)))
     return q_wwa, q_psd, Neffs
+
+
+CoherenceSignifResults = collections.namedtuple("CoherenceSignifResults", ["qs", "wtc_qs", "xwt_qs", "freq", "time", "coi"])
+
+
+def coherence_signif(y1, t1, y2, t2, tau=None, freq=None, number=200, qs=(0.95,), seed=0, smooth_factor=0.25,
+                     c=1 / (8 * np.pi ** 2), Neff_threshold=3, method="ar1sim", freq_method="log", freq_kwargs=None):
+    """Significance levels of a WWZ wavelet coherence from AR(1) surrogate PAIRS, everything between the two time axes
+    and the quantiles on the device.
+
+    Follows Coherence.signif_test (core/coherences.py:748-963): `number` surrogates of each series on its own time
+    axis (core/surrogateseries.py:90-181), for every pair the wavelet coherence of core/series.py:3586-3800 ->
+    utils/wavelet.py:1497-1687 on the grid of the original analysis, then per-cell ``mquantiles`` of the coherence
+    (wtc) and of the cross-wavelet amplitude (xwt) over the pairs.  Where the reference runs one process-pool task per
+    pair, here the surrogates of a series are ONE shared-axis batch (coefficients a1, a2 kept on the device), the
+    coherency smoothing of all pairs is one launch sequence (``wwzb200_wtc_dev``) and only the [nq, ntau, nf]
+    quantiles return.  The two surrogate sets draw from independent Philox streams (seed, seed + 1).
+    Device memory: about 10 x number x ntau x nf doubles."""
+    import ctypes
+    import torch
+    (y1c, t1c, tau1), (y2c, t2c, tau2), tau, freq = _wv.coherence_inputs(
+        np.asarray(y1, dtype=float), np.asarray(t1, dtype=float), np.asarray(y2, dtype=float), np.asarray(t2, dtype=float),
+        tau=tau, freq=freq, freq_method=freq_method, freq_kwargs=freq_kwargs)
+    _wv.assertPositiveInt(Neff_threshold)
+    L_box = _wv.wtc_boxcar_length(freq)
+    if L_box < 1:
+        raise IndexError("the scale-smoothing window of wtc is empty for this frequency axis")
+    S, nt, nf = int(number), tau.size, freq.size
+    ncell = nt * nf
+    probs = _lib.f64(np.atleast_1d(qs))
+    nq = probs.size
+    L = _lib.lib()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    st = torch.cuda.current_stream().cuda_stream
+    up = lambda x: torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64)).to(dev)
+    d_freq, d_probs = up(freq), up(probs)
+    coeff = []
+    for k, (yc, tc, tau_k) in enumerate(((y1c, t1c, tau1), (y2c, t2c, tau2))):
+        d_tau = up(tau_k)               # each series on its own prepared tau (see wavelet.coherence_inputs)
+        mu = float(np.mean(yc))                                          # core/surrogateseries.py:137-139
+        flags = _lib.STANDARDIZE
+        if method == "ar1sim":
+            sig, tau_est = float(np.std(yc)), float(tau_estimation(yc, tc))
+        elif method == "uar1":
+            tau_est, sig = (float(v) for v in uar1_fit(yc, tc))
+            flags |= _lib.UAR1
+        else:
+            raise ValueError("surrogate method must be 'ar1sim' or 'uar1'")
+        d_ts, d_om = up(tc), up(_wv.make_omega(tc, freq))
+        d_Y = torch.empty((S, tc.size), dtype=torch.float64, device=dev)
+        _lib.check(L.wwzb200_surrogates_block_dev(d_ts.data_ptr(), tc.size, tau_est, sig, mu, S, 0,
+                                                  (int(seed) + k) & 0xFFFFFFFFFFFFFFFF, flags & _lib.UAR1, d_Y.data_ptr(), st))
+        d_a1 = torch.empty((S, nt, nf), dtype=torch.float64, device=dev)
+        d_a2 = torch.empty((S, nt, nf), dtype=torch.float64, device=dev)
+        d_ne = torch.empty((nt, nf), dtype=torch.float64, device=dev)
+        _lib.check(L.wwzb200_kirchner_shared_axis_dev(d_ts.data_ptr(), d_Y.data_ptr(), tc.size, S, d_tau.data_ptr(), nt,
+                                                      d_om.data_ptr(), nf, float(c), int(Neff_threshold), 0,
+                                                      flags & ~_lib.UAR1, d_ne.data_ptr(), None, None, None, d_a1.data_ptr(),
+                                                      d_a2.data_ptr(), None, st))
+        coeff.append((d_a1, d_a2))
+        del d_Y
+    d_coh = torch.empty((S, nt, nf), dtype=torch.float64, device=dev)
+    d_xwa = torch.empty((S, nt, nf), dtype=torch.float64, device=dev)
+    _lib.check(L.wwzb200_wtc_dev(coeff[0][0].data_ptr(), coeff[0][1].data_ptr(), coeff[1][0].data_ptr(), coeff[1][1].data_ptr(),
+                                 S, nt, nf, d_freq.data_ptr(), float(np.median(np.diff(tau))), float(smooth_factor), L_box,
+                                 d_coh.data_ptr(), None, d_xwa.data_ptr(), st))
+    del coeff
+    d_q = torch.empty((2, nq, ncell), dtype=torch.float64, device=dev)
+    _lib.check(L.wwzb200_quantiles_dev(d_coh.data_ptr(), S, ncell, d_probs.data_ptr(), nq, d_q[0].data_ptr(), st))
+    _lib.check(L.wwzb200_quantiles_dev(d_xwa.data_ptr(), S, ncell, d_probs.data_ptr(), nq, d_q[1].data_ptr(), st))
+    q = d_q.cpu().numpy().reshape(2, nq, nt, nf)
+    return CoherenceSignifResults(qs=probs, wtc_qs=q[0], xwt_qs=q[1], freq=freq, time=tau,
+                                  coi=_wv.make_coi(tau, Neff_threshold=Neff_threshold))

@@ -1537,6 +1537,73 @@ int wwzb200_ar1_signif(const double *ts, int64_t nts, double tau_est, double sig
     return 0;
 }
 
+static int check_wtc_args(const void *a1, const void *a2, const void *b1, const void *b2, int64_t S, int64_t nt, int64_t nf,
+                          const void *freq, double dt_tau, double smooth, int64_t boxcar, const void *coh, int *npad)
+{
+    if (S < 0 || nt < 1 || nf < 1) return fail(WWZB200_ERR_ARG, "bad sizes");
+    if (S && (!a1 || !a2 || !b1 || !b2 || !freq || !coh)) return fail(WWZB200_ERR_ARG, "null pointer");
+    if (!(dt_tau > 0) || !(smooth >= 0)) return fail(WWZB200_ERR_ARG, "dt_tau must be positive, smooth_factor non-negative");
+    if (boxcar < 1) return fail(WWZB200_ERR_ARG, "boxcar length must be >= 1 (the reference's rect() needs int(round(0.6/dj*2)) >= 1)");
+    int p = 1;
+    while (p < nt) p <<= 1;                 // int(2 ** ceil(log2(ntau))), utils/wavelet.py:2310
+    if (p > (1 << 20)) return fail(WWZB200_ERR_ARG, "tau axis too long");
+    *npad = p;
+    return 0;
+}
+
+int wwzb200_wtc_dev(const double *d_a1, const double *d_a2, const double *d_b1, const double *d_b2, int64_t S, int64_t nt,
+                    int64_t nf, const double *d_freq, double dt_tau, double smooth_factor, int64_t boxcar, double *d_coh,
+                    double *d_phase, double *d_xw_amplitude, void *stream)
+{
+    int npad = 0;
+    int rc = check_wtc_args(d_a1, d_a2, d_b1, d_b2, S, nt, nf, d_freq, dt_tau, smooth_factor, boxcar, d_coh, &npad);
+    if (rc || S == 0) return rc;
+    std::lock_guard<std::mutex> lock(g_mu);
+    Workspace *w;
+    if ((rc = workspace(&w))) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    ScratchScope scope(w, st);
+    if ((rc = scope.begin())) return rc;
+    double *d_g, *d_T;
+    if ((rc = wsbuf(w, "wtc_g", (size_t)npad * (size_t)nf, &d_g))) return rc;
+    if ((rc = wsbuf(w, "wtc_T", (size_t)S * 4 * (size_t)nt * (size_t)nf, &d_T))) return rc;
+    CU(wwz::launch_wtc(d_a1, d_a2, d_b1, d_b2, S, nt, nf, d_freq, dt_tau, smooth_factor, npad, (int)boxcar, d_g, d_T, d_coh,
+                       d_phase, d_xw_amplitude, st));
+    return 0;
+}
+
+int wwzb200_wtc(const double *a1, const double *a2, const double *b1, const double *b2, int64_t S, int64_t nt, int64_t nf,
+                const double *freq, double dt_tau, double smooth_factor, int64_t boxcar, double *coh, double *phase,
+                double *xw_amplitude)
+{
+    int npad = 0;
+    int rc = check_wtc_args(a1, a2, b1, b2, S, nt, nf, freq, dt_tau, smooth_factor, boxcar, coh, &npad);
+    if (rc || S == 0) return rc;
+    std::lock_guard<std::mutex> lock(g_mu);
+    Workspace *w;
+    if ((rc = workspace(&w))) return rc;
+    cudaStream_t st = w->stream;
+    ScratchScope scope(w, st);
+    if ((rc = scope.begin())) return rc;
+    const size_t cnt = (size_t)S * (size_t)nt * (size_t)nf;
+    double *d_io, *d_g, *d_T;
+    if ((rc = wsbuf(w, "wtc_io", 7 * cnt + (size_t)nf, &d_io))) return rc;
+    if ((rc = wsbuf(w, "wtc_g", (size_t)npad * (size_t)nf, &d_g))) return rc;
+    if ((rc = wsbuf(w, "wtc_T", 4 * cnt, &d_T))) return rc;
+    double *d_in[4] = {d_io, d_io + cnt, d_io + 2 * cnt, d_io + 3 * cnt};
+    double *d_coh = d_io + 4 * cnt, *d_ph = d_io + 5 * cnt, *d_xa = d_io + 6 * cnt, *d_freq = d_io + 7 * cnt;
+    const double *h_in[4] = {a1, a2, b1, b2};
+    for (int i = 0; i < 4; ++i) CU(cudaMemcpyAsync(d_in[i], h_in[i], sizeof(double) * cnt, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_freq, freq, sizeof(double) * nf, cudaMemcpyHostToDevice, st));
+    CU(wwz::launch_wtc(d_in[0], d_in[1], d_in[2], d_in[3], S, nt, nf, d_freq, dt_tau, smooth_factor, npad, (int)boxcar, d_g,
+                       d_T, d_coh, phase ? d_ph : nullptr, xw_amplitude ? d_xa : nullptr, st));
+    CU(cudaMemcpyAsync(coh, d_coh, sizeof(double) * cnt, cudaMemcpyDeviceToHost, st));
+    if (phase) CU(cudaMemcpyAsync(phase, d_ph, sizeof(double) * cnt, cudaMemcpyDeviceToHost, st));
+    if (xw_amplitude) CU(cudaMemcpyAsync(xw_amplitude, d_xa, sizeof(double) * cnt, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return 0;
+}
+
 int wwzb200_measure_fp64_peak(double *tflops, double *ms)
 {
     if (!tflops || !ms) return fail(WWZB200_ERR_ARG, "null pointer");

@@ -215,6 +215,12 @@ cudaError_t launch_quantiles(const double *d_X, int64_t S, int64_t stride, int64
                              int64_t nq, double *d_q, unsigned long long *d_scratch, int64_t scratch_ctas, int sms,
                              cudaStream_t st, int64_t seg_len = 0, int64_t seg_stride = 0);
 
+// Wavelet transform coherency of coefficient pairs (wwz_coherence.cu): coefficients and outputs [S][nt][nf];
+// d_g [npad][nf] and d_T [S][4][nt][nf] are scratch; L = boxcar length over the scale axis (>= 1).
+cudaError_t launch_wtc(const double *d_a1, const double *d_a2, const double *d_b1, const double *d_b2, int64_t S, int64_t nt,
+                       int64_t nf, const double *d_freq, double dt_tau, double smooth, int npad, int L, double *d_g,
+                       double *d_T, double *d_coh, double *d_phase, double *d_xwa, cudaStream_t st);
+
 // FP64 FMA peak microbenchmark.
 cudaError_t run_fp64_peak(double *tflops, double *ms);
 

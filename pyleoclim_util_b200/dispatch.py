@@ -142,8 +142,9 @@ def _patch_core(pyleo, wavemod):
     Scal = core.scalograms.Scalogram
     MPSD = core.psds.MultiplePSD
     PSD = core.psds.PSD
+    Coh = core.coherences.Coherence
     orig = dict(ms_wavelet=MS.wavelet, ms_spectral=MS.spectral, mscal_q=MScal.quantiles, mpsd_q=MPSD.quantiles,
-                scal_signif=Scal.signif_test, psd_signif=PSD.signif_test)
+                scal_signif=Scal.signif_test, psd_signif=PSD.signif_test, coh_signif=Coh.signif_test)
 
     @functools.wraps(orig["ms_wavelet"])
     def ms_wavelet(self, method="cwt", settings={}, freq=None, freq_kwargs=None, verbose=False, mute_pbar=False):
@@ -309,14 +310,48 @@ def _patch_core(pyleo, wavemod):
         new.signif_method = method
         return new
 
+    @functools.wraps(orig["coh_signif"])
+    def coh_signif_test(self, number=200, method="ar1sim", seed=None, qs=[0.95], settings=None, mute_pbar=False):
+        """core/coherences.py:748-963 with the surrogate pairs as two shared-axis batches and the coherency smoothing
+        of all pairs on the device (batch.coherence_signif); every other case takes the reference's own path."""
+        args = getattr(self, "wave_args", None)
+        ok = (self.wave_method == "wwz" and isinstance(args, dict) and _fusable(self.timeseries1, args, method)
+              and _fusable(self.timeseries2, args, method) and "tau" in args and "freq" in args and not settings)
+        if not ok:
+            return orig["coh_signif"](self, number=number, method=method, seed=seed, qs=qs, settings=settings,
+                                      mute_pbar=mute_pbar)
+        if number == 0:
+            return self                                                # :872-873
+        from . import batch
+        ts1, ts2 = self.timeseries1, self.timeseries2
+        sg = batch.coherence_signif(ts1.value, ts1.time, ts2.value, ts2.time, tau=np.asarray(args["tau"], dtype=float),
+                                    freq=np.asarray(args["freq"], dtype=float), number=number, qs=qs,
+                                    seed=_fresh_seed() if seed is None else seed,
+                                    smooth_factor=args.get("smooth_factor", 0.25), c=args.get("c", 1 / (8 * np.pi ** 2)),
+                                    Neff_threshold=args.get("Neff_threshold", 3), method=method)
+        new = self.copy()
+
+        def levels(q):
+            return MScal(scalogram_list=[
+                Scal(frequency=self.frequency, time=self.time, amplitude=q[i], coi=self.coi, scale=self.scale,
+                     freq_method=self.freq_method, freq_kwargs=self.freq_kwargs, label=f"{qs[i]*100:g}%")
+                for i in range(len(qs))])
+
+        new.signif_qs = [levels(sg.wtc_qs), levels(sg.xwt_qs)]          # :944-951: WTC quantiles, then XWT quantiles
+        new.signif_method = method
+        new.qs = qs
+        return new
+
     MS.wavelet, MS.spectral = ms_wavelet, ms_spectral
     MScal.quantiles, MPSD.quantiles = mscal_quantiles, mpsd_quantiles
     Scal.signif_test, PSD.signif_test = scal_signif_test, psd_signif_test
+    Coh.signif_test = coh_signif_test
 
     def undo():
         MS.wavelet, MS.spectral = orig["ms_wavelet"], orig["ms_spectral"]
         MScal.quantiles, MPSD.quantiles = orig["mscal_q"], orig["mpsd_q"]
         Scal.signif_test, PSD.signif_test = orig["scal_signif"], orig["psd_signif"]
+        Coh.signif_test = orig["coh_signif"]
 
     return undo
 

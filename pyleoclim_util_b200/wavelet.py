@@ -356,3 +356,109 @@ def wwz_psd(ys, ts, freq=None, freq_method="log", freq_kwargs=None, tau=None, c=
     else:
         psd = wwa2psd(wwa, ts_cut, wwz_Neffs, freq=wwz_freq, Neff_threshold=Neff_threshold)
     return PsdResults(psd=psd, freq=freq)
+
+
+# ------------------------------------------------------------------------------------------------
+# wavelet coherence: utils/wavelet.py:1497-1687 (wwz_coherence), :2201-2364 (xwt, wtc)
+# ------------------------------------------------------------------------------------------------
+CoherenceResults = collections.namedtuple(
+    "Results", ["xw_coherence", "xw_amplitude", "xw_phase", "xwt", "freq", "time", "coi", "scale"])
+
+
+def coherence_grid(y1, t1, y2, t2, tau=None, freq=None, freq_method="log", freq_kwargs=None, verbose=False):
+    """The common (tau, freq) grid and the two truncated series of ``wwz_coherence`` (utils/wavelet.py:1621-1658):
+    default tau over the overlap of the two axes, default freq from the first axis, both series prepared on it, and
+    the two prepared grids reconciled when they differ.  Returns (y1_cut, t1_cut, y2_cut, t2_cut, tau, freq)."""
+    if tau is None:                                                      # :1621-1629
+        lb, ub = max(np.min(t1), np.min(t2)), min(np.max(t1), np.max(t2))
+        inside = t1[(t1 >= lb) & (t1 <= ub)]
+        tau = np.linspace(lb, ub, np.size(inside) // 10)
+        print(f'Setting tau={tau[:3]}...{tau[-3:]}, ntau={np.size(tau)}')
+    if freq is None:                                                     # :1631-1634
+        freq = make_freq_vector(t1, method=freq_method, **({} if freq_kwargs is None else freq_kwargs.copy()))
+        print(f'Setting freq={freq[:3]}...{freq[-3:]}, nf={np.size(freq)}')
+    y1_cut, t1_cut, freq1, tau1 = prepare_wwz(y1, t1, freq=freq, tau=tau)   # :1636-1637
+    y2_cut, t2_cut, freq2, tau2 = prepare_wwz(y2, t2, freq=freq, tau=tau)
+    if np.size(tau1) != np.size(tau2) or np.any(tau1 != tau2):            # :1639-1646
+        if verbose:
+            print('inconsistent `tau`, recalculating...')
+        tau = np.linspace(min(np.min(tau1), np.min(tau2)), max(np.max(tau1), np.max(tau2)),
+                          max(np.size(tau1), np.size(tau2)))
+    else:
+        tau = tau1
+    if np.size(freq1) != np.size(freq2) or np.any(freq1 != freq2):        # :1648-1655
+        if verbose:
+            print('inconsistent `freq`, recalculating...')
+        freq = np.linspace(min(np.min(freq1), np.min(freq2)), max(np.max(freq1), np.max(freq2)),
+                           max(np.size(freq1), np.size(freq2)))
+    else:
+        freq = freq1
+    if freq[0] == 0:
+        freq = freq[1:]                                                  # :1657-1658
+    return y1_cut, t1_cut, y2_cut, t2_cut, np.ascontiguousarray(tau, dtype=float), np.ascontiguousarray(freq, dtype=float)
+
+
+def coherence_inputs(y1, t1, y2, t2, tau=None, freq=None, freq_method="log", freq_kwargs=None, verbose=False):
+    """What the two transforms of ``wwz_coherence`` actually see.  The reference hands the truncated series and the
+    common grid to ``wwz`` (utils/wavelet.py:1660-1663), whose own ``prepare_wwz`` (:1474) runs once more on each
+    series: it may repair tau for that series (:2151-2169) and truncates the series to the tau span (:2192-2193), so
+    the two coefficient sets can sit on slightly different tau values while wtc, coi and the returned `time` use the
+    common tau.  Returns ((ys1, ts1, tau1), (ys2, ts2, tau2), tau, freq)."""
+    y1c, t1c, y2c, t2c, tau, freq = coherence_grid(y1, t1, y2, t2, tau=tau, freq=freq, freq_method=freq_method,
+                                                   freq_kwargs=freq_kwargs, verbose=verbose)
+    y1p, t1p, f1, tau1 = prepare_wwz(y1c, t1c, freq=freq, tau=tau)
+    y2p, t2p, f2, tau2 = prepare_wwz(y2c, t2c, freq=freq, tau=tau)
+    if np.size(tau1) != np.size(tau) or np.size(tau2) != np.size(tau) or np.size(f1) != np.size(freq):
+        raise ValueError("the two series do not share one (tau, freq) grid")   # the reference fails in wtc's broadcast
+    return (y1p, t1p, np.ascontiguousarray(tau1, dtype=float)), (y2p, t2p, np.ascontiguousarray(tau2, dtype=float)), tau, freq
+
+
+def wtc_boxcar_length(freq):
+    """int(round(0.6 / dj * 2)) with dj = log2(scale[0] / scale[-1]) / N, scale = 1 / freq (utils/wavelet.py:2331-2349)."""
+    scales = 1 / np.asarray(freq, dtype=float)
+    dj = np.log2(scales[0] / scales[-1]) / np.size(scales)
+    return int(np.round(0.6 / dj * 2))
+
+
+def wtc_cuda(a1_1, a2_1, a1_2, a2_2, freq, tau, smooth_factor=0.25, want_phase=True, want_amplitude=True):
+    """Wavelet transform coherency (utils/wavelet.py:2240-2364) and cross-wavelet amplitude (:2230) of coefficient
+    pairs on the device (C-ABI ``wwzb200_wtc``).  Coefficient arrays [ntau, nf] or [S, ntau, nf] (coeff = a1 - i a2)."""
+    arrs = [_lib.f64(x) for x in (a1_1, a2_1, a1_2, a2_2)]
+    shape = arrs[0].shape
+    if any(a.shape != shape for a in arrs) or len(shape) not in (2, 3):
+        raise ValueError("coefficient arrays must share the shape [ntau, nf] or [S, ntau, nf]")
+    S = 1 if len(shape) == 2 else shape[0]
+    nt, nf = shape[-2], shape[-1]
+    freq = _lib.f64(freq)
+    L = wtc_boxcar_length(freq)
+    if L < 1:
+        raise IndexError("the scale-smoothing window of wtc is empty for this frequency axis")     # rect(0) in the reference
+    coh = np.empty(shape)
+    ph = np.empty(shape) if want_phase else None
+    amp = np.empty(shape) if want_amplitude else None
+    _lib.check(_lib.lib().wwzb200_wtc(*[_lib.ptr(a) for a in arrs], S, nt, nf, _lib.ptr(freq),
+                                      float(np.median(np.diff(tau))), float(smooth_factor), L, _lib.ptr(coh), _lib.ptr(ph),
+                                      _lib.ptr(amp)))
+    return coh, ph, amp
+
+
+def wwz_coherence(y1, t1, y2, t2, smooth_factor=0.25, tau=None, freq=None, freq_method="log", freq_kwargs=None,
+                  c=1 / (8 * np.pi ** 2), Neff_threshold=3, nproc=8, detrend=False, sg_kwargs=None, verbose=False,
+                  method="Kirchner_cuda", gaussianize=False, standardize=True):
+    """``pyleoclim.utils.wavelet.wwz_coherence`` (utils/wavelet.py:1497-1687) with both transforms and the coherency
+    smoothing on the device.  Same signature and Results (xw_coherence, xw_amplitude, xw_phase, xwt, freq, time, coi,
+    scale)."""
+    if standardize:
+        warnings.warn("Standardizing the timeseries")                    # :1618-1619
+    (y1p, t1p, tau1), (y2p, t2p, tau2), tau, freq = coherence_inputs(y1, t1, y2, t2, tau=tau, freq=freq,
+                                                                     freq_method=freq_method, freq_kwargs=freq_kwargs,
+                                                                     verbose=verbose)
+    kern = get_wwz_func(nproc, method)
+    kw = dict(c=c, Neff_threshold=Neff_threshold, nproc=nproc, detrend=detrend, sg_kwargs=sg_kwargs,
+              gaussianize=gaussianize, standardize=standardize)
+    _, _, _, co1 = kern(y1p, t1p, freq, tau1, **kw)                      # :1660-1663 (each on its own prepared grid)
+    _, _, _, co2 = kern(y2p, t2p, freq, tau2, **kw)
+    coh, ph, amp = wtc_cuda(co1[1], co1[2], co2[1], co2[2], freq, tau, smooth_factor=smooth_factor)
+    prod = (co1[1] - co1[2] * 1j) * np.conj(co2[1] - co2[2] * 1j)        # :1664-1665, :2229
+    return CoherenceResults(xw_coherence=coh, xw_amplitude=amp, xw_phase=ph, xwt=prod, freq=freq, time=tau,
+                            coi=make_coi(tau, Neff_threshold=Neff_threshold), scale=1 / freq)

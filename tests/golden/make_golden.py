@@ -224,8 +224,38 @@ def cleaning():
          amplitude=ref["amplitude"], Neffs=ref["Neffs"], phase=ref["phase"])
 
 
+def coherence():
+    """wwz_coherence (utils/wavelet.py:1497-1687) of two uneven series on a common grid, and wtc / xwt (:2201-2364) of
+    their coefficients: case A with the default 50 taus (npad = 64, even boxcar), case B with 21 taus and a frequency
+    axis whose boxcar length is odd, case C whose second series has a hiatus (Neff-masked cells: NaN propagation
+    through the FFT smoothing and the boxcar)."""
+    out = {}
+    cases = {"A": (260, 240, None, 41), "B": (150, 170, 21, 23), "C": (200, 220, 30, 17)}
+    for name, (n1, n2, ntau, nf) in cases.items():
+        t1, y1 = synth.uneven_ar1(n1, 31)
+        t2, y2 = synth.uneven_ar1(n2, 32)
+        if name == "C":
+            keep = (t2 < 0.45 * t2.max()) | (t2 > 0.7 * t2.max())
+            t2, y2 = t2[keep], y2[keep]
+        lo, hi = max(t1.min(), t2.min()), min(t1.max(), t2.max())
+        tau = np.linspace(lo, hi, 50 if ntau is None else ntau)
+        freq = synth.freq_log(t1, nf)
+        r = W.wwz_coherence(y1, t1, y2, t2, tau=tau, freq=freq, nproc=1, method="Kirchner_numba")
+        # the grid the reference settled on (:1640-1657 reconcile the two prepared grids) and the coefficients the two
+        # transforms return on the truncated series (:1638-1639, :1660-1665)
+        y1c, t1c, _, _ = W.prepare_wwz(y1, t1, freq=freq, tau=tau)
+        y2c, t2c, _, _ = W.prepare_wwz(y2, t2, freq=freq, tau=tau)
+        r1 = W.wwz(y1c, t1c, tau=r.time, freq=r.freq, nproc=1, method="Kirchner_numba")
+        r2 = W.wwz(y2c, t2c, tau=r.time, freq=r.freq, nproc=1, method="Kirchner_numba")
+        for k, v in dict(t1=t1, y1=y1, t2=t2, y2=y2, tau_in=tau, tau=r.time, freq=r.freq, xw_coherence=r.xw_coherence, xw_phase=r.xw_phase,
+                         xw_amplitude=r.xw_amplitude, xwt=r.xwt, coi=r.coi, a1_1=r1.coeff[1], a2_1=r1.coeff[2],
+                         a1_2=r2.coeff[1], a2_2=r2.coeff[2]).items():
+            out[name + "_" + k] = v
+    save("coherence", **out)
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["benthic", "soi", "synth_small", "edge", "c2_subsample", "c5_sample",
-                             "surrogates", "uar1", "foster", "freq_vectors", "cleaning"]
+                             "surrogates", "uar1", "foster", "freq_vectors", "cleaning", "coherence"]
     for name in which:
         globals()[name]()

@@ -119,3 +119,34 @@ def test_class_level_timings(pyleo, cuda_standins, capsys):
     with open(os.path.join(os.path.dirname(os.path.dirname(__file__)), "gpurun_out", "class_level_timings.txt"), "w") as f:
         for k, v in out.items():
             f.write("%s: %.4f\n" % (k, v))
+
+
+def test_coherence_and_its_signif_test_on_the_device(pyleo, cuda_standins, monkeypatch):
+    """SURVEY.md 8f rank 2 through the real classes: Series.wavelet_coherence(method='wwz') with the CUDA kernel against
+    the reference's own Kirchner path, and Coherence.signif_test (core/coherences.py:748-963) taking the batched device
+    pipeline (two shared-axis batches + wwzb200_wtc_dev + device quantiles) instead of one pool task per pair."""
+    s1, s2 = T._series(pyleo, 220, 3, "a"), T._series(pyleo, 200, 4, "b")
+    calls = []
+    real = B.coherence_signif
+    monkeypatch.setattr(B, "coherence_signif", lambda *a, **k: (calls.append(k.get("number")), real(*a, **k))[1])
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        coh = s1.wavelet_coherence(s2, method="wwz", settings={"method": "Kirchner_cuda"})
+        ref = s1.wavelet_coherence(s2, method="wwz", settings={"method": "Kirchner", "nproc": 1})
+        sig = coh.signif_test(number=12, qs=[0.9, 0.95], seed=5)
+    assert_same_nan_mask(coh.wtc, ref.wtc)
+    assert max_rel(coh.wtc, ref.wtc) < 1e-8 and max_rel(coh.xwt, ref.xwt) < 1e-8
+    assert calls == [12] and sig is not coh and sig.signif_method == "ar1sim" and sig.qs == [0.9, 0.95]
+    assert len(sig.signif_qs) == 2 and all(type(m).__name__ == "MultipleScalogram" for m in sig.signif_qs)
+    for ms in sig.signif_qs:
+        assert [q.label for q in ms.scalogram_list] == ["90%", "95%"]
+        for q in ms.scalogram_list:
+            assert q.amplitude.shape == coh.wtc.shape and np.array_equal(q.time, coh.time)
+            assert np.array_equal(q.frequency, coh.frequency)
+    lo, hi = (q.amplitude for q in sig.signif_qs[0].scalogram_list)
+    m = ~np.isnan(lo)
+    assert m.any() and (hi[m] >= lo[m]).all() and (hi[m] <= 1 + 1e-12).all()
+    # anything the batched path does not cover goes to the reference's own implementation
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        assert ref.signif_test(number=0) is ref

@@ -182,3 +182,29 @@ def test_oracle_against_live_reference_if_present():
     ref = W.kirchner_basic(y, t, freq, tau, standardize=True)
     got = O.kirchner(y, t, freq, tau, standardize=True, mode=2)
     assert_scalogram_parity(as_dict(*got), as_dict(*ref), amp_rtol=1e-12, phase_atol=1e-12, what="live kirchner_basic")
+
+
+@pytest.mark.parametrize("case", ["A", "B", "C"])
+def test_coherence_restatement_vs_reference_outputs(case):
+    """the oracle's wtc / xwt / wwz_coherence (utils/wavelet.py:1497-1687, :2201-2364) against
+    outputs of the reference's own wwz_coherence -- default 50 taus with a grid the reference re-derives (A), an even
+    scale-smoothing window (B), Neff-masked cells whose NaN spreads through the smoothing (C)."""
+    g = golden("coherence")
+    G = lambda k: g[case + "_" + k]
+    c1, c2 = G("a1_1") - 1j * G("a2_1"), G("a1_2") - 1j * G("a2_2")
+    coh, ph = O.wtc(c1, c2, 1 / G("freq"), G("tau"))
+    assert np.array_equal(coh, G("xw_coherence"), equal_nan=True) and np.array_equal(ph, G("xw_phase"), equal_nan=True)
+    prod, amp, _ = O.xwt(c1, c2)
+    assert np.array_equal(amp, G("xw_amplitude"), equal_nan=True)
+    # the reference transforms the series as truncated by the FIRST prepare_wwz (on the tau it was given, :1636-1637)
+    y1c, t1c, _, _ = O.prepare_wwz(G("y1"), G("t1"), freq=G("freq"), tau=G("tau_in"))
+    y2c, t2c, _, _ = O.prepare_wwz(G("y2"), G("t2"), freq=G("freq"), tau=G("tau_in"))
+    r = O.wwz_coherence(y1c, t1c, y2c, t2c, tau=G("tau"), freq=G("freq"))
+    assert np.array_equal(np.isnan(r.xw_coherence), np.isnan(G("xw_coherence")))
+    assert max_rel(r.xw_coherence, G("xw_coherence")) < 1e-9 and max_rel(r.xw_amplitude, G("xw_amplitude")) < 1e-9
+    # the product's host-side grid logic reproduces the grid the reference settled on
+    from pyleoclim_util_b200 import wavelet as WV
+    _, _, _, _, tau, freq = WV.coherence_grid(G("y1"), G("t1"), G("y2"), G("t2"), tau=G("tau_in"), freq=G("freq"))
+    assert np.array_equal(tau, G("tau")) and np.array_equal(freq, G("freq"))
+    assert WV.wtc_boxcar_length(freq) == O.boxcar_length(1 / freq)
+
