@@ -682,8 +682,9 @@ def run_ours(args):
         "algorithmic_note": "50 flop x every (cell, point) pair of the grid / time: above the FP64 peak because the kernel shares "
                             "one exp2 pair between 8 tau-adjacent cells and never touches points whose weight is below 2^-100 "
                             "of a cell's largest; both are parity-tested cell for cell",
-        "traffic": 44.0e6, "traffic_note": "dram__bytes_read + write per launch from ncu --set full (profiles/r02_rec_kernel_ncu.txt): "
-                   "the 32 MB of basis rows once + the partial-sum slabs; FP64-pipe bound, not HBM bound",
+        "traffic": 46.0e6, "traffic_note": "dram__bytes_read + write per launch from ncu --set full (profiles/r02_rec_kernel_ncu.txt): "
+                   "33.8 MB read (the basis rows once) + 12.5 MB written (the partial-sum slabs) against 24 MB of algorithmic output; "
+                   "FP64-pipe bound, not HBM bound",
         "dense_direct_kernel": {
             "kernel": "wwz_cells_kernel<2, 8> with WWZB200_DENSE: every (cell, point) pair evaluated with its own exp2",
             "algorithmic_tflops": dense_tf, "frac_of_fp64_peak": (dense_tf / fp64_tf) if dense_tf else None,

@@ -223,11 +223,26 @@ def wwz_ragged(members, c=1 / (8 * np.pi ** 2), Neff_threshold=3, standardize=Tr
         # a point or two): one C call, every kernel launched once per group.  Shorter frequency axes are padded with NaN
         # (a NaN frequency gives a NaN column, like a frequency above Nyquist) and the padding is sliced off again.
         nf = max(nfs)
-        F = np.full((len(members), nf), np.nan)
-        for m, f in enumerate(fr_l):
-            F[m, : f.size] = f
-        out = wwz_members(np.stack(ts_l), np.stack([_lib.f64(m[0]) for m in members]), np.stack(tau_l), F, c=c,
-                          Neff_threshold=Neff_threshold, standardize=standardize,
+        M_, n_, nt_ = len(members), ts_l[0].size, tau_l[0].size
+        # packed inputs in page-locked (pooled) buffers: one concatenate per matrix (np.stack on a thousand small arrays
+        # costs more than the transform)
+        T, TAU = _lib.output_empty((M_, n_)), np.empty((M_, nt_))
+        np.concatenate(ts_l, out=T.reshape(-1))
+        np.concatenate(tau_l, out=TAU.reshape(-1))
+        if min(nfs) == nf:
+            F = np.empty((M_, nf))
+            np.concatenate(fr_l, out=F.reshape(-1))
+        else:
+            F = np.full((M_, nf), np.nan)
+            for m in range(M_):
+                F[m, : nfs[m]] = fr_l[m]
+        first = members[0][0]
+        if all(m[0] is first for m in members):
+            Yv = _lib.f64(first)                        # one value vector shared by all members (ys_stride = 0)
+        else:
+            Yv = _lib.output_empty((M_, n_))
+            np.concatenate([_lib.f64(m[0]) for m in members], out=Yv.reshape(-1))
+        out = wwz_members(T, Yv, TAU, F, c=c, Neff_threshold=Neff_threshold, standardize=standardize,
                           psd_Neff_threshold=psd_Neff_threshold, flags=flags)
         res, psds = out if psd_Neff_threshold is not None else (out, None)
         if min(nfs) != nf:

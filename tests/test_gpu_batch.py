@@ -416,3 +416,83 @@ def test_config3_size_significance_test():
     # about 5% of the target's cells exceed the 95% level of red noise of the same persistence
     frac = np.mean(target.amplitude[m] > sg.amplitude_qs[2][m])
     assert 0.0 < frac < 0.5
+
+
+def test_calls_on_different_streams_and_threads_do_not_race_on_the_scratch():
+    """the *_dev entry points share one scratch set per device.  Calls enqueued on different streams
+    are ordered on the device (each call waits for the end marker of the previous one), and the host entry points hold
+    the library lock through their final synchronisation, so concurrent Python threads get the results of serial calls."""
+    import threading
+    import torch
+    L = _lib.lib()
+    dev = torch.device("cuda", 0)
+    cases = []
+    for seed, (n, nt, nf) in enumerate([(900, 64, 40), (700, 48, 33), (1100, 80, 25)]):
+        t, y = synth.uneven_ar1(n, 50 + seed)
+        tau, freq = np.linspace(t.min(), t.max(), nt), synth.freq_log(t, nf)
+        ys, om = WV.standardize(y)[0], WV.make_omega(t, freq)
+        serial = WV.kirchner_cuda(ys, t, freq, tau)
+        cases.append((t, ys, tau, om, serial))
+    streams = [torch.cuda.Stream(device=dev) for _ in cases]
+    outs, keep = [], []
+    for (t, ys, tau, om, _), st in zip(cases, streams):       # back to back, no synchronisation in between
+        d = [torch.from_numpy(np.ascontiguousarray(v)).to(dev) for v in (t, ys, tau, om)]
+        o = torch.empty((6, tau.size, om.size), dtype=torch.float64, device=dev)
+        keep.append(d)
+        outs.append(o)
+    torch.cuda.synchronize()
+    for (t, ys, tau, om, _), st, d, o in zip(cases, streams, keep, outs):
+        _lib.check(L.wwzb200_kirchner_dev(d[0].data_ptr(), d[1].data_ptr(), t.size, d[2].data_ptr(), tau.size, d[3].data_ptr(),
+                                          om.size, 1 / (8 * np.pi ** 2), 3, 3, 0, *[o[i].data_ptr() for i in range(6)], None,
+                                          om.size, st.cuda_stream))
+    torch.cuda.synchronize()
+    for (_, _, _, _, serial), o in zip(cases, outs):
+        g = o.cpu().numpy()
+        assert np.array_equal(g[4], serial[0], equal_nan=True) and np.array_equal(g[0], serial[2], equal_nan=True)
+    # host entry points from concurrent threads
+    rng = np.random.default_rng(3)
+    X = [rng.standard_normal((300 + 40 * i, 500)) for i in range(4)]
+    want = [B.quantiles(x, [0.5, 0.95]) for x in X]
+    tt, _ = synth.uneven_ar1(400, 9)
+    want_s = [B.ar1_surrogates(tt, 4.0, number=50 + i, seed=i) for i in range(4)]
+    got, got_s = [None] * 4, [None] * 4
+
+    def work(i):
+        for _ in range(5):
+            got[i] = B.quantiles(X[i], [0.5, 0.95])
+            got_s[i] = B.ar1_surrogates(tt, 4.0, number=50 + i, seed=i)
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    [x.start() for x in th]
+    [x.join() for x in th]
+    for i in range(4):
+        assert np.array_equal(got[i], want[i], equal_nan=True) and np.array_equal(got_s[i], want_s[i])
+
+
+
+def test_member_batch_on_device_pointers():
+    """wwzb200_kirchner_members_dev (members resident in HBM, caller's stream) equals the host entry point."""
+    import torch
+    axes, y = synth.age_ensemble(350, 6)
+    T = np.stack(axes)
+    tau = np.stack([np.linspace(t.min(), t.max(), 19) for t in axes])
+    freq = np.stack([synth.freq_log(t, 21) for t in axes])
+    host = B.wwz_members(T, y, tau, freq, psd_Neff_threshold=3)
+    dev = torch.device("cuda", 0)
+    d = [torch.from_numpy(np.ascontiguousarray(v)).to(dev) for v in (T, y, tau, freq)]
+    out = torch.empty((6, 6, 19, 21), dtype=torch.float64, device=dev)
+    psd = torch.empty((6, 21), dtype=torch.float64, device=dev)
+    stats = torch.empty((6, 2), dtype=torch.float64, device=dev)
+    st = torch.cuda.Stream(device=dev)
+    torch.cuda.synchronize()
+    _lib.check(_lib.lib().wwzb200_kirchner_members_dev(
+        d[0].data_ptr(), d[1].data_ptr(), 0, 6, 350, d[2].data_ptr(), 19, d[3].data_ptr(), 21, 1 / (8 * np.pi ** 2), 3, 3,
+        _lib.STANDARDIZE | _lib.FREQ_HZ, *[out[i].data_ptr() for i in range(6)], psd.data_ptr(), stats.data_ptr(), st.cuda_stream))
+    st.synchronize()
+    g, p = out.cpu().numpy(), psd.cpu().numpy()
+    for m in range(6):
+        assert np.array_equal(g[4, m], host[0][m].amplitude, equal_nan=True)
+        assert np.array_equal(g[0, m], host[0][m].Neffs, equal_nan=True)
+        assert np.array_equal(p[m], host[1][m], equal_nan=True)
+    s = stats.cpu().numpy()
+    assert np.allclose(s[:, 0], np.mean(y)) and np.allclose(s[:, 1], np.std(y))

@@ -160,3 +160,16 @@ def test_len_bd_ghost_padding_documented_behaviour():
     assert np.array_equal(ts_cut[np.isin(ts_cut, t)], t)
     left = ys_cut[ts_cut < t[0]]
     assert left.size and np.allclose(left, (2 * y[0] - y[1:7][::-1])[-left.size:])      # odd reflection about the first sample
+
+
+def test_surrogate_blocks_are_equal_segments():
+    """distributed.surrogate_blocks: blocks of ceil(number / world), the last ranks take what is left -- every block
+    but the last non-empty one has the same length (the layout wwzb200_quantiles_segments_dev reads in place)."""
+    from pyleoclim_util_b200 import distributed as D
+    for number, world in [(10000, 8), (10, 4), (3, 8), (64, 2), (1, 1)]:
+        per, blocks = D.surrogate_blocks(number, world)
+        assert len(blocks) == world and blocks[0][0] == 0 and blocks[-1][1] == number
+        sizes = [b - a for a, b in blocks]
+        assert sum(sizes) == number and all(x == per for x in sizes[:(number - 1) // per])
+        assert all(a2 == b1 for (_, b1), (a2, _) in zip(blocks, blocks[1:]))
+

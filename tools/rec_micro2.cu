@@ -1,0 +1,64 @@
+// Developer microbenchmark (round 2): the COMPLETE loop body of the tau-recurrence kernel (exp2 pair, product tree, 56
+// accumulations, two points per iteration) from registers and a shared-memory table only -- is the instruction
+// sequence itself what caps the kernel at ~71% of the FP64 pipe, and does the register budget matter?
+#include <cstdio>
+#include <cuda_runtime.h>
+#include "../pyleoclim_util_b200/csrc/wwz_device.cuh"
+using namespace wwz;
+template <int VAR, int MINB> __global__ void __launch_bounds__(128, MINB) kfull(double* out, int iters, const double* g) {
+    __shared__ double tbl[16];
+    load_exp2_table(tbl, threadIdx.x);
+    __syncthreads();
+    constexpr int M = 8;
+    double W[M], Q[M], Ws[M], Wc[M], Wy[M], Wys[M], Wyc[M];
+    for (int r = 0; r < M; ++r) W[r] = Q[r] = Ws[r] = Wc[r] = Wy[r] = Wys[r] = Wyc[r] = g[r] * threadIdx.x;
+    const double kap = g[8], tau0 = g[9] + 0.01 * threadIdx.x, step16 = g[10];
+    double t = g[11], y = g[12], s = g[13], c = g[14];
+    const double d = g[15];
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < (VAR == 1 ? 1 : 2); ++u) {
+            t += d; s = -s; c += d; y += d;               // stand-in for the loaded point
+            const double ys = y * s, yc = y * c;
+            double w0, rho;
+            gauss_weight_ratio(kap * (t - tau0), step16, tbl, w0, rho);
+            double wv[M];
+            const double rho2 = rho * rho, rho4 = rho2 * rho2;
+            wv[0] = w0; wv[1] = w0 * rho; wv[2] = w0 * rho2; wv[3] = wv[1] * rho2;
+            wv[4] = w0 * rho4; wv[5] = wv[1] * rho4; wv[6] = wv[2] * rho4; wv[7] = wv[3] * rho4;
+#pragma unroll
+            for (int r = 0; r < M; ++r) {
+                const double w = wv[r];
+                W[r] += w; Q[r] = fma(w, w, Q[r]); Ws[r] = fma(w, s, Ws[r]); Wc[r] = fma(w, c, Wc[r]);
+                Wy[r] = fma(w, y, Wy[r]); Wys[r] = fma(w, ys, Wys[r]); Wyc[r] = fma(w, yc, Wyc[r]);
+            }
+        }
+    }
+    double res = 0; for (int r = 0; r < M; ++r) res += W[r] + Q[r] + Ws[r] + Wc[r] + Wy[r] + Wys[r] + Wyc[r];
+    if (res == 123.456) out[0] = res;
+}
+template <typename K> void run(const char* name, K kern, double* d_out, double* d_g, int bps, int pts, double fp64_per_pt) {
+    int sms; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    const int blocks = sms * bps, iters = 1 << 12;
+    cudaEvent_t t0, t1; cudaEventCreate(&t0); cudaEventCreate(&t1);
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+        cudaEventRecord(t0); kern<<<blocks, 128>>>(d_out, iters, d_g); cudaEventRecord(t1); cudaEventSynchronize(t1);
+        float t; cudaEventElapsedTime(&t, t0, t1); if (rep >= 1 && t < best) best = t;
+    }
+    const double cyc = best * 1e-3 * 1.965e9 / iters / bps / pts;     // SMSP cycles per (warp, point)
+    printf("%-40s warps/SMSP=%d  %7.3f ms  %6.1f cyc/warp-point (ideal %4.0f)  pipe %.1f%%\n", name, bps, best, cyc, 2 * fp64_per_pt,
+           100.0 * 2 * fp64_per_pt / cyc);
+}
+int main() {
+    double h[16] = {0.1, 0.2, 0.3, 0.4, 0.5, 0.6, 0.7, 0.8, 0.37, 0.0, 0.05, 0.0, 0.3, 0.6, 0.8, 1e-3};
+    double *d_g, *d_out; cudaMalloc(&d_g, sizeof h); cudaMalloc(&d_out, 8); cudaMemcpy(d_g, h, sizeof h, cudaMemcpyHostToDevice);
+    // 88 loop FP64 + 4 stand-in adds + 2 products per point
+    for (int bps : {2, 3}) {
+        if (bps <= 3) run("full body, unroll 2, 168 regs", kfull<0, 3>, d_out, d_g, bps, 2, 94);
+        if (bps <= 3) run("full body, unroll 1, 168 regs", kfull<1, 3>, d_out, d_g, bps, 1, 94);
+        if (bps <= 2) run("full body, unroll 2, 255 regs", kfull<0, 2>, d_out, d_g, bps, 2, 94);
+        if (bps <= 2) run("full body, unroll 1, 255 regs", kfull<1, 2>, d_out, d_g, bps, 1, 94);
+    }
+    return 0;
+}
