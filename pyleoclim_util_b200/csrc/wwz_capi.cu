@@ -78,8 +78,12 @@ struct Workspace {
     } prepared;
     std::string prefix;   // scratch namespace of the stream currently being enqueued on
     int sms = 0;
+    bool fuse_zeroed = false;         // counters of the fused epilogue ("tile_cnt", "blk_cnt") have been cleared
+    int64_t fuse_zeroed_tiles = 0;
     double *h_in = nullptr;   // page-locked staging of the single-series inputs
     size_t h_in_count = 0;
+    unsigned int *h_progress = nullptr;   // page-locked, mapped: progress flags of the fused epilogue + 2 summary words
+    unsigned int progress_epoch = 0;
 
     int get(const char *name, size_t bytes, void **out)
     {
@@ -108,6 +112,9 @@ struct Workspace {
         if (h_in) cudaFreeHost(h_in);
         h_in = nullptr;
         h_in_count = 0;
+        if (h_progress) cudaFreeHost(h_progress);
+        h_progress = nullptr;
+        fuse_zeroed = false;
     }
 };
 
@@ -222,10 +229,21 @@ int cells_per_lane_hint(int64_t nt, int64_t nf, int sms)
 
 // The transform on device-resident inputs.  Outputs may alias caller memory (row stride given).
 // d_psd != NULL adds the wwa2psd reduction; tspan < 0 means "take max-min of d_ts on the device".
+// Progress reports of a transform whose epilogue is fused into the recurrence kernel: the tau axis in blocks of whole
+// tiles; flag[b] (page-locked, mapped host memory) becomes `epoch` once every cell of block b is final in device memory.
+struct Progress {
+    volatile unsigned int *flag = nullptr;   // in: kMaxProgressBlocks entries
+    unsigned int epoch = 0;                  // in
+    int blocks = 0;                          // out: number of blocks in use (0: the transform does not report)
+    int64_t block_taus = 0;                  // out: taus per block
+};
+constexpr int kMaxProgressBlocks = 32;
+
 int transform_device(Workspace *w, const double *d_ts, const double *d_ys, int64_t n, const double *d_tau,
                      int64_t nt, const double *d_omega, int64_t nf, double c, int64_t thr, int64_t psd_thr,
                      uint32_t flags, double *d_neffs, double *d_a0, double *d_a1, double *d_a2, double *d_wwa,
-                     double *d_phase, double *d_psd, int64_t row_stride, double tspan, cudaStream_t st)
+                     double *d_phase, double *d_psd, int64_t row_stride, double tspan, cudaStream_t st,
+                     Progress *progress = nullptr)
 {
     using namespace wwz;
     const int64_t ncell = nt * nf;
@@ -274,7 +292,14 @@ int transform_device(Workspace *w, const double *d_ts, const double *d_ys, int64
             const char *e = getenv("WWZB200_NO_TILE_DIRECT");
             if (e && *e && atoi(e)) tile_direct = false;
         }
-        const int segs = point_segments(n, nt, nf, allow_rec);   // (not on tile_direct: windowed == dense bit for bit)
+        int segs = point_segments(n, nt, nf, allow_rec);   // (not on tile_direct: windowed == dense bit for bit)
+        // progress reports (streamed output): point segments of ~250 points, so that a work item is short against the
+        // launch and whole tau blocks are final early (config 2: a 1000-point item takes 0.2-0.5 ms of a 0.55 ms launch)
+        const bool want_progress = progress && progress->flag && allow_rec && !foster && w->prefix.empty();
+        if (want_progress) {
+            const char *e = getenv("WWZB200_POINT_SEGMENTS");
+            if (!(e && *e)) segs = (int)std::max<int64_t>(segs, std::min<int64_t>(8, n / 250));
+        }
         const int64_t seg_len = (((n + segs - 1) / segs + 15) / 16) * 16;
         CellPlan plan = plan_cells(n, nt, nf, cells_per_lane_hint(nt, nf, w->sms), seg_len);
         unsigned long long *d_walked = nullptr;   // profiling: warp-points evaluated by the recurrence kernel
@@ -310,6 +335,61 @@ int transform_device(Workspace *w, const double *d_ts, const double *d_ys, int64
         CU(launch_setup(d_omega, nf, d_tau, nt, d_ts, n, c, allow_rec, cut_bits, d_kappa, d_dcut, d_grid, d_rec_row, d_gap,
                         d_unsorted, d_mm, st));   // also zeroes the unsorted flag and d_fix_count (adjacent ints)
         unsigned int *d_queue = reinterpret_cast<unsigned int *>(d_unsorted) + 2;   // zeroed by launch_setup
+        // Fused epilogue: with a single frequency batch (and Kirchner's projection) the recurrence kernel finishes its
+        // own cells -- the warp that completes the last point segment of a tile adds the slabs and writes the outputs --
+        // and finalize_kernel is left with the rows of the direct flavour.
+        // It costs the kernel ~4% (measured on config 2) and saves the epilogue launch about half of that, so it is
+        // used where it pays: when finished tau blocks are streamed to the host (WWZB200_FUSED_EPILOGUE=1 forces it,
+        // =0 forbids it).
+        bool fuse_on = want_progress && nf_batch == nf;
+        {
+            const char *e = getenv("WWZB200_FUSED_EPILOGUE");
+            if (e && *e) fuse_on = atoi(e) != 0 && allow_rec && !foster && nf_batch == nf && w->prefix.empty();
+        }
+        RecFuse fuse{};
+        if (fuse_on) {
+            unsigned int *d_tile_cnt, *d_blk_cnt;
+            if ((rc = wsbuf(w, "tile_cnt", (size_t)rec_tile_count(rplan, nf, 1), &d_tile_cnt))) return rc;
+            if ((rc = wsbuf(w, "blk_cnt", (size_t)kMaxProgressBlocks, &d_blk_cnt))) return rc;
+            if (!w->fuse_zeroed || w->fuse_zeroed_tiles < rec_tile_count(rplan, nf, 1)) {
+                // the counters are left zeroed by every launch: cleared when the buffer is new (or has grown)
+                CU(cudaMemsetAsync(d_tile_cnt, 0, sizeof(unsigned int) * (size_t)rec_tile_count(rplan, nf, 1), st));
+                CU(cudaMemsetAsync(d_blk_cnt, 0, sizeof(unsigned int) * kMaxProgressBlocks, st));
+                w->fuse_zeroed = true;
+                w->fuse_zeroed_tiles = rec_tile_count(rplan, nf, 1);
+            }
+            fuse.omega = d_omega;
+            fuse.m_omega = 0;
+            fuse.row_stride = row_stride;
+            fuse.thr = (double)thr;
+            fuse.neffs = d_neffs;
+            fuse.a0 = d_a0;
+            fuse.a1 = d_a1;
+            fuse.a2 = d_a2;
+            fuse.wwa = d_wwa;
+            fuse.phase = d_phase;
+            fuse.tile_cnt = d_tile_cnt;
+            fuse.fix_count = d_fix_count;
+            fuse.fix_list = d_fix_list;
+            fuse.fix_cap = (unsigned int)ncell;
+            fuse.unfused = reinterpret_cast<unsigned int *>(d_unsorted) + 6;   // zeroed by launch_setup
+            if (want_progress && fuse_on) {
+                // tau blocks of whole tiles, at least ~1.5 MB of output each
+                const int tiles_g = rec_tau_tiles(rplan), tile_taus = rec_tile_taus(rplan);
+                int want = (int)std::min<int64_t>(16, std::max<int64_t>(1, 6 * ncell * 8 / (3 << 19)));
+                {
+                    const char *e = getenv("WWZB200_PROGRESS_BLOCKS");
+                    if (e && *e) want = std::max(1, std::min(kMaxProgressBlocks, atoi(e)));
+                }
+                const int blk_gt = std::max(1, (tiles_g + want - 1) / want);
+                fuse.blk_cnt = d_blk_cnt;
+                fuse.blk_flag = progress->flag;
+                fuse.blk_epoch = progress->epoch;
+                fuse.blk_gt = blk_gt;
+                progress->blocks = (tiles_g + blk_gt - 1) / blk_gt;
+                progress->block_taus = (int64_t)blk_gt * tile_taus;
+            }
+        }
         for (int64_t k0 = 0; k0 < nf; k0 += nf_batch) {
             const int64_t nb = std::min<int64_t>(nf_batch, nf - k0);
             CU(launch_basis(d_ts, d_ys, n, plan.n_pad, d_omega + k0, nb, d_ty, d_basis, k0 == 0, false, st));
@@ -329,7 +409,8 @@ int transform_device(Workspace *w, const double *d_ts, const double *d_ys, int64
             }
             if (allow_rec)
                 CU(launch_rec(rplan, d_ty, d_basis, d_ts, n, d_tau, nt, d_kappa, d_dcut, d_gap, d_unsorted, k0, nb, nf, segs,
-                              seg_len, d_rec_row, d_grid, d_sums, d_queue, d_walked, w->sms, st));
+                              seg_len, d_rec_row, d_grid, d_sums, d_queue, d_walked, w->sms, st, 1, 0, 0,
+                              fuse_on ? &fuse : nullptr));
             if (tile_direct)
                 CU(launch_rec(dplan, d_ty, d_basis, d_ts, n, d_tau, nt, d_kappa, d_dcut, d_gap, d_unsorted, k0, nb, nf, segs,
                               seg_len, allow_rec ? d_rec_row : nullptr, d_grid, d_sums, d_queue + 2, nullptr, w->sms, st_direct));
@@ -376,7 +457,8 @@ int transform_device(Workspace *w, const double *d_ts, const double *d_ys, int64
                                       w->sms, st));
         } else {
             CU(launch_finalize(d_sums, d_tau, d_omega, nt, nf, (double)thr, d_neffs, d_a0, d_a1, d_a2, d_wwa, d_phase,
-                               row_stride, d_fix_count, d_fix_list, (unsigned int)ncell, segs, st));
+                               row_stride, d_fix_count, d_fix_list, (unsigned int)ncell, segs, st,
+                               fuse_on ? d_rec_row : nullptr));
             CU(launch_faithful(d_ts, d_ys, n, d_tau, d_omega, nt, nf, c, (double)thr, d_fix_count, d_fix_list,
                                (unsigned int)ncell, d_neffs, d_a0, d_a1, d_a2, d_wwa, d_phase, row_stride, w->sms, st));
         }
@@ -444,15 +526,75 @@ int host_transform(const double *ts, const double *ys, int64_t n, const double *
         const auto mm = std::minmax_element(ts, ts + n);
         tspan = *mm.second - *mm.first;   // utils/wavelet.py:1270 (np.max(ts)-np.min(ts))
     }
-    rc = transform_device(w, d_ts, d_ys, n, d_tau, nt, d_om, nf, c, thr, psd_thr, flags, o_neff, o_a0, o_a1, o_a2, o_wwa, o_ph, psd ? o_psd : nullptr, nf, tspan, st);
-    if (rc) return rc;
     const size_t cb = sizeof(double) * (size_t)ncell;
-    // six outputs laid out back to back by the caller (one [6, nt, nf] block, as the Python layer allocates them):
-    // one DMA instead of six
-    const bool one_block = ncell && Neffs && a0 == Neffs + ncell && a1 == a0 + ncell && a2 == a1 + ncell &&
-                           wwa == a2 + ncell && phase == wwa + ncell;
-    if (one_block) {
-        CU(cudaMemcpyAsync(Neffs, o_neff, 6 * cb, cudaMemcpyDeviceToHost, st));
+    // six outputs at one pitch in caller memory (one [6, nt, nf] block, as the Python layer allocates them, or the tau
+    // rows of a rank inside a larger [6, NT, nf] block): one (2-D) DMA instead of six
+    const ptrdiff_t pitch = (Neffs && a0) ? a0 - Neffs : 0;
+    const bool one_block = ncell && Neffs && a0 && a1 && a2 && wwa && phase && pitch >= (ptrdiff_t)ncell &&
+                           a1 - a0 == pitch && a2 - a1 == pitch && wwa - a2 == pitch && phase - wwa == pitch;
+    // Streaming: when the recurrence kernel finishes its own cells (fused epilogue), finished blocks of tau rows leave
+    // for the host on the copy engine while later tiles are still being computed.  The kernel reports a block through
+    // a flag in page-locked host memory; this thread polls the flags and enqueues the copies.
+    Progress pg;
+    bool stream_out = one_block && 6 * cb >= ((size_t)4 << 20);
+    {
+        const char *e = getenv("WWZB200_NO_STREAMED_OUTPUT");
+        if (e && *e && atoi(e)) stream_out = false;
+    }
+    if (stream_out) {
+        if (!w->h_progress) {
+            CU(cudaHostAlloc(&w->h_progress, sizeof(unsigned int) * (kMaxProgressBlocks + 2), cudaHostAllocMapped));
+            memset(w->h_progress, 0, sizeof(unsigned int) * (kMaxProgressBlocks + 2));
+        }
+        unsigned int *d_flag = nullptr;
+        CU(cudaHostGetDevicePointer(&d_flag, w->h_progress, 0));
+        pg.flag = d_flag;
+        pg.epoch = ++w->progress_epoch;
+        if (pg.epoch == 0) pg.epoch = ++w->progress_epoch;
+    }
+    rc = transform_device(w, d_ts, d_ys, n, d_tau, nt, d_om, nf, c, thr, psd_thr, flags, o_neff, o_a0, o_a1, o_a2, o_wwa, o_ph,
+                          psd ? o_psd : nullptr, nf, tspan, st, stream_out ? &pg : nullptr);
+    if (rc) return rc;
+    bool copied = false;
+    if (stream_out && pg.blocks > 0) {
+        // the two words that decide whether the streamed copies are the final ones: tiles the recurrence kernel left to
+        // finalize_kernel, cells that faithful_cells_kernel rewrote
+        int *d_flags_dev;
+        if ((rc = wsbuf(w, "flags", wwz::kFlagInts, &d_flags_dev))) return rc;
+        volatile unsigned int *const hp = w->h_progress;
+        unsigned int *const h_sum = w->h_progress + kMaxProgressBlocks;
+        CU(cudaMemcpyAsync(&h_sum[0], d_flags_dev + 1, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));   // deep-underflow cells
+        CU(cudaMemcpyAsync(&h_sum[1], d_flags_dev + 6, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));   // unfused tiles
+        bool all_reported = true;
+        for (int b = 0; b < pg.blocks; ++b) {
+            unsigned int spins = 0;
+            bool seen = true;
+            while (hp[b] != pg.epoch) {
+                if ((++spins & 0x3ff) == 0) {
+                    const cudaError_t q = cudaStreamQuery(st);
+                    if (q == cudaSuccess) {          // everything has run: the flag is there now, or will never be
+                        seen = hp[b] == pg.epoch;
+                        break;
+                    }
+                    if (q != cudaErrorNotReady) CU(q);
+                }
+            }
+            if (!seen) {
+                all_reported = false;
+                break;
+            }
+            const int64_t j0 = (int64_t)b * pg.block_taus, rows = std::min<int64_t>(pg.block_taus, nt - j0);
+            CU(cudaMemcpy2DAsync(Neffs + j0 * nf, sizeof(double) * (size_t)pitch, o_neff + j0 * nf, cb,
+                                 sizeof(double) * (size_t)(rows * nf), 6, cudaMemcpyDeviceToHost, w->copy));
+        }
+        CU(cudaStreamSynchronize(st));
+        copied = all_reported && h_sum[0] == 0 && h_sum[1] == 0;
+        CU(cudaStreamSynchronize(w->copy));
+    }
+    if (copied) {
+        // every block went out final
+    } else if (one_block) {
+        CU(cudaMemcpy2DAsync(Neffs, sizeof(double) * (size_t)pitch, o_neff, cb, cb, 6, cudaMemcpyDeviceToHost, st));
     } else if (ncell) {
         if (Neffs) CU(cudaMemcpyAsync(Neffs, o_neff, cb, cudaMemcpyDeviceToHost, st));
         if (a0) CU(cudaMemcpyAsync(a0, o_a0, cb, cudaMemcpyDeviceToHost, st));

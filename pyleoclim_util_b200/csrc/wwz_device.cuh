@@ -205,6 +205,46 @@ __device__ __forceinline__ double *amp_row(const AmpScatterDev &sc, double *amp,
 }
 
 // ----------------------------------------------------------------------------------------------
+// Per-cell epilogue shared by finalize_kernel (wwz_kernels.cu) and the fused epilogue of the recurrence flavour
+// (wwz_rec.cu): Neff, the mask with numba's NaN semantics, and a0, a1, a2 from the seven sums
+// acc = {W, Q, Ws, Wc, Wy, Wys, Wyc} (utils/wavelet.py:991-1032 reduced as in DESIGN.md section 2).
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cell_from_sums(const double (&acc)[7], double om, double tj, double thr, double &neff,
+                                               double &a0, double &a1, double &a2)
+{
+    const double W = acc[0], Q = acc[1];
+    neff = W * W / Q;
+    a0 = a1 = a2 = __longlong_as_double(0x7ff8000000000000LL);
+    if (neff > thr) {
+        const double Ws = acc[2], Wc = acc[3], Wy = acc[4], Wys = acc[5], Wyc = acc[6];
+        const double Y = Wy / W, S = Ws / W, C = Wc / W, YS = Wys / W, YC = Wyc / W;
+        const double cyc = YC - Y * C;
+        const double cys = YS - Y * S;
+        const double th = om * tj;
+        const double eps = fma(om, tj, -th);
+        double s0, c0;
+        sincos(th, &s0, &c0);
+        const double st = fma(eps, c0, s0), ct = fma(-eps, s0, c0);
+        a0 = Y;
+        a1 = 2.0 * (ct * cyc + st * cys);
+        a2 = 2.0 * (ct * cys - st * cyc);
+    }
+}
+
+__device__ __forceinline__ void store_cell(int64_t o, double neff, double a0, double a1, double a2,
+                                           double *__restrict__ neffs, double *__restrict__ a0o,
+                                           double *__restrict__ a1o, double *__restrict__ a2o,
+                                           double *__restrict__ wwa, double *__restrict__ phase)
+{
+    neffs[o] = neff;
+    if (a0o) a0o[o] = a0;
+    if (a1o) a1o[o] = a1;
+    if (a2o) a2o[o] = a2;
+    if (wwa) wwa[o] = sqrt(a1 * a1 + a2 * a2);   // utils/wavelet.py:1044
+    if (phase) phase[o] = atan2(a2, a1);         // utils/wavelet.py:1045
+}
+
+// ----------------------------------------------------------------------------------------------
 // Warp-cooperative search on the sorted time axis (point windows of a tile of cells).
 // ----------------------------------------------------------------------------------------------
 // First index i in [a, b) with ts[i] >= x (UPPER = false) or ts[i] > x (UPPER = true); b if there is none.

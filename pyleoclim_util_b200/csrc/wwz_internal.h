@@ -50,6 +50,28 @@ struct RecPlan {
     int smem_bytes;       // dynamic shared memory of the CTA
 };
 RecPlan plan_rec(int64_t n, int64_t nt, int64_t nf, int64_t seg_len, int cells_per_lane = kRecCells);
+// Fused epilogue of the recurrence flavour (launch_rec, optional): the warp that finishes the last point segment of a
+// tile writes the tile's finished cells itself; finalize_kernel then only takes the rows of the direct flavour
+// (launch_finalize*, skip_rec_rows).  tile_cnt: one zeroed counter per (tile, member) of the launch (rec_tile_count;
+// left zeroed).  unfused: counts the tiles whose rows all belong to the direct flavour.  blk_cnt / blk_flag (optional):
+// progress per block of blk_gt tiles along tau -- blk_flag[b] (page-locked host memory, mapped) is set to blk_epoch once
+// every cell of the block's taus is final in device memory; blk_cnt: zeroed device counters, one per block.
+struct RecFuse {
+    const double *omega;
+    int64_t m_omega, row_stride;
+    double thr;
+    double *neffs, *a0, *a1, *a2, *wwa, *phase;
+    unsigned int *tile_cnt, *fix_count, *fix_list;
+    unsigned int fix_cap;
+    unsigned int *unfused;
+    unsigned int *blk_cnt;
+    volatile unsigned int *blk_flag;
+    unsigned int blk_epoch;
+    int blk_gt;
+};
+int64_t rec_tile_count(const RecPlan &plan, int64_t nf_batch, int64_t members);
+int rec_tau_tiles(const RecPlan &plan);   // tiles along the tau axis
+int rec_tile_taus(const RecPlan &plan);   // taus covered by one tile
 // d_queue: two zeroed ints (work queue; left zeroed by the launch).  d_rec_row: rows marked 1 belong to the recurrence
 // flavour, rows marked 0 to the direct flavour (null: the launch takes every row).
 cudaError_t launch_rec(const RecPlan &plan, const double2 *d_ty, const double2 *d_basis, const double *d_ts, int64_t n,
@@ -57,7 +79,7 @@ cudaError_t launch_rec(const RecPlan &plan, const double2 *d_ty, const double2 *
                        const double *d_taugap, const int *d_unsorted, int64_t k0, int64_t nf_batch, int64_t nf_total, int segs,
                        int64_t seg_len, const unsigned char *d_rec_row, const double *d_grid, double *d_sums,
                        unsigned int *d_queue, unsigned long long *d_walked, int sms, cudaStream_t st, int64_t members = 1,
-                       int64_t m_ts = 0, int64_t m_tau = 0);
+                       int64_t m_ts = 0, int64_t m_tau = 0, const RecFuse *fuse = nullptr);
 
 // Per-frequency constants kappa4 = 4*omega*sqrt(c*log2 e) and dcut = distance beyond which a weight is below
 // 2^-cut_bits (1081 = exactly zero weights only; windowing); which rows the tau-recurrence flavour may take
@@ -91,7 +113,8 @@ cudaError_t launch_finalize_members(const double *d_sums, const double *d_tau, i
                                     int64_t m_omega, int64_t nt, int64_t nf, int64_t members, double neff_thr,
                                     double *d_neffs, double *d_a0, double *d_a1, double *d_a2, double *d_wwa,
                                     double *d_phase, int64_t out_row_stride, unsigned int *d_fix_count,
-                                    unsigned int *d_fix_list, unsigned int fix_cap, int segs, cudaStream_t st);
+                                    unsigned int *d_fix_list, unsigned int fix_cap, int segs, cudaStream_t st,
+                                    const unsigned char *d_skip_rows = nullptr);
 cudaError_t launch_faithful_members(const double *d_ts, int64_t m_ts, const double *d_ys, int64_t m_ys, int64_t n,
                                     const double *d_tau, int64_t m_tau, const double *d_omega, int64_t m_omega, int64_t nt,
                                     int64_t nf, int64_t members, double c, double neff_thr,
@@ -119,7 +142,7 @@ cudaError_t launch_finalize(const double *d_sums, const double *d_tau, const dou
                             int64_t nf, double neff_thr, double *d_neffs, double *d_a0, double *d_a1,
                             double *d_a2, double *d_wwa, double *d_phase, int64_t out_row_stride,
                             unsigned int *d_fix_count, unsigned int *d_fix_list, unsigned int fix_cap, int segs,
-                            cudaStream_t st);
+                            cudaStream_t st, const unsigned char *d_skip_rows = nullptr);
 
 // Faithful two-pass evaluation (one warp per cell) of the cells in fix_list (count read on the
 // device), or of every cell when fix_list is NULL.

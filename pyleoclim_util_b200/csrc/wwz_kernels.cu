@@ -744,26 +744,13 @@ cudaError_t launch_cells(const CellPlan &plan, const double2 *d_ty, const double
 // (W < 2^-200 or Q < 2^-400: tau inside a long data gap at high frequency), the cell index is
 // appended to `fix_list` and the cell is recomputed by faithful_cells_kernel.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void store_cell(int64_t o, double neff, double a0, double a1, double a2,
-                                           double *__restrict__ neffs, double *__restrict__ a0o,
-                                           double *__restrict__ a1o, double *__restrict__ a2o,
-                                           double *__restrict__ wwa, double *__restrict__ phase)
-{
-    neffs[o] = neff;
-    if (a0o) a0o[o] = a0;
-    if (a1o) a1o[o] = a1;
-    if (a2o) a2o[o] = a2;
-    if (wwa) wwa[o] = sqrt(a1 * a1 + a2 * a2);   // utils/wavelet.py:1044
-    if (phase) phase[o] = atan2(a2, a1);         // utils/wavelet.py:1045
-}
-
 __global__ void finalize_kernel(const double *__restrict__ sums, const double *__restrict__ tau,
                                 const double *__restrict__ omega, int64_t nt, int64_t nf, double thr,
                                 double *__restrict__ neffs, double *__restrict__ a0o, double *__restrict__ a1o,
                                 double *__restrict__ a2o, double *__restrict__ wwa, double *__restrict__ phase,
                                 int64_t row_stride, unsigned int *__restrict__ fix_count,
                                 unsigned int *__restrict__ fix_list, unsigned int fix_cap, int segs, int64_t members,
-                                int64_t m_tau, int64_t m_omega)
+                                int64_t m_tau, int64_t m_omega, const unsigned char *__restrict__ skip_rows)
 {
     int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int64_t nc = nt * nf;
@@ -771,6 +758,8 @@ __global__ void finalize_kernel(const double *__restrict__ sums, const double *_
     const int64_t gidx = idx;                    // index over all members (what the fix-up list records)
     const int64_t mem = idx / nc;
     idx -= mem * nc;
+    // rows finished by the fused epilogue of the recurrence flavour (wwz_rec.cu)
+    if (skip_rows && skip_rows[mem * nf + idx % nf]) return;
     {   // member of a batch: sums [member][segs][7][nc], outputs [member][nt][row_stride]
         sums += (size_t)mem * (size_t)segs * kNumSums * (size_t)nc;
         tau += mem * m_tau;
@@ -798,23 +787,8 @@ __global__ void finalize_kernel(const double *__restrict__ sums, const double *_
         const unsigned int slot = atomicAdd(fix_count, 1u);
         if (slot < fix_cap) fix_list[slot] = (unsigned int)gidx;
     }
-    const double neff = W * W / Q;
-    double a0 = CUDART_NAN, a1 = CUDART_NAN, a2 = CUDART_NAN;
-    if (neff > thr) {
-        const double Ws = acc[2], Wc = acc[3], Wy = acc[4], Wys = acc[5], Wyc = acc[6];
-        const double Y = Wy / W, S = Ws / W, C = Wc / W, YS = Wys / W, YC = Wyc / W;
-        const double cyc = YC - Y * C;
-        const double cys = YS - Y * S;
-        const double om = omega[k], tj = tau[j];
-        const double th = om * tj;
-        const double eps = fma(om, tj, -th);
-        double s0, c0;
-        sincos(th, &s0, &c0);
-        const double st = fma(eps, c0, s0), ct = fma(-eps, s0, c0);
-        a0 = Y;
-        a1 = 2.0 * (ct * cyc + st * cys);
-        a2 = 2.0 * (ct * cys - st * cyc);
-    }
+    double neff, a0, a1, a2;
+    cell_from_sums(acc, omega[k], tau[j], thr, neff, a0, a1, a2);
     store_cell(j * row_stride + k, neff, a0, a1, a2, neffs, a0o, a1o, a2o, wwa, phase);
 }
 
@@ -860,14 +834,15 @@ cudaError_t launch_finalize_members(const double *d_sums, const double *d_tau, i
                                     int64_t m_omega, int64_t nt, int64_t nf, int64_t members, double neff_thr,
                                     double *d_neffs, double *d_a0, double *d_a1, double *d_a2, double *d_wwa,
                                     double *d_phase, int64_t out_row_stride, unsigned int *d_fix_count,
-                                    unsigned int *d_fix_list, unsigned int fix_cap, int segs, cudaStream_t st)
+                                    unsigned int *d_fix_list, unsigned int fix_cap, int segs, cudaStream_t st,
+                                    const unsigned char *d_skip_rows)
 {
     const int64_t nc = nt * nf * members;
     if (nc <= 0) return cudaSuccess;
     finalize_kernel<<<(unsigned)((nc + 255) / 256), 256, 0, st>>>(d_sums, d_tau, d_omega, nt, nf, neff_thr, d_neffs,
                                                                   d_a0, d_a1, d_a2, d_wwa, d_phase, out_row_stride,
                                                                   d_fix_count, d_fix_list, fix_cap, segs, members, m_tau,
-                                                                  m_omega);
+                                                                  m_omega, d_skip_rows);
     bump_launch_counter();
     return cudaGetLastError();
 }
@@ -876,10 +851,10 @@ cudaError_t launch_finalize(const double *d_sums, const double *d_tau, const dou
                             int64_t nf, double neff_thr, double *d_neffs, double *d_a0, double *d_a1,
                             double *d_a2, double *d_wwa, double *d_phase, int64_t out_row_stride,
                             unsigned int *d_fix_count, unsigned int *d_fix_list, unsigned int fix_cap, int segs,
-                            cudaStream_t st)
+                            cudaStream_t st, const unsigned char *d_skip_rows)
 {
     return launch_finalize_members(d_sums, d_tau, 0, d_omega, 0, nt, nf, 1, neff_thr, d_neffs, d_a0, d_a1, d_a2, d_wwa,
-                                   d_phase, out_row_stride, d_fix_count, d_fix_list, fix_cap, segs, st);
+                                   d_phase, out_row_stride, d_fix_count, d_fix_list, fix_cap, segs, st, d_skip_rows);
 }
 
 cudaError_t launch_faithful_members(const double *d_ts, int64_t m_ts, const double *d_ys, int64_t m_ys, int64_t n,

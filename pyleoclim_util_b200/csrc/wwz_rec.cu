@@ -61,14 +61,30 @@ struct RecArgs {
     int row_stride2;     // basis row stride inside a stage, double2 units (odd multiple of 16 B: conflict-free rows)
     int stage_stride2;   // stage stride, double2 units
     int warp_stride;     // bytes of shared memory per warp (ring + barriers)
+    // ---- fused epilogue (FUSE = true): the warp that finishes the last point segment of a tile adds the slabs in
+    // order and writes the tile's finished cells -- no separate epilogue launch, and finished tau blocks can leave for
+    // the host while later tiles are still being computed
+    const double *omega;         // [member][nf_total] (m_omega = element stride between members)
+    long long m_omega, row_stride;
+    double thr;
+    double *o_neffs, *o_a0, *o_a1, *o_a2, *o_wwa, *o_phase;   // [member][nt][row_stride]; all but o_neffs may be null
+    unsigned int *tile_cnt;      // [member][tile] point segments finished (left zeroed by the launch)
+    unsigned int *fix_count, *fix_list;   // deep-underflow cells for faithful_cells_kernel (as finalize_kernel)
+    unsigned int fix_cap;
+    unsigned int *unfused;       // number of tiles skipped here (their rows belong to the direct flavour: finalize_kernel)
+    unsigned int *blk_cnt;       // null = no progress reports; [tau block] finished work items (left zeroed)
+    volatile unsigned int *blk_flag;   // page-locked host memory, mapped: [tau block] := blk_epoch when the block is final
+    unsigned int blk_epoch;
+    int blk_gt;                  // tiles along tau per block
 };
 
 // NREG = register budget per thread (__maxnreg__: ptxas interleaves the weight evaluation of the next point with the
 // accumulations of the current one only when it has the registers for both).  Every warp of a CTA is an independent
 // worker; the number of warps per CTA is a launch parameter.
-template <int M, bool REC, int NREG>
+template <int M, bool REC, int NREG, bool FUSE>
 __global__ void __maxnreg__(NREG) wwz_tile_kernel(const RecArgs a)
 {
+    static_assert(!FUSE || REC, "the fused epilogue exists for the recurrence flavour");
     const int kRecWarps = blockDim.x >> 5;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ double tbl[16];
@@ -99,13 +115,49 @@ __global__ void __maxnreg__(NREG) wwz_tile_kernel(const RecArgs a)
         if (lane == 0) item = atomicAdd(&a.queue[0], 1u);
         item = __shfl_sync(0xffffffffu, item, 0);
         if ((long long)item >= a.nitems) break;
-        // items are numbered tile-major (low frequencies = long windows first), then member, point segment fastest
-        const unsigned int per_tile = (unsigned)a.segs * (unsigned)a.members;
-        const long long tile = item / per_tile;
-        const unsigned int rem = item - (unsigned)tile * per_tile;
-        const int mem = (int)(rem / (unsigned)a.segs);
-        const int seg = (int)(rem - (unsigned)mem * (unsigned)a.segs);
-        const int kt = (int)(tile / a.tiles_g), gt = (int)(tile - (long long)kt * a.tiles_g);
+        // items are numbered tile-major (low frequencies = long windows first), then member, point segment fastest;
+        // with progress reports (FUSE, one member): tau block by tau block, inside a block again lowest rows first, so
+        // that whole tau blocks of the output are final early and every block still starts with its longest windows
+        long long tile;
+        int mem, seg, kt, gt;
+        if (FUSE && a.blk_gt > 0) {
+            const unsigned int tiles_k = (unsigned)(a.ntiles / a.tiles_g);
+            const unsigned int full = tiles_k * (unsigned)a.blk_gt * (unsigned)a.segs;   // items of a whole block
+            const unsigned int b = item / full;
+            const unsigned int rem = item - b * full;
+            const unsigned int ngt = (unsigned)min(a.blk_gt, a.tiles_g - (int)b * a.blk_gt);
+            kt = (int)(rem / (ngt * (unsigned)a.segs));
+            const unsigned int r2 = rem - (unsigned)kt * ngt * (unsigned)a.segs;
+            gt = (int)b * a.blk_gt + (int)(r2 / (unsigned)a.segs);
+            seg = (int)(r2 % (unsigned)a.segs);
+            mem = 0;
+            tile = (long long)kt * a.tiles_g + gt;
+        } else {
+            const unsigned int per_tile = (unsigned)a.segs * (unsigned)a.members;
+            tile = item / per_tile;
+            const unsigned int rem = item - (unsigned)tile * per_tile;
+            mem = (int)(rem / (unsigned)a.segs);
+            seg = (int)(rem - (unsigned)mem * (unsigned)a.segs);
+            kt = (int)(tile / a.tiles_g);
+            gt = (int)(tile - (long long)kt * a.tiles_g);
+        }
+        // progress of the tile's tau block (FUSE): one count per work item once nothing of it is left to write
+        auto report = [&]() {
+            if constexpr (FUSE) {
+                if (a.blk_gt > 0 && lane == 0) {
+                    const int tiles_k = (int)(a.ntiles / a.tiles_g);
+                    const int b = gt / a.blk_gt;
+                    const unsigned int target =
+                        (unsigned)(min(a.blk_gt, a.tiles_g - b * a.blk_gt) * tiles_k) * (unsigned)a.segs;
+                    __threadfence();
+                    if (atomicAdd(&a.blk_cnt[b], 1u) == target - 1) {
+                        a.blk_cnt[b] = 0;
+                        __threadfence_system();
+                        a.blk_flag[b] = a.blk_epoch;
+                    }
+                }
+            }
+        };
         // this member's inputs and scratch
         const double2 *const m_ty = a.ty + (size_t)mem * (size_t)a.n_pad;
         const double2 *const m_basis = a.basis + (size_t)mem * (size_t)a.nf_batch * (size_t)a.n_pad * 2;
@@ -123,7 +175,13 @@ __global__ void __maxnreg__(NREG) wwz_tile_kernel(const RecArgs a)
         const int rows = min(TR, a.nf_batch - kt * TR);       // rows of this tile that exist
         bool ok = g < a.G && kb < a.nf_batch;
         if (ok && m_rec) ok = (m_rec[a.k0 + kb] != 0) == REC;
-        if (!__any_sync(0xffffffffu, ok)) continue;           // every row of the tile belongs to the other flavour
+        if (!__any_sync(0xffffffffu, ok)) {                   // every row of the tile belongs to the other flavour
+            if constexpr (FUSE) {
+                if (seg == 0 && lane == 0) atomicAdd(a.unfused, 1u);
+                report();
+            }
+            continue;
+        }
 
         const long long p0 = (long long)seg * a.seg_len;
         const long long p1 = min(a.n, p0 + a.seg_len);
@@ -309,6 +367,53 @@ __global__ void __maxnreg__(NREG) wwz_tile_kernel(const RecArgs a)
                 }
             }
         }
+        if constexpr (FUSE) {
+            // the last segment of the tile to finish adds the slabs in order (the same order as finalize_kernel) and
+            // writes the tile's cells; rows of the tile that belong to the direct flavour (!ok) are left to finalize_kernel
+            bool last = true;
+            if (a.segs > 1) {
+                __threadfence();
+                __syncwarp();
+                unsigned int done = 0;
+                unsigned int *const cnt = a.tile_cnt + (size_t)mem * (size_t)a.ntiles + (size_t)tile;
+                if (lane == 0) {
+                    done = atomicAdd(cnt, 1u);
+                    if (done == (unsigned)a.segs - 1) *cnt = 0;
+                }
+                done = __shfl_sync(0xffffffffu, done, 0);
+                last = done == (unsigned)a.segs - 1;
+                if (last) __threadfence();
+            }
+            if (last && ok) {
+                const long long kcol = (long long)a.k0 + kb;
+                const size_t nc = (size_t)a.ncell_total;
+                const double om = a.omega[(long long)mem * a.m_omega + kcol];
+                const long long oo = (long long)mem * a.nt * a.row_stride;
+#pragma unroll 1
+                for (int r = 0; r < M; ++r) {
+                    const int j = g * M + r;
+                    if (j >= a.nt) break;
+                    const size_t idx = (size_t)j * (size_t)a.nf_total + (size_t)kcol;
+                    double acc[kNumSums];
+#pragma unroll
+                    for (int x = 0; x < kNumSums; ++x) acc[x] = __ldcg(&m_sums[(size_t)x * nc + idx]);
+                    for (int sg = 1; sg < a.segs; ++sg) {
+                        const double *slab = m_sums + (size_t)sg * kNumSums * nc;
+#pragma unroll
+                        for (int x = 0; x < kNumSums; ++x) acc[x] += __ldcg(&slab[(size_t)x * nc + idx]);
+                    }
+                    if (a.fix_list && (acc[0] < 0x1p-200 || acc[1] < 0x1p-400)) {
+                        const unsigned int slot = atomicAdd(a.fix_count, 1u);
+                        if (slot < a.fix_cap) a.fix_list[slot] = (unsigned int)((size_t)mem * nc + idx);
+                    }
+                    double neff, c0, c1, c2;
+                    cell_from_sums(acc, om, m_taup[j], a.thr, neff, c0, c1, c2);
+                    store_cell(oo + (long long)j * a.row_stride + kcol, neff, c0, c1, c2, a.o_neffs, a.o_a0, a.o_a1, a.o_a2,
+                               a.o_wwa, a.o_phase);
+                }
+            }
+            report();
+        }
     }
 
     if (lane == 0) {
@@ -364,12 +469,12 @@ RecPlan plan_rec(int64_t n, int64_t nt, int64_t nf, int64_t seg_len, int cells_p
     return p;
 }
 
-template <int M, bool REC, int NREG>
+template <int M, bool REC, int NREG, bool FUSE>
 static cudaError_t launch_tiles_m(const RecPlan &plan, RecArgs &a, int sms, cudaStream_t st)
 {
     const int WARPS = plan.warps;
     static SmemOptIn done;
-    cudaError_t e = ensure_dynamic_smem(wwz_tile_kernel<M, REC, NREG>, plan.smem_bytes, done);
+    cudaError_t e = ensure_dynamic_smem(wwz_tile_kernel<M, REC, NREG, FUSE>, plan.smem_bytes, done);
     if (e != cudaSuccess) return e;
     // resident CTAs per SM for this shared-memory size (cached per device: the query is a host-side computation)
     static int cached_smem[kMaxDevices], cached_ctas[kMaxDevices], cached_warps[kMaxDevices];
@@ -381,7 +486,7 @@ static cudaError_t launch_tiles_m(const RecPlan &plan, RecArgs &a, int sms, cuda
     if (tracked && cached_ctas[dev] > 0 && cached_smem[dev] == plan.smem_bytes && cached_warps[dev] == WARPS) {
         per_sm = cached_ctas[dev];
     } else {
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wwz_tile_kernel<M, REC, NREG>, WARPS * 32,
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wwz_tile_kernel<M, REC, NREG, FUSE>, WARPS * 32,
                                                           (size_t)plan.smem_bytes);
         if (e != cudaSuccess) return e;
         if (per_sm < 1) per_sm = 1;
@@ -393,17 +498,25 @@ static cudaError_t launch_tiles_m(const RecPlan &plan, RecArgs &a, int sms, cuda
     }
     const int64_t want = (a.nitems + WARPS - 1) / WARPS;
     const int64_t ctas = std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)sms * per_sm));
-    wwz_tile_kernel<M, REC, NREG><<<(unsigned)ctas, WARPS * 32, plan.smem_bytes, st>>>(a);
+    wwz_tile_kernel<M, REC, NREG, FUSE><<<(unsigned)ctas, WARPS * 32, plan.smem_bytes, st>>>(a);
     bump_launch_counter();
     return cudaGetLastError();
 }
+
+int64_t rec_tile_count(const RecPlan &plan, int64_t nf_batch, int64_t members)
+{
+    const int TG = 1 << plan.tg_log2, TR = 32 >> plan.tg_log2;
+    return (int64_t)((plan.groups + TG - 1) / TG) * ((nf_batch + TR - 1) / TR) * members;
+}
+int rec_tau_tiles(const RecPlan &plan) { return (plan.groups + (1 << plan.tg_log2) - 1) >> plan.tg_log2; }
+int rec_tile_taus(const RecPlan &plan) { return plan.cells_per_lane << plan.tg_log2; }
 
 cudaError_t launch_rec(const RecPlan &plan, const double2 *d_ty, const double2 *d_basis, const double *d_ts, int64_t n,
                        const double *d_tau, int64_t nt, const double *d_kappa, const double *d_dcut,
                        const double *d_taugap, const int *d_unsorted, int64_t k0, int64_t nf_batch, int64_t nf_total, int segs,
                        int64_t seg_len, const unsigned char *d_rec_row, const double *d_grid, double *d_sums,
                        unsigned int *d_queue, unsigned long long *d_walked, int sms, cudaStream_t st, int64_t members,
-                       int64_t m_ts, int64_t m_tau)
+                       int64_t m_ts, int64_t m_tau, const RecFuse *fuse)
 {
     if (nf_batch <= 0 || nt <= 0 || members <= 0) return cudaSuccess;
     RecArgs a{};
@@ -445,9 +558,31 @@ cudaError_t launch_rec(const RecPlan &plan, const double2 *d_ty, const double2 *
     a.stage_stride2 = plan.stage_bytes / 16;
     a.warp_stride = plan.warp_bytes;
     if (plan.cells_per_lane == kRecCells) {
-        return launch_tiles_m<kRecCells, true, 168>(plan, a, sms, st);
+        if (fuse) {
+            a.omega = fuse->omega;
+            a.m_omega = fuse->m_omega;
+            a.row_stride = fuse->row_stride;
+            a.thr = fuse->thr;
+            a.o_neffs = fuse->neffs;
+            a.o_a0 = fuse->a0;
+            a.o_a1 = fuse->a1;
+            a.o_a2 = fuse->a2;
+            a.o_wwa = fuse->wwa;
+            a.o_phase = fuse->phase;
+            a.tile_cnt = fuse->tile_cnt;
+            a.fix_count = fuse->fix_count;
+            a.fix_list = fuse->fix_list;
+            a.fix_cap = fuse->fix_cap;
+            a.unfused = fuse->unfused;
+            a.blk_cnt = fuse->blk_cnt;
+            a.blk_flag = fuse->blk_flag;
+            a.blk_epoch = fuse->blk_epoch;
+            a.blk_gt = fuse->blk_gt;      // 0: no progress reports, frequency-major tile order
+            return launch_tiles_m<kRecCells, true, 168, true>(plan, a, sms, st);
+        }
+        return launch_tiles_m<kRecCells, true, 168, false>(plan, a, sms, st);
     }
-    return launch_tiles_m<kTileDirectCells, false, 128>(plan, a, sms, st);
+    return launch_tiles_m<kTileDirectCells, false, 128, false>(plan, a, sms, st);
 }
 
 }  // namespace wwz

@@ -54,7 +54,7 @@ int main() {
     double h[16] = {0.1, 0.2, 0.3, 0.4, 0.5, 0.6, 0.7, 0.8, 0.37, 0.0, 0.05, 0.0, 0.3, 0.6, 0.8, 1e-3};
     double *d_g, *d_out; cudaMalloc(&d_g, sizeof h); cudaMalloc(&d_out, 8); cudaMemcpy(d_g, h, sizeof h, cudaMemcpyHostToDevice);
     // 88 loop FP64 + 4 stand-in adds + 2 products per point
-    for (int bps : {2, 3}) {
+    for (int bps : {1, 2, 3}) {
         if (bps <= 3) run("full body, unroll 2, 168 regs", kfull<0, 3>, d_out, d_g, bps, 2, 94);
         if (bps <= 3) run("full body, unroll 1, 168 regs", kfull<1, 3>, d_out, d_g, bps, 1, 94);
         if (bps <= 2) run("full body, unroll 2, 255 regs", kfull<0, 2>, d_out, d_g, bps, 2, 94);
