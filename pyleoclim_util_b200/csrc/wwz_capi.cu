@@ -536,7 +536,8 @@ int host_transform(const double *ts, const double *ys, int64_t n, const double *
     // for the host on the copy engine while later tiles are still being computed.  The kernel reports a block through
     // a flag in page-locked host memory; this thread polls the flags and enqueues the copies.
     Progress pg;
-    bool stream_out = one_block && 6 * cb >= ((size_t)4 << 20);
+    const int n_out = (Neffs != nullptr) + (a0 != nullptr) + (a1 != nullptr) + (a2 != nullptr) + (wwa != nullptr) + (phase != nullptr);
+    bool stream_out = ncell && n_out * cb >= ((size_t)4 << 20);
     {
         const char *e = getenv("WWZB200_NO_STREAMED_OUTPUT");
         if (e && *e && atoi(e)) stream_out = false;
@@ -584,8 +585,16 @@ int host_transform(const double *ts, const double *ys, int64_t n, const double *
                 break;
             }
             const int64_t j0 = (int64_t)b * pg.block_taus, rows = std::min<int64_t>(pg.block_taus, nt - j0);
-            CU(cudaMemcpy2DAsync(Neffs + j0 * nf, sizeof(double) * (size_t)pitch, o_neff + j0 * nf, cb,
-                                 sizeof(double) * (size_t)(rows * nf), 6, cudaMemcpyDeviceToHost, w->copy));
+            const size_t bb = sizeof(double) * (size_t)(rows * nf);
+            if (one_block) {
+                CU(cudaMemcpy2DAsync(Neffs + j0 * nf, sizeof(double) * (size_t)pitch, o_neff + j0 * nf, cb, bb, 6,
+                                     cudaMemcpyDeviceToHost, w->copy));
+            } else {
+                double *const dst[6] = {Neffs, a0, a1, a2, wwa, phase};
+                const double *const src[6] = {o_neff, o_a0, o_a1, o_a2, o_wwa, o_ph};
+                for (int i = 0; i < 6; ++i)
+                    if (dst[i]) CU(cudaMemcpyAsync(dst[i] + j0 * nf, src[i] + j0 * nf, bb, cudaMemcpyDeviceToHost, w->copy));
+            }
         }
         CU(cudaStreamSynchronize(st));
         copied = all_reported && h_sum[0] == 0 && h_sum[1] == 0;

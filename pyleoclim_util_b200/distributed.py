@@ -6,6 +6,8 @@ The surrogate significance test is sharded the same way -- every rank draws the 
 surrogate streams (same seed) and evaluates all S surrogates on its own tau rows, so the per-cell
 quantiles need no exchange either; only the [nq, rows, nf] quantile tiles are gathered.
 """
+import ctypes
+
 import numpy as np
 
 from . import wavelet as _wv
@@ -273,6 +275,25 @@ def _device_blocks(pd_ys, ts_cut, tau, omega, c, Neff_threshold, flags, group, w
     counts = [b - a for a, b in blocks]
     a, b = blocks[rank]
     hmax = max(max(counts), 1)
+    if gather and root_only and tuple(want) == (4, 5, 0, 1, 2, 3) and _shared_segments.on_one_host(group):
+        # host='root', all six outputs: the consumer is rank 0 and there is no all-gather.  Every rank runs the HOST entry
+        # point on its tau block with its six output pointers inside one page-locked shared-memory buffer (library
+        # order, one pitch): finished tau blocks cross the rank's own PCIe link while the kernel is still computing
+        # (streamed output, wwz_capi.cu) and rank 0 reads the assembled planes in place.
+        L = _lib.lib()
+        sg = _shared_segments.acquire(6 * nt * nf * 8, group)
+        if b > a:
+            f64 = lambda x: np.ascontiguousarray(x, dtype=np.float64)
+            h_ts, h_ys, h_tau, h_om = f64(ts_cut), f64(pd_ys), f64(tau[a:b]), f64(omega)
+            outs = [ctypes.cast(sg["addr"] + (i * nt + a) * nf * 8, _lib._dp) for i in range(6)]
+            _lib.check(L.wwzb200_kirchner(_lib.ptr(h_ts), _lib.ptr(h_ys), h_ts.size, _lib.ptr(h_tau), b - a, _lib.ptr(h_om),
+                                          nf, float(c), int(Neff_threshold), int(flags), *outs))
+        _shared_segments.landed(group)                  # rank 0 waits until every block has landed (shared-memory flags)
+        if rank == 0:
+            v = _shared_segments.view(sg, (6, nt, nf))
+            return [v[i] for i in want], None
+        sg["free"] = True
+        return None, None
     up = lambda x: torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64)).to(dev, non_blocking=True)
     d_ts, d_ys, d_om = up(ts_cut), up(pd_ys), up(omega)
     d_tau = up(tau[a:b]) if b > a else torch.zeros(1, dtype=torch.float64, device=dev)

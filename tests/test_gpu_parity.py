@@ -474,3 +474,70 @@ def test_config5_stratified_cells_against_the_oracle():
           "%d masked" % (ref["amplitude"].size, amp_err, low_err, ph_err, int((~m).sum())))
     assert low_err < 1e-9
 
+
+
+# ------------------------------------------------------------------ streamed output of the host entry points
+def _stream_case(monkeypatch, t, y, tau, freq, c=1 / (8 * np.pi ** 2), pinned=True, separate=False):
+    """The same host call with the output copied in one piece after the last kernel and streamed block by block
+    (fused epilogue of the recurrence kernel + progress flags, wwz_capi.cu); same point segments in both runs."""
+    om = WV.make_omega(t, freq)
+    monkeypatch.setenv("WWZB200_POINT_SEGMENTS", "8")
+    monkeypatch.setenv("WWZB200_NO_STREAMED_OUTPUT", "1")
+    one = WV._transform(y, t, tau, om, c, 3, pinned=pinned)
+    monkeypatch.delenv("WWZB200_NO_STREAMED_OUTPUT")
+    if not separate:
+        return one, WV._transform(y, t, tau, om, c, 3, pinned=pinned)
+    # six separately allocated outputs (no common pitch): the blocks leave as six copies each
+    L = _lib.lib()
+    outs = [np.full((tau.size, freq.size), -7.0) for _ in range(6)]
+    _lib.check(L.wwzb200_kirchner(_lib.ptr(_lib.f64(t)), _lib.ptr(_lib.f64(y)), t.size, _lib.ptr(_lib.f64(tau)), tau.size,
+                                  _lib.ptr(om), freq.size, float(c), 3, 0, *[_lib.ptr(o) for o in outs]))
+    neffs, a0, a1, a2, wwa, phase = outs
+    return one, (wwa, phase, neffs, (a0, a1, a2), None)
+
+
+def test_streamed_output_is_the_single_copy_result_at_config2_size(monkeypatch):
+    t, y, tau, freq = synth.config_grid("C2")
+    ys = WV.standardize(y)[0]
+    for c in (1 / (8 * np.pi ** 2), 1e-3):
+        one, streamed = _stream_case(monkeypatch, t, ys, tau, freq, c=c)
+        for a, b in zip(_bits(one), _bits(streamed)):
+            assert np.array_equal(a, b)
+    # and against the oracle on rows of both ends and the interior of the tau axis (every block boundary region)
+    O = oracle()
+    rows = np.r_[0:3, 62:66, 498:502, 997:1000]
+    ref = O.kirchner(ys, t, freq, tau[rows], c=1 / (8 * np.pi ** 2), mode=0)
+    monkeypatch.delenv("WWZB200_POINT_SEGMENTS")
+    got = WV._transform(ys, t, tau, WV.make_omega(t, freq), 1 / (8 * np.pi ** 2), 3)
+    assert_scalogram_parity(as_dict(got[0][rows], got[1][rows], got[2][rows], tuple(x[rows] for x in got[3])), as_dict(*ref),
+                            what="streamed output, config 2")
+
+
+def test_streamed_output_with_separately_allocated_outputs(monkeypatch):
+    t, y, tau, freq = synth.config_grid("C2")
+    ys = WV.standardize(y)[0]
+    one, streamed = _stream_case(monkeypatch, t, ys, tau[:640], freq, pinned=False, separate=True)
+    for a, b in zip(_bits(one), _bits(streamed)):
+        assert np.array_equal(a, b)
+
+
+def test_streamed_output_falls_back_when_other_kernels_own_cells(monkeypatch):
+    """Blocks that left early are only final if the recurrence kernel owned every row and no cell went to the faithful
+    kernel; otherwise everything is copied again at the end.  (a) a coarse tau axis: the highest rows exceed
+    kappa*dtau = 8 and belong to the direct kernel; (b) a hiatus: deep-underflow cells recomputed by the faithful kernel."""
+    t, y, tau, freq = synth.config_grid("C2")
+    ys = WV.standardize(y)[0]
+    tau_coarse = np.linspace(t.min(), t.max(), 1200)[::4]              # 300 taus, dtau ~ 6.7
+    freq_big = synth.freq_log(t, 2000)                                  # 300 x 2000 cells = 28.8 MB of output
+    one, streamed = _stream_case(monkeypatch, t, ys, tau_coarse, freq_big)
+    for a, b in zip(_bits(one), _bits(streamed)):
+        assert np.array_equal(a, b)
+    om = WV.make_omega(t, freq_big)
+    kap_d = 4 * om * np.sqrt(np.log2(np.e) / (8 * np.pi ** 2)) * (tau_coarse[1] - tau_coarse[0])
+    assert (kap_d > 8).any() and (kap_d <= 8).any()                     # both kernels had rows
+    tg = np.concatenate([t[:800], t[800:] + 900.0])
+    tau_g = np.linspace(tg.min(), tg.max(), 640)
+    one, streamed = _stream_case(monkeypatch, tg, ys, tau_g, freq)
+    for a, b in zip(_bits(one), _bits(streamed)):
+        assert np.array_equal(a, b)
+    assert np.isnan(one[0]).any()                                       # the hiatus masks cells
