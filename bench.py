@@ -727,10 +727,12 @@ def run_ours(args):
                     "bytes_note": "per rank: the four input vectors of both calls up, the rank's six output planes and psd back",
                     "ms_per_step": 1e3 * api_s / args.steps,
                     "path": ("pyleoclim_util_b200.wavelet.wwz + .wwz_psd (the reference's wwz / wwz_psd signatures) on host "
-                             "NumPy arrays; results land in pooled page-locked NumPy arrays") if world == 1 else
+                             "NumPy arrays; results land in pooled page-locked NumPy arrays; the wwz call streams finished blocks of "
+                             "tau rows to the host while the kernel is still computing (fused epilogue + progress flags)") if world == 1 else
                             ("pyleoclim_util_b200.distributed.wwz_tau_sharded(host='root') + .wwz_psd_tau_sharded on host "
-                             "NumPy arrays, every rank: prepare, tau block on its GPU, D2H of the block over the rank's own "
-                             "PCIe link into one page-locked shared-memory buffer that rank 0 returns; psd all-reduced"),
+                             "NumPy arrays, every rank: prepare, tau block on its GPU through the host entry point, finished "
+                             "blocks of tau rows streamed over the rank's own PCIe link into one page-locked shared-memory "
+                             "buffer that rank 0 returns; psd all-reduced"),
                     "c_abi_ms_per_step": 1e3 * cabi_s / args.steps,
                     "c_abi_path": "wwzb200_kirchner + wwzb200_kirchner_psd on pre-allocated pinned host buffers"},
             "host_binding": ("rank pinned to the %d CPUs next to its GPU (sysfs local_cpulist)" % len(numa_cpus)) if numa_cpus

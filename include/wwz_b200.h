@@ -32,6 +32,14 @@
  * different streams are ordered on the device instead of racing on the scratch -- results are always those of the
  * serial order of the calls, and concurrency between two library calls on one device is not available.  Growing a
  * scratch buffer frees the old one (cudaFree synchronises the device).
+ *
+ * Streamed output.  When a host-pointer transform returns at least 4 MB of per-cell outputs, finished blocks of tau rows
+ * are copied to the caller's buffers while later cells are still being computed: the recurrence kernel finishes its own
+ * cells (its warps add the partial sums of a tile and write Neff, coefficients, amplitude and phase themselves) and
+ * reports every finished tau block through a flag in page-locked host memory that the calling thread polls.  If another
+ * kernel turns out to own cells of the grid (rows beyond the recurrence, deep-underflow cells), everything is copied
+ * again after the last kernel -- the values returned are the same either way.  Page-locked output buffers
+ * (wwzb200_alloc_pinned / wwzb200_host_register) make the copies DMAs.  WWZB200_NO_STREAMED_OUTPUT=1 turns it off.
  */
 #ifndef WWZ_B200_H
 #define WWZ_B200_H

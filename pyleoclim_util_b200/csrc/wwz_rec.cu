@@ -33,6 +33,7 @@
 #include <math_constants.h>
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 
 #include "wwz_device.cuh"
@@ -76,6 +77,9 @@ struct RecArgs {
     volatile unsigned int *blk_flag;   // page-locked host memory, mapped: [tau block] := blk_epoch when the block is final
     unsigned int blk_epoch;
     int blk_gt;                  // tiles along tau per block
+#ifdef WWZ_TRACE
+    unsigned long long *trace;   // developer build only (-DWWZ_TRACE): [item][8] timeline of the work items, tools/trace_items.py
+#endif
 };
 
 // NREG = register budget per thread (__maxnreg__: ptxas interleaves the weight evaluation of the next point with the
@@ -115,6 +119,11 @@ __global__ void __maxnreg__(NREG) wwz_tile_kernel(const RecArgs a)
         if (lane == 0) item = atomicAdd(&a.queue[0], 1u);
         item = __shfl_sync(0xffffffffu, item, 0);
         if ((long long)item >= a.nitems) break;
+#ifdef WWZ_TRACE
+        unsigned long long tr0 = 0, tr1 = 0, tr_first = 0, tr_loop = 0;
+        long long clk_pts = 0, clk_mark = 0;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tr0));
+#endif
         // items are numbered tile-major (low frequencies = long windows first), then member, point segment fastest;
         // with progress reports (FUSE, one member): tau block by tau block, inside a block again lowest rows first, so
         // that whole tau blocks of the output are final early and every block still starts with its longest windows
@@ -254,6 +263,9 @@ __global__ void __maxnreg__(NREG) wwz_tile_kernel(const RecArgs a)
             }
         }
 
+#ifdef WWZ_TRACE
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tr1));
+#endif
         double W[M], Q[M], Ws[M], Wc[M], Wy[M], Wys[M], Wyc[M];
 #pragma unroll
         for (int r = 0; r < M; ++r) W[r] = Q[r] = Ws[r] = Wc[r] = Wy[r] = Wys[r] = Wyc[r] = 0.0;
@@ -263,6 +275,10 @@ __global__ void __maxnreg__(NREG) wwz_tile_kernel(const RecArgs a)
         for (int i = 0; i < nchunks; ++i) {
             mbar_wait(&full[s], (ph >> s) & 1u);
             ph ^= 1u << s;
+#ifdef WWZ_TRACE
+            if (i == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tr_first));
+            clk_mark = clock64();
+#endif
             const double2 *const st = stage_base + (size_t)s * a.stage_stride2;
             const double2 *const row = st + row_off;
             const int cnt = (int)min((long long)P, p1 - p0 - (long long)(c_lo + i) * P);
@@ -334,6 +350,9 @@ __global__ void __maxnreg__(NREG) wwz_tile_kernel(const RecArgs a)
                     ysc = yscn;
                 }
             }
+#ifdef WWZ_TRACE
+            clk_pts += clock64() - clk_mark;
+#endif
             __syncwarp();
             if (i + kStages < nchunks) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -342,6 +361,9 @@ __global__ void __maxnreg__(NREG) wwz_tile_kernel(const RecArgs a)
             if (++s == kStages) s = 0;
         }
 
+#ifdef WWZ_TRACE
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tr_loop));
+#endif
         if (nchunks > 0) {
             const long long first = (long long)c_lo * P, last = min(p1 - p0, (long long)(c_lo + nchunks) * P);
             walked += (unsigned long long)(last - first);
@@ -414,6 +436,24 @@ __global__ void __maxnreg__(NREG) wwz_tile_kernel(const RecArgs a)
             }
             report();
         }
+#ifdef WWZ_TRACE
+        if (a.trace && lane == 0) {
+            unsigned long long tr2;
+            unsigned int smid;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tr2));
+            asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+            const long long pts = nchunks > 0 ? min(p1 - p0, (long long)(c_lo + nchunks) * P) - (long long)c_lo * P : 0;
+            unsigned long long *const tr = a.trace + 8 * (size_t)item;
+            tr[0] = tr0;                               // item taken from the queue
+            tr[1] = tr1;                               // window found, first copies issued
+            tr[2] = tr2;                               // partial sums (and, fused, cells) written
+            tr[3] = (unsigned long long)pts;           // points walked
+            tr[4] = (unsigned long long)clk_pts;       // SM cycles inside the point loops
+            tr[5] = smid;
+            tr[6] = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+            tr[7] = ((tr_first ? tr_first - tr1 : 0) << 32) | (tr2 - tr_loop);   // wait for the first chunk | epilogue (ns)
+        }
+#endif
     }
 
     if (lane == 0) {
@@ -557,6 +597,32 @@ cudaError_t launch_rec(const RecPlan &plan, const double2 *d_ty, const double2 *
     a.row_stride2 = (int)(plan.row_stride / 16);
     a.stage_stride2 = plan.stage_bytes / 16;
     a.warp_stride = plan.warp_bytes;
+#ifdef WWZ_TRACE
+    {
+        // developer build: the previous traced launch is appended to $WWZB200_TRACE (binary) before the next one starts
+        static unsigned long long *buf = nullptr;
+        static int64_t pending = 0;
+        const char *path = getenv("WWZB200_TRACE");
+        a.trace = nullptr;
+        if (path && *path) {
+            if (!buf) cudaMallocManaged(&buf, (size_t)64 << 20);
+            if (pending) {
+                cudaDeviceSynchronize();
+                FILE *f = fopen(path, "ab");
+                if (f) {
+                    fwrite(&pending, 8, 1, f);
+                    fwrite(buf, 64, (size_t)pending, f);
+                    fclose(f);
+                }
+                pending = 0;
+            }
+            if (plan.cells_per_lane == kRecCells && a.nitems * 64 <= ((int64_t)64 << 20)) {
+                a.trace = buf;
+                pending = a.nitems;
+            }
+        }
+    }
+#endif
     if (plan.cells_per_lane == kRecCells) {
         if (fuse) {
             a.omega = fuse->omega;
