@@ -23,8 +23,13 @@ namespace {
 thread_local std::string g_err;
 std::mutex g_mu;
 
+// Counts the CUDA failures of the process: scratch that relies on a launch leaving its device counters zeroed (the
+// fused epilogue) is cleared again after any of them.
+unsigned int g_cuda_failures = 0;
+
 int fail(int code, const char *fmt, ...)
 {
+    if (code == WWZB200_ERR_CUDA) ++g_cuda_failures;
     char buf[512];
     va_list ap;
     va_start(ap, fmt);
@@ -80,6 +85,7 @@ struct Workspace {
     int sms = 0;
     bool fuse_zeroed = false;         // counters of the fused epilogue ("tile_cnt", "blk_cnt") have been cleared
     int64_t fuse_zeroed_tiles = 0;
+    unsigned int fuse_zeroed_gen = 0;
     double *h_in = nullptr;   // page-locked staging of the single-series inputs
     size_t h_in_count = 0;
     unsigned int *h_progress = nullptr;   // page-locked, mapped: progress flags of the fused epilogue + 2 summary words
@@ -351,12 +357,13 @@ int transform_device(Workspace *w, const double *d_ts, const double *d_ys, int64
             unsigned int *d_tile_cnt, *d_blk_cnt;
             if ((rc = wsbuf(w, "tile_cnt", (size_t)rec_tile_count(rplan, nf, 1), &d_tile_cnt))) return rc;
             if ((rc = wsbuf(w, "blk_cnt", (size_t)kMaxProgressBlocks, &d_blk_cnt))) return rc;
-            if (!w->fuse_zeroed || w->fuse_zeroed_tiles < rec_tile_count(rplan, nf, 1)) {
+            if (!w->fuse_zeroed || w->fuse_zeroed_tiles < rec_tile_count(rplan, nf, 1) || w->fuse_zeroed_gen != g_cuda_failures) {
                 // the counters are left zeroed by every launch: cleared when the buffer is new (or has grown)
                 CU(cudaMemsetAsync(d_tile_cnt, 0, sizeof(unsigned int) * (size_t)rec_tile_count(rplan, nf, 1), st));
                 CU(cudaMemsetAsync(d_blk_cnt, 0, sizeof(unsigned int) * kMaxProgressBlocks, st));
                 w->fuse_zeroed = true;
                 w->fuse_zeroed_tiles = rec_tile_count(rplan, nf, 1);
+                w->fuse_zeroed_gen = g_cuda_failures;
             }
             fuse.omega = d_omega;
             fuse.m_omega = 0;
