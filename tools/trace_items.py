@@ -66,3 +66,9 @@ while pos < raw.size and k < len(cases):
              / (edges[i + 1] - edges[i]) * CYC / 1.965 / (4 * sms) for i in range(20)]
     print("   items in flight per 5% slice of the launch:   " + " ".join("%4d" % o for o in occ))
     print("   FP64 pipe share per slice (%d cycles/point): " % CYC + " ".join("%.2f" % o for o in share))
+    sm = rec[:, 5]
+    tot = np.array([pts[sm == s].sum() for s in range(sms)])
+    fin = np.array([en[sm == s].max() if (sm == s).any() else 0 for s in range(sms)])
+    print("   per SM: points walked min %d, median %d, max %d; last item done at min %.0f, median %.0f, max %.0f us; points per us min %.0f, median %.0f, max %.0f"
+          % (tot.min(), np.median(tot), tot.max(), fin.min() / 1e3, np.median(fin) / 1e3, fin.max() / 1e3,
+             (tot / np.maximum(fin, 1)).min() * 1e3, np.median(tot / np.maximum(fin, 1)) * 1e3, (tot / np.maximum(fin, 1)).max() * 1e3))
