@@ -311,7 +311,14 @@ int transform_device(Workspace *w, const double *d_ts, const double *d_ys, int64
         unsigned long long *d_walked = nullptr;   // profiling: warp-points evaluated by the recurrence kernel
         if (g_profile && (rc = wsbuf(w, "walked", 1, &d_walked))) return rc;
         RecPlan rplan{}, dplan{};
-        if (allow_rec) rplan = plan_rec(n, nt, nf, seg_len, kRecCells);
+        // tabulated rho growth (one exp2 chain per point instead of two) where the windows are long: long series on
+        // long tau axes (config 5: 266 -> 250 ms; config 2, n = 2000: 1.4%, left on the exact pair)
+        bool rho_growth = nt >= 128 && n >= 8192 && w->prefix.empty();
+        {
+            const char *e = getenv("WWZB200_RHO_GROWTH");
+            if (e && *e) rho_growth = atoi(e) != 0 && w->prefix.empty();
+        }
+        if (allow_rec) rplan = plan_rec(n, nt, nf, seg_len, kRecCells, rho_growth);
         if (tile_direct) dplan = plan_rec(n, nt, nf, seg_len, kTileDirectCells);
         {   // one row stride of the basis scratch for all kernels of the transform
             int64_t np = tile_direct ? dplan.n_pad : plan.n_pad;
@@ -331,6 +338,8 @@ int transform_device(Workspace *w, const double *d_ts, const double *d_ys, int64
         double2 *d_ty, *d_basis;
         if ((rc = wsbuf(w, "ty", (size_t)plan.n_pad, &d_ty))) return rc;
         if ((rc = wsbuf(w, "basis", (size_t)nf_batch * (size_t)plan.n_pad * 2, &d_basis))) return rc;
+        double *d_estep = nullptr;    // recurrence flavour: growth of rho from point to point, per (row, point)
+        if (allow_rec && rplan.growth && (rc = wsbuf(w, "estep", (size_t)rec_estep_count(rplan, nf_batch, 1), &d_estep))) return rc;
         if ((rc = wsbuf(w, "sums", (size_t)segs * (size_t)kNumSums * (size_t)ncell, &d_sums))) return rc;
         double *d_sums2 = nullptr;   // Foster: sums of the second pass (y := cos)
         if (foster && (rc = wsbuf(w, "sums2", (size_t)segs * (size_t)kNumSums * (size_t)ncell, &d_sums2))) return rc;
@@ -417,7 +426,7 @@ int transform_device(Workspace *w, const double *d_ts, const double *d_ys, int64
             if (allow_rec)
                 CU(launch_rec(rplan, d_ty, d_basis, d_ts, n, d_tau, nt, d_kappa, d_dcut, d_gap, d_unsorted, k0, nb, nf, segs,
                               seg_len, d_rec_row, d_grid, d_sums, d_queue, d_walked, w->sms, st, 1, 0, 0,
-                              fuse_on ? &fuse : nullptr));
+                              fuse_on ? &fuse : nullptr, d_estep));
             if (tile_direct)
                 CU(launch_rec(dplan, d_ty, d_basis, d_ts, n, d_tau, nt, d_kappa, d_dcut, d_gap, d_unsorted, k0, nb, nf, segs,
                               seg_len, allow_rec ? d_rec_row : nullptr, d_grid, d_sums, d_queue + 2, nullptr, w->sms, st_direct));
@@ -442,7 +451,7 @@ int transform_device(Workspace *w, const double *d_ts, const double *d_ys, int64
                 }
                 if (allow_rec)
                     CU(launch_rec(rplan, d_ty, d_basis, d_ts, n, d_tau, nt, d_kappa, d_dcut, d_gap, d_unsorted, k0, nb, nf, segs,
-                                  seg_len, d_rec_row, d_grid, d_sums2, d_queue, nullptr, w->sms, st));
+                                  seg_len, d_rec_row, d_grid, d_sums2, d_queue, nullptr, w->sms, st, 1, 0, 0, nullptr, d_estep));
                 if (tile_direct)
                     CU(launch_rec(dplan, d_ty, d_basis, d_ts, n, d_tau, nt, d_kappa, d_dcut, d_gap, d_unsorted, k0, nb, nf,
                                   segs, seg_len, allow_rec ? d_rec_row : nullptr, d_grid, d_sums2, d_queue + 2, nullptr, w->sms,
@@ -811,6 +820,7 @@ int members_device(Workspace *w, const double *d_ts, int64_t m_ts, const double 
     if ((rc = wsbuf(w, "ty", (size_t)(M * n_pad), &d_ty))) return rc;
     if ((rc = wsbuf(w, "basis", (size_t)M * (size_t)nf * (size_t)n_pad * 2, &d_basis))) return rc;
     if ((rc = wsbuf(w, "sums", (size_t)M * (size_t)segs * kNumSums * (size_t)ncell, &d_sums))) return rc;
+    double *d_estep = nullptr;     // (no tabulated rho growth for member batches: a table per member costs more than it saves)
     if (freq_hz) {
         if ((rc = wsbuf(w, "mb_fnyq", (size_t)M, &d_fnyq))) return rc;
         if ((rc = wsbuf(w, "mb_omega", (size_t)(M * nf), &d_omega))) return rc;
@@ -842,7 +852,7 @@ int members_device(Workspace *w, const double *d_ts, int64_t m_ts, const double 
         CU(cudaEventRecord(w->side_fork, st));
         CU(cudaStreamWaitEvent(w->side, w->side_fork, 0));
         CU(launch_rec(rplan, d_ty, d_basis, d_ts, n, d_tau, nt, d_kappa, d_dcut, d_gap, d_flags, 0, nf, nf, segs, seg_len,
-                      d_rec_row, d_grid, d_sums, d_queue, nullptr, w->sms, st, M, m_ts, m_tau));
+                      d_rec_row, d_grid, d_sums, d_queue, nullptr, w->sms, st, M, m_ts, m_tau, nullptr, d_estep));
     }
     CU(launch_rec(dplan, d_ty, d_basis, d_ts, n, d_tau, nt, d_kappa, d_dcut, d_gap, d_flags, 0, nf, nf, segs, seg_len,
                   allow_rec ? d_rec_row : nullptr, d_grid, d_sums, d_queue + 2, nullptr, w->sms, st_direct, M, m_ts, m_tau));

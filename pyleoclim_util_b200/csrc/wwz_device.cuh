@@ -186,6 +186,48 @@ __device__ __forceinline__ void gauss_weight_ratio(double a, double step16, cons
     rho = __hiloint2double(tiny ? 0 : hir, tiny ? 0 : __double2loint(pr));
 }
 
+// The two halves of gauss_weight_ratio on their own, for the loop that advances rho from point to point
+// (rho_{i+1} = rho_i * E_i, E tabulated per (row, point)) and evaluates it afresh once per chunk.
+// gauss_weight_flag: w_0 and whether it was flushed; exp2_sixteenth: 2^(b/16) for |b| < 2^15.
+__device__ __forceinline__ double gauss_weight_flag(double a, const double *__restrict__ tbl, bool &tiny)
+{
+    const double z = fma(-a, a, kShift);
+    const double Nf = z - kShift;
+    const double g = fma(-a, a, -Nf);
+    const int N = __double2loint(z);
+    const double T = tbl[N & 15];
+    double p = c_exp2t[6];
+    p = fma(p, g, c_exp2t[5]);
+    p = fma(p, g, c_exp2t[4]);
+    p = fma(p, g, c_exp2t[3]);
+    p = fma(p, g, c_exp2t[2]);
+    p = fma(p, g, c_exp2t[1]);
+    p = fma(p, g, c_exp2t[0]);
+    p *= T;
+    tiny = __double_as_longlong(z) < kTinyBits;
+    const int hi = __double2hiint(p) + ((N >> 4) << 20);
+    return __hiloint2double(tiny ? 0 : hi, tiny ? 0 : __double2loint(p));
+}
+
+__device__ __forceinline__ double exp2_sixteenth(double b, const double *__restrict__ tbl)
+{
+    const double zr = b + kShift;
+    const double Nrf = zr - kShift;
+    const double gr = b - Nrf;
+    const int Nr = __double2loint(zr);
+    const double Tr = tbl[Nr & 15];
+    double pr = c_exp2t[6];
+    pr = fma(pr, gr, c_exp2t[5]);
+    pr = fma(pr, gr, c_exp2t[4]);
+    pr = fma(pr, gr, c_exp2t[3]);
+    pr = fma(pr, gr, c_exp2t[2]);
+    pr = fma(pr, gr, c_exp2t[1]);
+    pr = fma(pr, gr, c_exp2t[0]);
+    pr *= Tr;
+    const int hir = __double2hiint(pr) + ((Nr >> 4) << 20);
+    return __hiloint2double(hir, __double2loint(pr));
+}
+
 // The table lives in shared memory; call from the first 16 threads of a CTA before a barrier.
 __device__ __forceinline__ void load_exp2_table(double *tbl, int tid)
 {

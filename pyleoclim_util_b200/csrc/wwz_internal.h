@@ -41,6 +41,8 @@ struct RecPlan {
     int cells_per_lane;   // kRecCells = tau-recurrence flavour, kTileDirectCells = direct flavour
     int groups;           // G = ceil(nt / cells_per_lane) tau-groups per frequency row
     int tg_log2;          // a warp tile is 2^tg_log2 tau-groups x (32 >> tg_log2) frequency rows
+    int growth;           // 1: stages carry the [P][TR] block of rho growth factors (recurrence flavour)
+    int stages;           // stages of a warp's ring
     int points;           // P: points per stage of a warp's ring
     int64_t n_pad;
     int64_t row_stride;   // smem basis row stride in bytes (P*32 + 16)
@@ -49,7 +51,8 @@ struct RecPlan {
     int warps, nreg;      // CTA shape: warps per CTA, register budget per thread
     int smem_bytes;       // dynamic shared memory of the CTA
 };
-RecPlan plan_rec(int64_t n, int64_t nt, int64_t nf, int64_t seg_len, int cells_per_lane = kRecCells);
+// rho_growth: recurrence flavour with the tabulated growth of rho (launch_rec then needs the d_estep scratch)
+RecPlan plan_rec(int64_t n, int64_t nt, int64_t nf, int64_t seg_len, int cells_per_lane = kRecCells, bool rho_growth = false);
 // Fused epilogue of the recurrence flavour (launch_rec, optional): the warp that finishes the last point segment of a
 // tile writes the tile's finished cells itself; finalize_kernel then only takes the rows of the direct flavour
 // (launch_finalize*, skip_rec_rows).  tile_cnt: one zeroed counter per (tile, member) of the launch (rec_tile_count;
@@ -79,7 +82,10 @@ cudaError_t launch_rec(const RecPlan &plan, const double2 *d_ty, const double2 *
                        const double *d_taugap, const int *d_unsorted, int64_t k0, int64_t nf_batch, int64_t nf_total, int segs,
                        int64_t seg_len, const unsigned char *d_rec_row, const double *d_grid, double *d_sums,
                        unsigned int *d_queue, unsigned long long *d_walked, int sms, cudaStream_t st, int64_t members = 1,
-                       int64_t m_ts = 0, int64_t m_tau = 0, const RecFuse *fuse = nullptr);
+                       int64_t m_ts = 0, int64_t m_tau = 0, const RecFuse *fuse = nullptr, double *d_estep = nullptr);
+// doubles of the optional d_estep scratch of a recurrence-flavour launch (per point and row: the growth of rho to the next
+// point; with it the kernel advances rho by one multiplication per point)
+int64_t rec_estep_count(const RecPlan &plan, int64_t nf_batch, int64_t members);
 
 // Per-frequency constants kappa4 = 4*omega*sqrt(c*log2 e) and dcut = distance beyond which a weight is below
 // 2^-cut_bits (1081 = exactly zero weights only; windowing); which rows the tau-recurrence flavour may take

@@ -53,6 +53,9 @@ struct RecArgs {
     const unsigned char *rec_row;
     const double *grid;
     double *sums;
+    const double *estep;          // REC, optional: [member][row tile][n_pad][TR] growth of rho from a point to the next
+    int e_off2;                   // offset of the [P][TR] growth block inside a stage, double2 units
+    int stages;                   // stages of a warp's ring in use (<= kStages)
     unsigned int *queue;          // [0] next work item, [1] warps that have left (self-resetting)
     unsigned long long *walked;   // profiling only (may be null): (lane, point) pairs actually evaluated, summed over warps
     long long n, n_pad, ncell_total, seg_len, ntiles, nitems;
@@ -82,6 +85,30 @@ struct RecArgs {
 #endif
 };
 
+// Growth of rho = 2^(kappa4^2 dtau (t - tau_0)/8) from point i to point i+1: E = 2^(kappa4^2 dtau (t_{i+1} - t_i)/8).  It depends
+// on (row, point) only, so the recurrence flavour advances rho with one multiplication per point instead of a second
+// exp2 chain per (lane, point).  Laid out [row tile][point][TR]: a chunk of a tile is one contiguous bulk copy.
+__global__ void __launch_bounds__(256) rho_growth_kernel(const RecArgs a, double *__restrict__ estep)
+{
+    const int TR = 32 >> a.tg_log2;
+    const long long per_mem = (long long)((a.nf_batch + TR - 1) / TR) * a.n_pad * TR;
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= per_mem * a.members) return;
+    const int mem = (int)(e / per_mem);
+    const long long q = e - (long long)mem * per_mem;
+    const int r = (int)(q % TR);
+    const long long i = (q / TR) % a.n_pad;
+    const int kb = (int)(q / ((long long)TR * a.n_pad)) * TR + r;
+    double v = 1.0;
+    if (kb < a.nf_batch && i + 1 < a.n) {
+        const double *const ts = a.ts + (long long)mem * a.m_ts;
+        const double kap = a.kappa[(size_t)mem * a.nf_total + a.k0 + kb];
+        const double step16 = 2.0 * kap * a.grid[2 * mem];
+        v = exp2(kap * (ts[i + 1] - ts[i]) * step16 * 0.0625);
+    }
+    estep[e] = v;
+}
+
 // NREG = register budget per thread (__maxnreg__: ptxas interleaves the weight evaluation of the next point with the
 // accumulations of the current one only when it has the registers for both).  Every warp of a CTA is an independent
 // worker; the number of warps per CTA is a launch parameter.
@@ -100,7 +127,7 @@ __global__ void __maxnreg__(NREG) wwz_tile_kernel(const RecArgs a)
     const int P = a.P;
     unsigned char *const wbase = smem_raw + (size_t)warp * a.warp_stride;
     double2 *const stage_base = reinterpret_cast<double2 *>(wbase);
-    uint64_t *const full = reinterpret_cast<uint64_t *>(wbase + (size_t)kStages * a.stage_stride2 * sizeof(double2));
+    uint64_t *const full = reinterpret_cast<uint64_t *>(wbase + (size_t)a.stages * a.stage_stride2 * sizeof(double2));
     if (lane == 0) {
 #pragma unroll
         for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
@@ -236,7 +263,9 @@ __global__ void __maxnreg__(NREG) wwz_tile_kernel(const RecArgs a)
         const int c_lo = (int)((i0 - p0) / P);
         const int nchunks = (i1 > i0) ? (int)((i1 - p0 + P - 1) / P) - c_lo : 0;
 
-        const uint32_t bytes = (uint32_t)P * 16u + (uint32_t)rows * (uint32_t)P * 32u;
+        const bool use_e = REC && a.estep != nullptr;
+        const uint32_t e_bytes = use_e ? (uint32_t)P * (uint32_t)TR * 8u : 0u;
+        const uint32_t bytes = (uint32_t)P * 16u + (uint32_t)rows * (uint32_t)P * 32u + e_bytes;
         auto issue = [&](int c, int sg) {
             // lane 0 starts the bulk copy of the (t, y) pairs, lanes 0..rows-1 one basis row each, of chunk c into
             // stage sg; the stage was last read before the __syncwarp that precedes every call
@@ -251,6 +280,9 @@ __global__ void __maxnreg__(NREG) wwz_tile_kernel(const RecArgs a)
                 const size_t row = (size_t)(kt * TR + lane);
                 tma_load_1d(st + P + (size_t)lane * a.row_stride2, m_basis + (row * (size_t)a.n_pad + start) * 2,
                             (uint32_t)P * 32u, &full[sg]);
+            } else if (use_e && lane == rows) {
+                const double *const m_e = a.estep + (size_t)mem * (size_t)((a.nf_batch + TR - 1) / TR) * (size_t)a.n_pad * TR;
+                tma_load_1d(st + a.e_off2, m_e + ((size_t)kt * (size_t)a.n_pad + start) * TR, e_bytes, &full[sg]);
             }
         };
         {
@@ -258,8 +290,8 @@ __global__ void __maxnreg__(NREG) wwz_tile_kernel(const RecArgs a)
             int sg = s;
 #pragma unroll
             for (int u = 0; u < kStages; ++u) {
-                if (u < nchunks) issue(c_lo + u, sg);
-                if (++sg == kStages) sg = 0;
+                if (u < a.stages && u < nchunks) issue(c_lo + u, sg);
+                if (++sg == a.stages) sg = 0;
             }
         }
 
@@ -287,7 +319,51 @@ __global__ void __maxnreg__(NREG) wwz_tile_kernel(const RecArgs a)
             double2 sc = row[0], ysc = row[1];
             if constexpr (REC) {
                 static_assert(M == 8, "the power tree below is written for 8 cells per lane");
-                {
+                // rho advanced from point to point by the tabulated growth E (one multiplication instead of a second
+                // exp2 chain), from an exact value at the first point of the chunk -- as long as no lane's rho leaves
+                // the range of a double inside the chunk (the exponent a D/8 at both ends of the chunk below 900 in
+                // magnitude; t is sorted, so it is monotone in between); otherwise, and on unsorted axes, the exact pair
+                bool fast = false;
+                if (use_e && sorted) {
+                    const double b0 = kap * (st[0].x - tau_r[0]) * step16, b1 = kap * (st[cnt - 1].x - tau_r[0]) * step16;
+                    fast = __all_sync(0xffffffffu, fabs(b0) < 14400.0 && fabs(b1) < 14400.0);
+                }
+                if (fast) {
+                    const double *const erow = reinterpret_cast<const double *>(st + a.e_off2) + r_loc;
+                    double rho_c = exp2_sixteenth(kap * (st[0].x - tau_r[0]) * step16, tbl);
+#pragma unroll 2
+                    for (int p = 0; p < cnt; ++p) {
+                        const double2 ty = st[p];
+                        const double2 sc_ = row[2 * p];
+                        const double2 ysc_ = row[2 * p + 1];
+                        const double grow = erow[p * TR];
+                        bool tiny;
+                        const double w0 = gauss_weight_flag(kap * (ty.x - tau_r[0]), tbl, tiny);
+                        const double rho = tiny ? 0.0 : rho_c;
+                        rho_c *= grow;
+                        double wv[M];
+                        const double rho2 = rho * rho, rho4 = rho2 * rho2;
+                        wv[0] = w0;
+                        wv[1] = w0 * rho;
+                        wv[2] = w0 * rho2;
+                        wv[3] = wv[1] * rho2;
+                        wv[4] = w0 * rho4;
+                        wv[5] = wv[1] * rho4;
+                        wv[6] = wv[2] * rho4;
+                        wv[7] = wv[3] * rho4;
+#pragma unroll
+                        for (int r = 0; r < M; ++r) {
+                            const double w = wv[r];
+                            W[r] += w;
+                            Q[r] = fma(w, w, Q[r]);
+                            Ws[r] = fma(w, sc_.x, Ws[r]);
+                            Wc[r] = fma(w, sc_.y, Wc[r]);
+                            Wy[r] = fma(w, ty.y, Wy[r]);
+                            Wys[r] = fma(w, ysc_.x, Wys[r]);
+                            Wyc[r] = fma(w, ysc_.y, Wyc[r]);
+                        }
+                    }
+                } else {
                     // two points per iteration: their exp2 pairs interleave (four independent chains); w_0 rho^m
                     // through a depth-3 product tree
 #pragma unroll 2
@@ -354,11 +430,11 @@ __global__ void __maxnreg__(NREG) wwz_tile_kernel(const RecArgs a)
             clk_pts += clock64() - clk_mark;
 #endif
             __syncwarp();
-            if (i + kStages < nchunks) {
+            if (i + a.stages < nchunks) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                issue(c_lo + i + kStages, s);
+                issue(c_lo + i + a.stages, s);
             }
-            if (++s == kStages) s = 0;
+            if (++s == a.stages) s = 0;
         }
 
 #ifdef WWZ_TRACE
@@ -470,7 +546,7 @@ __global__ void __maxnreg__(NREG) wwz_tile_kernel(const RecArgs a)
 
 // Tile shape: 8 tau-groups x 4 rows when the tau axis is long; on small tau grids (the reference default is 50)
 // tau-compact tiles -- one or two tau-groups x 32 / 16 rows -- so that the point windows prune.
-RecPlan plan_rec(int64_t n, int64_t nt, int64_t nf, int64_t seg_len, int cells_per_lane)
+RecPlan plan_rec(int64_t n, int64_t nt, int64_t nf, int64_t seg_len, int cells_per_lane, bool rho_growth)
 {
     RecPlan p{};
     const int M = cells_per_lane;
@@ -491,7 +567,18 @@ RecPlan plan_rec(int64_t n, int64_t nt, int64_t nf, int64_t seg_len, int cells_p
     const int TR = 32 >> tg_log2;
     // ring budget per warp: ~14 KB at 12 warps per SM (recurrence flavour, 3 CTAs), ~12 KB at 16 (direct, 4 CTAs)
     const int64_t budget = M == kRecCells ? 14336 : 12288;
-    int64_t P = (budget / kStages - 16 * TR) / (16 + 32 * TR);
+    // Recurrence flavour with the tabulated growth of rho (single transforms on long tau axes: long windows): room for
+    // the [P][TR] growth block in every stage, and two stages of longer chunks -- a chunk takes ~10 us of arithmetic
+    // against ~1 us for its bulk copies, and every chunk costs ~1000 cycles of hand-over.  Member batches and small
+    // grids (windows of two or three chunks: all of them in flight at once) keep three stages and no table.
+    p.growth = (M == kRecCells && rho_growth) ? 1 : 0;
+    {
+        const char *e = getenv("WWZB200_NO_RHO_GROWTH");
+        if (e && *e && atoi(e)) p.growth = 0;
+    }
+    const int64_t e_per_pt = p.growth ? 8 * TR : 0;
+    p.stages = p.growth ? 2 : kStages;
+    int64_t P = (budget / p.stages - 16 * TR) / (16 + 32 * TR + e_per_pt);
     P &= ~(int64_t)1;
     const int64_t span = seg_len > 0 ? std::min(seg_len, n) : n;
     if (P > span) P = ((span + 1) / 2) * 2;
@@ -499,8 +586,8 @@ RecPlan plan_rec(int64_t n, int64_t nt, int64_t nf, int64_t seg_len, int cells_p
     p.points = (int)P;
     p.n_pad = ((n + P + 15) / 16) * 16;
     p.row_stride = P * 32 + 16;                         // an odd number of 16 B units: rows never share a bank group
-    p.stage_bytes = (int)(P * 16 + (int64_t)TR * p.row_stride);
-    p.warp_bytes = ((kStages * p.stage_bytes + kStages * 8 + 127) / 128) * 128;   // ring, then the barriers
+    p.stage_bytes = (int)(P * 16 + (int64_t)TR * p.row_stride + P * e_per_pt);
+    p.warp_bytes = ((p.stages * p.stage_bytes + kStages * 8 + 127) / 128) * 128;   // ring, then the barriers
     // CTA shape: 4 independent warps; 168 registers -> 3 CTAs = 12 warps per SM for the recurrence flavour (3 warps per
     // SMSP is all the register file holds at 168; budgets between 168 and 255 all give 2), 128 -> 16 for the direct one
     p.warps = 4;
@@ -548,6 +635,11 @@ int64_t rec_tile_count(const RecPlan &plan, int64_t nf_batch, int64_t members)
     const int TG = 1 << plan.tg_log2, TR = 32 >> plan.tg_log2;
     return (int64_t)((plan.groups + TG - 1) / TG) * ((nf_batch + TR - 1) / TR) * members;
 }
+int64_t rec_estep_count(const RecPlan &plan, int64_t nf_batch, int64_t members)
+{
+    const int TR = 32 >> plan.tg_log2;
+    return ((nf_batch + TR - 1) / TR) * plan.n_pad * TR * members;
+}
 int rec_tau_tiles(const RecPlan &plan) { return (plan.groups + (1 << plan.tg_log2) - 1) >> plan.tg_log2; }
 int rec_tile_taus(const RecPlan &plan) { return plan.cells_per_lane << plan.tg_log2; }
 
@@ -556,7 +648,7 @@ cudaError_t launch_rec(const RecPlan &plan, const double2 *d_ty, const double2 *
                        const double *d_taugap, const int *d_unsorted, int64_t k0, int64_t nf_batch, int64_t nf_total, int segs,
                        int64_t seg_len, const unsigned char *d_rec_row, const double *d_grid, double *d_sums,
                        unsigned int *d_queue, unsigned long long *d_walked, int sms, cudaStream_t st, int64_t members,
-                       int64_t m_ts, int64_t m_tau, const RecFuse *fuse)
+                       int64_t m_ts, int64_t m_tau, const RecFuse *fuse, double *d_estep)
 {
     if (nf_batch <= 0 || nt <= 0 || members <= 0) return cudaSuccess;
     RecArgs a{};
@@ -596,6 +688,17 @@ cudaError_t launch_rec(const RecPlan &plan, const double2 *d_ty, const double2 *
     if (a.nitems >= ((int64_t)1 << 32)) return cudaErrorInvalidValue;
     a.row_stride2 = (int)(plan.row_stride / 16);
     a.stage_stride2 = plan.stage_bytes / 16;
+    a.stages = plan.stages;
+    a.e_off2 = (int)((plan.points * 16 + (int64_t)TR * plan.row_stride) / 16);
+    a.estep = nullptr;
+    if (plan.cells_per_lane == kRecCells && plan.growth && d_estep) {
+        const int64_t cnt = ((nf_batch + TR - 1) / TR) * plan.n_pad * TR * members;
+        rho_growth_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(a, d_estep);
+        bump_launch_counter();
+        cudaError_t ee = cudaGetLastError();
+        if (ee != cudaSuccess) return ee;
+        a.estep = d_estep;
+    }
     a.warp_stride = plan.warp_bytes;
 #ifdef WWZ_TRACE
     {

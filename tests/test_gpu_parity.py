@@ -541,3 +541,37 @@ def test_streamed_output_falls_back_when_other_kernels_own_cells(monkeypatch):
     for a, b in zip(_bits(one), _bits(streamed)):
         assert np.array_equal(a, b)
     assert np.isnan(one[0]).any()                                       # the hiatus masks cells
+
+
+# ------------------------------------------------------------------ tabulated growth of rho (recurrence flavour, long series)
+def test_rho_growth_table_agrees_with_the_exact_pair(monkeypatch):
+    """Long series advance rho = 2^(a D/8) from point to point with a tabulated factor (one exp2 chain per point instead of
+    two), re-evaluated exactly at every chunk start; chunks in which a lane's exponent could leave the range of a double
+    (a hiatus) and unsorted axes take the exact pair.  Forced on here at config 2 size and on a series with a hiatus."""
+    t, y, tau, freq = synth.config_grid("C2")
+    ys = WV.standardize(y)[0]
+    tg = np.concatenate([t[:800], t[800:] + 5000.0])                     # a hiatus 2.5 times the span of the series
+    cases = [(t, tau), (tg, np.linspace(tg.min(), tg.max(), 640))]
+    for tt, ta in cases:
+        monkeypatch.setenv("WWZB200_RHO_GROWTH", "0")
+        exact = WV.kirchner_cuda(ys, tt, freq, ta)
+        monkeypatch.setenv("WWZB200_RHO_GROWTH", "1")
+        table = WV.kirchner_cuda(ys, tt, freq, ta)
+        assert_same_nan_mask(table[0], exact[0])
+        assert_same_nan_mask(table[2], exact[2])
+        assert max_rel(table[0], exact[0]) < 1e-11
+        assert max_rel(table[2], exact[2]) < 1e-12
+        assert max_phase_abs(table[1], exact[1]) < 1e-11
+    O = oracle()
+    rows = np.r_[0:2, 499:501, 998:1000]
+    ref = O.kirchner(ys, t, freq, tau[rows], mode=0)
+    got = WV.kirchner_cuda(ys, t, freq, tau)
+    assert_scalogram_parity(as_dict(got[0][rows], got[1][rows], got[2][rows], tuple(x[rows] for x in got[3])), as_dict(*ref),
+                            what="rho growth table, config 2")
+    # an unsorted axis never uses the table (the growth factors assume ascending time)
+    perm = np.random.default_rng(0).permutation(t.size)
+    a = WV.kirchner_cuda(ys[perm], t[perm], freq, tau[:256])
+    monkeypatch.setenv("WWZB200_RHO_GROWTH", "0")
+    b = WV.kirchner_cuda(ys[perm], t[perm], freq, tau[:256])
+    for x, z in zip(_bits(a), _bits(b)):
+        assert np.array_equal(x, z)
