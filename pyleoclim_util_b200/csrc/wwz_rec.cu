@@ -9,7 +9,8 @@
 //    support of its Gaussian weights is a short index range of the sorted time axis;
 //  * every warp finds the range of its own tile (warp-cooperative 32-ary search on ts) and walks only
 //    that: points whose weight is below 2^-100 of the largest weight of every cell of the tile are never touched;
-//  * every warp stages its own points: a private 3-stage shared-memory ring filled by 1-D TMA bulk copies
+//  * every warp stages its own points: a private shared-memory ring (three stages; two longer ones with the growth
+//    table of rho, see the REC loop) filled by 1-D TMA bulk copies
 //    (cp.async.bulk + mbarrier complete_tx) that the warp issues itself -- no producer warp, no CTA-wide
 //    barrier in the loop;
 //  * the grid is PERSISTENT: one launch = (SMs x resident CTAs) CTAs whose warps pull (tile, point segment) items
