@@ -187,6 +187,9 @@ int wsbuf(Workspace *w, const char *name, size_t count, T **out)
     return rc;
 }
 
+// Bytes of basis rows kept at once: grids whose rows need more are transformed in frequency batches.  8 GiB of the 180 GB:
+// config 5 (6.5 GB of rows) then runs as ONE launch of the cell kernels instead of four (250.6 -> 241.2 ms: three ramps
+// and tails fewer), and a sharded run of it (a rank's launches are short) gains more.
 size_t basis_budget_bytes()
 {
     const char *e = getenv("WWZB200_BASIS_BYTES");
@@ -194,7 +197,7 @@ size_t basis_budget_bytes()
         double v = atof(e);
         if (v >= 1 << 20) return (size_t)v;
     }
-    return (size_t)2 << 30;
+    return (size_t)8 << 30;
 }
 
 // Number of point-axis segments.  CTA-wide direct kernel: enough that (cells x segments) fills the machine for several
