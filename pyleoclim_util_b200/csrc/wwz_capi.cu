@@ -340,7 +340,13 @@ int transform_device(Workspace *w, const double *d_ts, const double *d_ys, int64
         nf_batch = std::min<int64_t>(std::min<int64_t>(nf_batch, nf), 65535);
         double2 *d_ty, *d_basis;
         if ((rc = wsbuf(w, "ty", (size_t)plan.n_pad, &d_ty))) return rc;
-        if ((rc = wsbuf(w, "basis", (size_t)nf_batch * (size_t)plan.n_pad * 2, &d_basis))) return rc;
+        // (a device that cannot give the whole budget -- other tenants -- gets smaller frequency batches instead of an error)
+        while ((rc = wsbuf(w, "basis", (size_t)nf_batch * (size_t)plan.n_pad * 2, &d_basis)) == WWZB200_ERR_NOMEM &&
+               nf_batch > 64) {
+            cudaGetLastError();
+            nf_batch = (nf_batch + 1) / 2;
+        }
+        if (rc) return rc;
         double *d_estep = nullptr;    // recurrence flavour: growth of rho from point to point, per (row, point)
         if (allow_rec && rplan.growth && (rc = wsbuf(w, "estep", (size_t)rec_estep_count(rplan, nf_batch, 1), &d_estep))) return rc;
         if ((rc = wsbuf(w, "sums", (size_t)segs * (size_t)kNumSums * (size_t)ncell, &d_sums))) return rc;
